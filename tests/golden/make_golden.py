@@ -1,0 +1,187 @@
+"""Generate the golden vectors that pin `oracle/xml_oracle.py` to the REAL reference.
+
+Run in the build container only (it imports jayleicn/TVRetrieval from /root/reference, which does not
+exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It executes the unmodified reference model + drivers (model_xml.py, inference.py, temporal_nms.py, ...)
+on small seeded synthetic datasets and writes `tests/golden/<case>.npz` holding the weights, the
+inputs and every reference output the tests compare against.  Shims: `easydict`, `h5py.File`
+(tests/golden/_shims) and `numpy.int` (reference inference.py:289,293 uses the removed alias).
+"""
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REFERENCE = os.environ.get("XML_REFERENCE_ROOT", "/root/reference")
+sys.path[:0] = [os.path.join(HERE, "_shims"), REFERENCE, REPO]
+np.int = int  # noqa
+
+import torch  # noqa: E402
+from easydict import EasyDict  # noqa: E402
+from baselines.crossmodal_moment_localization.model_xml import XML, xml_base_config  # noqa: E402
+from baselines.crossmodal_moment_localization import inference as ref_inf  # noqa: E402
+from baselines.clip_alignment_with_language.inference import (  # noqa: E402
+    post_processing_vcmr_nms, post_processing_svmr_nms, get_submission_top_n)
+from utils.temporal_nms import temporal_non_maximum_suppression  # noqa: E402
+
+from tvretrieval_b200.synthetic import SyntheticEvalDataset  # noqa: E402
+
+CASES = {
+    # BASELINE.json configs[0] analogue: video-only, SVMR-only driver (reference inference.py:107-167)
+    "video_only_svmr": dict(
+        cfg=dict(ctx_mode="video", merge_two_stream=False, cross_att=False, hidden_size=64, n_heads=4,
+                 visual_input_size=48, query_input_size=40, sub_input_size=40, max_ctx_l=32, max_desc_l=12),
+        data=dict(n_videos=10, n_queries=10, seed=11), ctx_bsz=4, q_bsz=4, max_n_videos=5,
+        max_before_nms=40, tasks=("SVMR",)),
+    # the north-star path: video_sub, cross attention, merged ConvSE, full VCMR/SVMR/VR driver
+    "video_sub_vcmr": dict(
+        cfg=dict(ctx_mode="video_sub", merge_two_stream=True, cross_att=True, hidden_size=64, n_heads=4,
+                 visual_input_size=48, query_input_size=40, sub_input_size=40, max_ctx_l=32, max_desc_l=12),
+        data=dict(n_videos=24, n_queries=12, seed=12), ctx_bsz=10, q_bsz=5, max_n_videos=8,
+        max_before_nms=50, tasks=("VCMR", "SVMR", "VR")),
+    # two streams, no cross attention, per-stream ConvSE averaged (reference model_xml.py:580-585)
+    "video_sub_nocross": dict(
+        cfg=dict(ctx_mode="video_sub", merge_two_stream=False, cross_att=False, hidden_size=32, n_heads=2,
+                 visual_input_size=24, query_input_size=20, sub_input_size=28, max_ctx_l=24, max_desc_l=8),
+        data=dict(n_videos=14, n_queries=9, seed=13), ctx_bsz=6, q_bsz=4, max_n_videos=6,
+        max_before_nms=30, tasks=("VCMR", "SVMR", "VR")),
+}
+
+
+def make_opt(case, cfg):
+    return EasyDict(eval_context_bsz=case["ctx_bsz"], eval_query_bsz=case["q_bsz"], num_workers=0,
+                    pin_memory=False, device=torch.device("cpu"), ctx_mode=cfg["ctx_mode"],
+                    external_inference_vr_res_path=None, q2c_alpha=20.0, min_pred_l=2, max_pred_l=16,
+                    max_ctx_l=cfg["max_ctx_l"], clip_length=1.5, debug=False)
+
+
+def preds_to_array(res_list):
+    """list of {desc_id, desc, predictions=[[vid, st, ed, score]...]} -> (Nq, K, 4) float64 (+ counts)."""
+    k = max(len(e["predictions"]) for e in res_list)
+    out = np.zeros((len(res_list), k, 4), dtype=np.float64)
+    cnt = np.zeros(len(res_list), dtype=np.int64)
+    for i, e in enumerate(res_list):
+        p = np.asarray(e["predictions"], dtype=np.float64).reshape(-1, 4)
+        out[i, :len(p)] = p
+        cnt[i] = len(p)
+    return out, cnt
+
+
+def run_case(name, case):
+    cfg = copy.deepcopy(xml_base_config)
+    cfg.update(case["cfg"])
+    torch.manual_seed(2018)
+    model = XML(cfg).eval()
+    ds = SyntheticEvalDataset(max_ctx_l=cfg.max_ctx_l, max_desc_l=cfg.max_desc_l,
+                              video_dim=cfg.visual_input_size, sub_dim=cfg.sub_input_size,
+                              query_dim=cfg.query_input_size, ctx_mode=cfg.ctx_mode, min_ctx_l=3, **case["data"])
+    opt = make_opt(case, cfg)
+    out = {"cfg_json": json.dumps({k: v for k, v in cfg.items()}),
+           "case_json": json.dumps({k: (list(v) if isinstance(v, tuple) else v) for k, v in case.items()})}
+    for k, v in model.state_dict().items():
+        out["w/" + k] = v.numpy()
+    out["ctx_lens"] = np.asarray(ds.ctx_lens)
+    out["video2idx"] = np.asarray([ds.video2idx[v["vid_name"]] for v in ds.video_data])
+    out["query_gt_meta_idx"] = np.asarray([int(q["vid_name"].split("_")[1]) for q in ds.query_data])
+    for i in range(len(ds.video_data)):
+        if ds.use_video:
+            out["video_feat/%d" % i] = ds.video_feats[i].numpy()
+        if ds.use_sub:
+            out["sub_feat/%d" % i] = ds.sub_feats[i].numpy()
+    for i, q in enumerate(ds.query_feats):
+        out["query_feat/%d" % i] = q.numpy()
+
+    with torch.no_grad():
+        ctx = ref_inf.compute_context_info(model, ds, opt)
+        for k in ("video_feat1", "video_feat2", "video_mask", "sub_feat1", "sub_feat2", "sub_mask"):
+            if ctx[k] is not None:
+                out["ctx/" + k] = ctx[k].numpy()
+
+        # raw model outputs for all queries in one batch, cross=True (reference model_xml.py:553-586)
+        from baselines.crossmodal_moment_localization.start_end_dataset import start_end_collate, \
+            prepare_batch_inputs
+        ds.set_data_mode("query")
+        ds.load_gt_vid_name_for_query(True)
+        batch = start_end_collate([ds[i] for i in range(len(ds))])
+        inputs = prepare_batch_inputs(batch[1], device=opt.device)
+        out["query_feat_padded"] = inputs["query_feat"].numpy()
+        out["query_mask"] = inputs["query_mask"].numpy()
+        vq, sq = model.encode_query(inputs["query_feat"], inputs["query_mask"])
+        out["video_query"], out["sub_query"] = vq.numpy(), sq.numpy()
+        q2c, st, ed = model.get_pred_from_raw_query(
+            inputs["query_feat"], inputs["query_mask"], ctx["video_feat1"], ctx["video_feat2"], ctx["video_mask"],
+            ctx["sub_feat1"], ctx["sub_feat2"], ctx["sub_mask"], cross=True)
+        out["cross/q2c"], out["cross/st"], out["cross/ed"] = q2c.numpy(), st.numpy(), ed.numpy()
+
+        # cross=False (in-batch) outputs on each query's GT video, as the SVMR-only driver feeds them
+        gt = torch.as_tensor(out["query_gt_meta_idx"])
+        pick = lambda t: None if t is None else t[gt]  # noqa: E731
+        q2c, st, ed = model.get_pred_from_raw_query(
+            inputs["query_feat"], inputs["query_mask"], pick(ctx["video_feat1"]), pick(ctx["video_feat2"]),
+            pick(ctx["video_mask"]), pick(ctx["sub_feat1"]), pick(ctx["sub_feat2"]), pick(ctx["sub_mask"]),
+            cross=False)
+        out["inbatch/q2c"], out["inbatch/st"], out["inbatch/ed"] = q2c.numpy(), st.numpy(), ed.numpy()
+
+        if "VCMR" in case["tasks"]:
+            res = ref_inf.compute_query2ctx_info(model, ds, opt, ctx, max_before_nms=case["max_before_nms"],
+                                                 max_n_videos=case["max_n_videos"], tasks=case["tasks"])
+        else:
+            res = ref_inf.compute_query2ctx_info_svmr_only(model, ds, opt, ctx,
+                                                           max_before_nms=case["max_before_nms"],
+                                                           max_n_videos=case["max_n_videos"], tasks=case["tasks"])
+        for task, lst in res.items():
+            arr, cnt = preds_to_array(lst)
+            out["res/%s" % task], out["res/%s_count" % task] = arr, cnt
+            out["res/%s_desc_id" % task] = np.asarray([e["desc_id"] for e in lst])
+
+        # optional NMS post-processing (reference inference.py:507-515), thd 0.5
+        nms_funcs = {"SVMR": post_processing_svmr_nms, "VCMR": post_processing_vcmr_nms}
+        for task, fn in nms_funcs.items():
+            if task in res:
+                lst = fn(copy.deepcopy(res[task]), nms_thd=0.5, max_before_nms=case["max_before_nms"],
+                         max_after_nms=20)
+                arr, cnt = preds_to_array(lst)
+                out["nms/%s" % task], out["nms/%s_count" % task] = arr, cnt
+        top = get_submission_top_n(dict(video2idx=ds.video2idx, **copy.deepcopy(res)), top_n=7)
+        for task in res:
+            out["top7/%s" % task] = preds_to_array(top[task])[0]
+
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def nms_vectors():
+    """Known-answer vectors for utils/temporal_nms.py:25-74 on random span lists (incl. edge cases)."""
+    rng = np.random.RandomState(7)
+    out = {}
+    n_cases = 0
+    for n in (1, 2, 3, 17, 60, 150):
+        for thd in (0.3, 0.5, 0.7):
+            st = np.floor(rng.rand(n) * 40) * 1.5
+            ln = (np.floor(rng.rand(n) * 14) + 3) * 1.5
+            sc = np.round(rng.rand(n), 3)  # rounded -> some exact score ties
+            preds = [[float(a), float(a + b), float(c)] for a, b, c in zip(st, ln, sc)]
+            kept = temporal_non_maximum_suppression(copy.deepcopy(preds), thd, max_after_nms=100)
+            out["in/%d" % n_cases] = np.asarray(preds, dtype=np.float64).reshape(-1, 3)
+            out["thd/%d" % n_cases] = np.float64(thd)
+            out["out/%d" % n_cases] = np.asarray(kept, dtype=np.float64).reshape(-1, 3)
+            n_cases += 1
+    out["n_cases"] = np.int64(n_cases)
+    path = os.path.join(HERE, "temporal_nms.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(4)
+    for case_name, case_def in CASES.items():
+        run_case(case_name, case_def)
+    nms_vectors()

@@ -1,0 +1,68 @@
+"""Load the committed golden fixtures (tests/golden/*.npz, produced by make_golden.py from the real
+reference) as torch tensors + rebuilt context/query batches."""
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASE_NAMES = ("video_only_svmr", "video_sub_vcmr", "video_sub_nocross")
+
+
+class GoldenCase:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.z = z
+        self.cfg = json.loads(str(z["cfg_json"]))
+        self.case = json.loads(str(z["case_json"]))
+        self.weights = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w/")}
+        self.ctx_lens = z["ctx_lens"].tolist()
+        self.n_videos = len(self.ctx_lens)
+        self.use_video = "video" in self.cfg["ctx_mode"]
+        self.use_sub = "sub" in self.cfg["ctx_mode"]
+        self.video_feats = [torch.from_numpy(z["video_feat/%d" % i]) for i in range(self.n_videos)] \
+            if self.use_video else None
+        self.sub_feats = [torch.from_numpy(z["sub_feat/%d" % i]) for i in range(self.n_videos)] \
+            if self.use_sub else None
+        self.n_queries = len(z["query_gt_meta_idx"])
+        self.query_feats = [torch.from_numpy(z["query_feat/%d" % i]) for i in range(self.n_queries)]
+        self.query_feat = torch.from_numpy(z["query_feat_padded"])
+        self.query_mask = torch.from_numpy(z["query_mask"])
+        self.video2idx = z["video2idx"]
+        self.query_gt_meta_idx = z["query_gt_meta_idx"]
+
+    def t(self, key):
+        return torch.from_numpy(self.z[key]) if key in self.z.files else None
+
+    def ctx(self):
+        return {k: self.t("ctx/" + k) for k in
+                ("video_feat1", "video_feat2", "video_mask", "sub_feat1", "sub_feat2", "sub_mask")}
+
+    @staticmethod
+    def pad(seqs):
+        width = max(len(s) for s in seqs)
+        feat = torch.zeros(len(seqs), width, seqs[0].shape[1])
+        mask = torch.zeros(len(seqs), width)
+        for i, s in enumerate(seqs):
+            feat[i, :len(s)] = s
+            mask[i, :len(s)] = 1
+        return feat, mask
+
+    def context_batches(self):
+        """Same batching as the reference DataLoader(shuffle=False, batch_size=eval_context_bsz) +
+        start_end_collate (pad to the batch max)."""
+        bsz = self.case["ctx_bsz"]
+        for lo in range(0, self.n_videos, bsz):
+            b = {}
+            if self.use_video:
+                b["video_feat"], b["video_mask"] = self.pad(self.video_feats[lo:lo + bsz])
+            if self.use_sub:
+                b["sub_feat"], b["sub_mask"] = self.pad(self.sub_feats[lo:lo + bsz])
+            yield b
+
+    def query_batches(self):
+        bsz = self.case["q_bsz"]
+        for lo in range(0, self.n_queries, bsz):
+            yield lo, self.pad(self.query_feats[lo:lo + bsz])
