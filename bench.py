@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the XML full-corpus VCMR query path (BASELINE.json metric: queries/sec, 21.8K-video shape).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of ALL queries (default 10,000) over the whole encoded corpus (default 21,793 videos,
+L<=128 clips, H=768, video_sub / resnet_i3d, synthetic features, random-init weights): query encoders ->
+video-level scores -> top-100 videos -> span distributions of the selected pairs -> top-200 moments.
+`value` times it with the raw query features already resident in HBM (CUDA events, max over ranks);
+`e2e` times the same through `VCMRSearcher.search_host` from pinned HOST buffers to host numpy results.
+The corpus (34 GB encoded) is far larger than L2, so no explicit L2 flush is needed between steps.
+`--impl reference` times the CPU oracle port of the reference's own query path (torch CPU ops, all host
+threads) on a bounded sample and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "queries/sec full-corpus VCMR (21.8K-video shape)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-videos", type=int, default=21793)
+    ap.add_argument("--n-queries", type=int, default=10000)
+    ap.add_argument("--max-ctx-l", type=int, default=128)
+    ap.add_argument("--hidden", type=int, default=768)
+    ap.add_argument("--video-dim", type=int, default=3072)
+    ap.add_argument("--ctx-bsz", type=int, default=200)
+    ap.add_argument("--query-chunk", type=int, default=2048)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def model_config(args):
+    from tvretrieval_b200.model_xml import xml_base_config
+    import copy
+    cfg = copy.deepcopy(xml_base_config)
+    cfg.update(hidden_size=args.hidden, max_ctx_l=args.max_ctx_l, max_desc_l=30, visual_input_size=args.video_dim,
+               query_input_size=768, sub_input_size=768, ctx_mode="video_sub")
+    return cfg
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "XML video_sub resnet_i3d full-corpus VCMR+VR: %d videos x %d queries, L<=%d, H=%d, Dv=%d, "
+                        "Lq<=30, top-100 videos, top-200 moments" % (args.n_videos, args.n_queries, args.max_ctx_l,
+                                                                     args.hidden, args.video_dim),
+            "n_videos": args.n_videos, "n_queries": args.n_queries, "max_ctx_l": args.max_ctx_l,
+            "hidden": args.hidden, "sharding": "videos/%d" % n_gpus, "l2": "inputs larger than L2 (no flush)",
+            "q2c_alpha": 20, "min_pred_l": 2, "max_pred_l": 16, "max_vcmr_video": 100, "max_before_nms": 200}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), smax.append(float(f[2])), power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def encode_corpus_shard(model, args, lens, vid_lo, vid_hi, device):
+    """Encodes videos [vid_lo, vid_hi) with exactly the batching of compute_context_info (global batches of
+    ctx_bsz videos in corpus order, each padded to its own max length)."""
+    from tvretrieval_b200.synthetic import corpus_batch
+    n, L, H = vid_hi - vid_lo, args.max_ctx_l, args.hidden
+    out = {k: torch.zeros(n, L, H, device=device) for k in ("video_feat1", "video_feat2", "sub_feat1", "sub_feat2")}
+    mask = torch.zeros(n, L, device=device)
+    bsz = args.ctx_bsz
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for b in range(vid_lo // bsz, (vid_hi - 1) // bsz + 1):
+            video, sub, m = corpus_batch(lens, b, bsz, args.video_dim, 768, device)
+            v1, v2, s1, s2 = model.encode_context(video, m, sub, m)
+            g_lo = b * bsz
+            lo, hi = max(g_lo, vid_lo), min(g_lo + len(m), vid_hi)
+            sl, dl = slice(lo - g_lo, hi - g_lo), slice(lo - vid_lo, hi - vid_lo)
+            w = m.shape[1]
+            for k, t in zip(("video_feat1", "video_feat2", "sub_feat1", "sub_feat2"), (v1, v2, s1, s2)):
+                out[k][dl, :w] = t[sl]
+            mask[dl, :w] = m[sl]
+    torch.cuda.synchronize()
+    out["video_mask"] = out["sub_mask"] = mask
+    return out, time.perf_counter() - t0
+
+
+def cpu_baseline(args, cfg, weights, ctx_dev, query_feat, query_mask):
+    """Oracle port of the reference's query path timed on the host cores, on a bounded sample: Q=50 queries (the
+    reference's eval_query_bsz) against the first Nv_s videos of the same encoded corpus; Nv_s is calibrated so the
+    sample takes about --cpu-seconds.  queries/sec is extrapolated linearly in Nv_s / Nv."""
+    from oracle import xml_oracle as O
+    n_thr = os.cpu_count() or 1
+    torch.set_num_threads(n_thr)
+    nq = min(50, len(query_feat))
+    qf, qm = query_feat[:nq].cpu(), query_mask[:nq].cpu()
+    n_total = ctx_dev["video_feat1"].shape[0]
+    k_vid = min(100, n_total)
+
+    def run(n_sub, reps):
+        ctx = {k: ctx_dev[k][:n_sub].cpu() for k in ("video_feat1", "video_feat2", "video_mask", "sub_feat1",
+                                                     "sub_feat2", "sub_mask")}
+        best = float("inf")
+        with torch.no_grad():
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                O.query_batch_tensor_section(cfg, weights, ctx, qf, qm, q2c_alpha=20.0, max_n_videos=min(k_vid, n_sub),
+                                             max_before_nms=200, min_pred_l=2, max_pred_l=16, canonical_ties=False)
+                best = min(best, time.perf_counter() - t0)
+        return best
+
+    n_cal = min(n_total, 400)
+    run(n_cal, 1)  # warm-up (thread pools, allocator)
+    t_cal = run(n_cal, 1)
+    n_sub = int(min(n_total, max(n_cal, n_cal * (args.cpu_seconds / 3.0) / max(t_cal, 1e-3))))
+    t = run(n_sub, 2)
+    qps_sample = nq / t
+    return {"value": qps_sample * n_sub / n_total, "unit": "queries/s", "cores": n_thr, "kind": "port",
+            "sample": "%d queries x first %d of %d videos (%.2f s per pass, best of 2), oracle port of the reference "
+                      "query path incl. full sort, torch CPU fp32; scaled by %d/%d to the full corpus"
+                      % (nq, n_sub, n_total, t, n_sub, n_total)}
+
+
+def run_ours(args):
+    from tvretrieval_b200 import _lib
+    from tvretrieval_b200.engine import CorpusIndex, PhaseTimer, VCMRSearcher
+    from tvretrieval_b200.model_xml import XML
+    from tvretrieval_b200.synthetic import corpus_lengths, synthetic_queries
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run for N>1" % (args.gpus, world))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    cfg = model_config(args)
+    torch.manual_seed(2018)
+    model = XML(cfg).eval()
+    weights_cpu = {k: v.clone() for k, v in model.state_dict().items()}
+    model = model.to(device)
+
+    lens = corpus_lengths(args.n_videos, args.max_ctx_l)
+    vid_lo = rank * args.n_videos // world
+    vid_hi = (rank + 1) * args.n_videos // world
+    ctx, t_enc = encode_corpus_shard(model, args, lens, vid_lo, vid_hi, device)
+    index = CorpusIndex.from_ctx_info(ctx, vid_lo=vid_lo)
+    keep_ctx = ctx if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    if keep_ctx is None:
+        del ctx
+    torch.cuda.empty_cache()
+
+    qf_cpu, qm_cpu = synthetic_queries(args.n_queries, 30, 768)
+    qf_pin, qm_pin = qf_cpu.pin_memory(), qm_cpu.pin_memory()
+    qf, qm = qf_pin.to(device), qm_pin.to(device)
+
+    if world == 1:
+        searcher = VCMRSearcher(model, index, query_chunk=args.query_chunk)
+    else:
+        from tvretrieval_b200.sharding import ShardedSearcher
+        searcher = ShardedSearcher(model, index, n_videos_total=args.n_videos, query_chunk=args.query_chunk)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        # ---- device-resident timing ----
+        for _ in range(args.warmup):
+            searcher.search(qf, qm)
+        timer = PhaseTimer()
+        searcher.timer = timer
+        sampler = ClockSampler(local_rank)
+        barrier()
+        launches0 = _lib.launch_count()
+        sampler.start()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(args.steps):
+            res = searcher.search(qf, qm)
+        end.record()
+        barrier()
+        clocks = sampler.stop()
+        launches = _lib.launch_count() - launches0
+        ms_total = max_over_ranks(start.elapsed_time(end))
+        phases = timer.totals_ms()
+        searcher.timer = None
+        assert res.span_score.shape == (args.n_queries, 200) and bool((res.span_score[:, 0] > 0).all())
+
+        # ---- end to end from pinned host buffers ----
+        e2e = None
+        if not args.no_e2e:
+            for _ in range(max(1, args.warmup // 2)):
+                searcher.search_host(qf_pin, qm_pin)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                out = searcher.search_host(qf_pin, qm_pin)
+            barrier()
+            t_e2e = max_over_ranks(time.perf_counter() - t0)
+            d2h = sum(v.nbytes for v in out.values())
+            e2e = {"value": args.n_queries * args.steps / t_e2e, "unit": "queries/s",
+                   "h2d_bytes_per_step": qf_pin.numel() * 4 + qm_pin.numel() * 4, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "api": "tvretrieval_b200.engine.VCMRSearcher.search_host (the call compute_query2ctx_info makes)"}
+
+    ms_per_step = ms_total / args.steps
+    value = args.n_queries / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel: the corpus query x clip contraction (video-level scores) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    n_local = vid_hi - vid_lo
+    s_pad = n_local * args.max_ctx_l
+    flops_per_step = 2.0 * 2 * args.hidden * s_pad * args.n_queries  # 2 modalities x 2*H*S_pad per query (padded)
+    n_calls = timer.counts().get("vr_scores", 1)
+    vr_ms_per_step = phases.get("vr_scores", 0.0) / args.steps
+    achieved = flops_per_step / (vr_ms_per_step / 1e3) / 1e12 if vr_ms_per_step > 0 else 0.0
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    roofline = {"bound": "tensor", "kernel": getattr(searcher, "vr_kernel_name", "gemm_simt_kernel (fp32 SIMT, EPI_VRMAX)"),
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                "flops_counted": "algorithmic 2*H*S_pad per modality per query, S_pad = n_videos*L (padded clips)",
+                "ms_per_step_in_kernel": vr_ms_per_step, "launches_per_step": n_calls / args.steps,
+                "share_of_step": vr_ms_per_step / ms_per_step}
+
+    line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+            "corpus_encode": {"videos_per_s": n_local / t_enc, "seconds": t_enc, "index_gb": index.nbytes() / 1e9}}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, cfg, weights_cpu, keep_ctx, qf_cpu, qm_cpu)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's own query path (no kernels, models or engine of this repo)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import xml_oracle as O
+    n_thr = os.cpu_count() or 1
+    torch.set_num_threads(n_thr)
+    cfg = dict(model_config(args))
+    w = O.init_weights(cfg)
+    nq = min(50, args.n_queries)
+    gen = torch.Generator().manual_seed(4321)
+    qlen = torch.randint(5, 31, (nq,), generator=gen)
+    qm = (torch.arange(30)[None] < qlen[:, None]).float()
+    qf = torch.nn.functional.normalize(torch.randn(nq, 30, 768, generator=gen), dim=-1) * qm.unsqueeze(2)
+    L, H = args.max_ctx_l, args.hidden
+
+    def make_ctx(n):
+        lens = torch.randint(L // 8, L + 1, (n,), generator=gen)
+        lens[0] = L
+        mask = (torch.arange(L)[None] < lens[:, None]).float()
+        ctx = {"video_mask": mask, "sub_mask": mask}
+        for k in ("video_feat1", "video_feat2", "sub_feat1", "sub_feat2"):
+            ctx[k] = torch.randn(n, L, H, generator=gen)
+        return ctx
+
+    def one_pass(ctx):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.query_batch_tensor_section(cfg, w, ctx, qf, qm, q2c_alpha=20.0, max_n_videos=min(100, len(ctx["video_mask"])),
+                                         max_before_nms=200, min_pred_l=2, max_pred_l=16, canonical_ties=False)
+        return time.perf_counter() - t0
+
+    n_cal = min(args.n_videos, 400)
+    cal = make_ctx(n_cal)
+    one_pass(cal)
+    t_cal = one_pass(cal)
+    budget = 150.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
+    n_sub = int(min(args.n_videos, max(n_cal, n_cal * min(budget, args.cpu_seconds) / 3.0 / max(t_cal, 1e-3))))
+    ctx = make_ctx(n_sub)
+    for _ in range(args.warmup):
+        one_pass(ctx)
+    times = [one_pass(ctx) for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    value = nq / t * n_sub / args.n_videos
+    sample = ("each step = %d queries (reference eval_query_bsz) x %d of %d videos, synthetic encoded corpus, torch CPU "
+              "fp32 oracle port of get_pred_from_raw_query(cross=True) + exp/softmax/topk/gather/einsum/band mask/"
+              "full sort; queries/s scaled by %d/%d to the full corpus" % (nq, n_sub, args.n_videos, n_sub, args.n_videos))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": n_thr, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,134 @@
+/* xmlb200 -- C ABI of the B200 (sm_100a) kernels behind the XML moment-retrieval inference path.
+ *
+ * This is the drop-in boundary.  The reference (jayleicn/TVRetrieval) is pure
+ * Python/PyTorch and has no FFI of its own; each entry point below replaces the PyTorch library calls of one
+ * reference call site (cited per function, paths relative to the reference root).  A maintainer binds it with
+ * ctypes exactly as tvretrieval_b200/_lib.py does (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into fp32 / int32 / uint8 row-major contiguous buffers that the caller
+ *     owns (borrowed for the duration of the call); outputs are caller-allocated;
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); all calls are asynchronous
+ *     on that stream, re-entrant, and keep no global mutable state besides the last-error text;
+ *   - return value: 0 = ok, < 0 = invalid argument / unsupported shape, > 0 = cudaError_t.  No call throws,
+ *     aborts, or falls back to another implementation.  xmlb_last_error() returns the message of the last
+ *     failing call made by the calling thread.
+ */
+#ifndef XMLB200_H
+#define XMLB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* xmlb_last_error(void);
+int xmlb_version(void);
+/* number of kernel launches issued through this library since load (bench.py: gpu_launches) */
+long long xmlb_launch_count(void);
+
+/* ---------------------------------------------------------------- encoder building blocks ---------- */
+
+/* out[r][:] = LayerNorm(x[r][:] + add[r % add_rows][:]) * gamma + beta        (add may be NULL)
+ * replaces nn.LayerNorm in LinearLayer (model_components.py:158-159), TrainablePositionalEncoding
+ * (:81-88; add = position table, add_rows = sequence length), BertSelfOutput (:316; add = residual,
+ * add_rows = rows) and the cross-attention residual norm (model_xml.py:371). */
+int xmlb_add_layernorm(const float* x, const float* add, long long add_rows, const float* gamma,
+                       const float* beta, float* out, long long rows, int dim, float eps, void* stream);
+
+/* out[rows][out_dim] = act(x[rows][in_dim] . weight[out_dim][in_dim]^T + bias + residual)
+ * replaces nn.Linear (+ReLU) in LinearLayer (model_components.py:160-163), the Q/K/V projections
+ * (:278-280), BertSelfOutput.dense (:314) and {video,sub}_query_linear (model_xml.py:459-460,524).
+ * bias / residual may be NULL; exact fp32 accumulation. */
+int xmlb_linear(const float* x, const float* weight, const float* bias, const float* residual, float* out,
+                long long rows, int out_dim, int in_dim, int relu, void* stream);
+
+/* Multi-head attention core, replaces BertSelfAttention.forward after the projections
+ * (model_components.py:277-303):  out = merge_heads(softmax(Q_h K_h^T / sqrt(dh) + (1 - mask) * -10000) V_h).
+ * q (batch, len_q, hidden); k, v (batch, len_k, hidden); mask float {0,1} addressed as
+ * mask[b * mask_batch_stride + i * mask_q_stride + j] (mask_q_stride = 0 broadcasts one key mask over the
+ * queries, = len_k gives a full (len_q, len_k) mask as the cross attention of model_xml.py:369-370 uses).
+ * scores_ws: workspace of batch * n_heads * len_q * len_k floats. */
+int xmlb_attention(const float* q, const float* k, const float* v, const float* mask,
+                   long long mask_batch_stride, long long mask_q_stride, float* out, float* scores_ws, int batch,
+                   int len_q, int len_k, int hidden, int n_heads, void* stream);
+
+/* Modular query pooling, replaces XML.get_modularized_queries (model_xml.py:410-423):
+ * a = softmax_tokens(mask_logits(encoded . w_mod^T)); out_m[n] = sum_t a[t][m] * encoded[n][t].
+ * w_mod (n_mod, hidden), n_mod in {1, 2}; out1 may be NULL when n_mod == 1. */
+int xmlb_modular_pool(const float* encoded, const float* mask, const float* w_mod, float* out0, float* out1,
+                      int n_queries, int len, int hidden, int n_mod, void* stream);
+
+/* out = x / max(||x||_2, eps) per row; replaces F.normalize (model_xml.py:446-447). */
+int xmlb_l2norm_rows(const float* x, float* out, long long rows, int dim, float eps, void* stream);
+
+/* row softmax (in place allowed); replaces F.softmax(dim=-1) (inference.py:153-154,321-322). */
+int xmlb_softmax_rows(const float* x, float* out, long long rows, int dim, void* stream);
+
+/* ---------------------------------------------------------------- query x corpus scoring ----------- */
+
+/* Video-level retrieval scores, replaces XML.get_video_level_scores x modalities + the average
+ * (model_xml.py:446-452, 572-574), exact-fp32 SIMT variant:
+ *   q2c[q][v] = mean over given modalities of  max_{l : mask[v][l] != 0} q_n[q] . feat1_n[v][l]   (-1e10 if none)
+ * Inputs must already be L2-normalised (xmlb_l2norm_rows).  A modality is skipped when its pointers are NULL.
+ * workspace: 2 * n_queries * n_videos floats. */
+int xmlb_vr_scores_f32(const float* q_video_n, const float* q_sub_n, const float* feat1_video_n,
+                       const float* feat1_sub_n, const float* video_mask, const float* sub_mask, float* q2c,
+                       float* workspace, int n_queries, int n_videos, int ctx_len, int hidden, void* stream);
+
+/* Similarity curves + ConvSE + mask (+ softmax), replaces XML.get_merged_st_ed_prob (model_xml.py:455-502),
+ * XML._get_st_ed_prob (:512-551) and the driver's softmax over clips (inference.py:321-322).
+ *   sim_x[q][v][l] = q_x[q] . feat2_x[v][l]                       for stream x in {a, b}
+ *   merged  : st = mask_logits(conv(w_st_a, (sim_a + sim_b) / 2), mask_a)
+ *   separate: st = mean_x mask_logits(conv(w_st_x, sim_x), mask_x)           (one or two streams)
+ * conv = cross-correlation, zero padding ksize/2, stride 1.  Output rows of ctx_len floats:
+ *   dense (chunk_ptr == NULL): row = q * n_videos + v for every (q, v);
+ *   list mode: for video v, entries e in [vid_ptr[v], vid_ptr[v+1]) give query entry_q[e] and output row
+ *   entry_out[e]; chunk_ptr = exclusive scan of ceil(count/32) (see xmlb_build_pair_lists); max_chunks >= chunk_ptr[n_videos].
+ * q_b/feat2_b/mask_b/w_*_b may be NULL (single stream). */
+int xmlb_span_logits(const float* q_a, const float* q_b, const float* feat2_a, const float* feat2_b,
+                     const float* mask_a, const float* mask_b, const float* w_st_a, const float* w_ed_a,
+                     const float* w_st_b, const float* w_ed_b, int ksize, int merged, int apply_softmax,
+                     int n_queries, int n_videos, int ctx_len, int hidden, const int* chunk_ptr, const int* vid_ptr,
+                     const int* entry_q, const int* entry_out, int max_chunks, float* out_st, float* out_ed,
+                     void* stream);
+
+/* Inverts top_idx (n_queries, n_slots) [global video ids] into per-video lists for xmlb_span_logits.
+ * Only ids in [vid_lo, vid_lo + n_videos) (this GPU's shard) and slots with slot_valid != 0 (NULL = all) are
+ * listed; entry_out = q * n_slots + slot.  counts_ws, cursor_ws: n_videos ints; vid_ptr, chunk_ptr: n_videos+1;
+ * entry_q, entry_out: n_queries * n_slots ints.  Replaces the advanced-index gather of inference.py:365-367. */
+int xmlb_build_pair_lists(const int* top_idx, const unsigned char* slot_valid, int n_queries, int n_slots,
+                          int vid_lo, int n_videos, int* counts_ws, int* cursor_ws, int* vid_ptr, int* chunk_ptr,
+                          int* entry_q, int* entry_out, void* stream);
+
+/* Per-row exact top-k, ranked (value desc, id asc | desc).  value = apply_exp ? exp(alpha * x) : x.
+ * ids (n_rows, n_cols) optional explicit ids (NULL: column index).  Replaces torch.exp + torch.topk of
+ * inference.py:317,347-348; returns an error when k > n_cols like torch.topk does.  k <= 1024. */
+int xmlb_topk_rows(const float* values, const int* ids, int n_rows, int n_cols, int k, float alpha, int apply_exp,
+                   int tie_desc, int* out_idx, float* out_val, void* stream);
+
+/* Band-limited span scoring + exact top-k, replaces inference.py:370-386 (VCMR) and inference.py:215-224 +
+ * utils/tensor_utils.py:133-141 (SVMR, n_slots = 1, video_score = NULL, tie_desc = 1):
+ *   score[j][m][n] = (st[q][j][m] * video_score[q][j]) * ed[q][j][n]   for min_l <= n - m < max_l, else 0
+ *   flat index = (j * ctx_len + m) * ctx_len + n;  rank by (score desc, flat index asc|desc); keep k.
+ * slot_valid (n_queries, n_slots) uint8 or NULL.  When fewer than k cells are positive, the rest is filled with
+ * zero-score cells in flat-index order if zero_fill_missing, else with (-1, 0). */
+int xmlb_span_topk(const float* st_prob, const float* ed_prob, const float* video_score,
+                   const unsigned char* slot_valid, int n_queries, int n_slots, int ctx_len, int min_l, int max_l,
+                   int k, int tie_desc, int zero_fill_missing, int* out_flat_idx, float* out_score, void* stream);
+
+/* Completes ranked lists whose tail is missing ((-1, 0) or non-positive) with zero-score cells of
+ * [0, total_cells) in flat-index order (used after the multi-GPU merge). */
+int xmlb_span_zero_fill(int* flat_idx, float* score, int n_queries, int k, long long total_cells, int tie_desc,
+                        void* stream);
+
+/* Greedy temporal NMS per query over ranked lists, replaces utils/temporal_nms.py:25-74 as wrapped by
+ * baselines/clip_alignment_with_language/inference.py:189-265.  video_idx NULL = one group (SVMR).
+ * out_idx (n_queries, max_out): indices into the input list, ranked; out_count (n_queries). n_in <= 1024. */
+int xmlb_temporal_nms(const int* video_idx, const float* st, const float* ed, const float* score,
+                      const int* n_valid, int n_queries, int n_in, double iou_thd, int max_per_group, int max_out,
+                      int* out_idx, int* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMLB200_H */

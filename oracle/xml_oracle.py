@@ -381,3 +381,58 @@ def vcmr_nms(preds, thd: float, max_before_nms: int, max_after_nms: int):
         for p in temporal_nms(g, thd):
             merged.append([vid] + p)
     return sorted(merged, key=lambda p: p[3], reverse=True)[:max_after_nms]
+
+
+# --------------------------------------------------------------------------------------
+# weights for timing-only runs (bench.py --impl reference): same shapes / init scheme as
+# XML.__init__ + reset_parameters (model_xml.py:52-201); values are NOT the reference's RNG stream.
+# --------------------------------------------------------------------------------------
+def init_weights(cfg, seed: int = 2018) -> Weights:
+    g = torch.Generator().manual_seed(seed)
+    h, std = cfg["hidden_size"], cfg.get("initializer_range", 0.02)
+    w: Weights = {}
+
+    def linear(name, out_dim, in_dim, bias=True):
+        w[name + ".weight"] = torch.randn(out_dim, in_dim, generator=g) * std
+        if bias:
+            w[name + ".bias"] = torch.zeros(out_dim)
+
+    def ln(name, dim):
+        w[name + ".weight"], w[name + ".bias"] = torch.ones(dim), torch.zeros(dim)
+
+    def block(name):
+        for p in ("query", "key", "value"):
+            linear(name + ".self." + p, h, h)
+        linear(name + ".output.dense", h, h)
+        ln(name + ".output.LayerNorm", h)
+
+    def proj(name, in_dim):
+        ln(name + ".LayerNorm", in_dim)
+        linear(name + ".net.1", h, in_dim)
+
+    def conv(name):
+        k = cfg.get("conv_kernel_size", 5)
+        w[name + ".weight"] = (torch.rand(1, 1, k, generator=g) * 2 - 1) / math.sqrt(k)
+
+    for name, n_pos in (("query_pos_embed", cfg["max_desc_l"]), ("ctx_pos_embed", cfg["max_ctx_l"])):
+        w[name + ".position_embeddings.weight"] = torch.randn(n_pos, h, generator=g) * std
+        ln(name + ".LayerNorm", h)
+    proj("query_input_proj", cfg["query_input_size"])
+    block("query_encoder")
+    streams = [s for s in ("video", "sub") if s in cfg["ctx_mode"]]
+    for s in streams:
+        proj(s + "_input_proj", cfg["visual_input_size"] if s == "video" else cfg["sub_input_size"])
+        block(s + "_encoder1"), block(s + "_encoder2")
+        if cfg["cross_att"]:
+            for p in ("query", "key", "value"):
+                linear(s + "_cross_att." + p, h, h)
+            ln(s + "_cross_layernorm", h)
+        else:
+            block(s + "_encoder3")
+        linear(s + "_query_linear", h, h)
+        if not cfg["merge_two_stream"]:
+            conv(s + "_st_predictor"), conv(s + "_ed_predictor")
+    linear("modular_vector_mapping", len(streams), h, bias=False)
+    if cfg["merge_two_stream"]:
+        conv("merged_st_predictor"), conv("merged_ed_predictor")
+    return w

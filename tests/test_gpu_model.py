@@ -1,0 +1,234 @@
+"""GPU parity of the drop-in XML model and drivers, through the C ABI, against
+(a) the committed golden vectors produced by the real reference (tests/golden/*.npz) and
+(b) the CPU oracle on larger TVR-shaped inputs (H=768, L=128, resnet_i3d features).
+Floating point: north_star tolerance 1e-3 relative (the asserts below use tighter bounds where they hold);
+ranked indices: exact wherever the oracle's own neighbouring scores differ by more than 1e-6 relative."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xml_oracle as O
+from tests.golden_io import CASE_NAMES, GoldenCase
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def close(got, want, rtol=1e-4, atol=1e-5):
+    got = got.detach().cpu() if torch.is_tensor(got) else torch.as_tensor(got)
+    want = want.detach().cpu() if torch.is_tensor(want) else torch.as_tensor(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    torch.testing.assert_close(got.double(), want.double(), rtol=rtol, atol=atol)
+
+
+def build_model(cfg, weights):
+    from tvretrieval_b200.model_xml import XML, AttrDict
+    model = XML(AttrDict(cfg))
+    model.load_state_dict(weights)
+    return model.to(DEV).eval()
+
+
+class Opt:
+    def __init__(self, case, cfg):
+        self.eval_context_bsz, self.eval_query_bsz = case["ctx_bsz"], case["q_bsz"]
+        self.num_workers, self.pin_memory, self.device = 0, False, torch.device(DEV)
+        self.ctx_mode, self.external_inference_vr_res_path = cfg["ctx_mode"], None
+        self.q2c_alpha, self.min_pred_l, self.max_pred_l = 20.0, 2, 16
+        self.max_ctx_l, self.clip_length, self.debug = cfg["max_ctx_l"], 1.5, False
+        self.max_before_nms, self.max_vcmr_video = case["max_before_nms"], case["max_n_videos"]
+
+
+@pytest.fixture(scope="module", params=CASE_NAMES)
+def golden(request):
+    g = GoldenCase(request.param)
+    from tvretrieval_b200.synthetic import SyntheticEvalDataset
+    ds = SyntheticEvalDataset(max_ctx_l=g.cfg["max_ctx_l"], max_desc_l=g.cfg["max_desc_l"],
+                              video_dim=g.cfg["visual_input_size"], sub_dim=g.cfg["sub_input_size"],
+                              query_dim=g.cfg["query_input_size"], ctx_mode=g.cfg["ctx_mode"], min_ctx_l=3,
+                              **g.case["data"])
+    # the dataset is regenerated from its seed; make sure it is the one the goldens were made from
+    assert ds.ctx_lens == g.ctx_lens
+    for i in range(g.n_queries):
+        assert torch.equal(ds.query_feats[i], g.query_feats[i])
+    g.ds = ds
+    g.model = build_model(g.cfg, g.weights)
+    g.opt = Opt(g.case, g.cfg)
+    return g
+
+
+def test_golden_context_encoding(golden):
+    from tvretrieval_b200 import inference as I
+    ctx = I.compute_context_info(golden.model, golden.ds, golden.opt)
+    assert [m["vid_name"] for m in ctx["video_metas"]] == [v["vid_name"] for v in golden.ds.video_data]
+    for k, want in golden.ctx().items():
+        if want is None:
+            assert ctx[k] is None
+        else:
+            close(ctx[k], want, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("cross", [True, False])
+def test_golden_pred_from_raw_query(golden, cross):
+    ctx = {k: (None if v is None else v.to(DEV)) for k, v in golden.ctx().items()}
+    if not cross:
+        gt = torch.as_tensor(golden.query_gt_meta_idx, device=DEV)
+        ctx = {k: (None if v is None else v[gt].contiguous()) for k, v in ctx.items()}
+    with torch.no_grad():
+        q2c, st, ed = golden.model.get_pred_from_raw_query(
+            golden.query_feat.to(DEV), golden.query_mask.to(DEV), ctx["video_feat1"], ctx["video_feat2"],
+            ctx["video_mask"], ctx["sub_feat1"], ctx["sub_feat2"], ctx["sub_mask"], cross=cross)
+    tag = "cross" if cross else "inbatch"
+    close(q2c, golden.t(tag + "/q2c"), rtol=1e-4, atol=2e-6)
+    want_st, want_ed = golden.t(tag + "/st"), golden.t(tag + "/ed")
+    close(st, want_st, rtol=1e-4, atol=5e-5), close(ed, want_ed, rtol=1e-4, atol=5e-5)
+    assert torch.equal(st.cpu() == -1e10, want_st == -1e10)
+
+
+def preds_array(lst):
+    k = max(len(e["predictions"]) for e in lst)
+    out = np.zeros((len(lst), k, 4))
+    for i, e in enumerate(lst):
+        out[i, :len(e["predictions"])] = np.asarray(e["predictions"], dtype=np.float64).reshape(-1, 4)
+    return out
+
+
+def assert_ranked_equal(got, ref, score_rtol=1e-4):
+    """Rows [video_idx, st, ed, score] must match exactly in the positive-score region, except where two
+    neighbouring reference scores are closer than 1e-6 relative (a tie no two fp32 implementations agree on)."""
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    np.testing.assert_allclose(got[..., 3], ref[..., 3], rtol=score_rtol, atol=1e-12)
+    pos = ref[..., 3] > 0
+    bad = (got[..., :3] != ref[..., :3]).any(-1) & pos
+    for q, r in zip(*np.nonzero(bad)):
+        s = ref[q, :, 3]
+        lo, hi = max(r - 1, 0), min(r + 1, len(s) - 1)
+        gap = min(abs(s[r] - s[lo]) if lo != r else np.inf, abs(s[r] - s[hi]) if hi != r else np.inf)
+        assert gap <= 1e-6 * abs(s[r]), "rank mismatch at query %d rank %d (gap %g)" % (q, r, gap)
+    return int(bad.sum())
+
+
+def test_golden_driver(golden):
+    from tvretrieval_b200 import inference as I
+    c = golden.case
+    ctx = I.compute_context_info(golden.model, golden.ds, golden.opt)
+    if "VCMR" in c["tasks"]:
+        res = I.compute_query2ctx_info(golden.model, golden.ds, golden.opt, ctx, max_before_nms=c["max_before_nms"],
+                                       max_n_videos=c["max_n_videos"], tasks=tuple(c["tasks"]))
+    else:
+        res = I.compute_query2ctx_info_svmr_only(golden.model, golden.ds, golden.opt, ctx,
+                                                 max_before_nms=c["max_before_nms"], max_n_videos=c["max_n_videos"])
+    assert sorted(res.keys()) == sorted(c["tasks"])
+    for task in c["tasks"]:
+        assert [e["desc_id"] for e in res[task]] == golden.z["res/%s_desc_id" % task].tolist()
+        assert all(isinstance(e["predictions"][0][0], int) and isinstance(e["predictions"][0][3], float)
+                   for e in res[task])
+        n_swapped = assert_ranked_equal(preds_array(res[task]), golden.z["res/" + task])
+        assert n_swapped == 0
+    # post-processing on the reference's own ranked lists: top-n truncation and NMS (thd 0.5)
+    for task, fn in (("VCMR", I.post_processing_vcmr_nms), ("SVMR", I.post_processing_svmr_nms)):
+        if task not in c["tasks"]:
+            continue
+        ref_in, ref_out, cnt = golden.z["res/" + task], golden.z["nms/" + task], golden.z["nms/%s_count" % task]
+        lst = [dict(desc_id=0, desc="", predictions=[[int(p[0]), p[1], p[2], p[3]] for p in row.tolist()])
+               for row in ref_in]
+        out = fn(copy.deepcopy(lst), nms_thd=0.5, max_before_nms=c["max_before_nms"], max_after_nms=20)
+        for q, e in enumerate(out):
+            assert len(e["predictions"]) == cnt[q]
+            assert np.array_equal(np.asarray(e["predictions"], dtype=np.float64).reshape(-1, 4), ref_out[q, :cnt[q]]), (task, q)
+        top = I.get_submission_top_n(dict(video2idx={}, **{task: copy.deepcopy(lst)}), top_n=7)
+        assert np.array_equal(preds_array(top[task]), golden.z["top7/" + task])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# TVR-shaped comparison against the oracle (BASELINE.json configs[1] dims, fewer videos so the CPU finishes fast)
+# ---------------------------------------------------------------------------------------------------------
+def tvr_case(ctx_mode, n_videos, n_queries, hidden, max_ctx_l, video_dim, seed):
+    from tvretrieval_b200.model_xml import XML, xml_base_config
+    from tvretrieval_b200.synthetic import SyntheticEvalDataset
+    cfg = copy.deepcopy(xml_base_config)
+    cfg.update(hidden_size=hidden, max_ctx_l=max_ctx_l, max_desc_l=30, visual_input_size=video_dim, ctx_mode=ctx_mode)
+    if ctx_mode != "video_sub":
+        cfg.update(merge_two_stream=False, cross_att=False)
+    torch.manual_seed(2018)
+    model = XML(cfg).eval()
+    ds = SyntheticEvalDataset(n_videos, n_queries, max_ctx_l, 30, video_dim, 768, 768, ctx_mode=ctx_mode, seed=seed,
+                              video_split=2048 if video_dim == 3072 else None)
+    weights = {k: v.clone() for k, v in model.state_dict().items()}
+    return cfg, model.to(DEV), weights, ds
+
+
+def oracle_batches(ds, bsz):
+    for lo in range(0, len(ds.video_data), bsz):
+        b = {}
+        if ds.use_video:
+            b["video_feat"], b["video_mask"] = GoldenCase.pad(ds.video_feats[lo:lo + bsz])
+        if ds.use_sub:
+            b["sub_feat"], b["sub_mask"] = GoldenCase.pad(ds.sub_feats[lo:lo + bsz])
+        yield b
+
+
+def test_tvr_shape_video_sub_vcmr():
+    """video_sub, resnet_i3d (Dv=3072), H=768, L=128: full driver vs oracle; ranks must be exact."""
+    from tvretrieval_b200 import inference as I
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    n_videos, n_queries, k_vid, k_span = 150, 24, 100, 200
+    cfg, model, weights, ds = tvr_case("video_sub", n_videos, n_queries, 768, 128, 3072, seed=1234)
+    case = dict(ctx_bsz=64, q_bsz=10, max_before_nms=k_span, max_n_videos=k_vid)
+    opt = Opt(case, cfg)
+    ctx = I.compute_context_info(model, ds, opt)
+    with torch.no_grad():
+        octx = O.context_info(cfg, weights, oracle_batches(ds, case["ctx_bsz"]))
+    for k in ("video_feat1", "video_feat2", "sub_feat1", "sub_feat2"):
+        close(ctx[k], octx[k], rtol=1e-3, atol=1e-4)
+    res = I.compute_query2ctx_info(model, ds, opt, ctx, max_before_nms=k_span, max_n_videos=k_vid,
+                                   tasks=("VCMR", "SVMR", "VR"))
+    qf, qm = GoldenCase.pad(ds.query_feats)
+    with torch.no_grad():
+        o = O.query_batch_tensor_section(cfg, weights, octx, qf, qm, q2c_alpha=20.0, max_n_videos=k_vid,
+                                         max_before_nms=k_span, min_pred_l=2, max_pred_l=16)
+    v2i = np.asarray([ds.video2idx[v["vid_name"]] for v in ds.video_data])
+    want_vcmr = O.decode_vcmr(o["span_flat_idx"].numpy(), o["span_score"].numpy(), o["top_video_idx"].numpy(), v2i,
+                              k_vid, 128, 1.5)
+    swapped = assert_ranked_equal(preds_array(res["VCMR"]), want_vcmr, score_rtol=1e-3)
+    assert swapped <= 2
+    want_vr = np.zeros((n_queries, k_vid, 4))
+    want_vr[..., 0] = v2i[o["top_video_idx"].numpy()]
+    want_vr[..., 3] = o["top_video_score"].numpy()
+    assert_ranked_equal(preds_array(res["VR"]), want_vr, score_rtol=1e-3)
+    gt = np.asarray([int(q["vid_name"].split("_")[1]) for q in ds.query_data])
+    rows = np.arange(n_queries)
+    sv = O.svmr_from_probs(o["st_prob"].numpy()[rows, gt], o["ed_prob"].numpy()[rows, gt], 1.5, 2, 16, k_span)
+    want_svmr = np.concatenate([np.broadcast_to(v2i[gt][:, None, None], (n_queries, k_span, 1)), sv], axis=-1)
+    assert_ranked_equal(preds_array(res["SVMR"]), want_svmr.astype(np.float64), score_rtol=1e-3)
+
+
+def test_tvr_shape_video_only_svmr():
+    """BASELINE.json configs[0]: video-only resnet (Dv=2048), 10 videos x 10 queries, L=32, H=768, SVMR-only."""
+    from tvretrieval_b200 import inference as I
+    cfg, model, weights, ds = tvr_case("video", 10, 10, 768, 32, 2048, seed=1234)
+    case = dict(ctx_bsz=200, q_bsz=100, max_before_nms=200, max_n_videos=100)
+    opt = Opt(case, cfg)
+    ctx = I.compute_context_info(model, ds, opt)
+    res = I.compute_query2ctx_info_svmr_only(model, ds, opt, ctx, max_before_nms=200)
+    with torch.no_grad():
+        octx = O.context_info(cfg, weights, oracle_batches(ds, 200))
+        gt = torch.as_tensor([int(q["vid_name"].split("_")[1]) for q in ds.query_data])
+        qf, qm = GoldenCase.pad(ds.query_feats)
+        _, st, ed = O.pred_from_raw_query(cfg, weights, qf, qm, octx["video_feat1"][gt], octx["video_feat2"][gt],
+                                          octx["video_mask"][gt], None, None, None, cross=False)
+    sv = O.svmr_from_probs(torch.softmax(st, -1).numpy(), torch.softmax(ed, -1).numpy(), 1.5, 2, 16, 200)
+    v2i = np.asarray([ds.video2idx[v["vid_name"]] for v in ds.video_data])
+    want = np.concatenate([np.broadcast_to(v2i[gt.numpy()][:, None, None], (10, 200, 1)), sv], axis=-1)
+    got = preds_array(res["SVMR"])
+    assert_ranked_equal(got, want.astype(np.float64), score_rtol=1e-3)
+    # zero-score tail (fewer than 200 in-band cells for short videos): same canonical order as the oracle
+    assert np.array_equal(got[..., :3], want[..., :3].astype(np.float64))
+
+
+def test_model_rejects_cpu_tensors():
+    from tvretrieval_b200._lib import XmlbError
+    cfg, model, weights, ds = tvr_case("video", 4, 4, 64, 16, 32, seed=3)
+    with pytest.raises(XmlbError):
+        model.cpu().encode_query(torch.randn(2, 5, 768), torch.ones(2, 5))

@@ -1,0 +1,294 @@
+"""GPU parity of every C-ABI kernel against the CPU oracle (oracle/xml_oracle.py) on seeded inputs.
+Tolerance for floating point: rtol 1e-4 / atol 1e-5 (north_star allows 1e-3 relative); masks, indices and
+rankings: exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import xml_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from tvretrieval_b200 import ops as _ops
+    return _ops
+
+
+def close(got, want, rtol=1e-4, atol=1e-5):
+    torch.testing.assert_close(got.detach().cpu().double(), want.detach().cpu().double(), rtol=rtol, atol=atol)
+
+
+def rand_mask(gen, n, length, min_len=1):
+    lens = torch.randint(min_len, length + 1, (n,), generator=gen)
+    lens[0] = length
+    return (torch.arange(length)[None] < lens[:, None]).float()
+
+
+@pytest.mark.parametrize("rows,dim", [(7, 64), (300, 768), (33, 3072), (5, 500)])
+def test_add_layernorm(ops, rows, dim):
+    g = torch.Generator().manual_seed(rows * dim)
+    x = torch.randn(rows, dim, generator=g) * 3 + 1
+    w, b = torch.randn(dim, generator=g), torch.randn(dim, generator=g)
+    want = torch.nn.functional.layer_norm(x, (dim,), w, b, 1e-5)
+    close(ops.add_layernorm(x.to(DEV), w.to(DEV), b.to(DEV)), want)
+    # + broadcast add (position table): rows = n * period
+    period = rows if rows < 8 else rows // 3 if rows % 3 == 0 else rows
+    table = torch.randn(period + 4, dim, generator=g)
+    want = torch.nn.functional.layer_norm(x + table[:period].repeat(rows // period, 1), (dim,), w, b, 1e-5)
+    close(ops.add_layernorm(x.to(DEV), w.to(DEV), b.to(DEV), add=table.to(DEV), add_rows=period), want)
+
+
+@pytest.mark.parametrize("rows,out_dim,in_dim", [(1, 8, 8), (50, 64, 48), (257, 130, 70), (1000, 768, 3072),
+                                                 (129, 768, 768), (64, 500, 500)])
+def test_linear(ops, rows, out_dim, in_dim):
+    g = torch.Generator().manual_seed(rows + out_dim)
+    x = torch.randn(rows, in_dim, generator=g)
+    w = torch.randn(out_dim, in_dim, generator=g) * 0.05
+    b = torch.randn(out_dim, generator=g)
+    r = torch.randn(rows, out_dim, generator=g)
+    close(ops.linear(x.to(DEV), w.to(DEV), b.to(DEV)), torch.nn.functional.linear(x, w, b))
+    close(ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), relu=True), torch.relu(torch.nn.functional.linear(x, w, b)))
+    close(ops.linear(x.to(DEV), w.to(DEV), None, residual=r.to(DEV)), torch.nn.functional.linear(x, w) + r)
+
+
+@pytest.mark.parametrize("n,lq,lk,hid,nh,full_mask", [(3, 12, 12, 64, 4, False), (5, 30, 30, 768, 4, False),
+                                                      (4, 97, 97, 256, 4, True), (2, 128, 128, 768, 4, True),
+                                                      (2, 17, 33, 32, 2, True)])
+def test_attention(ops, n, lq, lk, hid, nh, full_mask):
+    g = torch.Generator().manual_seed(n * lq + hid)
+    w = {}
+    for name in ("query", "key", "value"):
+        w["a.%s.weight" % name] = torch.randn(hid, hid, generator=g) * 0.05
+        w["a.%s.bias" % name] = torch.randn(hid, generator=g) * 0.1
+    xq, xk = torch.randn(n, lq, hid, generator=g), torch.randn(n, lk, hid, generator=g)
+    mk = rand_mask(g, n, lk)
+    if full_mask:  # cross-attention style mask incl. fully masked query rows (reference model_xml.py:369)
+        mask3 = rand_mask(g, n, lq).unsqueeze(2) * mk.unsqueeze(1)
+    else:
+        mask3 = mk.unsqueeze(1)
+    want = O.multi_head_attention(xq, xk, mask3, w, "a", nh)
+    lin = torch.nn.functional.linear
+    q = lin(xq, w["a.query.weight"], w["a.query.bias"]).to(DEV)
+    k = lin(xk, w["a.key.weight"], w["a.key.bias"]).to(DEV)
+    v = lin(xk, w["a.value.weight"], w["a.value.bias"]).to(DEV)
+    close(ops.attention(q, k, v, mask3.to(DEV), nh), want)
+
+
+@pytest.mark.parametrize("n,length,hid,n_mod", [(4, 12, 64, 2), (9, 30, 768, 2), (3, 8, 32, 1)])
+def test_modular_pool(ops, n, length, hid, n_mod):
+    g = torch.Generator().manual_seed(n + hid)
+    enc = torch.randn(n, length, hid, generator=g)
+    mask = rand_mask(g, n, length, 3)
+    w = {"modular_vector_mapping.weight": torch.randn(n_mod, hid, generator=g) * 0.1}
+    a, b = O.modular_queries(enc, mask, w)
+    ga, gb = ops.modular_pool(enc.to(DEV), mask.to(DEV), w["modular_vector_mapping.weight"].to(DEV))
+    close(ga, a), close(gb, b)
+
+
+def test_l2norm_and_softmax(ops):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(37, 768, generator=g)
+    x[3] = 0
+    close(ops.l2norm_rows(x.to(DEV)), torch.nn.functional.normalize(x, dim=-1), rtol=1e-6, atol=1e-8)
+    y = torch.randn(50, 100, generator=g) * 4
+    y[:, 60:] = -1e10
+    got = ops.softmax_rows(y.to(DEV))
+    close(got, torch.softmax(y, -1), rtol=1e-5, atol=1e-8)
+    assert (got[:, 60:] == 0).all()
+
+
+@pytest.mark.parametrize("nq,nv,length,hid,both", [(5, 7, 12, 64, True), (70, 130, 32, 96, True),
+                                                  (40, 260, 128, 768, True), (9, 11, 100, 500, False)])
+def test_vr_scores_f32(ops, nq, nv, length, hid, both):
+    g = torch.Generator().manual_seed(nq * nv)
+    qv, qs = torch.randn(nq, hid, generator=g), torch.randn(nq, hid, generator=g)
+    fv, fs = torch.randn(nv, length, hid, generator=g), torch.randn(nv, length, hid, generator=g)
+    mask = rand_mask(g, nv, length)
+    fv = fv * mask.unsqueeze(2)  # rows beyond the batch width are exact zeros in the real corpus
+    want = O.video_level_scores(qv, fv, mask)
+    if both:
+        want = (want + O.video_level_scores(qs, fs, mask)) / 2
+    n = lambda t: ops.l2norm_rows(t.to(DEV))  # noqa: E731
+    got = ops.vr_scores_f32(n(qv), n(qs) if both else None, n(fv), n(fs) if both else None, mask.to(DEV),
+                            mask.to(DEV) if both else None)
+    close(got, want, rtol=1e-4, atol=2e-6)
+
+
+def conv_taps(g, k=5):
+    return torch.randn(1, 1, k, generator=g) * 0.4
+
+
+@pytest.mark.parametrize("nq,nv,length,hid,mode", [(5, 6, 12, 64, "merged"), (37, 9, 32, 96, "merged"),
+                                                   (33, 5, 128, 768, "merged"), (7, 4, 100, 500, "two"),
+                                                   (6, 5, 24, 32, "one"), (3, 3, 200, 64, "merged")])
+@pytest.mark.parametrize("softmax", [False, True])
+def test_span_logits_dense(ops, nq, nv, length, hid, mode, softmax):
+    g = torch.Generator().manual_seed(nq * nv + length)
+    qv, qs = torch.randn(nq, hid, generator=g) * 0.2, torch.randn(nq, hid, generator=g) * 0.2
+    fv, fs = torch.randn(nv, length, hid, generator=g), torch.randn(nv, length, hid, generator=g)
+    vmask, smask = rand_mask(g, nv, length, 2), rand_mask(g, nv, length, 2)
+    taps = [conv_taps(g) for _ in range(4)]
+    eye = torch.eye(hid)
+    zero = torch.zeros(hid)
+    if mode == "merged":
+        w = {"video_query_linear.weight": eye, "video_query_linear.bias": zero, "sub_query_linear.weight": eye,
+             "sub_query_linear.bias": zero, "merged_st_predictor.weight": taps[0], "merged_ed_predictor.weight": taps[1]}
+        st, ed = O.merged_st_ed_logits(w, qv, fv, qs, fs, vmask, cross=True)
+        got = ops.span_logits(qv.to(DEV), fv.to(DEV), vmask.to(DEV), taps[0].to(DEV), taps[1].to(DEV), q_b=qs.to(DEV),
+                              feat2_b=fs.to(DEV), mask_b=vmask.to(DEV), merged=True, softmax=softmax)
+    else:
+        w = {"video_query_linear.weight": eye, "video_query_linear.bias": zero, "sub_query_linear.weight": eye,
+             "sub_query_linear.bias": zero, "video_st_predictor.weight": taps[0], "video_ed_predictor.weight": taps[1],
+             "sub_st_predictor.weight": taps[2], "sub_ed_predictor.weight": taps[3]}
+        st, ed = O.single_st_ed_logits(w, qv, fv, vmask, "video", cross=True)
+        if mode == "two":
+            st2, ed2 = O.single_st_ed_logits(w, qs, fs, smask, "sub", cross=True)
+            st, ed = (st + st2) / 2, (ed + ed2) / 2
+            got = ops.span_logits(qv.to(DEV), fv.to(DEV), vmask.to(DEV), taps[0].to(DEV), taps[1].to(DEV),
+                                  q_b=qs.to(DEV), feat2_b=fs.to(DEV), mask_b=smask.to(DEV), w_st_b=taps[2].to(DEV),
+                                  w_ed_b=taps[3].to(DEV), softmax=softmax)
+        else:
+            got = ops.span_logits(qv.to(DEV), fv.to(DEV), vmask.to(DEV), taps[0].to(DEV), taps[1].to(DEV),
+                                  softmax=softmax)
+    if softmax:
+        st, ed = torch.softmax(st, -1), torch.softmax(ed, -1)
+        close(got[0], st, rtol=2e-4, atol=1e-7), close(got[1], ed, rtol=2e-4, atol=1e-7)
+        pad = (vmask == 0).unsqueeze(0).expand_as(st) if mode != "two" else None
+        if pad is not None:
+            assert (got[0].cpu()[pad] == 0).all()
+    else:
+        close(got[0], st, rtol=1e-4, atol=2e-5), close(got[1], ed, rtol=1e-4, atol=2e-5)
+        assert torch.equal(got[0].cpu() == -1e10, st == -1e10)
+
+
+def test_span_logits_lists_match_dense(ops):
+    """Inverted-list mode (selected pairs) must reproduce the dense rows bit for bit."""
+    g = torch.Generator().manual_seed(77)
+    nq, nv, length, hid, slots = 150, 40, 64, 128, 9
+    qv, qs = torch.randn(nq, hid, generator=g).to(DEV), torch.randn(nq, hid, generator=g).to(DEV)
+    fv, fs = torch.randn(nv, length, hid, generator=g).to(DEV), torch.randn(nv, length, hid, generator=g).to(DEV)
+    mask = rand_mask(g, nv, length, 2).to(DEV)
+    t0, t1 = conv_taps(g).to(DEV), conv_taps(g).to(DEV)
+    top = torch.stack([torch.randperm(nv, generator=g)[:slots] for _ in range(nq)]).to(torch.int32).to(DEV)
+    top[:, 0] = 3  # one very popular video -> several 32-query chunks
+    dense_st, dense_ed = ops.span_logits(qv, fv, mask, t0, t1, q_b=qs, feat2_b=fs, mask_b=mask, merged=True,
+                                         softmax=True)
+    lists = ops.build_pair_lists(top, nv)
+    vp = lists.vid_ptr.cpu().numpy()
+    assert vp[-1] == nq * slots and (np.diff(vp) == np.bincount(top.cpu().numpy().ravel(), minlength=nv)).all()
+    st, ed = ops.span_logits(qv, fv, mask, t0, t1, q_b=qs, feat2_b=fs, mask_b=mask, merged=True, softmax=True,
+                             lists=lists)
+    rows = torch.arange(nq, device=DEV).unsqueeze(1)
+    assert torch.equal(st.view(nq, slots, length), dense_st[rows, top.long()])
+    assert torch.equal(ed.view(nq, slots, length), dense_ed[rows, top.long()])
+    # diagonal lists (cross=False path)
+    n = 30
+    lists = ops.diagonal_pair_lists(n, DEV)
+    st, _ = ops.span_logits(qv[:n], fv[:n], mask[:n], t0, t1, q_b=qs[:n], feat2_b=fs[:n], mask_b=mask[:n],
+                            merged=True, softmax=True, lists=lists)
+    idx = torch.arange(n, device=DEV)
+    assert torch.equal(st, dense_st[idx, idx])
+
+
+@pytest.mark.parametrize("rows,cols,k", [(3, 100, 100), (17, 2179, 100), (4, 21793, 100), (5, 333, 7), (2, 5000, 1000)])
+def test_topk_rows(ops, rows, cols, k):
+    g = torch.Generator().manual_seed(rows * cols)
+    x = torch.rand(rows, cols, generator=g) * 0.12 + 0.03
+    x[0, :50] = x[0, 60]  # exact ties straddling the cut
+    if cols > 200:
+        x[1, 100:160] = x[1].max() + 0.01
+    e = torch.exp(20.0 * x)
+    order = O.stable_desc_order(e)[:, :k]
+    idx, val = ops.topk_rows(x.to(DEV), k, alpha=20.0, apply_exp=True)
+    got_e = val.cpu()
+    # the device expf may differ from torch CPU exp in the last ulp: compare values loosely, order exactly
+    # wherever the oracle's own gap is not a tie within 2 ulp
+    close(got_e, torch.gather(e, 1, order), rtol=5e-7, atol=0)
+    want_idx = order.numpy()
+    got_idx = idx.cpu().numpy().astype(np.int64)
+    same = got_idx == want_idx
+    if not same.all():
+        ev = e.numpy()
+        for r, c in zip(*np.nonzero(~same)):
+            a, b = ev[r, got_idx[r, c]], ev[r, want_idx[r, c]]
+            assert abs(a - b) <= 4e-7 * abs(b), (r, c, a, b)
+    # raw (no exp) selection with explicit ids, ties by id ascending / descending
+    ids = torch.randperm(cols, generator=g).to(torch.int32).unsqueeze(0).repeat(rows, 1)
+    xi = torch.round(x * 2000) / 2000  # many exact ties
+    for tie_desc in (False, True):
+        idx, val = ops.topk_rows(xi.to(DEV), min(k, 64), ids=ids.to(DEV), tie_desc=tie_desc)
+        key = xi.double() * 1e9 + (ids.double() if tie_desc else -ids.double())
+        order = torch.sort(key, dim=1, descending=True)[1][:, :min(k, 64)]
+        assert torch.equal(idx.cpu().long(), torch.gather(ids.long(), 1, order))
+        assert torch.equal(val.cpu(), torch.gather(xi, 1, order))
+
+
+def test_topk_rows_rejects_k_larger_than_row(ops):
+    from tvretrieval_b200._lib import XmlbError
+    with pytest.raises(XmlbError):
+        ops.topk_rows(torch.rand(2, 10, device=DEV), 100)
+
+
+def oracle_span_topk(st, ed, vr, min_l, max_l, k, tie_desc=False):
+    span = torch.einsum("qvm,qv,qvn->qvmn", st, vr, ed) if vr is not None else torch.einsum("qvm,qvn->qvmn", st, ed)
+    span = span * torch.from_numpy(O.band_mask(st.shape[-1], min_l, max_l))
+    flat = span.reshape(len(span), -1)
+    if tie_desc:
+        order = torch.flip(torch.sort(flat, dim=1, descending=False, stable=True)[1], dims=[1])[:, :k]
+    else:
+        order = O.stable_desc_order(flat)[:, :k]
+    return order, torch.gather(flat, 1, order)
+
+
+@pytest.mark.parametrize("nq,slots,length,k", [(4, 100, 128, 200), (6, 8, 32, 50), (3, 100, 100, 200), (2, 5, 24, 1000),
+                                              (2, 30, 256, 200)])
+def test_span_topk_vcmr(ops, nq, slots, length, k):
+    g = torch.Generator().manual_seed(nq * slots + length)
+    mask = rand_mask(g, nq * slots, length, 3).view(nq, slots, length)
+    st = torch.softmax(torch.randn(nq, slots, length, generator=g) * 2 + (mask - 1) * 1e10, -1)
+    ed = torch.softmax(torch.randn(nq, slots, length, generator=g) * 2 + (mask - 1) * 1e10, -1)
+    vr = torch.exp(20 * (torch.rand(nq, slots, generator=g) * 0.1 + 0.03))
+    st[0, 0] = st[0, 1]  # duplicated rows -> exact score ties between slots
+    ed[0, 0] = ed[0, 1]
+    vr[0, 0] = vr[0, 1]
+    order, score = oracle_span_topk(st, ed, vr, 2, 16, k)
+    idx, val = ops.span_topk(st.to(DEV), ed.to(DEV), vr.to(DEV), 2, 16, k)
+    assert torch.equal(val.cpu(), score)  # (st*vr)*ed is bit-exact
+    assert torch.equal(idx.cpu().long(), order)
+
+
+def test_span_topk_zero_fill_and_svmr_ties(ops):
+    g = torch.Generator().manual_seed(3)
+    nq, length, k = 5, 20, 60
+    lens = [3, 5, 20, 4, 9]
+    st = torch.zeros(nq, 1, length)
+    ed = torch.zeros(nq, 1, length)
+    for i, n in enumerate(lens):
+        st[i, 0, :n] = torch.softmax(torch.randn(n, generator=g), 0)
+        ed[i, 0, :n] = torch.softmax(torch.randn(n, generator=g), 0)
+    for tie_desc in (False, True):
+        order, score = oracle_span_topk(st, ed, None, 2, 16, k, tie_desc=tie_desc)
+        idx, val = ops.span_topk(st.to(DEV), ed.to(DEV), None, 2, 16, k, tie_desc=tie_desc)
+        assert torch.equal(val.cpu(), score)
+        assert torch.equal(idx.cpu().long(), order), tie_desc
+    # without zero fill the tail is (-1, 0); span_zero_fill completes it identically
+    idx, val = ops.span_topk(st.to(DEV), ed.to(DEV), None, 2, 16, k, zero_fill=False)
+    assert (idx[0, 1:] == -1).all() and (val[0, 1:] == 0).all()
+    order, score = oracle_span_topk(st, ed, None, 2, 16, k)
+    idx, val = ops.span_zero_fill(idx, val, length * length)
+    assert torch.equal(idx.cpu().long(), order) and torch.equal(val.cpu(), score)
+
+
+def test_temporal_nms_known_answers(ops):
+    from tests.golden_io import GOLDEN_DIR
+    z = np.load(GOLDEN_DIR + "/temporal_nms.npz")
+    for i in range(int(z["n_cases"])):
+        preds = z["in/%d" % i]
+        order = np.argsort(-preds[:, 2], kind="stable")  # the kernel takes ranked lists
+        p = torch.from_numpy(preds[order]).float().to(DEV)
+        kept, cnt = ops.temporal_nms(p[None, :, 0], p[None, :, 1], p[None, :, 2], float(z["thd/%d" % i]), 100)
+        got = preds[order][kept[0, :int(cnt[0])].cpu().numpy()]
+        assert np.array_equal(got, z["out/%d" % i]), i

@@ -1,0 +1,100 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/xmlb200.h declares (no compute
+calls), the drop-in model keeps the reference's checkpoint layout, and the host-side helpers behave like the
+reference's."""
+import copy
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import xml_oracle as O
+from tests.golden_io import CASE_NAMES, GoldenCase
+
+
+def test_library_exports_every_declared_symbol():
+    from tvretrieval_b200 import _lib, build
+    build.build()
+    protos = _lib.parse_header()
+    assert len(protos) >= 16
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(handle, name), "libxmlb200.so does not export " + name
+    lib = _lib.lib()
+    assert lib.xmlb_version() >= 100
+    assert lib.xmlb_last_error() is not None
+
+
+def test_invalid_arguments_return_error_codes_not_crashes():
+    from tvretrieval_b200 import _lib
+    lib = _lib.lib()
+    rc = lib.xmlb_topk_rows(None, None, 1, 10, 5, 1.0, 0, 0, None, None, None)
+    assert rc < 0 and b"null" in lib.xmlb_last_error()
+    rc = lib.xmlb_span_topk(None, None, None, None, 1, 1, 8, 2, 16, 5000, 0, 1, None, None, None)
+    assert rc < 0
+    with pytest.raises(_lib.XmlbError):
+        _lib.check(rc, "xmlb_span_topk")
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_model_checkpoint_layout_and_seeded_init(name):
+    from tvretrieval_b200.model_xml import XML, AttrDict
+    g = GoldenCase(name)
+    torch.manual_seed(2018)
+    model = XML(AttrDict(g.cfg))
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(g.weights.keys())
+    for k, v in sd.items():
+        assert v.shape == g.weights[k].shape, k
+        assert torch.equal(v, g.weights[k]), "seeded init differs from the reference at " + k
+    model.load_state_dict(g.weights)
+    for attr in ("query_input_proj", "query_encoder", "query_pos_embed", "modular_vector_mapping", "config",
+                 "use_video", "use_sub"):
+        assert hasattr(model, attr)
+    if g.cfg["merge_two_stream"]:
+        out = model.merged_st_predictor(torch.zeros(3, 1, 9))  # callable on (n, 1, L) like profile_main.py uses it
+        assert out.shape == (3, 1, 9)
+
+
+def test_model_has_no_cpu_fallback():
+    from tvretrieval_b200._lib import XmlbError
+    from tvretrieval_b200.model_xml import XML, AttrDict
+    g = GoldenCase("video_only_svmr")
+    model = XML(AttrDict(g.cfg)).eval()
+    with pytest.raises(XmlbError):
+        model.encode_query(g.query_feat, g.query_mask)
+    with pytest.raises(NotImplementedError):
+        model(None, None, None, None, None, None, None, None, None)
+
+
+def test_unsupported_variants_fail_loudly():
+    from tvretrieval_b200.model_xml import XML, xml_base_config
+    for override in (dict(encoder_type="lstm"), dict(span_predictor_type="cat_linear"),
+                     dict(stack_conv_predictor_conv_kernel_sizes=[3, 5])):
+        cfg = copy.deepcopy(xml_base_config)
+        cfg.update(override)
+        with pytest.raises(NotImplementedError):
+            XML(cfg)
+
+
+def test_band_mask_and_collate_match_reference_semantics():
+    from tvretrieval_b200 import inference as I
+    for length, lo, hi in ((100, 2, 16), (128, 2, 16), (7, 0, 3)):
+        m = I.generate_min_max_length_mask((5, 8, length, length), lo, hi)
+        assert m.shape == (1, 1, length, length)
+        assert np.array_equal(m[0, 0], O.band_mask(length, lo, hi))
+    assert int(I.generate_min_max_length_mask((100, 100), 2, 16).sum()) == 1281
+    assert int(I.generate_min_max_length_mask((128, 128), 2, 16).sum()) == 1673
+    seqs = [torch.randn(3, 4), torch.randn(5, 4), torch.randn(1, 4)]
+    batch = [dict(meta=dict(i=i), model_inputs=dict(query_feat=s)) for i, s in enumerate(seqs)]
+    metas, out = I.start_end_collate(batch)
+    feat, mask = out["query_feat"]
+    assert feat.shape == (3, 5, 4) and mask.dtype == torch.float32
+    assert mask.sum(1).tolist() == [3, 5, 1] and torch.equal(feat[0, :3], seqs[0]) and (feat[0, 3:] == 0).all()
+    x = I.prepare_batch_inputs(out, device="cpu")
+    assert set(x) == {"query_feat", "query_mask"}
+    cat = I.cat_tensor([torch.ones(2, 3, 2), torch.ones(1, 5, 2)])
+    assert cat.shape == (3, 5, 2) and (cat[:2, 3:] == 0).all()
+    with pytest.raises(ValueError):
+        I.cat_tensor([torch.ones(2)])

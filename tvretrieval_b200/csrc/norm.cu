@@ -1,0 +1,94 @@
+// Row-wise HBM-bound kernels: (add +) LayerNorm, L2 normalisation, softmax.
+//   xmlb_add_layernorm : reference nn.LayerNorm(eps=1e-5) with the fused adds of
+//                        TrainablePositionalEncoding.forward (model_components.py:81-88),
+//                        BertSelfOutput.forward (:313-317) and the cross-attention residual (model_xml.py:371)
+//   xmlb_l2norm_rows   : F.normalize(x, dim=-1) (model_xml.py:446-447): x / max(||x||_2, 1e-12)
+//   xmlb_softmax_rows  : nn.Softmax(dim=-1) (model_components.py:293), F.softmax (inference.py:321-322)
+// One warp per row, 8 rows per CTA; rows are read through L1 so the 2nd/3rd pass never touch HBM.
+#include "common.cuh"
+#include "xmlb200.h"
+
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add,
+                                                            long long add_rows, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ out,
+                                                            long long rows, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  const float* ar = add ? add + (row % add_rows) * dim : nullptr;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s += ar ? xr[i] + ar[i] : xr[i];
+  const float mean = warp_sum(s) / (float)dim;
+  float v = 0.f;
+  for (int i = lane; i < dim; i += 32) {
+    const float d = (ar ? xr[i] + ar[i] : xr[i]) - mean;
+    v = fmaf(d, d, v);
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(v) / (float)dim + eps);
+  float* o = out + row * dim;
+  for (int i = lane; i < dim; i += 32) {
+    const float d = (ar ? xr[i] + ar[i] : xr[i]) - mean;
+    o[i] = fmaf(d * rstd, __ldg(gamma + i), __ldg(beta + i));
+  }
+}
+
+extern "C" int xmlb_add_layernorm(const float* x, const float* add, long long add_rows, const float* gamma,
+                                  const float* beta, float* out, long long rows, int dim, float eps, void* stream) {
+  XMLB_REQUIRE(x && gamma && beta && out && dim > 0 && rows >= 0, "xmlb_add_layernorm: bad argument");
+  XMLB_REQUIRE(!add || add_rows > 0, "xmlb_add_layernorm: add_rows must be > 0 when add is given");
+  if (rows == 0) return XMLB_OK;
+  add_layernorm_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, add, add_rows, gamma, beta, out,
+                                                                           rows, dim, eps);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                          long long rows, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s = fmaf(xr[i], xr[i], s);
+  const float denom = fmaxf(sqrtf(warp_sum(s)), eps);
+  float* o = out + row * dim;
+  for (int i = lane; i < dim; i += 32) o[i] = __fdiv_rn(xr[i], denom);
+}
+
+extern "C" int xmlb_l2norm_rows(const float* x, float* out, long long rows, int dim, float eps, void* stream) {
+  XMLB_REQUIRE(x && out && dim > 0 && rows >= 0, "xmlb_l2norm_rows: bad argument");
+  if (rows == 0) return XMLB_OK;
+  l2norm_rows_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, out, rows, dim, eps);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* x, float* out,  // in-place allowed
+                                                          
+                                                           long long rows, int dim) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * dim;
+  float m = -INFINITY;
+  for (int i = lane; i < dim; i += 32) m = fmaxf(m, xr[i]);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s += expf(xr[i] - m);
+  s = warp_sum(s);
+  float* o = out + row * dim;
+  for (int i = lane; i < dim; i += 32) o[i] = __fdiv_rn(expf(xr[i] - m), s);
+}
+
+extern "C" int xmlb_softmax_rows(const float* x, float* out, long long rows, int dim, void* stream) {
+  XMLB_REQUIRE(x && out && dim > 0 && rows >= 0, "xmlb_softmax_rows: bad argument");
+  if (rows == 0) return XMLB_OK;
+  softmax_rows_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, out, rows, dim);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}

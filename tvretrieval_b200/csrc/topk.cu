@@ -1,0 +1,381 @@
+// Exact top-k selection kernels (HBM/L2-bound, one CTA per query row):
+//   xmlb_topk_rows : exp(alpha * q2c) + torch.topk(k=max_n_videos)             -- reference inference.py:317,347-348
+//                    (also the k-way merge of per-GPU candidate lists, see sharding.py)
+//   xmlb_span_topk : einsum("qvm,qv,qvn->qvmn") * band mask, flatten, full sort, keep max_before_nms
+//                                                                                 -- reference inference.py:365-386
+//                    and the SVMR variant (outer product of one video)           -- inference.py:215-224,
+//                                                                                    utils/tensor_utils.py:133-141
+// The reference materialises and fully sorts 100*L*L floats per query; here only the ~14 in-band cells per
+// (video, start clip) are evaluated, on the fly, and the k best are found with a 3-pass (12/12/8 bit)
+// radix select over the score bits, ties resolved by flat index (second radix select, only when needed),
+// then a bitonic sort of the k winners.  Ranking is canonical: score descending, index ascending
+// (tie_desc=0) or descending (tie_desc=1, numpy's reversed argsort used by the SVMR path).
+#include "common.cuh"
+#include "xmlb200.h"
+
+namespace {
+
+constexpr int NT = 512;
+constexpr int HIST = 4096;
+constexpr int MAX_K = 1024;
+
+struct SelSmem {
+  int hist[HIST];
+  int warp_tot[NT / 32];
+  int sel_bin, sel_above, sel_count, total;
+  int count;
+  unsigned long long buf[MAX_K];
+};
+
+__device__ __forceinline__ unsigned int float_key(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Block-wide: find the largest bin b with sum_{b' >= b} hist[b'] >= want.  Results in sm.sel_*; sm.total = sum of all.
+__device__ void find_bin(SelSmem& sm, int nbins, int want) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int bpt = nbins >= NT ? nbins / NT : 1;
+  const int b0 = t * bpt;
+  int tsum = 0;
+  if (b0 < nbins)
+    for (int i = 0; i < bpt; ++i) tsum += sm.hist[b0 + i];
+  int inc = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) sm.warp_tot[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int x = lane < NT / 32 ? sm.warp_tot[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane < NT / 32) sm.warp_tot[lane] = x;
+    if (lane == NT / 32 - 1) sm.total = x;
+  }
+  __syncthreads();
+  const int total = sm.total;
+  const int prefix_incl = inc + (w ? sm.warp_tot[w - 1] : 0);
+  const int suffix_after = total - prefix_incl;  // sum over threads > t
+  if (b0 < nbins && suffix_after < want && want <= suffix_after + tsum) {
+    int acc = suffix_after;
+    for (int b = b0 + bpt - 1; b >= b0; --b) {
+      const int h = sm.hist[b];
+      if (acc + h >= want) {
+        sm.sel_bin = b, sm.sel_above = acc, sm.sel_count = h;
+        break;
+      }
+      acc += h;
+    }
+  }
+  __syncthreads();
+}
+
+// Radix select of the `want`-th largest 32-bit key among the candidates for which sel(key, idk, k) is true.
+// Returns false if fewer than `want` candidates exist (then `n_total` holds their number).
+template <class Gen, class Sel>
+__device__ bool radix_select(const Gen& gen, const Sel& sel, SelSmem& sm, int want, unsigned int& thr,
+                             int& n_equal, int& n_needed_equal, int& n_total) {
+  unsigned int prefix = 0, pmask = 0;
+  int remaining = want;
+  const int shifts[3] = {20, 8, 0};
+  const int nbins[3] = {4096, 4096, 256};
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = threadIdx.x; i < nbins[pass]; i += NT) sm.hist[i] = 0;
+    __syncthreads();
+    const int shift = shifts[pass];
+    const unsigned int bm = nbins[pass] - 1;
+    gen.for_each([&](unsigned int key, unsigned int idk) {
+      unsigned int k;
+      if (sel(key, idk, k) && (k & pmask) == prefix) atomicAdd(&sm.hist[(k >> shift) & bm], 1);
+    });
+    __syncthreads();
+    find_bin(sm, nbins[pass], remaining);
+    if (pass == 0) {
+      n_total = sm.total;
+      if (sm.total < want) return false;
+    }
+    remaining -= sm.sel_above;
+    prefix |= (unsigned int)sm.sel_bin << shift;
+    pmask |= bm << shift;
+    n_equal = sm.sel_count;
+    __syncthreads();
+  }
+  thr = prefix;
+  n_needed_equal = remaining;
+  return true;
+}
+
+__device__ void bitonic_sort_desc(unsigned long long* buf, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += NT) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool desc = (i & k) == 0;
+          const unsigned long long a = buf[i], b = buf[ixj];
+          if (desc ? (a < b) : (a > b)) buf[i] = b, buf[ixj] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Exact top-k by (key desc, idkey desc).  On return sm.buf[0..n_out) is sorted; returns n_out (= k unless
+// fewer than k candidates exist).
+template <class Gen>
+__device__ int block_topk(const Gen& gen, SelSmem& sm, int k) {
+  unsigned int thr = 0, thr2 = 0;
+  int n_equal = 0, need_equal = 0, n_total = 0;
+  bool use_thr2 = false;
+  const bool full = radix_select(gen, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; },
+                                 sm, k, thr, n_equal, need_equal, n_total);
+  if (full && n_equal > need_equal) {  // exact ties straddle the cut: keep the preferred ids among them
+    int ne2, need2, nt2;
+    const unsigned int t1 = thr;
+    radix_select(gen, [t1](unsigned int key, unsigned int idk, unsigned int& out) { out = idk; return key == t1; },
+                 sm, need_equal, thr2, ne2, need2, nt2);
+    use_thr2 = true;
+  }
+  int pow2 = 1;
+  while (pow2 < k) pow2 <<= 1;
+  for (int i = threadIdx.x; i < pow2; i += NT) sm.buf[i] = 0ull;
+  if (threadIdx.x == 0) sm.count = 0;
+  __syncthreads();
+  gen.for_each([&](unsigned int key, unsigned int idk) {
+    const bool take = !full || key > thr || (key == thr && (!use_thr2 || idk >= thr2));
+    if (take) {
+      const int pos = atomicAdd(&sm.count, 1);
+      if (pos < MAX_K) sm.buf[pos] = ((unsigned long long)key << 32) | idk;
+    }
+  });
+  __syncthreads();
+  const int n_out = min(sm.count, k);
+  bitonic_sort_desc(sm.buf, pow2);
+  return n_out;
+}
+
+// ------------------------------------------------------------------------------------------------------
+struct RowGen {
+  const float* row;
+  const int* ids;
+  int n;
+  float alpha;
+  int apply_exp, tie_desc;
+  template <class F>
+  __device__ void for_each(F f) const {
+    for (int c = threadIdx.x; c < n; c += NT) {
+      const float x = __ldg(row + c);
+      const float e = apply_exp ? expf(alpha * x) : x;
+      const unsigned int id = ids ? (unsigned int)__ldg(ids + c) : (unsigned int)c;
+      f(float_key(e), tie_desc ? id : ~id);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__ values, const int* __restrict__ ids,
+                                                       int n_cols, int k, float alpha, int apply_exp, int tie_desc,
+                                                       int* __restrict__ out_idx, float* __restrict__ out_val) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
+  const long long r = blockIdx.x;
+  RowGen gen{values + r * n_cols, ids ? ids + r * n_cols : nullptr, n_cols, alpha, apply_exp, tie_desc};
+  const int n_out = block_topk(gen, sm, k);
+  for (int i = threadIdx.x; i < k; i += NT) {
+    if (i < n_out) {
+      const unsigned long long e = sm.buf[i];
+      const unsigned int idk = (unsigned int)(e & 0xffffffffu);
+      out_idx[r * k + i] = (int)(tie_desc ? idk : ~idk);
+      out_val[r * k + i] = key_float((unsigned int)(e >> 32));
+    } else {
+      out_idx[r * k + i] = -1;
+      out_val[r * k + i] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+struct SpanGen {
+  const float* st;  // [n_slots][L] start probabilities of this query
+  const float* ed;
+  const float* vr;  // [n_slots] video scores (null -> 1)
+  const unsigned char* valid;  // [n_slots] or null
+  int n_slots, L, min_l, max_l, tie_desc;
+  template <class F>
+  __device__ void for_each(F f) const {
+    const int rows = n_slots * L;
+    for (int r = threadIdx.x; r < rows; r += NT) {
+      const int j = r / L, m = r - j * L;
+      if (valid && !valid[j]) continue;
+      float a = __ldg(st + r);
+      if (vr) a = __fmul_rn(a, __ldg(vr + j));  // (st * vr) first: the association torch.einsum uses
+      if (!(a > 0.f)) continue;
+      const int n_hi = min(m + max_l, L);
+      const float* e = ed + j * L;
+      for (int n = m + min_l; n < n_hi; ++n) {
+        const float s = __fmul_rn(a, __ldg(e + n));
+        if (s > 0.f) {
+          const unsigned int id = (unsigned int)(r * L + n);
+          f(float_key(s), tie_desc ? id : ~id);
+        }
+      }
+    }
+  }
+};
+
+// cells with score exactly 0 (out of band, padded clips, underflow) rank after every positive cell, ordered by
+// flat index like a stable sort of the reference's dense tensor would order them
+__device__ void zero_fill(SelSmem& sm, int n_pos, int k, long long total_cells, int tie_desc, int* out_idx,
+                          float* out_val) {
+  __shared__ int filled_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) filled_s = n_pos;
+  __syncthreads();
+  for (long long base = 0; base < total_cells; base += NT) {
+    const int filled = filled_s;
+    if (filled >= k) break;
+    const long long pos = base + t;
+    bool is_free = pos < total_cells;
+    const unsigned int cell = (unsigned int)(tie_desc ? total_cells - 1 - pos : pos);
+    if (is_free) {
+      const unsigned int idk = tie_desc ? cell : ~cell;
+      for (int i = 0; i < n_pos; ++i)
+        if ((unsigned int)(sm.buf[i] & 0xffffffffu) == idk) {
+          is_free = false;
+          break;
+        }
+    }
+    const unsigned int bal = __ballot_sync(0xffffffffu, is_free);
+    if (lane == 0) sm.warp_tot[w] = __popc(bal);
+    __syncthreads();
+    int before = __popc(bal & ((1u << lane) - 1));
+    int tot = 0;
+    for (int i = 0; i < NT / 32; ++i) {
+      if (i < w) before += sm.warp_tot[i];
+      tot += sm.warp_tot[i];
+    }
+    if (is_free && filled + before < k) {
+      out_idx[filled + before] = (int)cell;
+      out_val[filled + before] = 0.f;
+    }
+    __syncthreads();
+    if (t == 0) filled_s = filled + tot;
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int i = filled_s + t; i < k; i += NT) out_idx[i] = -1, out_val[i] = 0.f;
+}
+
+__global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__ st, const float* __restrict__ ed,
+                                                       const float* __restrict__ vr,
+                                                       const unsigned char* __restrict__ slot_valid, int n_slots,
+                                                       int L, int min_l, int max_l, int k, int tie_desc,
+                                                       int do_zero_fill, int* __restrict__ out_idx,
+                                                       float* __restrict__ out_val) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
+  const long long q = blockIdx.x;
+  SpanGen gen{st + q * n_slots * L, ed + q * n_slots * L, vr ? vr + q * n_slots : nullptr,
+              slot_valid ? slot_valid + q * n_slots : nullptr, n_slots, L, min_l, max_l, tie_desc};
+  const int n_out = block_topk(gen, sm, k);
+  int* oi = out_idx + q * k;
+  float* ov = out_val + q * k;
+  for (int i = threadIdx.x; i < k; i += NT) {
+    if (i < n_out) {
+      const unsigned long long e = sm.buf[i];
+      const unsigned int idk = (unsigned int)(e & 0xffffffffu);
+      oi[i] = (int)(tie_desc ? idk : ~idk);
+      ov[i] = key_float((unsigned int)(e >> 32));
+    } else if (!do_zero_fill) {
+      oi[i] = -1;
+      ov[i] = 0.f;
+    }
+  }
+  if (n_out < k && do_zero_fill) {
+    __syncthreads();
+    zero_fill(sm, n_out, k, (long long)n_slots * L * L, tie_desc, oi, ov);
+  }
+}
+
+// Zero fill for an already ranked list (multi-GPU merge): the first n_pos[r] entries of a row are the positive
+// cells, the rest is replaced by the zero-score cells in canonical flat-index order.
+__global__ void __launch_bounds__(NT) span_zero_fill_kernel(int* __restrict__ idx, float* __restrict__ val, int k,
+                                                            long long total_cells, int tie_desc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
+  __shared__ int n_pos_s;
+  int* oi = idx + (long long)blockIdx.x * k;
+  float* ov = val + (long long)blockIdx.x * k;
+  if (threadIdx.x == 0) n_pos_s = k;
+  __syncthreads();
+  for (int i = threadIdx.x; i < k; i += NT) {
+    const bool pos = oi[i] >= 0 && ov[i] > 0.f;
+    if (!pos) atomicMin(&n_pos_s, i);
+    const unsigned int id = (unsigned int)oi[i];
+    sm.buf[i] = tie_desc ? id : ~id;
+  }
+  __syncthreads();
+  const int n_pos = n_pos_s;
+  if (n_pos < k) zero_fill(sm, n_pos, k, total_cells, tie_desc, oi, ov);
+}
+
+}  // namespace
+
+static int check_topk_args(const char* who, int k) {
+  XMLB_REQUIRE(k >= 1 && k <= MAX_K, "%s: k must be in [1, %d]", who, MAX_K);
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_topk_rows(const float* values, const int* ids, int n_rows, int n_cols, int k, float alpha,
+                              int apply_exp, int tie_desc, int* out_idx, float* out_val, void* stream) {
+  XMLB_REQUIRE(values && out_idx && out_val, "xmlb_topk_rows: null pointer");
+  if (int rc = check_topk_args("xmlb_topk_rows", k)) return rc;
+  XMLB_REQUIRE(n_cols >= k, "xmlb_topk_rows: selected index k out of range (k=%d > %d columns)", k, n_cols);
+  if (n_rows == 0) return XMLB_OK;
+  XMLB_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
+  topk_rows_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(values, ids, n_cols, k, alpha, apply_exp,
+                                                                        tie_desc, out_idx, out_val);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_span_topk(const float* st_prob, const float* ed_prob, const float* video_score,
+                              const unsigned char* slot_valid, int n_queries, int n_slots, int ctx_len, int min_l,
+                              int max_l, int k, int tie_desc, int zero_fill_missing, int* out_flat_idx,
+                              float* out_score, void* stream) {
+  XMLB_REQUIRE(st_prob && ed_prob && out_flat_idx && out_score, "xmlb_span_topk: null pointer");
+  if (int rc = check_topk_args("xmlb_span_topk", k)) return rc;
+  XMLB_REQUIRE(n_slots >= 1 && ctx_len >= 1 && (long long)n_slots * ctx_len * ctx_len < (1ll << 31),
+               "xmlb_span_topk: n_slots*L*L must fit in int32");
+  XMLB_REQUIRE(min_l >= 0 && max_l > min_l, "xmlb_span_topk: need 0 <= min_l < max_l");
+  if (n_queries == 0) return XMLB_OK;
+  XMLB_CUDA(cudaFuncSetAttribute(span_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
+  span_topk_kernel<<<n_queries, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(
+      st_prob, ed_prob, video_score, slot_valid, n_slots, ctx_len, min_l, max_l, k, tie_desc, zero_fill_missing,
+      out_flat_idx, out_score);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_span_zero_fill(int* flat_idx, float* score, int n_queries, int k, long long total_cells,
+                                   int tie_desc, void* stream) {
+  XMLB_REQUIRE(flat_idx && score, "xmlb_span_zero_fill: null pointer");
+  if (int rc = check_topk_args("xmlb_span_zero_fill", k)) return rc;
+  if (n_queries == 0) return XMLB_OK;
+  span_zero_fill_kernel<<<n_queries, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(flat_idx, score, k, total_cells,
+                                                                                 tie_desc);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}

@@ -1,0 +1,173 @@
+"""Device-resident VCMR / VR / SVMR search engine: the query-side hot path kept on the GPU end to end.
+
+One `search()` call = the tensor section of reference `compute_query2ctx_info`
+(baselines/crossmodal_moment_localization/inference.py:302-389) for a batch of raw queries, restructured as
+  phase 1  query encoders -> video-level scores for the whole corpus -> exact top-k videos   (K1-K6, K10)
+  phase 2  similarity curves + ConvSE + softmax ONLY for the selected (query, video) pairs,
+           grouped per video through inverted lists so each video is read once per 32 queries  (K7-K9, K11)
+  phase 3  band-limited span scores + exact top-k moments                                    (K12, K13)
+instead of materialising (Nq, Nv, L) logits and sorting 100*L*L cells per query.  Results are identical to the
+reference's (same arithmetic per cell; ranking = score desc, index asc).
+"""
+import contextlib
+
+import torch
+
+from . import ops
+
+
+class PhaseTimer:
+    """CUDA-event timers around the phases of a search (events are recorded on the stream the kernels are
+    launched on).  bench.py uses it to report the dominant kernel's duration inside the timed region."""
+
+    def __init__(self):
+        self.spans = {}
+
+    @contextlib.contextmanager
+    def phase(self, name):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        yield
+        end.record()
+        self.spans.setdefault(name, []).append((start, end))
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        return {k: sum(s.elapsed_time(e) for s, e in v) for k, v in self.spans.items()}
+
+    def counts(self):
+        return {k: len(v) for k, v in self.spans.items()}
+
+    def reset(self):
+        self.spans = {}
+
+
+class CorpusIndex:
+    """Encoded corpus resident in HBM.  Built once from the output of `compute_context_info`
+    (reference inference.py:89-97); feat1 is L2-normalised at build time (the reference re-normalises it for
+    every query batch, model_xml.py:447)."""
+
+    def __init__(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
+                 sub_mask=None, vid_lo=0):
+        ref = video_feat1 if video_feat1 is not None else sub_feat1
+        self.n_videos, self.ctx_len, self.hidden = ref.shape
+        self.device = ref.device
+        self.vid_lo = vid_lo  # global id of the first video (multi-GPU shards)
+        self.video_feat1n = ops.l2norm_rows(video_feat1) if video_feat1 is not None else None
+        self.sub_feat1n = ops.l2norm_rows(sub_feat1) if sub_feat1 is not None else None
+        self.video_feat2 = video_feat2.contiguous() if video_feat2 is not None else None
+        self.sub_feat2 = sub_feat2.contiguous() if sub_feat2 is not None else None
+        self.video_mask = video_mask.contiguous() if video_mask is not None else None
+        self.sub_mask = sub_mask.contiguous() if sub_mask is not None else None
+
+    @classmethod
+    def from_ctx_info(cls, ctx_info, vid_lo=0):
+        return cls(ctx_info.get("video_feat1"), ctx_info.get("video_feat2"), ctx_info.get("video_mask"),
+                   ctx_info.get("sub_feat1"), ctx_info.get("sub_feat2"), ctx_info.get("sub_mask"), vid_lo=vid_lo)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in
+                   (self.video_feat1n, self.sub_feat1n, self.video_feat2, self.sub_feat2, self.video_mask,
+                    self.sub_mask) if t is not None)
+
+
+class SearchResult:
+    """Device tensors for one batch of queries."""
+    __slots__ = ("top_video_idx", "top_video_score", "span_flat_idx", "span_score", "svmr_flat_idx", "svmr_score")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+class VCMRSearcher:
+    def __init__(self, model, index, q2c_alpha=20.0, min_pred_l=2, max_pred_l=16, max_n_videos=100,
+                 max_before_nms=200, query_chunk=2048):
+        self.model, self.index = model, index
+        self.q2c_alpha = float(q2c_alpha)
+        self.min_pred_l, self.max_pred_l = int(min_pred_l), int(max_pred_l)
+        self.max_n_videos, self.max_before_nms = int(max_n_videos), int(max_before_nms)
+        self.query_chunk = int(query_chunk)
+        self.timer = None  # set to a PhaseTimer to time the phases
+
+    def _phase(self, name):
+        return self.timer.phase(name) if self.timer is not None else contextlib.nullcontext()
+
+    # ---- phases (also used one by one by the sharded searcher) -------------------------------------
+    def encode_queries(self, query_feat, query_mask):
+        return self.model.encode_query(query_feat, query_mask)
+
+    def video_scores(self, video_query, sub_query):
+        ix, m = self.index, self.model
+        return ops.vr_scores_f32(
+            ops.l2norm_rows(video_query) if m.use_video else None, ops.l2norm_rows(sub_query) if m.use_sub else None,
+            ix.video_feat1n if m.use_video else None, ix.sub_feat1n if m.use_sub else None,
+            ix.video_mask if m.use_video else None, ix.sub_mask if m.use_sub else None)
+
+    def span_probs(self, video_query, sub_query, lists):
+        """softmax-normalised start/end distributions for the listed (query, video) pairs -> (rows, L) x 2."""
+        ix = self.index
+        args = self.model.span_streams(video_query, sub_query, ix.video_feat2, ix.sub_feat2, ix.video_mask,
+                                       ix.sub_mask)
+        return ops.span_logits(softmax=True, lists=lists, **args)
+
+    # ---- single-GPU search ------------------------------------------------------------------------
+    def search(self, query_feat, query_mask, gt_video_idx=None, tasks=("VCMR", "VR")):
+        """query_feat (Nq, Lq, Dq), query_mask (Nq, Lq) on the index's device.  gt_video_idx (Nq,) int: corpus
+        position of each query's ground-truth video, needed for SVMR."""
+        outs = [self._search_chunk(query_feat[lo:lo + self.query_chunk], query_mask[lo:lo + self.query_chunk],
+                                   None if gt_video_idx is None else gt_video_idx[lo:lo + self.query_chunk], tasks)
+                for lo in range(0, len(query_feat), self.query_chunk)]
+        if len(outs) == 1:
+            return outs[0]
+        res = SearchResult()
+        for s in SearchResult.__slots__:
+            if getattr(outs[0], s) is not None:
+                setattr(res, s, torch.cat([getattr(o, s) for o in outs]))
+        return res
+
+    def _search_chunk(self, query_feat, query_mask, gt_video_idx, tasks):
+        ix = self.index
+        res = SearchResult()
+        nq = len(query_feat)
+        with self._phase("encode_query"):
+            video_query, sub_query = self.encode_queries(query_feat, query_mask)
+        if "VR" in tasks or "VCMR" in tasks:
+            with self._phase("vr_scores"):
+                q2c = self.video_scores(video_query, sub_query)
+            with self._phase("topk_videos"):
+                res.top_video_idx, res.top_video_score = ops.topk_rows(q2c, self.max_n_videos, alpha=self.q2c_alpha,
+                                                                       apply_exp=True)
+        if "VCMR" in tasks:
+            with self._phase("pair_lists"):
+                lists = ops.build_pair_lists(res.top_video_idx, ix.n_videos)
+            with self._phase("span_probs"):
+                st, ed = self.span_probs(video_query, sub_query, lists)
+            st = st.view(nq, self.max_n_videos, ix.ctx_len)
+            ed = ed.view(nq, self.max_n_videos, ix.ctx_len)
+            with self._phase("span_topk"):
+                res.span_flat_idx, res.span_score = ops.span_topk(st, ed, res.top_video_score, self.min_pred_l,
+                                                                  self.max_pred_l, self.max_before_nms)
+        if "SVMR" in tasks:
+            assert gt_video_idx is not None, "SVMR needs the ground-truth video of every query"
+            lists = ops.build_pair_lists(gt_video_idx.view(nq, 1), ix.n_videos)
+            st, ed = self.span_probs(video_query, sub_query, lists)
+            res.svmr_flat_idx, res.svmr_score = ops.span_topk(
+                st.view(nq, 1, ix.ctx_len), ed.view(nq, 1, ix.ctx_len), None, self.min_pred_l, self.max_pred_l,
+                self.max_before_nms, tie_desc=True)
+        return res
+
+    # ---- host-buffer entry point (the e2e path bench.py times) --------------------------------------
+    def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR")):
+        """Pinned host buffers in, numpy arrays out; H2D/D2H copies are part of the call."""
+        dev = self.index.device
+        qf = query_feat_cpu.to(dev, non_blocking=True)
+        qm = query_mask_cpu.to(dev, non_blocking=True)
+        gt = None if gt_video_idx_cpu is None else gt_video_idx_cpu.to(dev, non_blocking=True)
+        res = self.search(qf, qm, gt, tasks)
+        out = {}
+        for s in SearchResult.__slots__:
+            t = getattr(res, s)
+            if t is not None:
+                out[s] = t.cpu().numpy()
+        return out

@@ -1,0 +1,280 @@
+"""Drop-in `XML` (Cross-modal Moment Localization) whose inference methods run on the xmlb200 sm_100a kernels.
+
+Mirror of the public surface of reference baselines/crossmodal_moment_localization/model_xml.py (class `XML`,
+`xml_base_config`, `mask_logits`): same constructor, attribute names, `state_dict` keys
+and method signatures (`encode_context`, `encode_query`, `encode_input`, `get_modularized_queries`,
+`get_video_level_scores`, `get_merged_st_ed_prob`, `get_st_ed_prob`, `get_pred_from_raw_query`, ...), so the
+reference drivers and `baselines/profiling/profile_main.py` can use it unchanged.  Tensors must live on a CUDA
+device: there is no CPU or PyTorch-eager fallback.  Only `encoder_type="transformer"` with
+`span_predictor_type="conv"` (the shipped configuration) is implemented.
+"""
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .model_components import BertAttention, BertSelfAttention, LinearLayer, TrainablePositionalEncoding
+
+
+class AttrDict(dict):
+    """Attribute-accessible dict (stands in for easydict.EasyDict, which the reference uses for configs)."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __deepcopy__(self, memo):
+        return AttrDict({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+
+# same keys and defaults as reference model_xml.py:19-49
+xml_base_config = AttrDict(
+    merge_two_stream=True, cross_att=True, span_predictor_type="conv", encoder_type="transformer",
+    add_pe_rnn=False, visual_input_size=2048, query_input_size=768, sub_input_size=768, hidden_size=500,
+    conv_kernel_size=5, stack_conv_predictor_conv_kernel_sizes=-1, conv_stride=1, max_ctx_l=100, max_desc_l=30,
+    input_drop=0.1, drop=0.1, n_heads=4, ctx_mode="video_sub", margin=0.1, ranking_loss_type="hinge",
+    lw_neg_q=1, lw_neg_ctx=1, lw_st_ed=1, use_hard_negative=False, hard_pool_size=20, use_self_attention=True,
+    no_modular=False, pe_type="none", initializer_range=0.02)
+
+
+def mask_logits(target, mask):
+    """reference model_xml.py:640-641 (kept as a torch expression: it is part of the module's public API)."""
+    return target * mask + (1 - mask) * (-1e10)
+
+
+class XML(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        if config.encoder_type != "transformer":
+            raise NotImplementedError("xmlb200 implements encoder_type='transformer' only (got %r)"
+                                      % (config.encoder_type,))
+        if config.span_predictor_type != "conv":
+            raise NotImplementedError("xmlb200 implements span_predictor_type='conv' only")
+        if config.stack_conv_predictor_conv_kernel_sizes != -1:
+            raise NotImplementedError("stacked ConvSE predictors are marked 'do not use' upstream; unsupported")
+        if config.conv_stride != 1:
+            raise NotImplementedError("ConvSE stride must be 1")
+        hsz = config.hidden_size
+        att_cfg = AttrDict(hidden_size=hsz, intermediate_size=hsz, hidden_dropout_prob=config.drop,
+                           attention_probs_dropout_prob=config.drop, num_attention_heads=config.n_heads)
+
+        def conv_se():
+            k = config.conv_kernel_size
+            return nn.Conv1d(1, 1, kernel_size=k, stride=1, padding=k // 2, bias=False)
+
+        # registration order follows the reference constructor (model_xml.py:59-165) so that module traversal,
+        # and with it seeded initialisation, visits parameters in the same order
+        self.query_pos_embed = TrainablePositionalEncoding(config.max_desc_l, hsz, dropout=config.input_drop)
+        self.ctx_pos_embed = TrainablePositionalEncoding(config.max_ctx_l, hsz, dropout=config.input_drop)
+        self.query_input_proj = LinearLayer(config.query_input_size, hsz, layer_norm=True,
+                                            dropout=config.input_drop, relu=True)
+        self.query_encoder = BertAttention(att_cfg)
+        self.use_video = "video" in config.ctx_mode
+        self.use_sub = "sub" in config.ctx_mode
+        for name, used, in_dim in (("video", self.use_video, config.visual_input_size),
+                                   ("sub", self.use_sub, config.sub_input_size)):
+            if not used:
+                continue
+            setattr(self, name + "_input_proj", LinearLayer(in_dim, hsz, layer_norm=True,
+                                                            dropout=config.input_drop, relu=True))
+            setattr(self, name + "_encoder1", copy.deepcopy(self.query_encoder))
+            setattr(self, name + "_encoder2", copy.deepcopy(self.query_encoder))
+            if config.cross_att:
+                setattr(self, name + "_cross_att", BertSelfAttention(att_cfg))
+                setattr(self, name + "_cross_layernorm", nn.LayerNorm(hsz))
+            else:
+                setattr(self, name + "_encoder3", copy.deepcopy(self.query_encoder))
+            setattr(self, name + "_query_linear", nn.Linear(hsz, hsz))
+            if not config.merge_two_stream:
+                setattr(self, name + "_st_predictor", conv_se())
+                setattr(self, name + "_ed_predictor", conv_se())
+        self.modular_vector_mapping = nn.Linear(hsz, self.use_sub + self.use_video, bias=False)
+        self.temporal_criterion = nn.CrossEntropyLoss(reduction="mean")
+        if config.merge_two_stream:
+            self.merged_st_predictor = conv_se()
+            self.merged_ed_predictor = conv_se()
+        self._norm_cache = {}
+        self.reset_parameters()
+
+    # ------------------------------------------------------------------ parameters / config
+    def reset_parameters(self):
+        """Same scheme as reference model_xml.py:185-201: N(0, initializer_range) for Linear/Embedding weights,
+        zero Linear biases, LayerNorm (1, 0), default Conv1d init."""
+        std = self.config.initializer_range
+
+        def init(m):
+            if isinstance(m, (nn.Linear, nn.Embedding)):
+                m.weight.data.normal_(mean=0.0, std=std)
+            elif isinstance(m, nn.LayerNorm):
+                m.bias.data.zero_()
+                m.weight.data.fill_(1.0)
+            elif isinstance(m, nn.Conv1d):
+                m.reset_parameters()
+            if isinstance(m, nn.Linear) and m.bias is not None:
+                m.bias.data.zero_()
+
+        self.apply(init)
+
+    def set_hard_negative(self, use_hard_negative, hard_pool_size):
+        self.config.use_hard_negative = use_hard_negative
+        self.config.hard_pool_size = hard_pool_size
+
+    def set_train_st_ed(self, lw_st_ed):
+        self.config.lw_st_ed = lw_st_ed
+
+    def forward(self, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask, tef_feat, tef_mask,
+                st_ed_indices):
+        raise NotImplementedError(
+            "XML.forward is the training step (reference model_xml.py:212-251); this package covers the "
+            "inference hot path only (SURVEY.md section 8f lists training as a later row)")
+
+    # ------------------------------------------------------------------ encoders
+    def encode_input(self, feat, mask, input_proj_layer, encoder_layer, pos_embed_layer):
+        """reference model_xml.py:377-392: projection -> position + LN -> self-attention block."""
+        feat = pos_embed_layer(input_proj_layer(feat))
+        return encoder_layer(feat, mask.unsqueeze(1))
+
+    def encode_query(self, query_feat, query_mask):
+        encoded = self.encode_input(query_feat, query_mask, self.query_input_proj, self.query_encoder,
+                                    self.query_pos_embed)
+        return self.get_modularized_queries(encoded, query_mask)
+
+    def get_modularized_queries(self, encoded_query, query_mask, return_modular_att=False):
+        """reference model_xml.py:399-423."""
+        if self.config.no_modular:
+            raise NotImplementedError("no_modular=True is not supported")
+        if return_modular_att:
+            raise NotImplementedError("return_modular_att (visualisation only) is not supported")
+        return ops.modular_pool(encoded_query, query_mask, self.modular_vector_mapping.weight)
+
+    def cross_context_encoder(self, main_context_feat, main_context_mask, side_context_feat, side_context_mask,
+                              cross_att_layer, norm_layer, self_att_layer):
+        """reference model_xml.py:357-373."""
+        cross_mask = main_context_mask.unsqueeze(2) * side_context_mask.unsqueeze(1)  # (N, Lq, Lk) {0,1}
+        cross_out = cross_att_layer(main_context_feat, side_context_feat, side_context_feat, cross_mask)
+        residual_out = ops.add_layernorm(cross_out, norm_layer.weight, norm_layer.bias, add=main_context_feat,
+                                         eps=norm_layer.eps)
+        return self_att_layer(residual_out, main_context_mask.unsqueeze(1))
+
+    def cross_encode_context(self, video_feat, video_mask, sub_feat, sub_mask):
+        """reference model_xml.py:344-355."""
+        v1 = self.encode_input(video_feat, video_mask, self.video_input_proj, self.video_encoder1, self.ctx_pos_embed)
+        s1 = self.encode_input(sub_feat, sub_mask, self.sub_input_proj, self.sub_encoder1, self.ctx_pos_embed)
+        v2 = self.cross_context_encoder(v1, video_mask, s1, sub_mask, self.video_cross_att,
+                                        self.video_cross_layernorm, self.video_encoder2)
+        s2 = self.cross_context_encoder(s1, sub_mask, v1, video_mask, self.sub_cross_att,
+                                        self.sub_cross_layernorm, self.sub_encoder2)
+        return v1, v2, s1, s2
+
+    def non_cross_encode_context(self, context_feat, context_mask, module_name="video"):
+        """reference model_xml.py:297-329: feat1 = enc1(...), feat2 = enc3(enc2(feat1))."""
+        feat1 = self.encode_input(context_feat, context_mask, getattr(self, module_name + "_input_proj"),
+                                  getattr(self, module_name + "_encoder1"), self.ctx_pos_embed)
+        m3 = context_mask.unsqueeze(1)
+        feat2 = getattr(self, module_name + "_encoder2")(feat1, m3)
+        feat2 = getattr(self, module_name + "_encoder3")(feat2, m3)
+        return feat1, feat2
+
+    def encode_context(self, video_feat, video_mask, sub_feat, sub_mask):
+        """reference model_xml.py:331-342."""
+        if self.config.cross_att:
+            assert self.use_video and self.use_sub
+            return self.cross_encode_context(video_feat, video_mask, sub_feat, sub_mask)
+        v1 = v2 = s1 = s2 = None
+        if self.use_video:
+            v1, v2 = self.non_cross_encode_context(video_feat, video_mask, module_name="video")
+        if self.use_sub:
+            s1, s2 = self.non_cross_encode_context(sub_feat, sub_mask, module_name="sub")
+        return v1, v2, s1, s2
+
+    # ------------------------------------------------------------------ scoring
+    def _normalized_corpus(self, feat1):
+        """The reference re-normalises the whole corpus tensor on every call (model_xml.py:447); the result only
+        depends on the tensor, so it is cached per (storage, version)."""
+        key = (feat1.data_ptr(), tuple(feat1.shape), feat1._version)
+        hit = self._norm_cache.get(key)
+        if hit is None:
+            if len(self._norm_cache) > 8:
+                self._norm_cache.clear()
+            hit = ops.l2norm_rows(feat1)
+            self._norm_cache[key] = hit
+        return hit
+
+    def get_video_level_scores(self, modularied_query, context_feat1, context_mask):
+        """reference model_xml.py:436-453 -> (Nq, Nv)."""
+        return ops.vr_scores_f32(ops.l2norm_rows(modularied_query), None, self._normalized_corpus(context_feat1),
+                                 None, context_mask, None)
+
+    def get_merged_st_ed_prob(self, video_query, video_feat, sub_query, sub_feat, context_mask, cross=False,
+                              return_similaity=False):
+        """reference model_xml.py:455-502 -> masked st/ed logits."""
+        assert self.use_video and self.use_sub and self.config.span_predictor_type == "conv"
+        if return_similaity:
+            raise NotImplementedError("return_similaity (visualisation only) is not supported")
+        qv = ops.linear(video_query, self.video_query_linear.weight, self.video_query_linear.bias)
+        qs = ops.linear(sub_query, self.sub_query_linear.weight, self.sub_query_linear.bias)
+        lists = None if cross else ops.diagonal_pair_lists(len(qv), qv.device)
+        return ops.span_logits(qv, video_feat, context_mask, self.merged_st_predictor.weight,
+                               self.merged_ed_predictor.weight, q_b=qs, feat2_b=sub_feat, mask_b=context_mask,
+                               merged=True, lists=lists)
+
+    def get_st_ed_prob(self, modularied_query, context_feat2, context_mask, module_name="video", cross=False):
+        """reference model_xml.py:504-551 (single stream)."""
+        fc = getattr(self, module_name + "_query_linear")
+        q = ops.linear(modularied_query, fc.weight, fc.bias)
+        lists = None if cross else ops.diagonal_pair_lists(len(q), q.device)
+        return ops.span_logits(q, context_feat2, context_mask, getattr(self, module_name + "_st_predictor").weight,
+                               getattr(self, module_name + "_ed_predictor").weight, lists=lists)
+
+    def span_streams(self, video_query, sub_query, video_feat2, sub_feat2, video_mask, sub_mask):
+        """Arguments of ops.span_logits for this model's stream layout (merged / two streams / one stream)."""
+        if self.config.merge_two_stream and self.use_video and self.use_sub:
+            qv = ops.linear(video_query, self.video_query_linear.weight, self.video_query_linear.bias)
+            qs = ops.linear(sub_query, self.sub_query_linear.weight, self.sub_query_linear.bias)
+            return dict(q_a=qv, feat2_a=video_feat2, mask_a=video_mask, w_st_a=self.merged_st_predictor.weight,
+                        w_ed_a=self.merged_ed_predictor.weight, q_b=qs, feat2_b=sub_feat2, mask_b=video_mask,
+                        merged=True)
+        streams = []
+        for name, used, q, f2, m in (("video", self.use_video, video_query, video_feat2, video_mask),
+                                     ("sub", self.use_sub, sub_query, sub_feat2, sub_mask)):
+            if used:
+                fc = getattr(self, name + "_query_linear")
+                streams.append((ops.linear(q, fc.weight, fc.bias), f2, m,
+                                getattr(self, name + "_st_predictor").weight,
+                                getattr(self, name + "_ed_predictor").weight))
+        args = dict(zip(("q_a", "feat2_a", "mask_a", "w_st_a", "w_ed_a"), streams[0]), merged=False)
+        if len(streams) == 2:
+            args.update(zip(("q_b", "feat2_b", "mask_b", "w_st_b", "w_ed_b"), streams[1]))
+        return args
+
+    def video_scores(self, video_query, sub_query, video_feat1, sub_feat1, video_mask, sub_mask):
+        """q2c = mean over modalities of the per-modality masked max cosine (reference model_xml.py:572-574)."""
+        return ops.vr_scores_f32(
+            ops.l2norm_rows(video_query) if self.use_video else None,
+            ops.l2norm_rows(sub_query) if self.use_sub else None,
+            self._normalized_corpus(video_feat1) if self.use_video else None,
+            self._normalized_corpus(sub_feat1) if self.use_sub else None,
+            video_mask if self.use_video else None, sub_mask if self.use_sub else None)
+
+    def get_pred_from_raw_query(self, query_feat, query_mask, video_feat1, video_feat2, video_mask, sub_feat1,
+                                sub_feat2, sub_mask, cross=False):
+        """reference model_xml.py:553-586 -> (q2ctx_scores, st_logits, ed_logits); st/ed are masked logits
+        (-1e10 at padded clips).  cross=False: (N,N),(N,L),(N,L); cross=True: (Nq,Nv),(Nq,Nv,L),(Nq,Nv,L)."""
+        video_query, sub_query = self.encode_query(query_feat, query_mask)
+        q2c = self.video_scores(video_query, sub_query, video_feat1, sub_feat1, video_mask, sub_mask)
+        args = self.span_streams(video_query, sub_query, video_feat2, sub_feat2, video_mask, sub_mask)
+        lists = None if cross else ops.diagonal_pair_lists(len(video_query), video_query.device)
+        st, ed = ops.span_logits(lists=lists, **args)
+        return q2c, st, ed

@@ -1,0 +1,247 @@
+"""Thin tensor-level wrappers over the C ABI (include/xmlb200.h).  PyTorch is used only to own device
+memory and streams; every computation below is one or more hand-written sm_100a kernels.  All inputs must be
+CUDA fp32 (or int32/uint8 where stated) tensors; there is no CPU path."""
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.XmlbError("%s must be a CUDA tensor: the xmlb200 kernels have no CPU fallback" % name)
+    if t.dtype != torch.float32:
+        raise _lib.XmlbError("%s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _i32(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.XmlbError("%s must be a CUDA tensor" % name)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _u8(t, name):
+    if t is None:
+        return None
+    if t.dtype == torch.bool:
+        t = t.to(torch.uint8)
+    if t.dtype != torch.uint8 or not t.is_cuda:
+        raise _lib.XmlbError("%s must be a CUDA uint8/bool tensor" % name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
+    """LayerNorm(x + add[row % add_rows]) over the last dim."""
+    x = _f32(x, "x")
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    add = _f32(add, "add")
+    if add is not None and add_rows is None:
+        add_rows = add.numel() // dim
+    out = torch.empty_like(x)
+    rc = _lib.lib().xmlb_add_layernorm(_p(x), _p(add), add_rows or 0, _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")),
+                                       _p(out), rows, dim, eps, _stream())
+    _lib.check(rc, "xmlb_add_layernorm")
+    return out
+
+
+def linear(x, weight, bias=None, residual=None, relu=False):
+    x = _f32(x, "x")
+    weight = _f32(weight, "weight")
+    out_dim, in_dim = weight.shape
+    assert x.shape[-1] == in_dim, (x.shape, weight.shape)
+    rows = x.numel() // in_dim
+    out = torch.empty(x.shape[:-1] + (out_dim,), device=x.device, dtype=torch.float32)
+    residual = _f32(residual, "residual")
+    if residual is not None:
+        assert residual.shape == out.shape
+    rc = _lib.lib().xmlb_linear(_p(x), _p(weight), _p(_f32(bias, "bias")), _p(residual), _p(out), rows, out_dim,
+                                in_dim, int(relu), _stream())
+    _lib.check(rc, "xmlb_linear")
+    return out
+
+
+def attention(q, k, v, mask3, n_heads, max_batch=8192):
+    """q (N, Lq, H), k/v (N, Lk, H), mask3 (N, 1 or Lq, Lk) float {0,1} -> (N, Lq, H)."""
+    q, k, v, mask3 = _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(mask3, "mask")
+    n, lq, hid = q.shape
+    lk = k.shape[1]
+    assert mask3.shape[0] == n and mask3.shape[2] == lk and mask3.shape[1] in (1, lq), mask3.shape
+    out = torch.empty_like(q)
+    step = max(1, min(max_batch, 65535 // n_heads, max(1, (1 << 28) // max(1, n_heads * lq * lk))))
+    ws = torch.empty(min(n, step) * n_heads * lq * lk, device=q.device, dtype=torch.float32)
+    mq = 0 if mask3.shape[1] == 1 else lk
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        rc = _lib.lib().xmlb_attention(_p(q[lo:hi]), _p(k[lo:hi]), _p(v[lo:hi]), _p(mask3[lo:hi]),
+                                       mask3.shape[1] * lk, mq, _p(out[lo:hi]), _p(ws), hi - lo, lq, lk, hid,
+                                       n_heads, _stream())
+        _lib.check(rc, "xmlb_attention")
+    return out
+
+
+def modular_pool(encoded, mask, w_mod):
+    encoded, mask, w_mod = _f32(encoded, "encoded"), _f32(mask, "mask"), _f32(w_mod, "w_mod")
+    n, length, hid = encoded.shape
+    n_mod = w_mod.shape[0]
+    out0 = torch.empty(n, hid, device=encoded.device, dtype=torch.float32)
+    out1 = torch.empty_like(out0) if n_mod == 2 else None
+    rc = _lib.lib().xmlb_modular_pool(_p(encoded), _p(mask), _p(w_mod), _p(out0), _p(out1), n, length, hid, n_mod,
+                                      _stream())
+    _lib.check(rc, "xmlb_modular_pool")
+    return (out0, out1) if n_mod == 2 else (out0, out0)
+
+
+def l2norm_rows(x, eps=1e-12):
+    x = _f32(x, "x")
+    out = torch.empty_like(x)
+    dim = x.shape[-1]
+    rc = _lib.lib().xmlb_l2norm_rows(_p(x), _p(out), x.numel() // dim, dim, eps, _stream())
+    _lib.check(rc, "xmlb_l2norm_rows")
+    return out
+
+
+def softmax_rows(x):
+    x = _f32(x, "x")
+    out = torch.empty_like(x)
+    dim = x.shape[-1]
+    rc = _lib.lib().xmlb_softmax_rows(_p(x), _p(out), x.numel() // dim, dim, _stream())
+    _lib.check(rc, "xmlb_softmax_rows")
+    return out
+
+
+def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask):
+    """-> q2c (Nq, Nv).  Inputs already L2-normalised; a modality is skipped when None."""
+    ref_q = q_video_n if q_video_n is not None else q_sub_n
+    ref_c = feat1_video_n if feat1_video_n is not None else feat1_sub_n
+    nq, hid = ref_q.shape
+    nv, length, _ = ref_c.shape
+    out = torch.empty(nq, nv, device=ref_q.device, dtype=torch.float32)
+    ws = torch.empty(2, nq, nv, device=ref_q.device, dtype=torch.float32)
+    rc = _lib.lib().xmlb_vr_scores_f32(
+        _p(_f32(q_video_n, "q_video")), _p(_f32(q_sub_n, "q_sub")), _p(_f32(feat1_video_n, "feat1_video")),
+        _p(_f32(feat1_sub_n, "feat1_sub")), _p(_f32(video_mask, "video_mask")), _p(_f32(sub_mask, "sub_mask")),
+        _p(out), _p(ws), nq, nv, length, hid, _stream())
+    _lib.check(rc, "xmlb_vr_scores_f32")
+    return out
+
+
+class PairLists:
+    """Per-video inverted lists of (query, output row) built on device by xmlb_build_pair_lists."""
+
+    def __init__(self, vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_rows):
+        self.vid_ptr, self.chunk_ptr, self.entry_q, self.entry_out = vid_ptr, chunk_ptr, entry_q, entry_out
+        self.max_chunks, self.n_rows = max_chunks, n_rows
+
+
+def build_pair_lists(top_idx, n_videos, vid_lo=0, slot_valid=None):
+    """top_idx (Nq, n_slots) int32 global video ids -> PairLists over the videos [vid_lo, vid_lo + n_videos)."""
+    top_idx = _i32(top_idx, "top_idx")
+    nq, n_slots = top_idx.shape
+    dev = top_idx.device
+    n_pairs = nq * n_slots
+    ints = torch.empty(4 * n_videos + 2 + 2 * n_pairs, device=dev, dtype=torch.int32)
+    counts, cursor = ints[:n_videos], ints[n_videos:2 * n_videos]
+    vid_ptr = ints[2 * n_videos:3 * n_videos + 1]
+    chunk_ptr = ints[3 * n_videos + 1:4 * n_videos + 2]
+    entry_q = ints[4 * n_videos + 2:4 * n_videos + 2 + n_pairs]
+    entry_out = ints[4 * n_videos + 2 + n_pairs:]
+    rc = _lib.lib().xmlb_build_pair_lists(_p(top_idx), _p(_u8(slot_valid, "slot_valid")), nq, n_slots, vid_lo,
+                                          n_videos, _p(counts), _p(cursor), _p(vid_ptr), _p(chunk_ptr), _p(entry_q),
+                                          _p(entry_out), _stream())
+    _lib.check(rc, "xmlb_build_pair_lists")
+    max_chunks = (n_pairs + 31) // 32 + min(n_videos, n_pairs)
+    return PairLists(vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_pairs)
+
+
+def diagonal_pair_lists(n, device):
+    """Lists for the in-batch (cross=False) case: query i <-> video i."""
+    ar = torch.arange(n + 1, device=device, dtype=torch.int32)
+    return PairLists(ar, ar, ar[:n], ar[:n], n, n)
+
+
+def span_logits(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b=None, feat2_b=None, mask_b=None, w_st_b=None, w_ed_b=None,
+                merged=False, softmax=False, lists=None, out_rows=None):
+    """Dense (lists=None): -> st, ed of shape (Nq, Nv, L).  List mode: -> (out_rows, L) each."""
+    q_a, feat2_a = _f32(q_a, "q_a"), _f32(feat2_a, "feat2_a")
+    nq, hid = q_a.shape
+    nv, length, _ = feat2_a.shape
+    dev = q_a.device
+    w = [_f32(t.reshape(-1), "conv taps") if t is not None else None for t in (w_st_a, w_ed_a, w_st_b, w_ed_b)]
+    ksize = w[0].numel()
+    if lists is None:
+        st = torch.empty(nq, nv, length, device=dev, dtype=torch.float32)
+        ed = torch.empty_like(st)
+        lp = (None, None, None, None, 0)
+    else:
+        rows = lists.n_rows if out_rows is None else out_rows
+        # rows that no list entry covers (videos outside this shard) must read as zeros
+        st = torch.zeros(rows, length, device=dev, dtype=torch.float32)
+        ed = torch.zeros_like(st)
+        lp = (_p(lists.chunk_ptr), _p(lists.vid_ptr), _p(lists.entry_q), _p(lists.entry_out), lists.max_chunks)
+    rc = _lib.lib().xmlb_span_logits(
+        _p(q_a), _p(_f32(q_b, "q_b")), _p(feat2_a), _p(_f32(feat2_b, "feat2_b")), _p(_f32(mask_a, "mask_a")),
+        _p(_f32(mask_b, "mask_b")), _p(w[0]), _p(w[1]), _p(w[2]), _p(w[3]), ksize, int(merged), int(softmax), nq, nv,
+        length, hid, lp[0], lp[1], lp[2], lp[3], lp[4], _p(st), _p(ed), _stream())
+    _lib.check(rc, "xmlb_span_logits")
+    return st, ed
+
+
+def topk_rows(values, k, alpha=1.0, apply_exp=False, ids=None, tie_desc=False):
+    """-> (idx int32 (R, k), val fp32 (R, k)) ranked by (value desc, id asc)."""
+    values = _f32(values, "values")
+    n_rows, n_cols = values.shape
+    out_idx = torch.empty(n_rows, k, device=values.device, dtype=torch.int32)
+    out_val = torch.empty(n_rows, k, device=values.device, dtype=torch.float32)
+    rc = _lib.lib().xmlb_topk_rows(_p(values), _p(_i32(ids, "ids")), n_rows, n_cols, k, alpha, int(apply_exp),
+                                   int(tie_desc), _p(out_idx), _p(out_val), _stream())
+    _lib.check(rc, "xmlb_topk_rows")
+    return out_idx, out_val
+
+
+def span_topk(st_prob, ed_prob, video_score, min_l, max_l, k, slot_valid=None, tie_desc=False, zero_fill=True):
+    """st/ed (Nq, n_slots, L) probabilities, video_score (Nq, n_slots) or None -> flat idx int32, score (Nq, k)."""
+    st_prob, ed_prob = _f32(st_prob, "st_prob"), _f32(ed_prob, "ed_prob")
+    nq, n_slots, length = st_prob.shape
+    out_idx = torch.empty(nq, k, device=st_prob.device, dtype=torch.int32)
+    out_val = torch.empty(nq, k, device=st_prob.device, dtype=torch.float32)
+    rc = _lib.lib().xmlb_span_topk(_p(st_prob), _p(ed_prob), _p(_f32(video_score, "video_score")),
+                                   _p(_u8(slot_valid, "slot_valid")), nq, n_slots, length, min_l, max_l, k,
+                                   int(tie_desc), int(zero_fill), _p(out_idx), _p(out_val), _stream())
+    _lib.check(rc, "xmlb_span_topk")
+    return out_idx, out_val
+
+
+def span_zero_fill(flat_idx, score, total_cells, tie_desc=False):
+    assert flat_idx.dtype == torch.int32 and flat_idx.is_contiguous() and score.is_contiguous()
+    rc = _lib.lib().xmlb_span_zero_fill(_p(flat_idx), _p(score), flat_idx.shape[0], flat_idx.shape[1], total_cells,
+                                        int(tie_desc), _stream())
+    _lib.check(rc, "xmlb_span_zero_fill")
+    return flat_idx, score
+
+
+def temporal_nms(st, ed, score, iou_thd, max_out, video_idx=None, n_valid=None, max_per_group=100):
+    """Ranked lists (Nq, n) -> (kept idx int32 (Nq, max_out) into the input lists, count int32 (Nq,))."""
+    st, ed, score = _f32(st, "st"), _f32(ed, "ed"), _f32(score, "score")
+    nq, n_in = st.shape
+    out_idx = torch.empty(nq, max_out, device=st.device, dtype=torch.int32)
+    out_cnt = torch.empty(nq, device=st.device, dtype=torch.int32)
+    rc = _lib.lib().xmlb_temporal_nms(_p(_i32(video_idx, "video_idx")), _p(st), _p(ed), _p(score),
+                                      _p(_i32(n_valid, "n_valid")), nq, n_in, float(iou_thd), max_per_group, max_out,
+                                      _p(out_idx), _p(out_cnt), _stream())
+    _lib.check(rc, "xmlb_temporal_nms")
+    return out_idx, out_cnt

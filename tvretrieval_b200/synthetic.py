@@ -85,3 +85,40 @@ class SyntheticEvalDataset(torch.utils.data.Dataset):
         return dict(meta=dict(desc_id=raw["desc_id"], desc=raw["desc"],
                               vid_name=raw["vid_name"] if self.load_gt_video else None),
                     model_inputs=dict(query_feat=self.query_feats[index]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Large synthetic corpora generated batch by batch ON THE DEVICE (bench.py): the raw features of the
+# 21.8K-video shape are 34 GB and are never materialised at once.
+# ---------------------------------------------------------------------------------------------------
+def corpus_lengths(n_videos, max_ctx_l, seed=1234):
+    gen = torch.Generator().manual_seed(seed)
+    lens = torch.randint(max(1, max_ctx_l // 8), max_ctx_l + 1, (n_videos,), generator=gen)
+    lens[n_videos // 2] = max_ctx_l
+    return lens
+
+
+def corpus_batch(lens, batch_idx, bsz, video_dim, sub_dim, device, seed=1234, video_split=2048):
+    """Raw features of global context batch `batch_idx` (videos [batch_idx*bsz, ...)), padded to the batch max
+    like start_end_collate does.  Deterministic in (seed, batch_idx) regardless of which rank generates it."""
+    lo = batch_idx * bsz
+    bl = lens[lo:lo + bsz].to(device)
+    n, width = len(bl), int(bl.max())
+    gen = torch.Generator(device=device).manual_seed(seed * 1000003 + batch_idx)
+    mask = (torch.arange(width, device=device)[None] < bl[:, None]).float()
+    video = torch.randn(n, width, video_dim, generator=gen, device=device)
+    if video_split and 0 < video_split < video_dim:
+        video = torch.cat([_unit_rows(video[..., :video_split]), _unit_rows(video[..., video_split:])], dim=-1)
+    else:
+        video = _unit_rows(video)
+    sub = _unit_rows(torch.randn(n, width, sub_dim, generator=gen, device=device))
+    return video * mask.unsqueeze(2), sub * mask.unsqueeze(2), mask
+
+
+def synthetic_queries(n_queries, max_desc_l, query_dim, seed=4321):
+    """(Nq, max_desc_l, Dq) unit-norm rows, lengths ~ randint(5, max_desc_l + 1), zero padded; CPU tensors."""
+    gen = torch.Generator().manual_seed(seed)
+    lens = torch.randint(min(5, max_desc_l), max_desc_l + 1, (n_queries,), generator=gen)
+    mask = (torch.arange(max_desc_l)[None] < lens[:, None]).float()
+    feat = _unit_rows(torch.randn(n_queries, max_desc_l, query_dim, generator=gen)) * mask.unsqueeze(2)
+    return feat, mask
