@@ -75,6 +75,28 @@ int xmlb_vr_scores_f32(const float* q_video_n, const float* q_sub_n, const float
                        const float* feat1_sub_n, const float* video_mask, const float* sub_mask, float* q2c,
                        float* workspace, int n_queries, int n_videos, int ctx_len, int hidden, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM / TMA) variant of the video-level scores ------------------------------
+ * Operands are pre-split into 16-bit hi/lo halves (x = hi + lo, fp16 when is_bf16 == 0, else bf16) so that three
+ * tensor-core MMAs per k-step (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) reproduce the fp32 product.
+ *
+ * xmlb_split_rows: x (n_groups * group_in, k) fp32 -> hi, lo (n_groups * group_out, kpad) uint16; rows are
+ * regrouped from groups of group_in (clips of a video) to zero-padded groups of group_out, columns zero-padded
+ * to kpad (multiple of 64); normalize != 0 applies F.normalize (model_xml.py:446-447) first.
+ * xmlb_mask_bits: mask (n_videos, ctx_len) float {0,1} -> bits (n_videos, lp / 32), bit l%32 of word l/32. */
+int xmlb_split_rows(const float* x, long long n_groups, int group_in, int group_out, int k, int kpad,
+                    int normalize, int is_bf16, unsigned short* hi, unsigned short* lo, void* stream);
+int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream);
+
+/* q2c[q][v] = mean over given modalities of max_{l : bit set} q[q] . c[v * lp + l]; same contract as
+ * xmlb_vr_scores_f32 (model_xml.py:446-452, 572-574) on prepared operands: q_* (n_queries, kpad),
+ * c_* (n_videos * lp, kpad), mask_bits_* (n_videos, lp/32).  lp multiple of 32, <= 256.  Modality b optional (NULL).
+ * max_ctas: 0 = one persistent CTA per SM. */
+int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned short* q_lo_a, const unsigned short* q_hi_b,
+                      const unsigned short* q_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                      const unsigned short* c_hi_b, const unsigned short* c_lo_b, const unsigned int* mask_bits_a,
+                      const unsigned int* mask_bits_b, float* q2c, int n_queries, int n_videos, int lp, int kpad,
+                      int is_bf16, int max_ctas, void* stream);
+
 /* Similarity curves + ConvSE + mask (+ softmax), replaces XML.get_merged_st_ed_prob (model_xml.py:455-502),
  * XML._get_st_ed_prob (:512-551) and the driver's softmax over clips (inference.py:321-322).
  *   sim_x[q][v][l] = q_x[q] . feat2_x[v][l]                       for stream x in {a, b}

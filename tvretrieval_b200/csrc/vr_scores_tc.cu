@@ -1,0 +1,389 @@
+// Video-level retrieval scores on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), split-precision.
+//   replaces XML.get_video_level_scores x modalities + their average (reference model_xml.py:446-452, 572-574):
+//   q2c[q][v] = mean_mod  max_{l valid}  qn_mod[q] . c1n_mod[v][l]
+//
+// GEMM view: M = queries, N = corpus clips (a tile holds whole videos), K = hidden.  fp32-accurate products are
+// obtained from 16-bit tensor-core MMAs by splitting both operands x = hi + lo (hi = rn16(x), lo = rn16(x - hi))
+// and accumulating  A_hi B_hi + A_hi B_lo + A_lo B_hi  in the fp32 TMEM accumulator (3 MMAs per k-step; the
+// dropped lo*lo term is ~2^-16 (bf16) / 2^-22 (fp16) relative).  SURVEY.md section 7 "hard part 1" shows that
+// single bf16/tf32 products break the rank-exactness contract while this scheme keeps it.
+//
+// Kernel anatomy (persistent, one CTA per SM, 192 threads):
+//   warp 0      TMA producer: 4 tile loads per k-block (A_hi, A_lo, B_hi, B_lo; 128B swizzle) into a smem ring
+//   warp 1      MMA issuer (one elected thread): 12 tcgen05.mma per k-block into one of two TMEM accumulators
+//   warps 2..5  epilogue: tcgen05.ld the 128 x BLOCK_N fp32 accumulator, masked max over each video's clips
+//               (one thread = one query row, no shuffles), combine the two modalities, store q2c
+// The two modalities of a tile alternate between the two TMEM accumulators, so the epilogue of one overlaps the
+// MMAs of the other.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+#include "xmlb200.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int MAX_VPT = 8;   // videos per tile (BLOCK_N = vpt * lp <= 256, lp multiple of 32)
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 256;
+
+struct VrMaps {
+  CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2];
+};
+
+struct VrTcParams {
+  int n_queries, n_videos, lp, vpt, block_n, k_blocks, n_mod, m_tiles, n_tiles, stages;
+  const unsigned int* mask_bits[2];
+  float* out;
+  float divisor;
+  unsigned int idesc;
+};
+
+__global__ void __launch_bounds__(192, 1)
+vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const VrTcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_bytes = p.block_n * BLOCK_K * 2;
+  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int m = 0; m < p.n_mod; ++m) {
+      tc::tma_prefetch_desc(&maps.a_hi[m]);
+      tc::tma_prefetch_desc(&maps.a_lo[m]);
+      tc::tma_prefetch_desc(&maps.b_hi[m]);
+      tc::tma_prefetch_desc(&maps.b_lo[m]);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      tc::mbar_init(full_bar(s), 1);
+      tc::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar(a), 1);
+      tc::mbar_init(tempty_bar(a), 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
+        for (int mod = 0; mod < p.n_mod; ++mod) {
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            tc::mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            tc::mbar_expect_tx(full_bar(stage), (uint32_t)stage_bytes);
+            tc::tma_load_2d(sa, &maps.a_hi[mod], full_bar(stage), kb * BLOCK_K, m_tile * BLOCK_M);
+            tc::tma_load_2d(sa + A_BYTES, &maps.a_lo[mod], full_bar(stage), kb * BLOCK_K, m_tile * BLOCK_M);
+            tc::tma_load_2d(sa + 2 * A_BYTES, &maps.b_hi[mod], full_bar(stage), kb * BLOCK_K, n_tile * p.block_n);
+            tc::tma_load_2d(sa + 2 * A_BYTES + b_bytes, &maps.b_lo[mod], full_bar(stage), kb * BLOCK_K,
+                            n_tile * p.block_n);
+            if (++stage == p.stages) stage = 0, phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===================== MMA issuer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t unit = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int mod = 0; mod < p.n_mod; ++mod, ++unit) {
+          const uint32_t acc = unit & 1u, use = unit >> 1;
+          tc::mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+          tc::fence_after_sync();
+          const uint32_t tmem_acc = tmem_base + acc * ACC_COLS;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            tc::mbar_wait(full_bar(stage), phase);
+            tc::fence_after_sync();
+            const uint32_t sa = smem_base + stage * stage_bytes;
+            const uint64_t a_hi = tc::smem_desc_sw128(sa), a_lo = tc::smem_desc_sw128(sa + A_BYTES);
+            const uint64_t b_hi = tc::smem_desc_sw128(sa + 2 * A_BYTES);
+            const uint64_t b_lo = tc::smem_desc_sw128(sa + 2 * A_BYTES + b_bytes);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);  // advance 32 B inside the swizzle row
+              tc::umma_f16(tmem_acc, a_hi + off, b_lo + off, p.idesc, (kb | k) != 0);
+              tc::umma_f16(tmem_acc, a_lo + off, b_hi + off, p.idesc, 1u);
+              tc::umma_f16(tmem_acc, a_hi + off, b_hi + off, p.idesc, 1u);
+            }
+            tc::umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
+            if (++stage == p.stages) stage = 0, phase ^= 1u;
+          }
+          tc::umma_commit(tfull_bar(acc));  // accumulator complete
+        }
+      }
+    }
+  } else {  // ===================== epilogue warps 2..5 =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int chunks = p.lp >> 5;
+    uint32_t unit = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
+      const int q = m_tile * BLOCK_M + row;
+      float best[MAX_VPT];
+#pragma unroll
+      for (int j = 0; j < MAX_VPT; ++j) best[j] = 0.f;
+      for (int mod = 0; mod < p.n_mod; ++mod, ++unit) {
+        const uint32_t acc = unit & 1u, use = unit >> 1;
+        tc::mbar_wait(tfull_bar(acc), use & 1u);
+        tc::fence_after_sync();
+        const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
+        const unsigned int* __restrict__ bits = p.mask_bits[mod];
+#pragma unroll
+        for (int j = 0; j < MAX_VPT; ++j) {
+          if (j < p.vpt) {
+            const int v = n_tile * p.vpt + j;
+            float m = MASK_FILL;
+            for (int c = 0; c < chunks; ++c) {
+              uint32_t r[32];
+              tc::tmem_ld_32x32(taddr + j * p.lp + c * 32, r);
+              tc::tmem_ld_wait();
+              const unsigned int b = v < p.n_videos ? __ldg(bits + (long long)v * chunks + c) : 0u;
+              if (b == 0xffffffffu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m = (b >> i) & 1u ? fmaxf(m, __uint_as_float(r[i])) : m;
+              }
+            }
+            best[j] = mod == 0 ? m : __fadd_rn(best[j], m);
+          }
+        }
+        // accumulator fully read: hand it back to the MMA issuer
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+      }
+      if (q < p.n_queries) {
+#pragma unroll
+        for (int j = 0; j < MAX_VPT; ++j) {
+          const int v = n_tile * p.vpt + j;
+          if (j < p.vpt && v < p.n_videos) p.out[(long long)q * p.n_videos + v] = __fdiv_rn(best[j], p.divisor);
+        }
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// operand preparation: fp32 rows -> (optionally L2-normalised) hi/lo 16-bit rows, K padded to a multiple of 64,
+// rows regrouped from groups of `gin` to zero-padded groups of `gout` (clips of a video padded to lp).
+// One warp per output row.
+template <bool BF16>
+__device__ __forceinline__ void split16(float x, unsigned short& hi, unsigned short& lo) {
+  if (BF16) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h), lo = __bfloat16_as_ushort(l);
+  } else {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = __half_as_ushort(h), lo = __half_as_ushort(l);
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, long long rows_out, int k,
+                                                         int kpad, int gin, int gout, int normalize,
+                                                         unsigned short* __restrict__ hi,
+                                                         unsigned short* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const long long ro = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (ro >= rows_out) return;
+  const long long g = ro / gout;
+  const int l = (int)(ro - g * gout);
+  unsigned short* h = hi + ro * kpad;
+  unsigned short* o = lo + ro * kpad;
+  if (l >= gin) {
+    for (int i = lane; i < kpad; i += 32) h[i] = 0, o[i] = 0;
+    return;
+  }
+  const float* xr = x + (g * gin + l) * k;
+  float denom = 1.f;
+  if (normalize) {
+    float s = 0.f;
+    for (int i = lane; i < k; i += 32) s = fmaf(xr[i], xr[i], s);
+    denom = fmaxf(sqrtf(warp_sum(s)), 1e-12f);  // F.normalize eps
+  }
+  for (int i = lane; i < kpad; i += 32) {
+    unsigned short a = 0, b = 0;
+    if (i < k) split16<BF16>(normalize ? __fdiv_rn(xr[i], denom) : xr[i], a, b);
+    h[i] = a, o[i] = b;
+  }
+}
+
+__global__ void mask_bits_kernel(const float* __restrict__ mask, int n_videos, int len, int chunks,
+                                 unsigned int* __restrict__ bits) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // one thread per (video, chunk)
+  if (i >= (long long)n_videos * chunks) return;
+  const int v = (int)(i / chunks), c = (int)(i % chunks);
+  unsigned int b = 0;
+  for (int j = 0; j < 32; ++j) {
+    const int l = c * 32 + j;
+    if (l < len && mask[(long long)v * len + l] != 0.f) b |= 1u << j;
+  }
+  bits[i] = b;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+}  // namespace
+
+int xmlb_make_tmap_2d_u16(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long cols,
+                          unsigned int box_rows, unsigned int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  XMLB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  XMLB_REQUIRE(((uintptr_t)base & 15) == 0 && (cols * 2) % 16 == 0, "tensor map: base/pitch must be 16-byte aligned");
+  XMLB_REQUIRE(box_cols * 2 == 128 && box_rows >= 1 && box_rows <= 256, "tensor map: bad box");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XMLB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_split_rows(const float* x, long long n_groups, int group_in, int group_out, int k, int kpad,
+                               int normalize, int is_bf16, unsigned short* hi, unsigned short* lo, void* stream) {
+  XMLB_REQUIRE(x && hi && lo, "xmlb_split_rows: null pointer");
+  XMLB_REQUIRE(k >= 1 && kpad >= k && kpad % 64 == 0, "xmlb_split_rows: kpad must be a multiple of 64 and >= k");
+  XMLB_REQUIRE(group_in >= 1 && group_out >= group_in, "xmlb_split_rows: need 1 <= group_in <= group_out");
+  const long long rows_out = n_groups * group_out;
+  if (rows_out == 0) return XMLB_OK;
+  XMLB_REQUIRE(rows_out / 8 + 1 < (1ll << 31), "xmlb_split_rows: too many rows");
+  const int blocks = ceil_div(rows_out, 8);
+  if (is_bf16)
+    split_rows_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows_out, k, kpad, group_in, group_out,
+                                                                       normalize, hi, lo);
+  else
+    split_rows_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows_out, k, kpad, group_in, group_out,
+                                                                        normalize, hi, lo);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream) {
+  XMLB_REQUIRE(mask && bits, "xmlb_mask_bits: null pointer");
+  XMLB_REQUIRE(lp % 32 == 0 && lp >= ctx_len && ctx_len >= 1, "xmlb_mask_bits: lp must be a multiple of 32, >= ctx_len");
+  const long long n = (long long)n_videos * (lp / 32);
+  if (n == 0) return XMLB_OK;
+  mask_bits_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, n_videos, ctx_len, lp / 32, bits);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned short* q_lo_a,
+                                 const unsigned short* q_hi_b, const unsigned short* q_lo_b,
+                                 const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                                 const unsigned short* c_hi_b, const unsigned short* c_lo_b,
+                                 const unsigned int* mask_bits_a, const unsigned int* mask_bits_b, float* q2c,
+                                 int n_queries, int n_videos, int lp, int kpad, int is_bf16, int max_ctas,
+                                 void* stream) {
+  XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && mask_bits_a && q2c, "xmlb_vr_scores_tc: null pointer");
+  const bool two = q_hi_b != nullptr;
+  XMLB_REQUIRE(!two || (q_lo_b && c_hi_b && c_lo_b && mask_bits_b), "xmlb_vr_scores_tc: incomplete second modality");
+  XMLB_REQUIRE(lp >= 32 && lp <= 256 && lp % 32 == 0, "xmlb_vr_scores_tc: lp must be a multiple of 32 in [32, 256]");
+  XMLB_REQUIRE(kpad >= 64 && kpad % 64 == 0, "xmlb_vr_scores_tc: kpad must be a multiple of 64");
+  XMLB_REQUIRE((long long)n_videos * lp < (1ll << 31), "xmlb_vr_scores_tc: corpus too large for one call");
+  if (n_queries == 0 || n_videos == 0) return XMLB_OK;
+
+  VrTcParams p = {};
+  p.n_queries = n_queries, p.n_videos = n_videos, p.lp = lp;
+  p.vpt = 256 / lp < MAX_VPT ? 256 / lp : MAX_VPT;
+  p.block_n = p.vpt * lp;
+  p.k_blocks = kpad / BLOCK_K;
+  p.n_mod = two ? 2 : 1;
+  p.m_tiles = ceil_div(n_queries, BLOCK_M);
+  p.n_tiles = ceil_div(n_videos, p.vpt);
+  p.mask_bits[0] = mask_bits_a, p.mask_bits[1] = mask_bits_b;
+  p.out = q2c;
+  p.divisor = (float)p.n_mod;
+  p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
+  const int stage_bytes = 2 * A_BYTES + 2 * p.block_n * BLOCK_K * 2;
+  int stages = (227 * 1024 - 2048) / stage_bytes;
+  p.stages = stages > 4 ? 4 : stages;
+  XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_scores_tc: tile does not fit in shared memory");
+  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256;
+
+  VrMaps maps;
+  const unsigned long long corpus_rows = (unsigned long long)n_videos * lp;
+  const unsigned short* qh[2] = {q_hi_a, q_hi_b};
+  const unsigned short* ql[2] = {q_lo_a, q_lo_b};
+  const unsigned short* ch[2] = {c_hi_a, c_hi_b};
+  const unsigned short* cl[2] = {c_lo_a, c_lo_b};
+  for (int m = 0; m < p.n_mod; ++m) {
+    int rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[m], qh[m], n_queries, kpad, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[m], ql[m], n_queries, kpad, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi[m], ch[m], corpus_rows, kpad, p.block_n, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo[m], cl[m], corpus_rows, kpad, p.block_n, BLOCK_K))) return rc;
+  }
+  if (!two) {
+    maps.a_hi[1] = maps.a_hi[0], maps.a_lo[1] = maps.a_lo[0], maps.b_hi[1] = maps.b_hi[0], maps.b_lo[1] = maps.b_lo[0];
+  }
+
+  int dev = 0, sms = 0;
+  XMLB_CUDA(cudaGetDevice(&dev));
+  XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = sms;
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  const long long total = (long long)p.m_tiles * p.n_tiles;
+  if (total < grid) grid = (int)total;
+  XMLB_CUDA(cudaFuncSetAttribute(vr_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vr_scores_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
