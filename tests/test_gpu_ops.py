@@ -118,6 +118,43 @@ def test_vr_scores_f32(ops, nq, nv, length, hid, both):
     close(got, want, rtol=1e-4, atol=2e-6)
 
 
+@pytest.mark.parametrize("nq,nv,length,hid,both", [(5, 7, 12, 64, True), (300, 130, 32, 96, True),
+                                                  (200, 300, 128, 768, True), (9, 11, 100, 500, False),
+                                                  (130, 40, 256, 1024, True), (64, 1000, 100, 256, True)])
+@pytest.mark.parametrize("precision", ["f16x3", "bf16x3"])
+def test_vr_scores_tc(ops, nq, nv, length, hid, both, precision):
+    """tcgen05 split-precision kernel vs a float64 evaluation of reference get_video_level_scores; the exact-fp32
+    SIMT kernel is measured against the same float64 values for comparison."""
+    g = torch.Generator().manual_seed(nq * nv + hid)
+    qv, qs = torch.randn(nq, hid, generator=g), torch.randn(nq, hid, generator=g)
+    fv, fs = torch.randn(nv, length, hid, generator=g), torch.randn(nv, length, hid, generator=g)
+    vmask = (torch.rand(nv, length, generator=g) < 0.7).float()  # arbitrary (non-prefix) masks
+    vmask[:, 0] = 1
+    smask = rand_mask(g, nv, length)
+    if nv > 3:
+        smask[3] = 0  # a video without any valid clip scores -1e10
+    want = O.video_level_scores(qv.double(), fv.double(), vmask.double())
+    if both:
+        want = (want + O.video_level_scores(qs.double(), fs.double(), smask.double())) / 2
+    bf16 = precision == "bf16x3"
+    lp, kpad = (length + 31) // 32 * 32, (hid + 63) // 64 * 64
+    prep_q = lambda t: ops.split_rows(t.to(DEV), kpad=kpad, normalize=True, bf16=bf16)  # noqa: E731
+    prep_c = lambda t: ops.split_rows(t.to(DEV), length, lp, kpad, normalize=True, bf16=bf16)  # noqa: E731
+    got = ops.vr_scores_tc(prep_q(qv), prep_c(fv), ops.mask_bits(vmask.to(DEV), lp), nv, lp,
+                           q_b=prep_q(qs) if both else None, c_b=prep_c(fs) if both else None,
+                           bits_b=ops.mask_bits(smask.to(DEV), lp) if both else None, bf16=bf16)
+    torch.cuda.synchronize()
+    n = lambda t: ops.l2norm_rows(t.to(DEV))  # noqa: E731
+    f32 = ops.vr_scores_f32(n(qv), n(qs) if both else None, n(fv), n(fs) if both else None, vmask.to(DEV),
+                            smask.to(DEV) if both else None)
+    masked = want < -1e9
+    assert torch.equal(got.cpu() < -1e9, masked)
+    err_tc = (got.cpu().double() - want)[~masked].abs().max().item()
+    err_f32 = (f32.cpu().double() - want)[~masked].abs().max().item()
+    print("vr_scores %s: max abs err vs fp64 = %.3g (exact-fp32 SIMT kernel: %.3g)" % (precision, err_tc, err_f32))
+    assert err_tc <= (2e-6 if bf16 else 5e-7), (err_tc, err_f32)
+
+
 def conv_taps(g, k=5):
     return torch.randn(1, 1, k, generator=g) * 0.4
 

@@ -47,28 +47,52 @@ class CorpusIndex:
     (reference inference.py:89-97); feat1 is L2-normalised at build time (the reference re-normalises it for
     every query batch, model_xml.py:447)."""
 
+    PRECISIONS = ("f16x3", "bf16x3", "f32")
+
     def __init__(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
-                 sub_mask=None, vid_lo=0):
+                 sub_mask=None, vid_lo=0, precision="f16x3"):
+        """precision selects the video-level-score kernel: "f16x3" / "bf16x3" = tcgen05 tensor cores with
+        hi/lo-split operands (3 MMAs per product, fp32-accurate), "f32" = exact-fp32 SIMT kernel."""
+        assert precision in self.PRECISIONS, precision
         ref = video_feat1 if video_feat1 is not None else sub_feat1
         self.n_videos, self.ctx_len, self.hidden = ref.shape
         self.device = ref.device
         self.vid_lo = vid_lo  # global id of the first video (multi-GPU shards)
-        self.video_feat1n = ops.l2norm_rows(video_feat1) if video_feat1 is not None else None
-        self.sub_feat1n = ops.l2norm_rows(sub_feat1) if sub_feat1 is not None else None
+        self.precision = precision
+        self.video_feat1n = self.sub_feat1n = None
+        self.video_tc = self.sub_tc = self.video_bits = self.sub_bits = None
+        if precision == "f32":
+            self.video_feat1n = ops.l2norm_rows(video_feat1) if video_feat1 is not None else None
+            self.sub_feat1n = ops.l2norm_rows(sub_feat1) if sub_feat1 is not None else None
+        else:
+            # corpus operand of the tensor-core kernel: normalised, hi/lo split, each video's clips padded to a
+            # multiple of 32 rows, hidden padded to a multiple of 64 (zero fill)
+            self.lp = (self.ctx_len + 31) // 32 * 32
+            self.kpad = (self.hidden + 63) // 64 * 64
+            bf16 = precision == "bf16x3"
+            if video_feat1 is not None:
+                self.video_tc = ops.split_rows(video_feat1, self.ctx_len, self.lp, self.kpad, normalize=True, bf16=bf16)
+                self.video_bits = ops.mask_bits(video_mask, self.lp)
+            if sub_feat1 is not None:
+                self.sub_tc = ops.split_rows(sub_feat1, self.ctx_len, self.lp, self.kpad, normalize=True, bf16=bf16)
+                self.sub_bits = ops.mask_bits(sub_mask, self.lp)
         self.video_feat2 = video_feat2.contiguous() if video_feat2 is not None else None
         self.sub_feat2 = sub_feat2.contiguous() if sub_feat2 is not None else None
         self.video_mask = video_mask.contiguous() if video_mask is not None else None
         self.sub_mask = sub_mask.contiguous() if sub_mask is not None else None
 
     @classmethod
-    def from_ctx_info(cls, ctx_info, vid_lo=0):
+    def from_ctx_info(cls, ctx_info, vid_lo=0, precision="f16x3"):
         return cls(ctx_info.get("video_feat1"), ctx_info.get("video_feat2"), ctx_info.get("video_mask"),
-                   ctx_info.get("sub_feat1"), ctx_info.get("sub_feat2"), ctx_info.get("sub_mask"), vid_lo=vid_lo)
+                   ctx_info.get("sub_feat1"), ctx_info.get("sub_feat2"), ctx_info.get("sub_mask"), vid_lo=vid_lo,
+                   precision=precision)
 
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in
-                   (self.video_feat1n, self.sub_feat1n, self.video_feat2, self.sub_feat2, self.video_mask,
-                    self.sub_mask) if t is not None)
+        tensors = [self.video_feat1n, self.sub_feat1n, self.video_feat2, self.sub_feat2, self.video_mask,
+                   self.sub_mask, self.video_bits, self.sub_bits]
+        for pair in (self.video_tc, self.sub_tc):
+            tensors.extend(pair or ())
+        return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
 
 class SearchResult:
@@ -99,6 +123,14 @@ class VCMRSearcher:
 
     def video_scores(self, video_query, sub_query):
         ix, m = self.index, self.model
+        if ix.precision != "f32":
+            bf16 = ix.precision == "bf16x3"
+            ops_q = [ops.split_rows(q, kpad=ix.kpad, normalize=True, bf16=bf16) if used else None
+                     for q, used in ((video_query, m.use_video), (sub_query, m.use_sub))]
+            streams = [(q, c, b) for q, c, b in ((ops_q[0], ix.video_tc, ix.video_bits),
+                                                 (ops_q[1], ix.sub_tc, ix.sub_bits)) if q is not None]
+            a, b = streams[0], (streams[1] if len(streams) == 2 else (None, None, None))
+            return ops.vr_scores_tc(a[0], a[1], a[2], ix.n_videos, ix.lp, q_b=b[0], c_b=b[1], bits_b=b[2], bf16=bf16)
         return ops.vr_scores_f32(
             ops.l2norm_rows(video_query) if m.use_video else None, ops.l2norm_rows(sub_query) if m.use_sub else None,
             ix.video_feat1n if m.use_video else None, ix.sub_feat1n if m.use_sub else None,

@@ -140,6 +140,48 @@ def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, su
     return out
 
 
+def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=False):
+    """fp32 rows -> 16-bit (hi, lo) halves with x ~= hi + lo, for the split-precision tensor-core kernels.
+    x: (..., k) with rows grouped by `group_in`; output (n_groups * group_out, kpad) int16 tensors (raw bits)."""
+    x = _f32(x, "x")
+    k = x.shape[-1]
+    rows = x.numel() // k
+    assert rows % group_in == 0
+    n_groups = rows // group_in
+    kpad = kpad or (k + 63) // 64 * 64
+    hi = torch.empty(n_groups * group_out, kpad, device=x.device, dtype=torch.int16)
+    lo = torch.empty_like(hi)
+    rc = _lib.lib().xmlb_split_rows(_p(x), n_groups, group_in, group_out, k, kpad, int(normalize), int(bf16), _p(hi),
+                                    _p(lo), _stream())
+    _lib.check(rc, "xmlb_split_rows")
+    return hi, lo
+
+
+def mask_bits(mask, lp):
+    """(Nv, L) float {0,1} -> (Nv, lp // 32) int32 bit masks."""
+    mask = _f32(mask, "mask")
+    nv, length = mask.shape
+    bits = torch.empty(nv, lp // 32, device=mask.device, dtype=torch.int32)
+    rc = _lib.lib().xmlb_mask_bits(_p(mask), nv, length, lp, _p(bits), _stream())
+    _lib.check(rc, "xmlb_mask_bits")
+    return bits
+
+
+def vr_scores_tc(q_a, c_a, bits_a, n_videos, lp, q_b=None, c_b=None, bits_b=None, bf16=False, max_ctas=0):
+    """tcgen05 video-level scores on prepared operands: q_x = (hi, lo) of (Nq, kpad); c_x = (hi, lo) of
+    (Nv * lp, kpad); bits_x (Nv, lp/32).  -> q2c (Nq, Nv) fp32."""
+    nq, kpad = q_a[0].shape
+    assert c_a[0].shape == (n_videos * lp, kpad), (c_a[0].shape, n_videos, lp, kpad)
+    out = torch.empty(nq, n_videos, device=q_a[0].device, dtype=torch.float32)
+    qb = q_b if q_b is not None else (None, None)
+    cb = c_b if c_b is not None else (None, None)
+    rc = _lib.lib().xmlb_vr_scores_tc(_p(q_a[0]), _p(q_a[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
+                                      _p(cb[1]), _p(bits_a), _p(bits_b), _p(out), nq, n_videos, lp, kpad, int(bf16),
+                                      max_ctas, _stream())
+    _lib.check(rc, "xmlb_vr_scores_tc")
+    return out
+
+
 class PairLists:
     """Per-video inverted lists of (query, output row) built on device by xmlb_build_pair_lists."""
 
