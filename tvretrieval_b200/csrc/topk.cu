@@ -23,7 +23,7 @@ struct SelSmem {
   int hist[HIST];
   int warp_tot[NT / 32];
   int sel_bin, sel_above, sel_count, total;
-  int count;
+  int count, count_eq2;
   unsigned long long buf[MAX_K];
 };
 
@@ -137,22 +137,24 @@ __device__ int block_topk(const Gen& gen, SelSmem& sm, int k) {
   unsigned int thr = 0, thr2 = 0;
   int n_equal = 0, need_equal = 0, n_total = 0;
   bool use_thr2 = false;
+  int need_eq2 = 0;
   const bool full = radix_select(gen, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; },
                                  sm, k, thr, n_equal, need_equal, n_total);
   if (full && n_equal > need_equal) {  // exact ties straddle the cut: keep the preferred ids among them
-    int ne2, need2, nt2;
+    int ne2, nt2;
     const unsigned int t1 = thr;
     radix_select(gen, [t1](unsigned int key, unsigned int idk, unsigned int& out) { out = idk; return key == t1; },
-                 sm, need_equal, thr2, ne2, need2, nt2);
-    use_thr2 = true;
+                 sm, need_equal, thr2, ne2, need_eq2, nt2);
+    use_thr2 = true;  // ids are normally unique (need_eq2 == 1); duplicates are still counted exactly
   }
   int pow2 = 1;
   while (pow2 < k) pow2 <<= 1;
   for (int i = threadIdx.x; i < pow2; i += NT) sm.buf[i] = 0ull;
-  if (threadIdx.x == 0) sm.count = 0;
+  if (threadIdx.x == 0) sm.count = 0, sm.count_eq2 = 0;
   __syncthreads();
   gen.for_each([&](unsigned int key, unsigned int idk) {
-    const bool take = !full || key > thr || (key == thr && (!use_thr2 || idk >= thr2));
+    bool take = !full || key > thr || (key == thr && (!use_thr2 || idk > thr2));
+    if (!take && full && use_thr2 && key == thr && idk == thr2) take = atomicAdd(&sm.count_eq2, 1) < need_eq2;
     if (take) {
       const int pos = atomicAdd(&sm.count, 1);
       if (pos < MAX_K) sm.buf[pos] = ((unsigned long long)key << 32) | idk;

@@ -76,6 +76,20 @@ def all_gather_rows(t, group=None):
     return out
 
 
+def merge_ranked_lists(val, idx, k, group=None, tie_desc=False):
+    """All-gathers per-rank ranked candidate lists (val, idx) of shape (n, k_loc) -- missing entries marked by
+    idx < 0 -- and returns the global top-k by (val desc, idx asc|desc); missing entries come back as (-1, 0)."""
+    val = torch.where(idx < 0, torch.full_like(val, -1.0), val)  # missing entries rank below every candidate
+    g_val, g_idx = all_gather_cat(val, group), all_gather_cat(idx, group)
+    # the selection kernel wants distinct ids: give the missing entries distinct negative ones
+    cols = torch.arange(g_idx.shape[1], device=g_idx.device, dtype=g_idx.dtype)
+    g_idx = torch.where(g_idx < 0, -1 - cols, g_idx)
+    idx, val = ops.topk_rows(g_val, k, ids=g_idx, tie_desc=tie_desc)
+    missing = idx < 0
+    return torch.where(missing, torch.full_like(idx, -1), idx).contiguous(), \
+        torch.where(missing, torch.zeros_like(val), val).contiguous()
+
+
 def local_slot_mask(top_ids, vid_lo, vid_hi):
     """1 where a selected (global) video id belongs to this rank's shard."""
     return ((top_ids >= vid_lo) & (top_ids < vid_hi)).to(torch.uint8)
@@ -136,14 +150,8 @@ class ShardedSearcher(VCMRSearcher):
                 idx, val = ops.span_topk(st, ed, res.top_video_score, self.min_pred_l, self.max_pred_l, m,
                                          slot_valid=valid, zero_fill=False)
             with self._phase("merge_spans"):
-                val = torch.where(idx < 0, torch.full_like(val, -1.0), val)  # missing entries rank last
-                g_val, g_idx = all_gather_cat(val, self.group), all_gather_cat(idx, self.group)
-                idx, val = ops.topk_rows(g_val, m, ids=g_idx)
-                missing = val <= 0
-                idx = torch.where(missing, torch.full_like(idx, -1), idx)
-                val = torch.where(missing, torch.zeros_like(val), val)
-                res.span_flat_idx, res.span_score = ops.span_zero_fill(idx.contiguous(), val.contiguous(),
-                                                                       k * ix.ctx_len * ix.ctx_len)
+                idx, val = merge_ranked_lists(val, idx, m, self.group)
+                res.span_flat_idx, res.span_score = ops.span_zero_fill(idx, val, k * ix.ctx_len * ix.ctx_len)
         if "SVMR" in tasks:
             assert gt_video_idx is not None, "SVMR needs the ground-truth video of every query"
             m = self.max_before_nms
@@ -154,12 +162,6 @@ class ShardedSearcher(VCMRSearcher):
             idx, val = ops.span_topk(st.view(nq, 1, ix.ctx_len), ed.view(nq, 1, ix.ctx_len), None, self.min_pred_l,
                                      self.max_pred_l, m, slot_valid=valid, tie_desc=True, zero_fill=False)
             # exactly one rank owns each query's ground-truth video: the others contribute only (-1, 0) rows
-            val = torch.where(idx < 0, torch.full_like(val, -1.0), val)
-            g_val, g_idx = all_gather_cat(val, self.group), all_gather_cat(idx, self.group)
-            idx, val = ops.topk_rows(g_val, m, ids=g_idx, tie_desc=True)
-            missing = val <= 0
-            idx = torch.where(missing, torch.full_like(idx, -1), idx)
-            val = torch.where(missing, torch.zeros_like(val), val)
-            res.svmr_flat_idx, res.svmr_score = ops.span_zero_fill(idx.contiguous(), val.contiguous(),
-                                                                   ix.ctx_len * ix.ctx_len, tie_desc=True)
+            idx, val = merge_ranked_lists(val, idx, m, self.group, tie_desc=True)
+            res.svmr_flat_idx, res.svmr_score = ops.span_zero_fill(idx, val, ix.ctx_len * ix.ctx_len, tie_desc=True)
         return res
