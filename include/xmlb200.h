@@ -97,6 +97,13 @@ int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned short* q_lo_a
                       const unsigned int* mask_bits_b, float* q2c, int n_queries, int n_videos, int lp, int kpad,
                       int is_bf16, int max_ctas, void* stream);
 
+/* Tensor-core variant of xmlb_linear (same contract, model_components.py:160-163,278-280,314): x_* (rows, kpad)
+ * and w_* (out_dim, kpad) are the 16-bit (hi, lo) halves produced by xmlb_split_rows (normalize = 0).
+ * out / bias / residual must be 16-byte aligned. */
+int xmlb_linear_tc(const unsigned short* x_hi, const unsigned short* x_lo, const unsigned short* w_hi,
+                   const unsigned short* w_lo, const float* bias, const float* residual, float* out, long long rows,
+                   int out_dim, int kpad, int relu, int is_bf16, void* stream);
+
 /* Similarity curves + ConvSE + mask (+ softmax), replaces XML.get_merged_st_ed_prob (model_xml.py:455-502),
  * XML._get_st_ed_prob (:512-551) and the driver's softmax over clips (inference.py:321-322).
  *   sim_x[q][v][l] = q_x[q] . feat2_x[v][l]                       for stream x in {a, b}

@@ -1,0 +1,161 @@
+// Shared warp-specialised mainloop of the split-precision tcgen05 GEMM kernels (vr_scores_tc.cu, linear_tc.cu,
+// span_tc.cu).  One CTA = 192 threads:
+//   warp 0 lane 0 : TMA producer  -> tc_producer_loop
+//   warp 1 lane 0 : MMA issuer    -> tc_mma_loop
+//   warps 2..5    : epilogue (kernel specific), synchronised through tmem_full / tmem_empty barriers
+// Every kernel supplies a scheduler `Sched` whose next(UnitDesc&) enumerates, identically in every role, the work
+// units of this CTA.  A unit = one accumulation D[128 x n] = sum over k-blocks of A_tile . B_tile^T, with both
+// operands given as (hi, lo) 16-bit pairs: 3 MMAs per k-step (hi*lo + lo*hi + hi*hi), fp32 accumulate in TMEM.
+// Units alternate between two TMEM accumulators of 256 columns so that the epilogue of unit u overlaps the MMAs
+// of unit u+1.
+#pragma once
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 256;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct UnitDesc {
+  const CUtensorMap* a_hi;
+  const CUtensorMap* a_lo;
+  const CUtensorMap* b_hi;
+  const CUtensorMap* b_lo;
+  int a_row, b_row;   // first row of the A / B tile in their tensor maps
+  int k_blocks;       // number of 64-wide k-blocks to accumulate
+  uint32_t idesc;     // instruction descriptor (carries N of this unit)
+};
+
+// shared-memory carve-up (all offsets are shared-window addresses)
+struct Pipe {
+  uint32_t smem_base;   // 1024-aligned start of the stage ring
+  uint32_t bar_base;
+  int stages, stage_bytes, b_tile_bytes;
+  __device__ uint32_t full_bar(int s) const { return bar_base + 8u * s; }
+  __device__ uint32_t empty_bar(int s) const { return bar_base + 8u * (stages + s); }
+  __device__ uint32_t tfull_bar(int a) const { return bar_base + 8u * (2 * stages + a); }
+  __device__ uint32_t tempty_bar(int a) const { return bar_base + 8u * (2 * stages + 2 + a); }
+  __device__ uint32_t tmem_slot() const { return bar_base + 8u * (2 * stages + 4); }
+  __device__ uint32_t extra() const { return bar_base + 8u * (2 * stages + 4) + 16u; }  // kernel-specific scratch
+};
+
+__host__ __device__ inline int pipe_stage_bytes(int block_n) { return 2 * A_TILE_BYTES + 2 * block_n * BLOCK_K * 2; }
+// number of ring stages that fit next to `extra_bytes` of kernel-specific shared memory
+inline int pipe_stages(int block_n, int extra_bytes) {
+  const int s = (SMEM_LIMIT - 2048 - extra_bytes) / pipe_stage_bytes(block_n);
+  return s > 4 ? 4 : s;
+}
+inline size_t pipe_smem_bytes(int block_n, int stages, int extra_bytes) {
+  return 1024 + (size_t)stages * pipe_stage_bytes(block_n) + 256 + extra_bytes;
+}
+
+// Called by all 192 threads at kernel start.  Returns the TMEM base address.
+__device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw, int stages, int block_n,
+                                               int epilogue_arrivals) {
+  p.smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  p.stages = stages;
+  p.b_tile_bytes = block_n * BLOCK_K * 2;
+  p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.b_tile_bytes;
+  p.bar_base = p.smem_base + stages * p.stage_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(p.full_bar(s), 1);
+      mbar_init(p.empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(p.tfull_bar(a), 1);
+      mbar_init(p.tempty_bar(a), epilogue_arrivals);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(p.tmem_slot(), TMEM_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(p.tmem_slot()));
+  return tmem_base;
+}
+
+// Called by all threads at kernel end.
+__device__ __forceinline__ void pipe_teardown(uint32_t tmem_base) {
+  fence_before_sync();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <class Sched>
+__device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
+  int stage = 0;
+  uint32_t phase = 0;
+  UnitDesc u;
+  while (sched.next(u)) {
+    for (int kb = 0; kb < u.k_blocks; ++kb) {
+      mbar_wait(p.empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = p.smem_base + stage * p.stage_bytes;
+      mbar_expect_tx(p.full_bar(stage), (uint32_t)p.stage_bytes);
+      tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+      tma_load_2d(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+      tma_load_2d(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+      tma_load_2d(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+      if (++stage == p.stages) stage = 0, phase ^= 1u;
+    }
+  }
+}
+
+template <class Sched>
+__device__ __forceinline__ void tc_mma_loop(Sched sched, const Pipe& p, uint32_t tmem_base) {
+  int stage = 0;
+  uint32_t phase = 0, unit = 0;
+  UnitDesc u;
+  while (sched.next(u)) {
+    const uint32_t acc = unit & 1u, use = unit >> 1;
+    mbar_wait(p.tempty_bar(acc), (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
+    fence_after_sync();
+    const uint32_t tmem_acc = tmem_base + acc * ACC_COLS;
+    for (int kb = 0; kb < u.k_blocks; ++kb) {
+      mbar_wait(p.full_bar(stage), phase);
+      fence_after_sync();
+      const uint32_t sa = p.smem_base + stage * p.stage_bytes;
+      const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + A_TILE_BYTES);
+      const uint64_t b_hi = smem_desc_sw128(sa + 2 * A_TILE_BYTES);
+      const uint64_t b_lo = smem_desc_sw128(sa + 2 * A_TILE_BYTES + p.b_tile_bytes);
+#pragma unroll
+      for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+        const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);  // advance 32 B inside the 128 B swizzle row
+        umma_f16(tmem_acc, a_hi + off, b_lo + off, u.idesc, (kb | k) != 0);
+        umma_f16(tmem_acc, a_lo + off, b_hi + off, u.idesc, 1u);
+        umma_f16(tmem_acc, a_hi + off, b_hi + off, u.idesc, 1u);
+      }
+      umma_commit(p.empty_bar(stage));  // the smem stage is reusable once these MMAs have read it
+      if (++stage == p.stages) stage = 0, phase ^= 1u;
+    }
+    umma_commit(p.tfull_bar(acc));  // accumulator complete
+    ++unit;
+  }
+}
+
+// epilogue-side handshake helpers (warps 2..5; `unit` counts the units this CTA has consumed)
+__device__ __forceinline__ uint32_t epi_wait(const Pipe& p, uint32_t unit, uint32_t tmem_base) {
+  const uint32_t acc = unit & 1u, use = unit >> 1;
+  mbar_wait(p.tfull_bar(acc), use & 1u);
+  fence_after_sync();
+  const uint32_t quad = (threadIdx.x >> 5) & 3u;  // TMEM lane quadrant this warp may access
+  return tmem_base + acc * ACC_COLS + ((quad * 32u) << 16);
+}
+__device__ __forceinline__ void epi_release(const Pipe& p, uint32_t unit) {  // one arrival per epilogue warp
+  fence_before_sync();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(p.tempty_bar(unit & 1u));
+}
+
+}  // namespace tc

@@ -17,18 +17,14 @@
 // MMAs of the other.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
-#include "tc_common.cuh"
+#include "tc_pipeline.cuh"
 #include "xmlb200.h"
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one swizzle row
-constexpr int UMMA_K = 16;
-constexpr int MAX_VPT = 8;   // videos per tile (BLOCK_N = vpt * lp <= 256, lp multiple of 32)
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int TMEM_COLS = 512;
-constexpr int ACC_COLS = 256;
+using tc::BLOCK_K;
+using tc::BLOCK_M;
+constexpr int MAX_VPT = 8;  // videos per tile (BLOCK_N = vpt * lp <= 256, lp multiple of 32)
 
 struct VrMaps {
   CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2];
@@ -42,105 +38,39 @@ struct VrTcParams {
   unsigned int idesc;
 };
 
-__global__ void __launch_bounds__(192, 1)
-vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const VrTcParams p) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int b_bytes = p.block_n * BLOCK_K * 2;
-  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
-  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base address slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+// units of a CTA: tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (query tile fastest), each x n_mod modalities
+struct VrSched {
+  const VrMaps* maps;
+  const VrTcParams* p;
+  int tile, mod;
+  __device__ VrSched(const VrMaps* m, const VrTcParams* pp) : maps(m), p(pp), tile(blockIdx.x), mod(0) {}
+  __device__ bool next(tc::UnitDesc& u) {
+    if (tile >= p->m_tiles * p->n_tiles) return false;
+    u.a_hi = &maps->a_hi[mod], u.a_lo = &maps->a_lo[mod], u.b_hi = &maps->b_hi[mod], u.b_lo = &maps->b_lo[mod];
+    u.a_row = (tile % p->m_tiles) * BLOCK_M;
+    u.b_row = (tile / p->m_tiles) * p->block_n;
+    u.k_blocks = p->k_blocks;
+    u.idesc = p->idesc;
+    if (++mod == p->n_mod) mod = 0, tile += gridDim.x;
+    return true;
+  }
+};
 
+__global__ void __launch_bounds__(192, 1)
+vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrTcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  tc::Pipe pipe;
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
-    for (int m = 0; m < p.n_mod; ++m) {
-      tc::tma_prefetch_desc(&maps.a_hi[m]);
-      tc::tma_prefetch_desc(&maps.a_lo[m]);
-      tc::tma_prefetch_desc(&maps.b_hi[m]);
-      tc::tma_prefetch_desc(&maps.b_lo[m]);
-    }
-    for (int s = 0; s < p.stages; ++s) {
-      tc::mbar_init(full_bar(s), 1);
-      tc::mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      tc::mbar_init(tfull_bar(a), 1);
-      tc::mbar_init(tempty_bar(a), 4);
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  const int total_tiles = p.m_tiles * p.n_tiles;
-
   if (warp == 0) {
-    if (lane == 0) {  // ===================== TMA producer =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
-        for (int mod = 0; mod < p.n_mod; ++mod) {
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            tc::mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t sa = smem_base + stage * stage_bytes;
-            tc::mbar_expect_tx(full_bar(stage), (uint32_t)stage_bytes);
-            tc::tma_load_2d(sa, &maps.a_hi[mod], full_bar(stage), kb * BLOCK_K, m_tile * BLOCK_M);
-            tc::tma_load_2d(sa + A_BYTES, &maps.a_lo[mod], full_bar(stage), kb * BLOCK_K, m_tile * BLOCK_M);
-            tc::tma_load_2d(sa + 2 * A_BYTES, &maps.b_hi[mod], full_bar(stage), kb * BLOCK_K, n_tile * p.block_n);
-            tc::tma_load_2d(sa + 2 * A_BYTES + b_bytes, &maps.b_lo[mod], full_bar(stage), kb * BLOCK_K,
-                            n_tile * p.block_n);
-            if (++stage == p.stages) stage = 0, phase ^= 1u;
-          }
-        }
-      }
-    }
+    if (lane == 0) tc::tc_producer_loop(VrSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) {  // ===================== MMA issuer =====================
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t unit = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        for (int mod = 0; mod < p.n_mod; ++mod, ++unit) {
-          const uint32_t acc = unit & 1u, use = unit >> 1;
-          tc::mbar_wait(tempty_bar(acc), (use & 1u) ^ 1u);  // epilogue has drained this accumulator
-          tc::fence_after_sync();
-          const uint32_t tmem_acc = tmem_base + acc * ACC_COLS;
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            tc::mbar_wait(full_bar(stage), phase);
-            tc::fence_after_sync();
-            const uint32_t sa = smem_base + stage * stage_bytes;
-            const uint64_t a_hi = tc::smem_desc_sw128(sa), a_lo = tc::smem_desc_sw128(sa + A_BYTES);
-            const uint64_t b_hi = tc::smem_desc_sw128(sa + 2 * A_BYTES);
-            const uint64_t b_lo = tc::smem_desc_sw128(sa + 2 * A_BYTES + b_bytes);
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);  // advance 32 B inside the swizzle row
-              tc::umma_f16(tmem_acc, a_hi + off, b_lo + off, p.idesc, (kb | k) != 0);
-              tc::umma_f16(tmem_acc, a_lo + off, b_hi + off, p.idesc, 1u);
-              tc::umma_f16(tmem_acc, a_hi + off, b_hi + off, p.idesc, 1u);
-            }
-            tc::umma_commit(empty_bar(stage));  // smem stage reusable once these MMAs have read it
-            if (++stage == p.stages) stage = 0, phase ^= 1u;
-          }
-          tc::umma_commit(tfull_bar(acc));  // accumulator complete
-        }
-      }
-    }
+    if (lane == 0) tc::tc_mma_loop(VrSched(&maps, &p), pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;
     const int chunks = p.lp >> 5;
+    const int total_tiles = p.m_tiles * p.n_tiles;
     uint32_t unit = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
@@ -149,10 +79,7 @@ vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const VrTcParams p) {
 #pragma unroll
       for (int j = 0; j < MAX_VPT; ++j) best[j] = 0.f;
       for (int mod = 0; mod < p.n_mod; ++mod, ++unit) {
-        const uint32_t acc = unit & 1u, use = unit >> 1;
-        tc::mbar_wait(tfull_bar(acc), use & 1u);
-        tc::fence_after_sync();
-        const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
+        const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
         const unsigned int* __restrict__ bits = p.mask_bits[mod];
 #pragma unroll
         for (int j = 0; j < MAX_VPT; ++j) {
@@ -175,10 +102,7 @@ vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const VrTcParams p) {
             best[j] = mod == 0 ? m : __fadd_rn(best[j], m);
           }
         }
-        // accumulator fully read: hand it back to the MMA issuer
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(tempty_bar(acc));
+        tc::epi_release(pipe, unit);  // accumulator fully read: hand it back to the MMA issuer
       }
       if (q < p.n_queries) {
 #pragma unroll
@@ -189,13 +113,7 @@ vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const VrTcParams p) {
       }
     }
   }
-
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc::tmem_dealloc(tmem_base, TMEM_COLS);
-  }
+  tc::pipe_teardown(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -351,11 +269,9 @@ extern "C" int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned sh
   p.out = q2c;
   p.divisor = (float)p.n_mod;
   p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
-  const int stage_bytes = 2 * A_BYTES + 2 * p.block_n * BLOCK_K * 2;
-  int stages = (227 * 1024 - 2048) / stage_bytes;
-  p.stages = stages > 4 ? 4 : stages;
+  p.stages = tc::pipe_stages(p.block_n, 0);
   XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_scores_tc: tile does not fit in shared memory");
-  const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 256;
+  const size_t smem = tc::pipe_smem_bytes(p.block_n, p.stages, 0);
 
   VrMaps maps;
   const unsigned long long corpus_rows = (unsigned long long)n_videos * lp;

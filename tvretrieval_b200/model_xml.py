@@ -187,8 +187,16 @@ class XML(nn.Module):
         feat2 = getattr(self, module_name + "_encoder3")(feat2, m3)
         return feat1, feat2
 
+    # Linear-layer kernels used by encode_context: "f32" (exact SIMT, default: the corpus is encoded once and its
+    # padded rows feed ConvSE, so accuracy comes first) or "f16x3" / "bf16x3" (tcgen05, ~3x faster).
+    context_precision = "f32"
+
     def encode_context(self, video_feat, video_mask, sub_feat, sub_mask):
         """reference model_xml.py:331-342."""
+        with ops.linear_precision(self.context_precision):
+            return self._encode_context(video_feat, video_mask, sub_feat, sub_mask)
+
+    def _encode_context(self, video_feat, video_mask, sub_feat, sub_mask):
         if self.config.cross_att:
             assert self.use_video and self.use_sub
             return self.cross_encode_context(video_feat, video_mask, sub_feat, sub_mask)

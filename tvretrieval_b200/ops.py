@@ -1,6 +1,8 @@
 """Thin tensor-level wrappers over the C ABI (include/xmlb200.h).  PyTorch is used only to own device
 memory and streams; every computation below is one or more hand-written sm_100a kernels.  All inputs must be
 CUDA fp32 (or int32/uint8 where stated) tensors; there is no CPU path."""
+import weakref
+
 import torch
 
 from . import _lib
@@ -59,6 +61,54 @@ def add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
     return out
 
 
+# Precision of the Linear layers: "f16x3" / "bf16x3" = tcgen05 tensor cores with hi/lo-split operands (3 MMAs per
+# product, fp32 accumulate in TMEM), "f32" = exact-fp32 SIMT kernel (FMA, round-to-nearest).  Small problems always
+# use the latter.  Measured on B200: the tensor-core accumulator truncates instead of rounding, so the error grows
+# like (K/16 * 3 updates) * 0.5 ulp -- 2.6e-5 abs at K=768 for O(1) outputs vs 1e-6 for the SIMT kernel.  The corpus
+# (encoded once, off the query path) is therefore encoded with "f32" by default; queries use the tensor cores.
+_LINEAR_PRECISION = "f16x3"
+_TC_MIN_ROWS = 256
+_WEIGHT_SPLITS = {}
+
+
+def set_linear_precision(precision):
+    global _LINEAR_PRECISION
+    assert precision in ("f16x3", "bf16x3", "f32"), precision
+    _LINEAR_PRECISION = precision
+    _WEIGHT_SPLITS.clear()
+
+
+def get_linear_precision():
+    return _LINEAR_PRECISION
+
+
+class linear_precision:
+    """Context manager: `with ops.linear_precision("f32"): ...`"""
+
+    def __init__(self, precision):
+        self.precision = precision
+
+    def __enter__(self):
+        self.saved = _LINEAR_PRECISION
+        set_linear_precision(self.precision)
+
+    def __exit__(self, *exc):
+        set_linear_precision(self.saved)
+
+
+def _weight_split(weight, bf16):
+    """(hi, lo) of a weight matrix, cached per (tensor, version)."""
+    key = (weight.data_ptr(), tuple(weight.shape), bf16)
+    hit = _WEIGHT_SPLITS.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == weight._version:
+        return hit[2]
+    if len(_WEIGHT_SPLITS) > 256:
+        _WEIGHT_SPLITS.clear()
+    pair = split_rows(weight.detach(), bf16=bf16)
+    _WEIGHT_SPLITS[key] = (weakref.ref(weight), weight._version, pair)
+    return pair
+
+
 def linear(x, weight, bias=None, residual=None, relu=False):
     x = _f32(x, "x")
     weight = _f32(weight, "weight")
@@ -69,6 +119,14 @@ def linear(x, weight, bias=None, residual=None, relu=False):
     residual = _f32(residual, "residual")
     if residual is not None:
         assert residual.shape == out.shape
+    if _LINEAR_PRECISION != "f32" and rows >= _TC_MIN_ROWS:
+        bf16 = _LINEAR_PRECISION == "bf16x3"
+        w_hi, w_lo = _weight_split(weight, bf16)
+        x_hi, x_lo = split_rows(x, kpad=w_hi.shape[1], bf16=bf16)
+        rc = _lib.lib().xmlb_linear_tc(_p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo), _p(_f32(bias, "bias")), _p(residual),
+                                       _p(out), rows, out_dim, w_hi.shape[1], int(relu), int(bf16), _stream())
+        _lib.check(rc, "xmlb_linear_tc")
+        return out
     rc = _lib.lib().xmlb_linear(_p(x), _p(weight), _p(_f32(bias, "bias")), _p(residual), _p(out), rows, out_dim,
                                 in_dim, int(relu), _stream())
     _lib.check(rc, "xmlb_linear")
