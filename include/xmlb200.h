@@ -81,10 +81,12 @@ int xmlb_vr_scores_f32(const float* q_video_n, const float* q_sub_n, const float
  *
  * xmlb_split_rows: x (n_groups * group_in, k) fp32 -> hi, lo (n_groups * group_out, kpad) uint16; rows are
  * regrouped from groups of group_in (clips of a video) to zero-padded groups of group_out, columns zero-padded
- * to kpad (multiple of 64); normalize != 0 applies F.normalize (model_xml.py:446-447) first.
+ * to kpad (multiple of 64); normalize != 0 applies F.normalize (model_xml.py:446-447) first.  With row_index
+ * (n_groups * group_out ints, group_in = group_out = 1) output row r is taken from source row row_index[r]
+ * (negative = zero row): this gathers the valid clips into the packed corpus layout.
  * xmlb_mask_bits: mask (n_videos, ctx_len) float {0,1} -> bits (n_videos, lp / 32), bit l%32 of word l/32. */
-int xmlb_split_rows(const float* x, long long n_groups, int group_in, int group_out, int k, int kpad,
-                    int normalize, int is_bf16, unsigned short* hi, unsigned short* lo, void* stream);
+int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, int group_in, int group_out, int k,
+                    int kpad, int normalize, int is_bf16, unsigned short* hi, unsigned short* lo, void* stream);
 int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream);
 
 /* q2c[q][v] = mean over given modalities of max_{l : bit set} q[q] . c[v * lp + l]; same contract as
@@ -96,6 +98,17 @@ int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned short* q_lo_a
                       const unsigned short* c_hi_b, const unsigned short* c_lo_b, const unsigned int* mask_bits_a,
                       const unsigned int* mask_bits_b, float* q2c, int n_queries, int n_videos, int lp, int kpad,
                       int is_bf16, int max_ctas, void* stream);
+
+/* Packed ("ragged") variant of xmlb_vr_scores_tc: c_* hold only the valid clips, (n_packed_rows, kpad), videos
+ * packed whole into tiles of <= 256 consecutive rows.  tile_meta (n_tiles, 4) int = {first packed row, ordinal of the
+ * tile's first video, used columns, number of videos (<= 32)}; tile_starts (n_tiles, 8) = 256-bit map of columns where a video starts;
+ * order[ordinal] = original video index (column of q2c).  Videos without valid clips are not listed: the caller
+ * pre-fills their q2c columns with -1e10.  Both modalities must share the packing (same masks). */
+int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short* q_lo_a, const unsigned short* q_hi_b,
+                             const unsigned short* q_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                             const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* tile_meta,
+                             const unsigned int* tile_starts, const int* order, float* q2c, int n_queries, int n_videos,
+                             long long n_packed_rows, int n_tiles, int kpad, int is_bf16, int max_ctas, void* stream);
 
 /* Tensor-core variant of xmlb_linear (same contract, model_components.py:160-163,278-280,314): x_* (rows, kpad)
  * and w_* (out_dim, kpad) are the 16-bit (hi, lo) halves produced by xmlb_split_rows (normalize = 0).

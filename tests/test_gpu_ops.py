@@ -177,7 +177,41 @@ def test_vr_scores_tc(ops, nq, nv, length, hid, both, precision):
     err_tc = (got.cpu().double() - want)[~masked].abs().max().item()
     err_f32 = (f32.cpu().double() - want)[~masked].abs().max().item()
     print("vr_scores %s: max abs err vs fp64 = %.3g (exact-fp32 SIMT kernel: %.3g)" % (precision, err_tc, err_f32))
-    assert err_tc <= (2e-6 if bf16 else 5e-7), (err_tc, err_f32)
+    # the TMEM accumulator truncates: the error grows with the number of MMA updates (3 * K / 16)
+    assert err_tc <= (2e-6 if bf16 else 6e-7) * max(1.0, hid / 768), (err_tc, err_f32)
+
+
+@pytest.mark.parametrize("nq,nv,length,hid,both", [(5, 7, 12, 64, True), (300, 130, 32, 96, True),
+                                                  (200, 300, 128, 768, True), (9, 11, 100, 500, False),
+                                                  (130, 40, 256, 1024, True), (64, 1000, 100, 256, True)])
+@pytest.mark.parametrize("precision", ["f16x3", "bf16x3"])
+def test_vr_scores_tc_packed(ops, nq, nv, length, hid, both, precision):
+    """Packed (valid clips only, whole videos bin-packed into 256-row tiles) tcgen05 kernel vs float64."""
+    from tvretrieval_b200.engine import CorpusPacking
+    g = torch.Generator().manual_seed(nq * nv + hid + 1)
+    qv, qs = torch.randn(nq, hid, generator=g), torch.randn(nq, hid, generator=g)
+    fv, fs = torch.randn(nv, length, hid, generator=g), torch.randn(nv, length, hid, generator=g)
+    mask = (torch.rand(nv, length, generator=g) < 0.6).float() if nv % 2 else rand_mask(g, nv, length)
+    mask[0] = 1
+    if nv > 3:
+        mask[3] = 0  # a video without any valid clip scores -1e10
+    want = O.video_level_scores(qv.double(), fv.double(), mask.double())
+    if both:
+        want = (want + O.video_level_scores(qs.double(), fs.double(), mask.double())) / 2
+    bf16 = precision == "bf16x3"
+    kpad = (hid + 63) // 64 * 64
+    packing = CorpusPacking(mask.to(DEV))
+    assert packing.n_rows == int(mask.sum())
+    prep_q = lambda t: ops.split_rows(t.to(DEV), kpad=kpad, normalize=True, bf16=bf16)  # noqa: E731
+    prep_c = lambda t: ops.split_rows(t.to(DEV), kpad=kpad, normalize=True, bf16=bf16,  # noqa: E731
+                                      row_index=packing.src_rows)
+    got = ops.vr_scores_tc_packed(prep_q(qv), prep_c(fv), packing, nv, q_b=prep_q(qs) if both else None,
+                                  c_b=prep_c(fs) if both else None, bf16=bf16).cpu()
+    masked = want < -1e9
+    assert torch.equal(got < -1e9, masked) and (got[masked] == -1e10).all()
+    err = (got.double() - want)[~masked].abs().max().item()
+    print("vr_scores packed %s: max abs err vs fp64 = %.3g, tile fill %.3f" % (precision, err, packing.fill))
+    assert err <= (2e-6 if bf16 else 6e-7) * max(1.0, hid / 768), err
 
 
 def conv_taps(g, k=5):

@@ -25,6 +25,8 @@ namespace {
 using tc::BLOCK_K;
 using tc::BLOCK_M;
 constexpr int MAX_VPT = 8;  // videos per tile (BLOCK_N = vpt * lp <= 256, lp multiple of 32)
+constexpr int MAX_TILE_VIDEOS = 32;  // packed layout: at most this many videos share a tile
+constexpr int PACKED_EXTRA_SMEM = MAX_TILE_VIDEOS * 4 + 128 * (MAX_TILE_VIDEOS + 1) * 4;
 
 struct VrMaps {
   CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2];
@@ -117,6 +119,120 @@ vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Packed ("ragged") variant: only VALID clips are stored, whole videos are packed greedily into tiles of <= 256
+// consecutive rows (longest videos first), so no MMA work is spent on padded clips (44 % of the padded corpus at
+// the TVR length distribution).  Per tile: first packed row, first packed-video ordinal, number of used columns,
+// and a 256-bit map of the columns where a new video starts.  Both modalities share the packing.
+struct VrPackedParams {
+  int n_queries, n_videos, n_tiles, m_tiles, k_blocks, n_mod, stages;
+  const int* tile_meta;          // [n_tiles][4]: row_start, first ordinal, used columns, number of videos
+  const unsigned int* tile_starts;  // [n_tiles][8]
+  const int* order;              // [n_packed_videos] ordinal -> original video index
+  float* out;
+  float divisor;
+  unsigned int idesc;
+};
+
+struct VrPackedSched {
+  const VrMaps* maps;
+  const VrPackedParams* p;
+  int tile, mod;
+  __device__ VrPackedSched(const VrMaps* m, const VrPackedParams* pp) : maps(m), p(pp), tile(blockIdx.x), mod(0) {}
+  __device__ bool next(tc::UnitDesc& u) {
+    if (tile >= p->m_tiles * p->n_tiles) return false;
+    u.a_hi = &maps->a_hi[mod], u.a_lo = &maps->a_lo[mod], u.b_hi = &maps->b_hi[mod], u.b_lo = &maps->b_lo[mod];
+    u.a_row = (tile % p->m_tiles) * BLOCK_M;
+    u.b_row = __ldg(p->tile_meta + 4 * (tile / p->m_tiles));
+    u.k_blocks = p->k_blocks;
+    u.idesc = p->idesc;
+    if (++mod == p->n_mod) mod = 0, tile += gridDim.x;
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(192, 1)
+vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrPackedParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  tc::Pipe pipe;
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, 256, 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) tc::tc_producer_loop(VrPackedSched(&maps, &p), pipe);
+  } else if (warp == 1) {
+    if (lane == 0) tc::tc_mma_loop(VrPackedSched(&maps, &p), pipe, tmem_base);
+  } else {  // ===================== epilogue warps 2..5 =====================
+    // per-tile scratch in shared memory: original ids of the tile's videos and, per query row, the first
+    // modality's maxima (so that nothing on the accumulator-release path waits on global memory)
+    const uint32_t ids_s = pipe.extra();                              // int   [MAX_TILE_VIDEOS]
+    const uint32_t best_s = ids_s + MAX_TILE_VIDEOS * 4;               // float [128][MAX_TILE_VIDEOS + 1]
+    const int row = (warp & 3) * 32 + lane;
+    const int epi_tid = threadIdx.x - 64;
+    const uint32_t my_best = best_s + (uint32_t)row * (MAX_TILE_VIDEOS + 1) * 4;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    uint32_t unit = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
+      const int q = m_tile * BLOCK_M + row;
+      const bool q_ok = q < p.n_queries;
+      float* __restrict__ out_row = p.out + (long long)q * p.n_videos;
+      const int4 meta = __ldg(reinterpret_cast<const int4*>(p.tile_meta) + n_tile);  // row, first ordinal, used, n videos
+      const int used = meta.z;
+      const unsigned int* __restrict__ starts = p.tile_starts + 8 * n_tile;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's ids are no longer read
+      if (epi_tid < meta.w) {
+        const int id = __ldg(p.order + meta.y + epi_tid);
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(ids_s + 4u * epi_tid), "r"(id) : "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int mod = 0; mod < p.n_mod; ++mod, ++unit) {
+        const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
+        const bool last = mod == p.n_mod - 1;
+        int j = -1;
+        float cur = MASK_FILL;
+        auto flush = [&]() {
+          if (j < 0) return;
+          if (!last) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_best + 4u * j), "f"(cur) : "memory");
+          } else {
+            float v = cur;
+            if (mod != 0) {
+              float first;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(first) : "r"(my_best + 4u * j) : "memory");
+              v = __fadd_rn(first, cur);
+            }
+            int vid;
+            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(vid) : "r"(ids_s + 4u * j) : "memory");
+            if (q_ok) out_row[vid] = __fdiv_rn(v, p.divisor);
+          }
+        };
+        for (int c = 0; c < 8 && c * 32 < used; ++c) {  // warp-uniform
+          uint32_t r[32];
+          tc::tmem_ld_32x32(taddr + c * 32, r);
+          tc::tmem_ld_wait();
+          const unsigned int sb = __ldg(starts + c);
+          const int n_here = min(32, used - c * 32);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < n_here) {
+              if ((sb >> i) & 1u) {  // a new video starts at this column (uniform over the CTA)
+                flush();
+                ++j;
+                cur = MASK_FILL;
+              }
+              cur = fmaxf(cur, __uint_as_float(r[i]));
+            }
+          }
+        }
+        tc::epi_release(pipe, unit);  // all TMEM reads of this accumulator are done
+        flush();
+      }
+    }
+  }
+  tc::pipe_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // operand preparation: fp32 rows -> (optionally L2-normalised) hi/lo 16-bit rows, K padded to a multiple of 64,
 // rows regrouped from groups of `gin` to zero-padded groups of `gout` (clips of a video padded to lp).
 // One warp per output row.
@@ -134,22 +250,29 @@ __device__ __forceinline__ void split16(float x, unsigned short& hi, unsigned sh
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, long long rows_out, int k,
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x,
+                                                         const int* __restrict__ row_index, long long rows_out, int k,
                                                          int kpad, int gin, int gout, int normalize,
                                                          unsigned short* __restrict__ hi,
                                                          unsigned short* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const long long ro = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (ro >= rows_out) return;
-  const long long g = ro / gout;
-  const int l = (int)(ro - g * gout);
   unsigned short* h = hi + ro * kpad;
   unsigned short* o = lo + ro * kpad;
-  if (l >= gin) {
+  long long src;
+  if (row_index) {
+    src = row_index[ro];
+  } else {
+    const long long g = ro / gout;
+    const int l = (int)(ro - g * gout);
+    src = l < gin ? g * gin + l : -1;
+  }
+  if (src < 0) {
     for (int i = lane; i < kpad; i += 32) h[i] = 0, o[i] = 0;
     return;
   }
-  const float* xr = x + (g * gin + l) * k;
+  const float* xr = x + src * k;
   float denom = 1.f;
   if (normalize) {
     float s = 0.f;
@@ -211,8 +334,9 @@ int xmlb_make_tmap_2d_u16(CUtensorMap* out, const void* base, unsigned long long
   return XMLB_OK;
 }
 
-extern "C" int xmlb_split_rows(const float* x, long long n_groups, int group_in, int group_out, int k, int kpad,
-                               int normalize, int is_bf16, unsigned short* hi, unsigned short* lo, void* stream) {
+extern "C" int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, int group_in, int group_out,
+                               int k, int kpad, int normalize, int is_bf16, unsigned short* hi, unsigned short* lo,
+                               void* stream) {
   XMLB_REQUIRE(x && hi && lo, "xmlb_split_rows: null pointer");
   XMLB_REQUIRE(k >= 1 && kpad >= k && kpad % 64 == 0, "xmlb_split_rows: kpad must be a multiple of 64 and >= k");
   XMLB_REQUIRE(group_in >= 1 && group_out >= group_in, "xmlb_split_rows: need 1 <= group_in <= group_out");
@@ -221,11 +345,11 @@ extern "C" int xmlb_split_rows(const float* x, long long n_groups, int group_in,
   XMLB_REQUIRE(rows_out / 8 + 1 < (1ll << 31), "xmlb_split_rows: too many rows");
   const int blocks = ceil_div(rows_out, 8);
   if (is_bf16)
-    split_rows_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows_out, k, kpad, group_in, group_out,
-                                                                       normalize, hi, lo);
+    split_rows_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, group_in,
+                                                                       group_out, normalize, hi, lo);
   else
-    split_rows_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows_out, k, kpad, group_in, group_out,
-                                                                        normalize, hi, lo);
+    split_rows_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, group_in,
+                                                                        group_out, normalize, hi, lo);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
@@ -299,6 +423,62 @@ extern "C" int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned sh
   if (total < grid) grid = (int)total;
   XMLB_CUDA(cudaFuncSetAttribute(vr_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vr_scores_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short* q_lo_a,
+                                        const unsigned short* q_hi_b, const unsigned short* q_lo_b,
+                                        const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                                        const unsigned short* c_hi_b, const unsigned short* c_lo_b,
+                                        const int* tile_meta, const unsigned int* tile_starts, const int* order,
+                                        float* q2c, int n_queries, int n_videos, long long n_packed_rows, int n_tiles,
+                                        int kpad, int is_bf16, int max_ctas, void* stream) {
+  XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && tile_meta && tile_starts && order && q2c,
+               "xmlb_vr_scores_tc_packed: null pointer");
+  const bool two = q_hi_b != nullptr;
+  XMLB_REQUIRE(!two || (q_lo_b && c_hi_b && c_lo_b), "xmlb_vr_scores_tc_packed: incomplete second modality");
+  XMLB_REQUIRE(kpad >= 64 && kpad % 64 == 0, "xmlb_vr_scores_tc_packed: kpad must be a multiple of 64");
+  XMLB_REQUIRE(n_packed_rows > 0 && n_packed_rows < (1ll << 31), "xmlb_vr_scores_tc_packed: bad packed row count");
+  if (n_queries == 0 || n_tiles == 0) return XMLB_OK;
+  VrPackedParams p = {};
+  p.n_queries = n_queries, p.n_videos = n_videos, p.n_tiles = n_tiles;
+  p.m_tiles = ceil_div(n_queries, BLOCK_M);
+  p.k_blocks = kpad / BLOCK_K;
+  p.n_mod = two ? 2 : 1;
+  p.tile_meta = tile_meta, p.tile_starts = tile_starts, p.order = order;
+  p.out = q2c;
+  p.divisor = (float)p.n_mod;
+  p.idesc = tc::idesc_f16(BLOCK_M, 256, is_bf16 ? 1 : 0);
+  p.stages = tc::pipe_stages(256, PACKED_EXTRA_SMEM);
+  XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_scores_tc_packed: tile does not fit in shared memory");
+  const size_t smem = tc::pipe_smem_bytes(256, p.stages, PACKED_EXTRA_SMEM);
+  XMLB_REQUIRE(((uintptr_t)tile_meta & 15) == 0, "xmlb_vr_scores_tc_packed: tile_meta must be 16-byte aligned");
+  VrMaps maps;
+  const unsigned short* qh[2] = {q_hi_a, q_hi_b};
+  const unsigned short* ql[2] = {q_lo_a, q_lo_b};
+  const unsigned short* ch[2] = {c_hi_a, c_hi_b};
+  const unsigned short* cl[2] = {c_lo_a, c_lo_b};
+  for (int m = 0; m < p.n_mod; ++m) {
+    int rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[m], qh[m], n_queries, kpad, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[m], ql[m], n_queries, kpad, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi[m], ch[m], n_packed_rows, kpad, 256, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo[m], cl[m], n_packed_rows, kpad, 256, BLOCK_K))) return rc;
+  }
+  if (!two) {
+    maps.a_hi[1] = maps.a_hi[0], maps.a_lo[1] = maps.a_lo[0], maps.b_hi[1] = maps.b_hi[0], maps.b_lo[1] = maps.b_lo[0];
+  }
+  int dev = 0, sms = 0;
+  XMLB_CUDA(cudaGetDevice(&dev));
+  XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int grid = sms;
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  const long long total = (long long)p.m_tiles * p.n_tiles;
+  if (total < grid) grid = (int)total;
+  XMLB_CUDA(cudaFuncSetAttribute(vr_scores_tc_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vr_scores_tc_packed_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

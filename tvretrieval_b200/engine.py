@@ -11,6 +11,7 @@ reference's (same arithmetic per cell; ranking = score desc, index asc).
 """
 import contextlib
 
+import numpy as np
 import torch
 
 from . import ops
@@ -42,6 +43,59 @@ class PhaseTimer:
         self.spans = {}
 
 
+class CorpusPacking:
+    """Ragged layout of the corpus operand of the tensor-core VR kernel: only valid clips are stored; whole videos
+    are packed (longest first) into tiles of <= 256 consecutive rows, so a tile never splits a video."""
+    TILE = 256
+    MAX_VIDEOS = 32  # per tile (shared-memory scratch of the kernel epilogue)
+
+    def __init__(self, mask):
+        valid = (mask != 0).cpu().numpy()
+        n_videos, length = valid.shape
+        assert length <= self.TILE, "a video must fit in one tile"
+        lens = valid.sum(1)
+        # best-fit decreasing bin packing: open a tile with the longest remaining video, then keep adding the longest
+        # video that still fits (videos of equal length are taken in corpus order)
+        by_len = [[] for _ in range(self.TILE + 1)]
+        for v in range(n_videos - 1, -1, -1):
+            if lens[v] > 0:
+                by_len[lens[v]].append(v)  # pop() yields ascending video index
+        cnt = np.asarray([len(b) for b in by_len])
+        order, tile_of, metas = [], [], []  # metas: row_start, first ordinal, used columns
+        row = 0
+        while cnt.any():
+            t_row, t_ord, rem = row, len(order), self.TILE
+            while rem > 0 and len(order) - t_ord < self.MAX_VIDEOS:
+                fits = np.nonzero(cnt[:rem + 1])[0]
+                if len(fits) == 0:
+                    break
+                n = int(fits[-1])
+                order.append(by_len[n].pop())
+                tile_of.append(len(metas))
+                cnt[n] -= 1
+                rem -= n
+                row += n
+            metas.append((t_row, t_ord, self.TILE - rem, len(order) - t_ord))
+        order = np.asarray(order, dtype=np.int64)
+        tile_of = np.asarray(tile_of, dtype=np.int64)
+        olens = lens[order]
+        row_start = np.concatenate([[0], np.cumsum(olens)]).astype(np.int64)  # packed row of each video's first clip
+        meta = np.asarray(metas, dtype=np.int32).reshape(-1, 4)
+        starts = np.zeros((len(metas), 8), dtype=np.uint32)
+        col = row_start[:-1] - meta[tile_of, 0]
+        np.bitwise_or.at(starts, (tile_of, col // 32), (np.uint32(1) << (col % 32).astype(np.uint32)))
+        ii, ll = np.nonzero(valid[order])
+        dev = mask.device
+        self.n_rows, self.n_tiles = int(row_start[-1]), len(metas)
+        self.src_rows = torch.from_numpy((order[ii] * length + ll).astype(np.int32)).to(dev)
+        self.tile_meta = torch.from_numpy(meta).to(dev)
+        self.tile_starts = torch.from_numpy(starts.view(np.int32)).to(dev)
+        self.order = torch.from_numpy(order.astype(np.int32)).to(dev)
+        empty = np.nonzero(lens == 0)[0]
+        self.empty_ids = torch.from_numpy(empty).to(dev) if len(empty) else None
+        self.fill = self.n_rows / max(1, self.n_tiles * self.TILE)
+
+
 class CorpusIndex:
     """Encoded corpus resident in HBM.  Built once from the output of `compute_context_info`
     (reference inference.py:89-97); feat1 is L2-normalised at build time (the reference re-normalises it for
@@ -50,9 +104,10 @@ class CorpusIndex:
     PRECISIONS = ("f16x3", "bf16x3", "f32")
 
     def __init__(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
-                 sub_mask=None, vid_lo=0, precision="f16x3"):
+                 sub_mask=None, vid_lo=0, precision="f16x3", packed=True):
         """precision selects the video-level-score kernel: "f16x3" / "bf16x3" = tcgen05 tensor cores with
-        hi/lo-split operands (3 MMAs per product, fp32-accurate), "f32" = exact-fp32 SIMT kernel."""
+        hi/lo-split operands (3 MMAs per product, fp32-accurate), "f32" = exact-fp32 SIMT kernel.
+        packed=True stores only the valid clips for the tensor-core kernel (CorpusPacking)."""
         assert precision in self.PRECISIONS, precision
         ref = video_feat1 if video_feat1 is not None else sub_feat1
         self.n_videos, self.ctx_len, self.hidden = ref.shape
@@ -60,7 +115,9 @@ class CorpusIndex:
         self.vid_lo = vid_lo  # global id of the first video (multi-GPU shards)
         self.precision = precision
         self.video_feat1n = self.sub_feat1n = None
-        self.video_tc = self.sub_tc = self.video_bits = self.sub_bits = None
+        self.video_tc = self.sub_tc = self.video_bits = self.sub_bits = self.packing = None
+        if video_feat1 is not None and sub_feat1 is not None and not torch.equal(video_mask, sub_mask):
+            packed = False  # the packed layout shares one packing between the modalities
         if precision == "f32":
             self.video_feat1n = ops.l2norm_rows(video_feat1) if video_feat1 is not None else None
             self.sub_feat1n = ops.l2norm_rows(sub_feat1) if sub_feat1 is not None else None
@@ -70,22 +127,31 @@ class CorpusIndex:
             self.lp = (self.ctx_len + 31) // 32 * 32
             self.kpad = (self.hidden + 63) // 64 * 64
             bf16 = precision == "bf16x3"
-            if video_feat1 is not None:
-                self.video_tc = ops.split_rows(video_feat1, self.ctx_len, self.lp, self.kpad, normalize=True, bf16=bf16)
-                self.video_bits = ops.mask_bits(video_mask, self.lp)
-            if sub_feat1 is not None:
-                self.sub_tc = ops.split_rows(sub_feat1, self.ctx_len, self.lp, self.kpad, normalize=True, bf16=bf16)
-                self.sub_bits = ops.mask_bits(sub_mask, self.lp)
+            if packed:
+                self.packing = CorpusPacking(video_mask if video_mask is not None else sub_mask)
+                prep = lambda f: ops.split_rows(f, kpad=self.kpad, normalize=True, bf16=bf16,  # noqa: E731
+                                                row_index=self.packing.src_rows)
+                self.video_tc = prep(video_feat1) if video_feat1 is not None else None
+                self.sub_tc = prep(sub_feat1) if sub_feat1 is not None else None
+            else:
+                if video_feat1 is not None:
+                    self.video_tc = ops.split_rows(video_feat1, self.ctx_len, self.lp, self.kpad, normalize=True,
+                                                   bf16=bf16)
+                    self.video_bits = ops.mask_bits(video_mask, self.lp)
+                if sub_feat1 is not None:
+                    self.sub_tc = ops.split_rows(sub_feat1, self.ctx_len, self.lp, self.kpad, normalize=True,
+                                                 bf16=bf16)
+                    self.sub_bits = ops.mask_bits(sub_mask, self.lp)
         self.video_feat2 = video_feat2.contiguous() if video_feat2 is not None else None
         self.sub_feat2 = sub_feat2.contiguous() if sub_feat2 is not None else None
         self.video_mask = video_mask.contiguous() if video_mask is not None else None
         self.sub_mask = sub_mask.contiguous() if sub_mask is not None else None
 
     @classmethod
-    def from_ctx_info(cls, ctx_info, vid_lo=0, precision="f16x3"):
+    def from_ctx_info(cls, ctx_info, vid_lo=0, precision="f16x3", packed=True):
         return cls(ctx_info.get("video_feat1"), ctx_info.get("video_feat2"), ctx_info.get("video_mask"),
                    ctx_info.get("sub_feat1"), ctx_info.get("sub_feat2"), ctx_info.get("sub_mask"), vid_lo=vid_lo,
-                   precision=precision)
+                   precision=precision, packed=packed)
 
     def nbytes(self):
         tensors = [self.video_feat1n, self.sub_feat1n, self.video_feat2, self.sub_feat2, self.video_mask,
@@ -130,6 +196,8 @@ class VCMRSearcher:
             streams = [(q, c, b) for q, c, b in ((ops_q[0], ix.video_tc, ix.video_bits),
                                                  (ops_q[1], ix.sub_tc, ix.sub_bits)) if q is not None]
             a, b = streams[0], (streams[1] if len(streams) == 2 else (None, None, None))
+            if ix.packing is not None:
+                return ops.vr_scores_tc_packed(a[0], a[1], ix.packing, ix.n_videos, q_b=b[0], c_b=b[1], bf16=bf16)
             return ops.vr_scores_tc(a[0], a[1], a[2], ix.n_videos, ix.lp, q_b=b[0], c_b=b[1], bits_b=b[2], bf16=bf16)
         return ops.vr_scores_f32(
             ops.l2norm_rows(video_query) if m.use_video else None, ops.l2norm_rows(sub_query) if m.use_sub else None,

@@ -198,19 +198,24 @@ def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, su
     return out
 
 
-def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=False):
+def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=False, row_index=None):
     """fp32 rows -> 16-bit (hi, lo) halves with x ~= hi + lo, for the split-precision tensor-core kernels.
-    x: (..., k) with rows grouped by `group_in`; output (n_groups * group_out, kpad) int16 tensors (raw bits)."""
+    x: (..., k) with rows grouped by `group_in`; output (n_groups * group_out, kpad) int16 tensors (raw bits).
+    With row_index (int32, one source row per output row; negative = zero row) the rows are gathered instead."""
     x = _f32(x, "x")
     k = x.shape[-1]
     rows = x.numel() // k
-    assert rows % group_in == 0
-    n_groups = rows // group_in
     kpad = kpad or (k + 63) // 64 * 64
+    if row_index is not None:
+        row_index = _i32(row_index, "row_index")
+        n_groups, group_in, group_out = row_index.numel(), 1, 1
+    else:
+        assert rows % group_in == 0
+        n_groups = rows // group_in
     hi = torch.empty(n_groups * group_out, kpad, device=x.device, dtype=torch.int16)
     lo = torch.empty_like(hi)
-    rc = _lib.lib().xmlb_split_rows(_p(x), n_groups, group_in, group_out, k, kpad, int(normalize), int(bf16), _p(hi),
-                                    _p(lo), _stream())
+    rc = _lib.lib().xmlb_split_rows(_p(x), _p(row_index), n_groups, group_in, group_out, k, kpad, int(normalize),
+                                    int(bf16), _p(hi), _p(lo), _stream())
     _lib.check(rc, "xmlb_split_rows")
     return hi, lo
 
@@ -237,6 +242,22 @@ def vr_scores_tc(q_a, c_a, bits_a, n_videos, lp, q_b=None, c_b=None, bits_b=None
                                       _p(cb[1]), _p(bits_a), _p(bits_b), _p(out), nq, n_videos, lp, kpad, int(bf16),
                                       max_ctas, _stream())
     _lib.check(rc, "xmlb_vr_scores_tc")
+    return out
+
+
+def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=False, max_ctas=0):
+    """tcgen05 video-level scores on the packed (valid clips only) corpus; `packing` = engine.CorpusPacking."""
+    nq, kpad = q_a[0].shape
+    out = torch.empty(nq, n_videos, device=q_a[0].device, dtype=torch.float32)
+    qb = q_b if q_b is not None else (None, None)
+    cb = c_b if c_b is not None else (None, None)
+    rc = _lib.lib().xmlb_vr_scores_tc_packed(
+        _p(q_a[0]), _p(q_a[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]), _p(cb[1]),
+        _p(packing.tile_meta), _p(packing.tile_starts), _p(packing.order), _p(out), nq, n_videos, packing.n_rows,
+        packing.n_tiles, kpad, int(bf16), max_ctas, _stream())
+    _lib.check(rc, "xmlb_vr_scores_tc_packed")
+    if packing.empty_ids is not None:
+        out[:, packing.empty_ids] = -1e10  # videos without a valid clip (reference: every clip masked -> -1e10)
     return out
 
 
