@@ -83,10 +83,12 @@ int xmlb_vr_scores_f32(const float* q_video_n, const float* q_sub_n, const float
  * regrouped from groups of group_in (clips of a video) to zero-padded groups of group_out, columns zero-padded
  * to kpad (multiple of 64); normalize != 0 applies F.normalize (model_xml.py:446-447) first.  With row_index
  * (n_groups * group_out ints, group_in = group_out = 1) output row r is taken from source row row_index[r]
- * (negative = zero row): this gathers the valid clips into the packed corpus layout.
+ * (negative = zero row): this gathers the valid clips into the packed corpus layout.  Output row r is written at
+ * hi/lo[r * out_ld + out_col0 ...] (out_ld >= out_col0 + kpad), which lets two streams be concatenated along K.
  * xmlb_mask_bits: mask (n_videos, ctx_len) float {0,1} -> bits (n_videos, lp / 32), bit l%32 of word l/32. */
 int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, int group_in, int group_out, int k,
-                    int kpad, int normalize, int is_bf16, unsigned short* hi, unsigned short* lo, void* stream);
+                    int kpad, int out_ld, int out_col0, int normalize, int is_bf16, unsigned short* hi,
+                    unsigned short* lo, void* stream);
 int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream);
 
 /* q2c[q][v] = mean over given modalities of max_{l : bit set} q[q] . c[v * lp + l]; same contract as
@@ -136,11 +138,27 @@ int xmlb_span_logits(const float* q_a, const float* q_b, const float* feat2_a, c
 
 /* Inverts top_idx (n_queries, n_slots) [global video ids] into per-video lists for xmlb_span_logits.
  * Only ids in [vid_lo, vid_lo + n_videos) (this GPU's shard) and slots with slot_valid != 0 (NULL = all) are
- * listed; entry_out = q * n_slots + slot.  counts_ws, cursor_ws: n_videos ints; vid_ptr, chunk_ptr: n_videos+1;
+ * listed; entry_out = q * n_slots + slot; chunk_ptr = exclusive scan of ceil(list length / chunk) (chunk = 32 for
+ * xmlb_span_logits).  counts_ws, cursor_ws: n_videos ints; vid_ptr, chunk_ptr: n_videos+1;
  * entry_q, entry_out: n_queries * n_slots ints.  Replaces the advanced-index gather of inference.py:365-367. */
 int xmlb_build_pair_lists(const int* top_idx, const unsigned char* slot_valid, int n_queries, int n_slots,
-                          int vid_lo, int n_videos, int* counts_ws, int* cursor_ws, int* vid_ptr, int* chunk_ptr,
-                          int* entry_q, int* entry_out, void* stream);
+                          int vid_lo, int n_videos, int chunk, int* counts_ws, int* cursor_ws, int* vid_ptr,
+                          int* chunk_ptr, int* entry_q, int* entry_out, void* stream);
+
+/* ---- tensor-core variant of the similarity curves for the merged two-stream model (list mode only) -------
+ * xmlb_build_span_units: units[chunk_ptr[v] + c] = {v, vid_ptr[v] + c*chunk, entries in the chunk, 0} (int4 each)
+ * from lists built with the same `chunk`; the number of units is chunk_ptr[n_videos] (stays on the device).
+ * xmlb_span_probs_tc: same result as xmlb_span_logits(merged = 1, list mode) (model_xml.py:459-471,496-497 +
+ * inference.py:321-322): f2_* (n_videos * ctx_len, kcat) = hi/lo of [feat2_video | feat2_sub] concatenated along K
+ * (each stream zero-padded to kcat/2), qg_* (n_entries, kcat) = hi/lo of [q'_video | q'_sub] gathered in list
+ * order (xmlb_split_rows with row_index = entry_q).  ctx_len <= 128; block_n in {32, 64, 128} = chunk. */
+int xmlb_build_span_units(const int* vid_ptr, const int* chunk_ptr, int n_videos, int chunk, int* units,
+                          void* stream);
+int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo, const unsigned short* qg_hi,
+                       const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
+                       int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,
+                       int block_n, const int* units, const int* n_units, int max_units, const int* entry_out,
+                       float* out_st, float* out_ed, int is_bf16, void* stream);
 
 /* Per-row exact top-k, ranked (value desc, id asc | desc).  value = apply_exp ? exp(alpha * x) : x.
  * ids (n_rows, n_cols) optional explicit ids (NULL: column index).  Replaces torch.exp + torch.topk of

@@ -290,6 +290,46 @@ def test_span_logits_lists_match_dense(ops):
     assert torch.equal(st, dense_st[idx, idx])
 
 
+@pytest.mark.parametrize("nq,nv,length,hid,slots,chunk", [(150, 40, 64, 128, 9, 32), (300, 25, 128, 768, 12, 64),
+                                                          (40, 30, 100, 500, 7, 32), (700, 12, 128, 256, 8, 128),
+                                                          (64, 64, 32, 64, 1, 32)])
+@pytest.mark.parametrize("precision", ["f16x3", "bf16x3"])
+def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
+    """tcgen05 grouped similarity + ConvSE + softmax kernel vs the oracle (float64) on selected pairs."""
+    g = torch.Generator().manual_seed(nq + nv + hid)
+    qv, qs = torch.randn(nq, hid, generator=g) * 0.1, torch.randn(nq, hid, generator=g) * 0.1
+    fv, fs = torch.randn(nv, length, hid, generator=g), torch.randn(nv, length, hid, generator=g)
+    mask = rand_mask(g, nv, length, 2)
+    t0, t1 = conv_taps(g), conv_taps(g)
+    top = torch.stack([torch.randperm(nv, generator=g)[:slots] for _ in range(nq)]).to(torch.int32)
+    if slots > 1:
+        top[:, 0] = 3  # one video selected by every query: many chunks
+    eye, zero = torch.eye(hid).double(), torch.zeros(hid).double()
+    w = {"video_query_linear.weight": eye, "video_query_linear.bias": zero, "sub_query_linear.weight": eye,
+         "sub_query_linear.bias": zero, "merged_st_predictor.weight": t0.double(), "merged_ed_predictor.weight": t1.double()}
+    st, ed = O.merged_st_ed_logits(w, qv.double(), fv.double(), qs.double(), fs.double(), mask.double(), cross=True)
+    st, ed = torch.softmax(st, -1), torch.softmax(ed, -1)
+    rows = torch.arange(nq).unsqueeze(1)
+    want_st, want_ed = st[rows, top.long()], ed[rows, top.long()]
+    bf16 = precision == "bf16x3"
+    kpad = (hid + 63) // 64 * 64
+    f2cat = (torch.empty(nv * length, 2 * kpad, device=DEV, dtype=torch.int16),
+             torch.empty(nv * length, 2 * kpad, device=DEV, dtype=torch.int16))
+    ops.split_rows(fv.to(DEV), kpad=kpad, bf16=bf16, out=f2cat, out_col0=0)
+    ops.split_rows(fs.to(DEV), kpad=kpad, bf16=bf16, out=f2cat, out_col0=kpad)
+    pad = torch.nn.functional.pad
+    q_cat = torch.cat([pad(qv, (0, kpad - hid)), pad(qs, (0, kpad - hid))], 1).to(DEV)
+    lists = ops.build_pair_lists(top.to(DEV), nv, chunk=chunk)
+    got_st, got_ed = ops.span_probs_tc(f2cat, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length, bf16=bf16)
+    got_st, got_ed = got_st.view(nq, slots, length).cpu(), got_ed.view(nq, slots, length).cpu()
+    err = max((got_st.double() - want_st).abs().max().item(), (got_ed.double() - want_ed).abs().max().item())
+    rel = ((got_st.double() - want_st).abs() / want_st.clamp_min(1e-30))[want_st > 1e-6].max().item()
+    print("span_probs_tc %s: max abs err %.3g, max rel err %.3g" % (precision, err, rel))
+    close(got_st, want_st, rtol=2e-4, atol=1e-7), close(got_ed, want_ed, rtol=2e-4, atol=1e-7)
+    pad_pos = (mask == 0)[top.long()]
+    assert (got_st[pad_pos] == 0).all()
+
+
 @pytest.mark.parametrize("rows,cols,k", [(3, 100, 100), (17, 2179, 100), (4, 21793, 100), (5, 333, 7), (2, 5000, 1000)])
 def test_topk_rows(ops, rows, cols, k):
     g = torch.Generator().manual_seed(rows * cols)

@@ -249,8 +249,8 @@ __global__ void pair_count_kernel(const int* __restrict__ top_idx, const unsigne
   if (v >= 0 && v < n_videos) atomicAdd(counts + v, 1);
 }
 
-// single CTA, 1024 threads: exclusive scans of counts -> vid_ptr and of ceil(counts/32) -> chunk_ptr
-__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ counts, int n_videos,
+// single CTA, 1024 threads: exclusive scans of counts -> vid_ptr and of ceil(counts/chunk) -> chunk_ptr
+__global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__ counts, int n_videos, int chunk,
                                                          int* __restrict__ vid_ptr, int* __restrict__ chunk_ptr,
                                                          int* __restrict__ cursor) {
   __shared__ int warp_tot[2][32];
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(1024) pair_scan_kernel(const int* __restrict__
   for (int base = 0; base < n_videos; base += 1024) {
     const int i = base + t;
     const int c = i < n_videos ? counts[i] : 0;
-    int val[2] = {c, (c + 31) / 32};
+    int val[2] = {c, (c + chunk - 1) / chunk};
     int inc[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -322,12 +322,12 @@ __global__ void pair_fill_kernel(const int* __restrict__ top_idx, const unsigned
 }
 
 extern "C" int xmlb_build_pair_lists(const int* top_idx, const unsigned char* slot_valid, int n_queries, int n_slots,
-                                     int vid_lo, int n_videos, int* counts_ws, int* cursor_ws, int* vid_ptr,
-                                     int* chunk_ptr, int* entry_q, int* entry_out, void* stream_) {
+                                     int vid_lo, int n_videos, int chunk, int* counts_ws, int* cursor_ws,
+                                     int* vid_ptr, int* chunk_ptr, int* entry_q, int* entry_out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   XMLB_REQUIRE(top_idx && counts_ws && cursor_ws && vid_ptr && chunk_ptr && entry_q && entry_out,
                "xmlb_build_pair_lists: null pointer");
-  XMLB_REQUIRE(n_videos > 0 && n_slots > 0, "xmlb_build_pair_lists: bad shape");
+  XMLB_REQUIRE(n_videos > 0 && n_slots > 0 && chunk > 0, "xmlb_build_pair_lists: bad shape");
   const long long n_pairs = (long long)n_queries * n_slots;
   XMLB_REQUIRE(n_pairs < (1ll << 31), "xmlb_build_pair_lists: too many pairs");
   XMLB_CUDA(cudaMemsetAsync(counts_ws, 0, sizeof(int) * (size_t)n_videos, stream));
@@ -336,7 +336,7 @@ extern "C" int xmlb_build_pair_lists(const int* top_idx, const unsigned char* sl
                                                                  counts_ws);
     XMLB_LAUNCH_CHECK();
   }
-  pair_scan_kernel<<<1, 1024, 0, stream>>>(counts_ws, n_videos, vid_ptr, chunk_ptr, cursor_ws);
+  pair_scan_kernel<<<1, 1024, 0, stream>>>(counts_ws, n_videos, chunk, vid_ptr, chunk_ptr, cursor_ws);
   XMLB_LAUNCH_CHECK();
   if (n_pairs > 0) {
     pair_fill_kernel<<<ceil_div(n_pairs, 256), 256, 0, stream>>>(top_idx, slot_valid, n_pairs, n_slots, vid_lo,

@@ -1,0 +1,206 @@
+// Similarity curves of the selected (query, video) pairs on the tcgen05 tensor cores + ConvSE + mask + softmax.
+//   replaces XML.get_merged_st_ed_prob(cross=True) on gathered pairs and the driver's softmax
+//   (reference model_xml.py:459-471,496-497; inference.py:321-322,365-367) for the merged two-stream model.
+//
+// Grouped GEMM, one unit = one video x up to BLOCK_N of the queries that selected it (inverted lists):
+//   M = the video's clips (128 TMEM lanes),  N = queries of the list chunk,  K = 2 * Kpad: the video and subtitle
+//   streams are concatenated along K so that  q'_v . f2_v + q'_s . f2_s  is produced by the accumulator; sim = acc / 2.
+// A = feat2 (video || sub) of the corpus as 16-bit hi/lo halves, B = the projected queries gathered in list order
+// (so a list chunk is a contiguous row range for TMA).  Split precision: 3 MMAs per product, fp32 accumulate.
+// Epilogue: each thread owns one clip row of the accumulator, writes it transposed into shared memory; then each
+// warp takes whole queries: 5-tap ConvSE start/end detectors, mask_logits, softmax over the clips, coalesced store.
+#include "tc_pipeline.cuh"
+#include "xmlb200.h"
+
+namespace {
+
+using tc::BLOCK_K;
+using tc::BLOCK_M;
+constexpr int S_LD = 132;  // row pitch (floats) of the transposed similarity tile
+
+struct SpanTcMaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+struct SpanTcParams {
+  int n_videos, ctx_len, k_blocks, block_n, stages, ksize, softmax;
+  const int4* units;     // {video, first entry row, entries in this chunk, 0}
+  const int* n_units;    // device scalar
+  const int* entry_out;  // [E] output row of each list entry
+  const float* mask;     // [Nv][L]
+  const float* w_st;
+  const float* w_ed;
+  float* out_st;
+  float* out_ed;
+  unsigned int idesc;
+};
+
+struct SpanSched {
+  const SpanTcMaps* maps;
+  const SpanTcParams* p;
+  int u, n_units;
+  __device__ SpanSched(const SpanTcMaps* m, const SpanTcParams* pp)
+      : maps(m), p(pp), u(blockIdx.x), n_units(__ldg(pp->n_units)) {}
+  __device__ bool next(tc::UnitDesc& d) {
+    if (u >= n_units) return false;
+    const int4 m = __ldg(p->units + u);
+    d.a_hi = &maps->a_hi, d.a_lo = &maps->a_lo, d.b_hi = &maps->b_hi, d.b_lo = &maps->b_lo;
+    d.a_row = m.x * p->ctx_len;
+    d.b_row = m.y;
+    d.k_blocks = p->k_blocks;
+    d.idesc = p->idesc;
+    u += gridDim.x;
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(192, 1)
+span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_constant__ SpanTcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  tc::Pipe pipe;
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) tc::tc_producer_loop(SpanSched(&maps, &p), pipe);
+  } else if (warp == 1) {
+    if (lane == 0) tc::tc_mma_loop(SpanSched(&maps, &p), pipe, tmem_base);
+  } else {  // ===================== epilogue warps 2..5 =====================
+    float* S = reinterpret_cast<float*>(smem_raw + (pipe.extra() - tc::smem_u32(smem_raw)));  // [block_n][S_LD]
+    const int clip = (warp & 3) * 32 + lane;  // accumulator row owned in the TMEM phase
+    const int ew = warp - 2;                  // 0..3: queries handled in the ConvSE phase
+    const int L = p.ctx_len, pad = p.ksize / 2;
+    const int n_units = __ldg(p.n_units);
+    uint32_t unit = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit) {
+      const int4 m = __ldg(p.units + u);
+      const int v = m.x, e0 = m.y, ne = m.z;
+      const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
+      // ---- phase A: accumulator (clip x query) -> shared memory, transposed to (query x clip), halved
+      for (int c = 0; c * 32 < ne; ++c) {  // warp-uniform
+        uint32_t r[32];
+        tc::tmem_ld_32x32(taddr + c * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) S[(c * 32 + i) * S_LD + clip] = __fmul_rn(__uint_as_float(r[i]), 0.5f);
+      }
+      tc::epi_release(pipe, unit);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- phase B: per query: ConvSE start / end, mask_logits, softmax over clips
+      for (int j = ew; j < ne; j += 4) {
+        const float* s = S + j * S_LD;
+        const long long row = __ldg(p.entry_out + e0 + j);
+        float st[4], ed[4];
+        float mx_st = -INFINITY, mx_ed = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int l = lane + 32 * c;
+          st[c] = 0.f, ed[c] = 0.f;
+          if (l < L) {
+            float a = 0.f, b = 0.f;
+            for (int t = 0; t < p.ksize; ++t) {
+              const int src = l + t - pad;
+              const float x = (src >= 0 && src < L) ? s[src] : 0.f;
+              a = fmaf(__ldg(p.w_st + t), x, a);
+              b = fmaf(__ldg(p.w_ed + t), x, b);
+            }
+            const float mk = __ldg(p.mask + (long long)v * L + l);
+            st[c] = mask_logit(a, mk), ed[c] = mask_logit(b, mk);
+            mx_st = fmaxf(mx_st, st[c]), mx_ed = fmaxf(mx_ed, ed[c]);
+          }
+        }
+        if (p.softmax) {
+          mx_st = warp_max(mx_st), mx_ed = warp_max(mx_ed);
+          float s_st = 0.f, s_ed = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (lane + 32 * c < L) {
+              st[c] = expf(st[c] - mx_st), ed[c] = expf(ed[c] - mx_ed);
+              s_st += st[c], s_ed += ed[c];
+            }
+          }
+          s_st = warp_sum(s_st), s_ed = warp_sum(s_ed);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) st[c] = __fdiv_rn(st[c], s_st), ed[c] = __fdiv_rn(ed[c], s_ed);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int l = lane + 32 * c;
+          if (l < L) {
+            p.out_st[row * L + l] = st[c];
+            p.out_ed[row * L + l] = ed[c];
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // S may be overwritten by the next unit
+    }
+  }
+  tc::pipe_teardown(tmem_base);
+}
+
+// units[chunk_ptr[v] + c] = {v, vid_ptr[v] + c * chunk, min(chunk, remaining), 0}
+__global__ void span_units_kernel(const int* __restrict__ vid_ptr, const int* __restrict__ chunk_ptr, int n_videos,
+                                  int chunk, int4* __restrict__ units) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_videos) return;
+  const int e_lo = vid_ptr[v], e_hi = vid_ptr[v + 1];
+  int u = chunk_ptr[v];
+  for (int e = e_lo; e < e_hi; e += chunk, ++u) units[u] = make_int4(v, e, min(chunk, e_hi - e), 0);
+}
+
+}  // namespace
+
+extern "C" int xmlb_build_span_units(const int* vid_ptr, const int* chunk_ptr, int n_videos, int chunk, int* units,
+                                     void* stream) {
+  XMLB_REQUIRE(vid_ptr && chunk_ptr && units && n_videos > 0 && chunk > 0, "xmlb_build_span_units: bad argument");
+  XMLB_REQUIRE(((uintptr_t)units & 15) == 0, "xmlb_build_span_units: units must be 16-byte aligned");
+  span_units_kernel<<<ceil_div(n_videos, 256), 256, 0, (cudaStream_t)stream>>>(vid_ptr, chunk_ptr, n_videos, chunk,
+                                                                              reinterpret_cast<int4*>(units));
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,
+                                  const unsigned short* qg_hi, const unsigned short* qg_lo, const float* mask,
+                                  const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
+                                  int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
+                                  const int* n_units, int max_units, const int* entry_out, float* out_st,
+                                  float* out_ed, int is_bf16, void* stream) {
+  XMLB_REQUIRE(f2_hi && f2_lo && qg_hi && qg_lo && mask && w_st && w_ed && units && n_units && entry_out && out_st &&
+                   out_ed, "xmlb_span_probs_tc: null pointer");
+  XMLB_REQUIRE(ctx_len >= 1 && ctx_len <= BLOCK_M, "xmlb_span_probs_tc: ctx_len must be <= 128");
+  XMLB_REQUIRE(kcat >= 64 && kcat % 64 == 0, "xmlb_span_probs_tc: kcat must be a multiple of 64");
+  XMLB_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "xmlb_span_probs_tc: block_n must be 32, 64 or 128");
+  XMLB_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= 31, "xmlb_span_probs_tc: ksize must be odd and <= 31");
+  XMLB_REQUIRE(((uintptr_t)units & 15) == 0, "xmlb_span_probs_tc: units must be 16-byte aligned");
+  if (n_entries == 0 || max_units == 0 || n_videos == 0) return XMLB_OK;
+  SpanTcParams p = {};
+  p.n_videos = n_videos, p.ctx_len = ctx_len, p.k_blocks = kcat / BLOCK_K, p.block_n = block_n;
+  p.ksize = ksize, p.softmax = apply_softmax;
+  p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out;
+  p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed;
+  p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
+  const int extra = block_n * S_LD * (int)sizeof(float);
+  p.stages = tc::pipe_stages(block_n, extra);
+  XMLB_REQUIRE(p.stages >= 2, "xmlb_span_probs_tc: tile does not fit in shared memory");
+  const size_t smem = tc::pipe_smem_bytes(block_n, p.stages, extra);
+
+  SpanTcMaps maps;
+  int rc;
+  const unsigned long long corpus_rows = (unsigned long long)n_videos * ctx_len;
+  if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi, f2_hi, corpus_rows, kcat, BLOCK_M, BLOCK_K))) return rc;
+  if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo, f2_lo, corpus_rows, kcat, BLOCK_M, BLOCK_K))) return rc;
+  if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi, qg_hi, n_entries, kcat, block_n, BLOCK_K))) return rc;
+  if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo, qg_lo, n_entries, kcat, block_n, BLOCK_K))) return rc;
+
+  int dev = 0, sms = 0;
+  XMLB_CUDA(cudaGetDevice(&dev));
+  XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = max_units < sms ? max_units : sms;
+  XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  span_probs_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}

@@ -252,14 +252,15 @@ __device__ __forceinline__ void split16(float x, unsigned short& hi, unsigned sh
 template <bool BF16>
 __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x,
                                                          const int* __restrict__ row_index, long long rows_out, int k,
-                                                         int kpad, int gin, int gout, int normalize,
+                                                         int kpad, int out_ld, int out_col0, int gin, int gout,
+                                                         int normalize,
                                                          unsigned short* __restrict__ hi,
                                                          unsigned short* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const long long ro = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (ro >= rows_out) return;
-  unsigned short* h = hi + ro * kpad;
-  unsigned short* o = lo + ro * kpad;
+  unsigned short* h = hi + ro * out_ld + out_col0;
+  unsigned short* o = lo + ro * out_ld + out_col0;
   long long src;
   if (row_index) {
     src = row_index[ro];
@@ -335,8 +336,9 @@ int xmlb_make_tmap_2d_u16(CUtensorMap* out, const void* base, unsigned long long
 }
 
 extern "C" int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, int group_in, int group_out,
-                               int k, int kpad, int normalize, int is_bf16, unsigned short* hi, unsigned short* lo,
-                               void* stream) {
+                               int k, int kpad, int out_ld, int out_col0, int normalize, int is_bf16,
+                               unsigned short* hi, unsigned short* lo, void* stream) {
+  XMLB_REQUIRE(out_ld >= out_col0 + kpad && out_col0 >= 0, "xmlb_split_rows: need out_col0 + kpad <= out_ld");
   XMLB_REQUIRE(x && hi && lo, "xmlb_split_rows: null pointer");
   XMLB_REQUIRE(k >= 1 && kpad >= k && kpad % 64 == 0, "xmlb_split_rows: kpad must be a multiple of 64 and >= k");
   XMLB_REQUIRE(group_in >= 1 && group_out >= group_in, "xmlb_split_rows: need 1 <= group_in <= group_out");
@@ -345,11 +347,13 @@ extern "C" int xmlb_split_rows(const float* x, const int* row_index, long long n
   XMLB_REQUIRE(rows_out / 8 + 1 < (1ll << 31), "xmlb_split_rows: too many rows");
   const int blocks = ceil_div(rows_out, 8);
   if (is_bf16)
-    split_rows_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, group_in,
-                                                                       group_out, normalize, hi, lo);
+    split_rows_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, out_ld,
+                                                                       out_col0, group_in, group_out, normalize, hi,
+                                                                       lo);
   else
-    split_rows_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, group_in,
-                                                                        group_out, normalize, hi, lo);
+    split_rows_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, out_ld,
+                                                                        out_col0, group_in, group_out, normalize, hi,
+                                                                        lo);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

@@ -104,10 +104,12 @@ class CorpusIndex:
     PRECISIONS = ("f16x3", "bf16x3", "f32")
 
     def __init__(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
-                 sub_mask=None, vid_lo=0, precision="f16x3", packed=True):
+                 sub_mask=None, vid_lo=0, precision="f16x3", packed=True, merged_spans=True):
         """precision selects the video-level-score kernel: "f16x3" / "bf16x3" = tcgen05 tensor cores with
         hi/lo-split operands (3 MMAs per product, fp32-accurate), "f32" = exact-fp32 SIMT kernel.
-        packed=True stores only the valid clips for the tensor-core kernel (CorpusPacking)."""
+        packed=True stores only the valid clips for the tensor-core kernel (CorpusPacking).
+        merged_spans=True additionally keeps [feat2_video | feat2_sub] as hi/lo halves for the tensor-core
+        similarity-curve kernel of the merged two-stream model (needs both modalities, L <= 128)."""
         assert precision in self.PRECISIONS, precision
         ref = video_feat1 if video_feat1 is not None else sub_feat1
         self.n_videos, self.ctx_len, self.hidden = ref.shape
@@ -115,7 +117,7 @@ class CorpusIndex:
         self.vid_lo = vid_lo  # global id of the first video (multi-GPU shards)
         self.precision = precision
         self.video_feat1n = self.sub_feat1n = None
-        self.video_tc = self.sub_tc = self.video_bits = self.sub_bits = self.packing = None
+        self.video_tc = self.sub_tc = self.video_bits = self.sub_bits = self.packing = self.f2cat = None
         if video_feat1 is not None and sub_feat1 is not None and not torch.equal(video_mask, sub_mask):
             packed = False  # the packed layout shares one packing between the modalities
         if precision == "f32":
@@ -142,21 +144,29 @@ class CorpusIndex:
                     self.sub_tc = ops.split_rows(sub_feat1, self.ctx_len, self.lp, self.kpad, normalize=True,
                                                  bf16=bf16)
                     self.sub_bits = ops.mask_bits(sub_mask, self.lp)
+        if (precision != "f32" and merged_spans and video_feat2 is not None and sub_feat2 is not None
+                and self.ctx_len <= 128):
+            rows = self.n_videos * self.ctx_len
+            self.f2cat = (torch.empty(rows, 2 * self.kpad, device=self.device, dtype=torch.int16),
+                          torch.empty(rows, 2 * self.kpad, device=self.device, dtype=torch.int16))
+            bf16 = precision == "bf16x3"
+            ops.split_rows(video_feat2, kpad=self.kpad, bf16=bf16, out=self.f2cat, out_col0=0)
+            ops.split_rows(sub_feat2, kpad=self.kpad, bf16=bf16, out=self.f2cat, out_col0=self.kpad)
         self.video_feat2 = video_feat2.contiguous() if video_feat2 is not None else None
         self.sub_feat2 = sub_feat2.contiguous() if sub_feat2 is not None else None
         self.video_mask = video_mask.contiguous() if video_mask is not None else None
         self.sub_mask = sub_mask.contiguous() if sub_mask is not None else None
 
     @classmethod
-    def from_ctx_info(cls, ctx_info, vid_lo=0, precision="f16x3", packed=True):
+    def from_ctx_info(cls, ctx_info, vid_lo=0, precision="f16x3", packed=True, merged_spans=True):
         return cls(ctx_info.get("video_feat1"), ctx_info.get("video_feat2"), ctx_info.get("video_mask"),
                    ctx_info.get("sub_feat1"), ctx_info.get("sub_feat2"), ctx_info.get("sub_mask"), vid_lo=vid_lo,
-                   precision=precision, packed=packed)
+                   precision=precision, packed=packed, merged_spans=merged_spans)
 
     def nbytes(self):
         tensors = [self.video_feat1n, self.sub_feat1n, self.video_feat2, self.sub_feat2, self.video_mask,
                    self.sub_mask, self.video_bits, self.sub_bits]
-        for pair in (self.video_tc, self.sub_tc):
+        for pair in (self.video_tc, self.sub_tc, self.f2cat):
             tensors.extend(pair or ())
         return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
@@ -172,7 +182,7 @@ class SearchResult:
 
 class VCMRSearcher:
     def __init__(self, model, index, q2c_alpha=20.0, min_pred_l=2, max_pred_l=16, max_n_videos=100,
-                 max_before_nms=200, query_chunk=2048):
+                 max_before_nms=200, query_chunk=4096):
         self.model, self.index = model, index
         self.q2c_alpha = float(q2c_alpha)
         self.min_pred_l, self.max_pred_l = int(min_pred_l), int(max_pred_l)
@@ -204,9 +214,33 @@ class VCMRSearcher:
             ix.video_feat1n if m.use_video else None, ix.sub_feat1n if m.use_sub else None,
             ix.video_mask if m.use_video else None, ix.sub_mask if m.use_sub else None)
 
+    def use_span_tc(self):
+        m = self.model
+        return self.index.f2cat is not None and m.config.merge_two_stream and m.use_video and m.use_sub
+
+    def span_lists(self, top_idx, slot_valid=None):
+        """Inverted (video -> queries) lists of the selected pairs; the chunk size is the N tile of the tensor-core
+        similarity kernel (larger when many queries share a video), 32 for the SIMT kernel."""
+        ix = self.index
+        chunk = 32
+        if self.use_span_tc():
+            avg = top_idx.numel() / max(1, ix.n_videos)
+            chunk = 128 if avg >= 96 else 64 if avg >= 40 else 32
+        return ops.build_pair_lists(top_idx, ix.n_videos, vid_lo=ix.vid_lo, slot_valid=slot_valid, chunk=chunk)
+
     def span_probs(self, video_query, sub_query, lists):
         """softmax-normalised start/end distributions for the listed (query, video) pairs -> (rows, L) x 2."""
         ix = self.index
+        if self.use_span_tc():
+            m = self.model
+            qv = ops.linear(video_query, m.video_query_linear.weight, m.video_query_linear.bias)
+            qs = ops.linear(sub_query, m.sub_query_linear.weight, m.sub_query_linear.bias)
+            if ix.kpad != ix.hidden:
+                qv = torch.nn.functional.pad(qv, (0, ix.kpad - ix.hidden))
+                qs = torch.nn.functional.pad(qs, (0, ix.kpad - ix.hidden))
+            return ops.span_probs_tc(ix.f2cat, torch.cat([qv, qs], dim=1), lists, ix.video_mask,
+                                     m.merged_st_predictor.weight, m.merged_ed_predictor.weight, ix.ctx_len,
+                                     softmax=True, bf16=ix.precision == "bf16x3")
         args = self.model.span_streams(video_query, sub_query, ix.video_feat2, ix.sub_feat2, ix.video_mask,
                                        ix.sub_mask)
         return ops.span_logits(softmax=True, lists=lists, **args)
@@ -240,7 +274,7 @@ class VCMRSearcher:
                                                                        apply_exp=True)
         if "VCMR" in tasks:
             with self._phase("pair_lists"):
-                lists = ops.build_pair_lists(res.top_video_idx, ix.n_videos)
+                lists = self.span_lists(res.top_video_idx)
             with self._phase("span_probs"):
                 st, ed = self.span_probs(video_query, sub_query, lists)
             st = st.view(nq, self.max_n_videos, ix.ctx_len)
@@ -250,7 +284,7 @@ class VCMRSearcher:
                                                                   self.max_pred_l, self.max_before_nms)
         if "SVMR" in tasks:
             assert gt_video_idx is not None, "SVMR needs the ground-truth video of every query"
-            lists = ops.build_pair_lists(gt_video_idx.view(nq, 1), ix.n_videos)
+            lists = self.span_lists(gt_video_idx.view(nq, 1))
             st, ed = self.span_probs(video_query, sub_query, lists)
             res.svmr_flat_idx, res.svmr_score = ops.span_topk(
                 st.view(nq, 1, ix.ctx_len), ed.view(nq, 1, ix.ctx_len), None, self.min_pred_l, self.max_pred_l,

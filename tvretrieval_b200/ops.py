@@ -198,7 +198,8 @@ def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, su
     return out
 
 
-def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=False, row_index=None):
+def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=False, row_index=None, out=None,
+               out_col0=0):
     """fp32 rows -> 16-bit (hi, lo) halves with x ~= hi + lo, for the split-precision tensor-core kernels.
     x: (..., k) with rows grouped by `group_in`; output (n_groups * group_out, kpad) int16 tensors (raw bits).
     With row_index (int32, one source row per output row; negative = zero row) the rows are gathered instead."""
@@ -212,10 +213,14 @@ def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=Fals
     else:
         assert rows % group_in == 0
         n_groups = rows // group_in
-    hi = torch.empty(n_groups * group_out, kpad, device=x.device, dtype=torch.int16)
-    lo = torch.empty_like(hi)
-    rc = _lib.lib().xmlb_split_rows(_p(x), _p(row_index), n_groups, group_in, group_out, k, kpad, int(normalize),
-                                    int(bf16), _p(hi), _p(lo), _stream())
+    if out is None:
+        hi = torch.empty(n_groups * group_out, kpad, device=x.device, dtype=torch.int16)
+        lo = torch.empty_like(hi)
+    else:  # write into columns [out_col0, out_col0 + kpad) of preallocated (rows, out_ld) buffers
+        hi, lo = out
+        assert hi.shape[0] == n_groups * group_out and hi.shape == lo.shape and hi.is_contiguous()
+    rc = _lib.lib().xmlb_split_rows(_p(x), _p(row_index), n_groups, group_in, group_out, k, kpad, hi.shape[1],
+                                    out_col0, int(normalize), int(bf16), _p(hi), _p(lo), _stream())
     _lib.check(rc, "xmlb_split_rows")
     return hi, lo
 
@@ -264,29 +269,56 @@ def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=Fa
 class PairLists:
     """Per-video inverted lists of (query, output row) built on device by xmlb_build_pair_lists."""
 
-    def __init__(self, vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_rows):
+    def __init__(self, vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_rows, chunk=32):
         self.vid_ptr, self.chunk_ptr, self.entry_q, self.entry_out = vid_ptr, chunk_ptr, entry_q, entry_out
-        self.max_chunks, self.n_rows = max_chunks, n_rows
+        self.max_chunks, self.n_rows, self.chunk = max_chunks, n_rows, chunk
 
 
-def build_pair_lists(top_idx, n_videos, vid_lo=0, slot_valid=None):
+def build_pair_lists(top_idx, n_videos, vid_lo=0, slot_valid=None, chunk=32):
     """top_idx (Nq, n_slots) int32 global video ids -> PairLists over the videos [vid_lo, vid_lo + n_videos)."""
     top_idx = _i32(top_idx, "top_idx")
     nq, n_slots = top_idx.shape
     dev = top_idx.device
     n_pairs = nq * n_slots
-    ints = torch.empty(4 * n_videos + 2 + 2 * n_pairs, device=dev, dtype=torch.int32)
+    # entries of pairs that are not listed (other shards' videos) stay -1: "no row" for the gather kernels
+    ints = torch.full((4 * n_videos + 2 + 2 * n_pairs,), -1, device=dev, dtype=torch.int32)
     counts, cursor = ints[:n_videos], ints[n_videos:2 * n_videos]
     vid_ptr = ints[2 * n_videos:3 * n_videos + 1]
     chunk_ptr = ints[3 * n_videos + 1:4 * n_videos + 2]
     entry_q = ints[4 * n_videos + 2:4 * n_videos + 2 + n_pairs]
     entry_out = ints[4 * n_videos + 2 + n_pairs:]
     rc = _lib.lib().xmlb_build_pair_lists(_p(top_idx), _p(_u8(slot_valid, "slot_valid")), nq, n_slots, vid_lo,
-                                          n_videos, _p(counts), _p(cursor), _p(vid_ptr), _p(chunk_ptr), _p(entry_q),
-                                          _p(entry_out), _stream())
+                                          n_videos, chunk, _p(counts), _p(cursor), _p(vid_ptr), _p(chunk_ptr),
+                                          _p(entry_q), _p(entry_out), _stream())
     _lib.check(rc, "xmlb_build_pair_lists")
-    max_chunks = (n_pairs + 31) // 32 + min(n_videos, n_pairs)
-    return PairLists(vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_pairs)
+    max_chunks = (n_pairs + chunk - 1) // chunk + min(n_videos, n_pairs)
+    return PairLists(vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_pairs, chunk)
+
+
+def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, bf16=False, out_rows=None):
+    """tcgen05 similarity curves + ConvSE + mask (+ softmax) for listed (query, video) pairs of the merged model.
+    f2cat = (hi, lo) of [feat2_video | feat2_sub] (Nv * L, kcat); q_cat fp32 (Nq, kcat) = [q'_video | q'_sub] with
+    each half zero-padded to kcat / 2; lists built with chunk in {32, 64, 128}.  -> st, ed of shape (rows, L)."""
+    n_videos = f2cat[0].shape[0] // ctx_len
+    kcat = f2cat[0].shape[1]
+    assert q_cat.shape[1] == kcat and lists.chunk in (32, 64, 128)
+    dev = q_cat.device
+    units = torch.empty(lists.max_chunks * 4 + 4, device=dev, dtype=torch.int32)
+    rc = _lib.lib().xmlb_build_span_units(_p(lists.vid_ptr), _p(lists.chunk_ptr), n_videos, lists.chunk, _p(units),
+                                          _stream())
+    _lib.check(rc, "xmlb_build_span_units")
+    qg = split_rows(q_cat, kpad=kcat, bf16=bf16, row_index=lists.entry_q)  # queries gathered in list order
+    rows = lists.n_rows if out_rows is None else out_rows
+    st = torch.zeros(rows, ctx_len, device=dev, dtype=torch.float32)
+    ed = torch.zeros_like(st)
+    w_st, w_ed = _f32(w_st.reshape(-1), "w_st"), _f32(w_ed.reshape(-1), "w_ed")
+    rc = _lib.lib().xmlb_span_probs_tc(_p(f2cat[0]), _p(f2cat[1]), _p(qg[0]), _p(qg[1]), _p(_f32(mask, "mask")),
+                                       _p(w_st), _p(w_ed), w_st.numel(), int(softmax), n_videos, ctx_len, kcat,
+                                       lists.entry_q.numel(), lists.chunk, _p(units),
+                                       lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
+                                       _p(st), _p(ed), int(bf16), _stream())
+    _lib.check(rc, "xmlb_span_probs_tc")
+    return st, ed
 
 
 def diagonal_pair_lists(n, device):

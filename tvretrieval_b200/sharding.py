@@ -142,7 +142,7 @@ class ShardedSearcher(VCMRSearcher):
             m = self.max_before_nms
             with self._phase("pair_lists"):
                 valid = local_slot_mask(res.top_video_idx, vid_lo, vid_hi)
-                lists = ops.build_pair_lists(res.top_video_idx, ix.n_videos, vid_lo=vid_lo, slot_valid=valid)
+                lists = self.span_lists(res.top_video_idx, slot_valid=valid)
             with self._phase("span_probs"):
                 st, ed = self.span_probs(video_query, sub_query, lists)
             st, ed = st.view(nq, k, ix.ctx_len), ed.view(nq, k, ix.ctx_len)
@@ -157,7 +157,7 @@ class ShardedSearcher(VCMRSearcher):
             m = self.max_before_nms
             gt = gt_video_idx.view(nq, 1).to(torch.int32)
             valid = local_slot_mask(gt, vid_lo, vid_hi)
-            lists = ops.build_pair_lists(gt, ix.n_videos, vid_lo=vid_lo, slot_valid=valid)
+            lists = self.span_lists(gt, slot_valid=valid)
             st, ed = self.span_probs(video_query, sub_query, lists)
             idx, val = ops.span_topk(st.view(nq, 1, ix.ctx_len), ed.view(nq, 1, ix.ctx_len), None, self.min_pred_l,
                                      self.max_pred_l, m, slot_valid=valid, tie_desc=True, zero_fill=False)
