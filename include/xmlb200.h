@@ -94,30 +94,32 @@ int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigne
 /* q2c[q][v] = mean over given modalities of max_{l : bit set} q[q] . c[v * lp + l]; same contract as
  * xmlb_vr_scores_f32 (model_xml.py:446-452, 572-574) on prepared operands: q_* (n_queries, kpad),
  * c_* (n_videos * lp, kpad), mask_bits_* (n_videos, lp/32).  lp multiple of 32, <= 256.  Modality b optional (NULL).
- * max_ctas: 0 = one persistent CTA per SM. */
+ * max_ctas: 0 = one persistent CTA per SM.  sched_ws: one int of device scratch (the dynamic tile counter; every
+ * tensor-core entry point takes one and zeroes it itself). */
 int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned short* q_lo_a, const unsigned short* q_hi_b,
                       const unsigned short* q_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                       const unsigned short* c_hi_b, const unsigned short* c_lo_b, const unsigned int* mask_bits_a,
-                      const unsigned int* mask_bits_b, float* q2c, int n_queries, int n_videos, int lp, int kpad,
-                      int is_bf16, int max_ctas, void* stream);
+                      const unsigned int* mask_bits_b, float* q2c, int* sched_ws, int n_queries, int n_videos, int lp,
+                      int kpad, int is_bf16, int max_ctas, void* stream);
 
 /* Packed ("ragged") variant of xmlb_vr_scores_tc: c_* hold only the valid clips, (n_packed_rows, kpad), videos
  * packed whole into tiles of <= 256 consecutive rows.  tile_meta (n_tiles, 4) int = {first packed row, ordinal of the
- * tile's first video, used columns, number of videos (<= 32)}; tile_starts (n_tiles, 8) = 256-bit map of columns where a video starts;
- * order[ordinal] = original video index (column of q2c).  Videos without valid clips are not listed: the caller
- * pre-fills their q2c columns with -1e10.  Both modalities must share the packing (same masks). */
+ * tile's first video, used columns, number of videos (<= 32)}; tile_starts (n_tiles, 8) = 256-bit map of columns
+ * where a video starts.  q2c (n_queries, n_videos) is written in PACKED ORDINAL order: column o is the o-th packed
+ * video (the caller keeps the ordinal -> video id table and passes it to xmlb_topk_rows as shared ids); columns of
+ * videos that are not packed (no valid clip) are not written.  Both modalities share the packing (same masks). */
 int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short* q_lo_a, const unsigned short* q_hi_b,
                              const unsigned short* q_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                              const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* tile_meta,
-                             const unsigned int* tile_starts, const int* order, float* q2c, int n_queries, int n_videos,
+                             const unsigned int* tile_starts, float* q2c, int* sched_ws, int n_queries, int n_videos,
                              long long n_packed_rows, int n_tiles, int kpad, int is_bf16, int max_ctas, void* stream);
 
 /* Tensor-core variant of xmlb_linear (same contract, model_components.py:160-163,278-280,314): x_* (rows, kpad)
  * and w_* (out_dim, kpad) are the 16-bit (hi, lo) halves produced by xmlb_split_rows (normalize = 0).
  * out / bias / residual must be 16-byte aligned. */
 int xmlb_linear_tc(const unsigned short* x_hi, const unsigned short* x_lo, const unsigned short* w_hi,
-                   const unsigned short* w_lo, const float* bias, const float* residual, float* out, long long rows,
-                   int out_dim, int kpad, int relu, int is_bf16, void* stream);
+                   const unsigned short* w_lo, const float* bias, const float* residual, float* out, int* sched_ws,
+                   long long rows, int out_dim, int kpad, int relu, int is_bf16, void* stream);
 
 /* Similarity curves + ConvSE + mask (+ softmax), replaces XML.get_merged_st_ed_prob (model_xml.py:455-502),
  * XML._get_st_ed_prob (:512-551) and the driver's softmax over clips (inference.py:321-322).
@@ -158,13 +160,14 @@ int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,
                        const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
                        int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,
                        int block_n, const int* units, const int* n_units, int max_units, const int* entry_out,
-                       float* out_st, float* out_ed, int is_bf16, void* stream);
+                       float* out_st, float* out_ed, int* sched_ws, int is_bf16, void* stream);
 
 /* Per-row exact top-k, ranked (value desc, id asc | desc).  value = apply_exp ? exp(alpha * x) : x.
- * ids (n_rows, n_cols) optional explicit ids (NULL: column index).  Replaces torch.exp + torch.topk of
+ * ids: optional explicit ids (NULL: column index), (n_rows, n_cols) when ids_shared == 0, one (n_cols) table shared
+ * by all rows when ids_shared != 0.  Replaces torch.exp + torch.topk of
  * inference.py:317,347-348; returns an error when k > n_cols like torch.topk does.  k <= 1024. */
-int xmlb_topk_rows(const float* values, const int* ids, int n_rows, int n_cols, int k, float alpha, int apply_exp,
-                   int tie_desc, int* out_idx, float* out_val, void* stream);
+int xmlb_topk_rows(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k, float alpha,
+                   int apply_exp, int tie_desc, int* out_idx, float* out_val, void* stream);
 
 /* Band-limited span scoring + exact top-k, replaces inference.py:370-386 (VCMR) and inference.py:215-224 +
  * utils/tensor_utils.py:133-141 (SVMR, n_slots = 1, video_score = NULL, tie_desc = 1):

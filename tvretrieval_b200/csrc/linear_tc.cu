@@ -21,22 +21,23 @@ struct LinParams {
   const float* bias;
   const float* residual;
   float* out;
+  int* tile_counter;  // zeroed before the launch
   unsigned int idesc;
 };
 
 struct LinSched {  // output-feature tile fastest: the activation tile is re-read from L2 by its sibling tiles
   const LinMaps* maps;
   const LinParams* p;
-  int tile;
-  __device__ LinSched(const LinMaps* m, const LinParams* pp) : maps(m), p(pp), tile(blockIdx.x) {}
+  __device__ LinSched(const LinMaps* m, const LinParams* pp) : maps(m), p(pp) {}
   __device__ bool next(tc::UnitDesc& u) {
+    const int tile = atomicAdd(p->tile_counter, 1);
     if (tile >= p->m_tiles * p->n_tiles) return false;
     u.a_hi = &maps->a_hi, u.a_lo = &maps->a_lo, u.b_hi = &maps->b_hi, u.b_lo = &maps->b_lo;
     u.a_row = (tile / p->n_tiles) * BLOCK_M;
     u.b_row = (tile % p->n_tiles) * p->block_n;
     u.k_blocks = p->k_blocks;
     u.idesc = p->idesc;
-    tile += gridDim.x;
+    u.tag0 = tile, u.tag1 = 0;
     return true;
   }
 };
@@ -45,19 +46,18 @@ __global__ void __launch_bounds__(192, 1)
 linear_tc_kernel(const __grid_constant__ LinMaps maps, const __grid_constant__ LinParams p) {
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 4);
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
     if (lane == 0) tc::tc_producer_loop(LinSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(LinSched(&maps, &p), pipe, tmem_base);
+    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
     const int row_in_tile = (warp & 3) * 32 + lane;
-    const int total_tiles = p.m_tiles * p.n_tiles;
     const bool vec_ok = (p.out_dim & 3) == 0;
-    uint32_t unit = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++unit) {
+    int t, tag1;
+    for (uint32_t unit = 0; tc::epi_next(pipe, unit, t, tag1); ++unit) {
       const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
       const long long row = (long long)m_tile * BLOCK_M + row_in_tile;
       const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
@@ -110,8 +110,9 @@ linear_tc_kernel(const __grid_constant__ LinMaps maps, const __grid_constant__ L
 
 extern "C" int xmlb_linear_tc(const unsigned short* x_hi, const unsigned short* x_lo, const unsigned short* w_hi,
                               const unsigned short* w_lo, const float* bias, const float* residual, float* out,
-                              long long rows, int out_dim, int kpad, int relu, int is_bf16, void* stream) {
-  XMLB_REQUIRE(x_hi && x_lo && w_hi && w_lo && out, "xmlb_linear_tc: null pointer");
+                              int* sched_ws, long long rows, int out_dim, int kpad, int relu, int is_bf16,
+                              void* stream) {
+  XMLB_REQUIRE(x_hi && x_lo && w_hi && w_lo && out && sched_ws, "xmlb_linear_tc: null pointer");
   XMLB_REQUIRE(rows >= 0 && rows < (1ll << 31) - 256 && out_dim >= 1, "xmlb_linear_tc: bad shape");
   XMLB_REQUIRE(kpad >= 64 && kpad % 64 == 0, "xmlb_linear_tc: kpad must be a multiple of 64");
   XMLB_REQUIRE(((uintptr_t)out & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0) &&
@@ -124,7 +125,7 @@ extern "C" int xmlb_linear_tc(const unsigned short* x_hi, const unsigned short* 
   p.block_n = out_dim >= 256 ? 256 : (out_dim + 15) / 16 * 16;
   p.m_tiles = ceil_div(rows, BLOCK_M);
   p.n_tiles = ceil_div(out_dim, p.block_n);
-  p.relu = relu, p.bias = bias, p.residual = residual, p.out = out;
+  p.relu = relu, p.bias = bias, p.residual = residual, p.out = out, p.tile_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
   p.stages = tc::pipe_stages(p.block_n, 0);
   XMLB_REQUIRE(p.stages >= 2, "xmlb_linear_tc: tile does not fit in shared memory");
@@ -142,6 +143,7 @@ extern "C" int xmlb_linear_tc(const unsigned short* x_hi, const unsigned short* 
   XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long total = (long long)p.m_tiles * p.n_tiles;
   const int grid = total < sms ? (int)total : sms;
+  XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
   XMLB_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   linear_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
   xmlb_count_launch(1);

@@ -32,16 +32,17 @@ struct SpanTcParams {
   const float* w_ed;
   float* out_st;
   float* out_ed;
+  int* unit_counter;  // zeroed before the launch
   unsigned int idesc;
 };
 
 struct SpanSched {
   const SpanTcMaps* maps;
   const SpanTcParams* p;
-  int u, n_units;
-  __device__ SpanSched(const SpanTcMaps* m, const SpanTcParams* pp)
-      : maps(m), p(pp), u(blockIdx.x), n_units(__ldg(pp->n_units)) {}
+  int n_units;
+  __device__ SpanSched(const SpanTcMaps* m, const SpanTcParams* pp) : maps(m), p(pp), n_units(__ldg(pp->n_units)) {}
   __device__ bool next(tc::UnitDesc& d) {
+    const int u = atomicAdd(p->unit_counter, 1);
     if (u >= n_units) return false;
     const int4 m = __ldg(p->units + u);
     d.a_hi = &maps->a_hi, d.a_lo = &maps->a_lo, d.b_hi = &maps->b_hi, d.b_lo = &maps->b_lo;
@@ -49,7 +50,7 @@ struct SpanSched {
     d.b_row = m.y;
     d.k_blocks = p->k_blocks;
     d.idesc = p->idesc;
-    u += gridDim.x;
+    d.tag0 = u, d.tag1 = 0;
     return true;
   }
 };
@@ -58,21 +59,20 @@ __global__ void __launch_bounds__(192, 1)
 span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_constant__ SpanTcParams p) {
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 4);
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
     if (lane == 0) tc::tc_producer_loop(SpanSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(SpanSched(&maps, &p), pipe, tmem_base);
+    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
     float* S = reinterpret_cast<float*>(smem_raw + (pipe.extra() - tc::smem_u32(smem_raw)));  // [block_n][S_LD]
     const int clip = (warp & 3) * 32 + lane;  // accumulator row owned in the TMEM phase
     const int ew = warp - 2;                  // 0..3: queries handled in the ConvSE phase
     const int L = p.ctx_len, pad = p.ksize / 2;
-    const int n_units = __ldg(p.n_units);
-    uint32_t unit = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++unit) {
+    int u, tag1;
+    for (uint32_t unit = 0; tc::epi_next(pipe, unit, u, tag1); ++unit) {
       const int4 m = __ldg(p.units + u);
       const int v = m.x, e0 = m.y, ne = m.z;
       const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
@@ -166,9 +166,9 @@ extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned sh
                                   const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
                                   int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
                                   const int* n_units, int max_units, const int* entry_out, float* out_st,
-                                  float* out_ed, int is_bf16, void* stream) {
+                                  float* out_ed, int* sched_ws, int is_bf16, void* stream) {
   XMLB_REQUIRE(f2_hi && f2_lo && qg_hi && qg_lo && mask && w_st && w_ed && units && n_units && entry_out && out_st &&
-                   out_ed, "xmlb_span_probs_tc: null pointer");
+                   out_ed && sched_ws, "xmlb_span_probs_tc: null pointer");
   XMLB_REQUIRE(ctx_len >= 1 && ctx_len <= BLOCK_M, "xmlb_span_probs_tc: ctx_len must be <= 128");
   XMLB_REQUIRE(kcat >= 64 && kcat % 64 == 0, "xmlb_span_probs_tc: kcat must be a multiple of 64");
   XMLB_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "xmlb_span_probs_tc: block_n must be 32, 64 or 128");
@@ -179,7 +179,7 @@ extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned sh
   p.n_videos = n_videos, p.ctx_len = ctx_len, p.k_blocks = kcat / BLOCK_K, p.block_n = block_n;
   p.ksize = ksize, p.softmax = apply_softmax;
   p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out;
-  p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed;
+  p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed, p.unit_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
   const int extra = block_n * S_LD * (int)sizeof(float);
   p.stages = tc::pipe_stages(block_n, extra);
@@ -198,6 +198,7 @@ extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned sh
   XMLB_CUDA(cudaGetDevice(&dev));
   XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = max_units < sms ? max_units : sms;
+  XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
   XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   span_probs_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
   xmlb_count_launch(1);

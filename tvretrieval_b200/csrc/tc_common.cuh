@@ -68,14 +68,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// Shared-memory matrix descriptor, K-major operand, 128B swizzle, rows of 64 16-bit elements (128 B):
-// 8-row x 128 B swizzle atoms stacked along M/N every 1024 B (SBO); LBO unused for swizzled K-major.
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptor, K-major operand whose rows are exactly one swizzle span wide
+// (SWIZZLE_BYTES = 128: rows of 64 16-bit elements, 64: rows of 32): 8-row swizzle atoms stacked along M/N every
+// 8 * SWIZZLE_BYTES (SBO); LBO unused for swizzled K-major.
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t smem_addr) {
+  static_assert(SWIZZLE_BYTES == 128 || SWIZZLE_BYTES == 64, "supported swizzle spans");
   uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // bits [0,14)  start address >> 4
-  d |= (uint64_t)(1024 >> 4) << 32;             // bits [32,46) stride byte offset >> 4
-  d |= (uint64_t)1 << 46;                       // bits [46,48) descriptor version = 1 (sm_100)
-  d |= (uint64_t)2 << 61;                       // bits [61,64) layout = SWIZZLE_128B
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // bits [0,14)  start address >> 4
+  d |= (uint64_t)((8 * SWIZZLE_BYTES) >> 4) << 32;         // bits [32,46) stride byte offset >> 4
+  d |= (uint64_t)1 << 46;                                  // bits [46,48) descriptor version = 1 (sm_100)
+  d |= (uint64_t)(SWIZZLE_BYTES == 128 ? 2 : 4) << 61;     // bits [61,64) layout = SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 
@@ -121,7 +124,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------- host side
-// Encodes a 2D tiled tensor map over a row-major [rows][cols] array of 16-bit elements with 128B swizzle.
-// box = {box_cols (must be 64 -> 128 B), box_rows}.  Returns XMLB_OK or an error code (message set).
+// Encodes a 2D tiled tensor map over a row-major [rows][cols] array of 16-bit elements; the swizzle span equals the
+// box width: box_cols = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B.  Returns XMLB_OK or an error code (message set).
 int xmlb_make_tmap_2d_u16(CUtensorMap* out, const void* base, unsigned long long rows, unsigned long long cols,
                           unsigned int box_rows, unsigned int box_cols);

@@ -185,12 +185,14 @@ struct RowGen {
 };
 
 __global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__ values, const int* __restrict__ ids,
-                                                       int n_cols, int k, float alpha, int apply_exp, int tie_desc,
+                                                       int ids_shared, int n_cols, int k, float alpha, int apply_exp,
+                                                       int tie_desc,
                                                        int* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   const long long r = blockIdx.x;
-  RowGen gen{values + r * n_cols, ids ? ids + r * n_cols : nullptr, n_cols, alpha, apply_exp, tie_desc};
+  RowGen gen{values + r * n_cols, ids ? ids + (ids_shared ? 0 : r * n_cols) : nullptr, n_cols, alpha, apply_exp,
+             tie_desc};
   const int n_out = block_topk(gen, sm, k);
   for (int i = threadIdx.x; i < k; i += NT) {
     if (i < n_out) {
@@ -337,15 +339,15 @@ static int check_topk_args(const char* who, int k) {
   return XMLB_OK;
 }
 
-extern "C" int xmlb_topk_rows(const float* values, const int* ids, int n_rows, int n_cols, int k, float alpha,
-                              int apply_exp, int tie_desc, int* out_idx, float* out_val, void* stream) {
+extern "C" int xmlb_topk_rows(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k,
+                              float alpha, int apply_exp, int tie_desc, int* out_idx, float* out_val, void* stream) {
   XMLB_REQUIRE(values && out_idx && out_val, "xmlb_topk_rows: null pointer");
   if (int rc = check_topk_args("xmlb_topk_rows", k)) return rc;
   XMLB_REQUIRE(n_cols >= k, "xmlb_topk_rows: selected index k out of range (k=%d > %d columns)", k, n_cols);
   if (n_rows == 0) return XMLB_OK;
   XMLB_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
-  topk_rows_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(values, ids, n_cols, k, alpha, apply_exp,
-                                                                        tie_desc, out_idx, out_val);
+  topk_rows_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(values, ids, ids_shared, n_cols, k, alpha,
+                                                                        apply_exp, tie_desc, out_idx, out_val);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

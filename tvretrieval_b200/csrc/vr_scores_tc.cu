@@ -26,7 +26,7 @@ using tc::BLOCK_K;
 using tc::BLOCK_M;
 constexpr int MAX_VPT = 8;  // videos per tile (BLOCK_N = vpt * lp <= 256, lp multiple of 32)
 constexpr int MAX_TILE_VIDEOS = 32;  // packed layout: at most this many videos share a tile
-constexpr int PACKED_EXTRA_SMEM = MAX_TILE_VIDEOS * 4 + 128 * (MAX_TILE_VIDEOS + 1) * 4;
+constexpr int PACKED_EXTRA_SMEM = 128 * (MAX_TILE_VIDEOS + 1) * 4;
 
 struct VrMaps {
   CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2];
@@ -36,24 +36,29 @@ struct VrTcParams {
   int n_queries, n_videos, lp, vpt, block_n, k_blocks, n_mod, m_tiles, n_tiles, stages;
   const unsigned int* mask_bits[2];
   float* out;
+  int* tile_counter;  // zeroed before the launch
   float divisor;
   unsigned int idesc;
 };
 
-// units of a CTA: tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (query tile fastest), each x n_mod modalities
+// tiles are claimed from a global counter (query tile fastest), each tile = n_mod consecutive units
 struct VrSched {
   const VrMaps* maps;
   const VrTcParams* p;
   int tile, mod;
-  __device__ VrSched(const VrMaps* m, const VrTcParams* pp) : maps(m), p(pp), tile(blockIdx.x), mod(0) {}
+  __device__ VrSched(const VrMaps* m, const VrTcParams* pp) : maps(m), p(pp), tile(0), mod(0) {}
   __device__ bool next(tc::UnitDesc& u) {
-    if (tile >= p->m_tiles * p->n_tiles) return false;
+    if (mod == 0) {
+      tile = atomicAdd(p->tile_counter, 1);
+      if (tile >= p->m_tiles * p->n_tiles) return false;
+    }
     u.a_hi = &maps->a_hi[mod], u.a_lo = &maps->a_lo[mod], u.b_hi = &maps->b_hi[mod], u.b_lo = &maps->b_lo[mod];
     u.a_row = (tile % p->m_tiles) * BLOCK_M;
     u.b_row = (tile / p->m_tiles) * p->block_n;
     u.k_blocks = p->k_blocks;
     u.idesc = p->idesc;
-    if (++mod == p->n_mod) mod = 0, tile += gridDim.x;
+    u.tag0 = tile, u.tag1 = mod;
+    if (++mod == p->n_mod) mod = 0;
     return true;
   }
 };
@@ -62,51 +67,46 @@ __global__ void __launch_bounds__(192, 1)
 vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrTcParams p) {
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 4);
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
     if (lane == 0) tc::tc_producer_loop(VrSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(VrSched(&maps, &p), pipe, tmem_base);
+    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
     const int row = (warp & 3) * 32 + lane;
     const int chunks = p.lp >> 5;
-    const int total_tiles = p.m_tiles * p.n_tiles;
-    uint32_t unit = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
-      const int q = m_tile * BLOCK_M + row;
-      float best[MAX_VPT];
+    float best[MAX_VPT];
+    int tile, mod;
+    for (uint32_t unit = 0; tc::epi_next(pipe, unit, tile, mod); ++unit) {
+      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+      const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
+      const unsigned int* __restrict__ bits = p.mask_bits[mod];
 #pragma unroll
-      for (int j = 0; j < MAX_VPT; ++j) best[j] = 0.f;
-      for (int mod = 0; mod < p.n_mod; ++mod, ++unit) {
-        const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
-        const unsigned int* __restrict__ bits = p.mask_bits[mod];
+      for (int j = 0; j < MAX_VPT; ++j) {
+        if (j < p.vpt) {
+          const int v = n_tile * p.vpt + j;
+          float m = MASK_FILL;
+          for (int c = 0; c < chunks; ++c) {
+            uint32_t r[32];
+            tc::tmem_ld_32x32(taddr + j * p.lp + c * 32, r);
+            tc::tmem_ld_wait();
+            const unsigned int b = v < p.n_videos ? __ldg(bits + (long long)v * chunks + c) : 0u;
+            if (b == 0xffffffffu) {
 #pragma unroll
-        for (int j = 0; j < MAX_VPT; ++j) {
-          if (j < p.vpt) {
-            const int v = n_tile * p.vpt + j;
-            float m = MASK_FILL;
-            for (int c = 0; c < chunks; ++c) {
-              uint32_t r[32];
-              tc::tmem_ld_32x32(taddr + j * p.lp + c * 32, r);
-              tc::tmem_ld_wait();
-              const unsigned int b = v < p.n_videos ? __ldg(bits + (long long)v * chunks + c) : 0u;
-              if (b == 0xffffffffu) {
+              for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+            } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) m = (b >> i) & 1u ? fmaxf(m, __uint_as_float(r[i])) : m;
-              }
+              for (int i = 0; i < 32; ++i) m = (b >> i) & 1u ? fmaxf(m, __uint_as_float(r[i])) : m;
             }
-            best[j] = mod == 0 ? m : __fadd_rn(best[j], m);
           }
+          best[j] = mod == 0 ? m : __fadd_rn(best[j], m);
         }
-        tc::epi_release(pipe, unit);  // accumulator fully read: hand it back to the MMA issuer
       }
-      if (q < p.n_queries) {
+      tc::epi_release(pipe, unit);  // accumulator fully read: hand it back to the MMA issuer
+      const int q = m_tile * BLOCK_M + row;
+      if (mod == p.n_mod - 1 && q < p.n_queries) {
 #pragma unroll
         for (int j = 0; j < MAX_VPT; ++j) {
           const int v = n_tile * p.vpt + j;
@@ -127,25 +127,54 @@ struct VrPackedParams {
   int n_queries, n_videos, n_tiles, m_tiles, k_blocks, n_mod, stages;
   const int* tile_meta;          // [n_tiles][4]: row_start, first ordinal, used columns, number of videos
   const unsigned int* tile_starts;  // [n_tiles][8]
-  const int* order;              // [n_packed_videos] ordinal -> original video index
   float* out;
+  int* tile_counter;  // zeroed before the launch
   float divisor;
   unsigned int idesc;
 };
+
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+  float m[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) m[i] = fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 16]));
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) m[i] = fmaxf(m[i], m[i + w]);
+  return m[0];
+}
+__device__ __forceinline__ float masked_max32(const uint32_t (&r)[32], unsigned int mask) {
+  float m[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float a = (mask >> i) & 1u ? __uint_as_float(r[i]) : MASK_FILL;
+    const float b = (mask >> (i + 16)) & 1u ? __uint_as_float(r[i + 16]) : MASK_FILL;
+    m[i] = fmaxf(a, b);
+  }
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) m[i] = fmaxf(m[i], m[i + w]);
+  return m[0];
+}
 
 struct VrPackedSched {
   const VrMaps* maps;
   const VrPackedParams* p;
   int tile, mod;
-  __device__ VrPackedSched(const VrMaps* m, const VrPackedParams* pp) : maps(m), p(pp), tile(blockIdx.x), mod(0) {}
+  __device__ VrPackedSched(const VrMaps* m, const VrPackedParams* pp) : maps(m), p(pp), tile(0), mod(0) {}
   __device__ bool next(tc::UnitDesc& u) {
-    if (tile >= p->m_tiles * p->n_tiles) return false;
+    if (mod == 0) {
+      tile = atomicAdd(p->tile_counter, 1);
+      if (tile >= p->m_tiles * p->n_tiles) return false;
+    }
     u.a_hi = &maps->a_hi[mod], u.a_lo = &maps->a_lo[mod], u.b_hi = &maps->b_hi[mod], u.b_lo = &maps->b_lo[mod];
     u.a_row = (tile % p->m_tiles) * BLOCK_M;
     u.b_row = __ldg(p->tile_meta + 4 * (tile / p->m_tiles));
     u.k_blocks = p->k_blocks;
     u.idesc = p->idesc;
-    if (++mod == p->n_mod) mod = 0, tile += gridDim.x;
+    u.tag0 = tile, u.tag1 = mod;
+    if (++mod == p->n_mod) mod = 0;
     return true;
   }
 };
@@ -154,79 +183,76 @@ __global__ void __launch_bounds__(192, 1)
 vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrPackedParams p) {
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, 256, 4);
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
     if (lane == 0) tc::tc_producer_loop(VrPackedSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(VrPackedSched(&maps, &p), pipe, tmem_base);
+    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
-    // per-tile scratch in shared memory: original ids of the tile's videos and, per query row, the first
-    // modality's maxima (so that nothing on the accumulator-release path waits on global memory)
-    const uint32_t ids_s = pipe.extra();                              // int   [MAX_TILE_VIDEOS]
-    const uint32_t best_s = ids_s + MAX_TILE_VIDEOS * 4;               // float [128][MAX_TILE_VIDEOS + 1]
+    // per query row, the first modality's maxima are parked in shared memory (nothing on the accumulator-release
+    // path waits on global memory).  Scores are written in PACKED ORDINAL order: the videos of a tile are adjacent
+    // columns, so the 4-byte stores of neighbouring tiles complete whole sectors (writing by original video id
+    // scattered them: 7x DRAM write amplification and L2 pollution).
+    const uint32_t best_s = pipe.extra();  // float [128][MAX_TILE_VIDEOS + 1]
     const int row = (warp & 3) * 32 + lane;
-    const int epi_tid = threadIdx.x - 64;
     const uint32_t my_best = best_s + (uint32_t)row * (MAX_TILE_VIDEOS + 1) * 4;
-    const int total_tiles = p.m_tiles * p.n_tiles;
-    uint32_t unit = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
+    int tile, mod;
+    for (uint32_t unit = 0; tc::epi_next(pipe, unit, tile, mod); ++unit) {
+      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
       const int q = m_tile * BLOCK_M + row;
       const bool q_ok = q < p.n_queries;
-      float* __restrict__ out_row = p.out + (long long)q * p.n_videos;
       const int4 meta = __ldg(reinterpret_cast<const int4*>(p.tile_meta) + n_tile);  // row, first ordinal, used, n videos
       const int used = meta.z;
+      float* __restrict__ out_row = p.out + (long long)q * p.n_videos + meta.y;
       const unsigned int* __restrict__ starts = p.tile_starts + 8 * n_tile;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's ids are no longer read
-      if (epi_tid < meta.w) {
-        const int id = __ldg(p.order + meta.y + epi_tid);
-        asm volatile("st.shared.s32 [%0], %1;" ::"r"(ids_s + 4u * epi_tid), "r"(id) : "memory");
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int mod = 0; mod < p.n_mod; ++mod, ++unit) {
-        const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
-        const bool last = mod == p.n_mod - 1;
-        int j = -1;
-        float cur = MASK_FILL;
-        auto flush = [&]() {
-          if (j < 0) return;
-          if (!last) {
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_best + 4u * j), "f"(cur) : "memory");
-          } else {
-            float v = cur;
-            if (mod != 0) {
-              float first;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(first) : "r"(my_best + 4u * j) : "memory");
-              v = __fadd_rn(first, cur);
-            }
-            int vid;
-            asm volatile("ld.shared.s32 %0, [%1];" : "=r"(vid) : "r"(ids_s + 4u * j) : "memory");
-            if (q_ok) out_row[vid] = __fdiv_rn(v, p.divisor);
+      const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
+      const bool last = mod == p.n_mod - 1;
+      int j = -1;
+      float cur = MASK_FILL;
+      auto flush = [&]() {
+        if (j < 0) return;
+        if (!last) {
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_best + 4u * j), "f"(cur) : "memory");
+        } else {
+          float v = cur;
+          if (mod != 0) {
+            float first;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(first) : "r"(my_best + 4u * j) : "memory");
+            v = __fadd_rn(first, cur);
           }
-        };
-        for (int c = 0; c < 8 && c * 32 < used; ++c) {  // warp-uniform
-          uint32_t r[32];
-          tc::tmem_ld_32x32(taddr + c * 32, r);
-          tc::tmem_ld_wait();
-          const unsigned int sb = __ldg(starts + c);
-          const int n_here = min(32, used - c * 32);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i < n_here) {
-              if ((sb >> i) & 1u) {  // a new video starts at this column (uniform over the CTA)
-                flush();
-                ++j;
-                cur = MASK_FILL;
-              }
-              cur = fmaxf(cur, __uint_as_float(r[i]));
+          if (q_ok) out_row[j] = __fdiv_rn(v, p.divisor);
+        }
+      };
+      for (int c = 0; c < 8 && c * 32 < used; ++c) {  // warp-uniform
+        uint32_t r[32];
+        tc::tmem_ld_32x32(taddr + c * 32, r);
+        tc::tmem_ld_wait();
+        const int n_here = min(32, used - c * 32);
+        const unsigned int valid = n_here == 32 ? 0xffffffffu : (1u << n_here) - 1u;
+        unsigned int sb = __ldg(starts + c) & valid;
+        if (sb == 0u && n_here == 32) {  // the whole chunk continues the current video: branch-free max tree
+          cur = fmaxf(cur, max32(r));
+        } else {  // walk the video segments of this chunk (all conditions are uniform over the CTA)
+          int pos = 0;
+          while (true) {
+            const int nxt = sb ? __ffs(sb) - 1 : n_here;  // next video start, or end of the used columns
+            if (nxt > pos) {
+              const unsigned int seg = (nxt == 32 ? 0xffffffffu : (1u << nxt) - 1u) & ~((1u << pos) - 1u);
+              cur = fmaxf(cur, masked_max32(r, seg));
             }
+            if (nxt >= n_here) break;
+            flush();  // a new video starts at column nxt
+            ++j;
+            cur = MASK_FILL;
+            pos = nxt;
+            sb &= sb - 1u;
           }
         }
-        tc::epi_release(pipe, unit);  // all TMEM reads of this accumulator are done
-        flush();
       }
+      tc::epi_release(pipe, unit);  // all TMEM reads of this accumulator are done
+      flush();
     }
   }
   tc::pipe_teardown(tmem_base);
@@ -323,13 +349,15 @@ int xmlb_make_tmap_2d_u16(CUtensorMap* out, const void* base, unsigned long long
   EncodeTiledFn fn = get_encode_fn();
   XMLB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   XMLB_REQUIRE(((uintptr_t)base & 15) == 0 && (cols * 2) % 16 == 0, "tensor map: base/pitch must be 16-byte aligned");
-  XMLB_REQUIRE(box_cols * 2 == 128 && box_rows >= 1 && box_rows <= 256, "tensor map: bad box");
+  XMLB_REQUIRE((box_cols == 64 || box_cols == 32) && box_rows >= 1 && box_rows <= 256, "tensor map: bad box");
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   XMLB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return XMLB_OK;
@@ -375,9 +403,10 @@ extern "C" int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned sh
                                  const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                                  const unsigned short* c_hi_b, const unsigned short* c_lo_b,
                                  const unsigned int* mask_bits_a, const unsigned int* mask_bits_b, float* q2c,
-                                 int n_queries, int n_videos, int lp, int kpad, int is_bf16, int max_ctas,
-                                 void* stream) {
-  XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && mask_bits_a && q2c, "xmlb_vr_scores_tc: null pointer");
+                                 int* sched_ws, int n_queries, int n_videos, int lp, int kpad, int is_bf16,
+                                 int max_ctas, void* stream) {
+  XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && mask_bits_a && q2c && sched_ws,
+               "xmlb_vr_scores_tc: null pointer");
   const bool two = q_hi_b != nullptr;
   XMLB_REQUIRE(!two || (q_lo_b && c_hi_b && c_lo_b && mask_bits_b), "xmlb_vr_scores_tc: incomplete second modality");
   XMLB_REQUIRE(lp >= 32 && lp <= 256 && lp % 32 == 0, "xmlb_vr_scores_tc: lp must be a multiple of 32 in [32, 256]");
@@ -395,6 +424,7 @@ extern "C" int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned sh
   p.n_tiles = ceil_div(n_videos, p.vpt);
   p.mask_bits[0] = mask_bits_a, p.mask_bits[1] = mask_bits_b;
   p.out = q2c;
+  p.tile_counter = sched_ws;
   p.divisor = (float)p.n_mod;
   p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
   p.stages = tc::pipe_stages(p.block_n, 0);
@@ -425,6 +455,7 @@ extern "C" int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned sh
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   const long long total = (long long)p.m_tiles * p.n_tiles;
   if (total < grid) grid = (int)total;
+  XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
   XMLB_CUDA(cudaFuncSetAttribute(vr_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vr_scores_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
   xmlb_count_launch(1);
@@ -436,10 +467,11 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
                                         const unsigned short* q_hi_b, const unsigned short* q_lo_b,
                                         const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                                         const unsigned short* c_hi_b, const unsigned short* c_lo_b,
-                                        const int* tile_meta, const unsigned int* tile_starts, const int* order,
-                                        float* q2c, int n_queries, int n_videos, long long n_packed_rows, int n_tiles,
+                                        const int* tile_meta, const unsigned int* tile_starts, float* q2c,
+                                        int* sched_ws, int n_queries, int n_videos, long long n_packed_rows,
+                                        int n_tiles,
                                         int kpad, int is_bf16, int max_ctas, void* stream) {
-  XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && tile_meta && tile_starts && order && q2c,
+  XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && tile_meta && tile_starts && q2c && sched_ws,
                "xmlb_vr_scores_tc_packed: null pointer");
   const bool two = q_hi_b != nullptr;
   XMLB_REQUIRE(!two || (q_lo_b && c_hi_b && c_lo_b), "xmlb_vr_scores_tc_packed: incomplete second modality");
@@ -451,8 +483,9 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   p.m_tiles = ceil_div(n_queries, BLOCK_M);
   p.k_blocks = kpad / BLOCK_K;
   p.n_mod = two ? 2 : 1;
-  p.tile_meta = tile_meta, p.tile_starts = tile_starts, p.order = order;
+  p.tile_meta = tile_meta, p.tile_starts = tile_starts;
   p.out = q2c;
+  p.tile_counter = sched_ws;
   p.divisor = (float)p.n_mod;
   p.idesc = tc::idesc_f16(BLOCK_M, 256, is_bf16 ? 1 : 0);
   p.stages = tc::pipe_stages(256, PACKED_EXTRA_SMEM);
@@ -481,6 +514,7 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   const long long total = (long long)p.m_tiles * p.n_tiles;
   if (total < grid) grid = (int)total;
+  XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
   XMLB_CUDA(cudaFuncSetAttribute(vr_scores_tc_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vr_scores_tc_packed_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
   xmlb_count_launch(1);

@@ -92,7 +92,9 @@ class CorpusPacking:
         self.tile_starts = torch.from_numpy(starts.view(np.int32)).to(dev)
         self.order = torch.from_numpy(order.astype(np.int32)).to(dev)
         empty = np.nonzero(lens == 0)[0]
-        self.empty_ids = torch.from_numpy(empty).to(dev) if len(empty) else None
+        self.n_packed = len(order)
+        # ordinal -> video id for every column of the score matrix (videos without valid clips come last)
+        self.order_full = torch.from_numpy(np.concatenate([order, empty]).astype(np.int32)).to(dev)
         self.fill = self.n_rows / max(1, self.n_tiles * self.TILE)
 
 
@@ -197,7 +199,16 @@ class VCMRSearcher:
     def encode_queries(self, query_feat, query_mask):
         return self.model.encode_query(query_feat, query_mask)
 
-    def video_scores(self, video_query, sub_query):
+    def score_ids(self):
+        """Column -> (global) video id table of video_scores(ordinal=True), or None when columns are video ids."""
+        ix = self.index
+        if ix.packing is None:
+            return None
+        return ix.packing.order_full + ix.vid_lo if ix.vid_lo else ix.packing.order_full
+
+    def video_scores(self, video_query, sub_query, ordinal=False):
+        """(Nq, Nv) video-level scores.  ordinal=True leaves the columns in the kernel's native order (see
+        score_ids) instead of re-ordering them by video id -- what the top-k that follows wants."""
         ix, m = self.index, self.model
         if ix.precision != "f32":
             bf16 = ix.precision == "bf16x3"
@@ -207,7 +218,8 @@ class VCMRSearcher:
                                                  (ops_q[1], ix.sub_tc, ix.sub_bits)) if q is not None]
             a, b = streams[0], (streams[1] if len(streams) == 2 else (None, None, None))
             if ix.packing is not None:
-                return ops.vr_scores_tc_packed(a[0], a[1], ix.packing, ix.n_videos, q_b=b[0], c_b=b[1], bf16=bf16)
+                return ops.vr_scores_tc_packed(a[0], a[1], ix.packing, ix.n_videos, q_b=b[0], c_b=b[1], bf16=bf16,
+                                               ordinal=ordinal)
             return ops.vr_scores_tc(a[0], a[1], a[2], ix.n_videos, ix.lp, q_b=b[0], c_b=b[1], bits_b=b[2], bf16=bf16)
         return ops.vr_scores_f32(
             ops.l2norm_rows(video_query) if m.use_video else None, ops.l2norm_rows(sub_query) if m.use_sub else None,
@@ -268,10 +280,10 @@ class VCMRSearcher:
             video_query, sub_query = self.encode_queries(query_feat, query_mask)
         if "VR" in tasks or "VCMR" in tasks:
             with self._phase("vr_scores"):
-                q2c = self.video_scores(video_query, sub_query)
+                q2c = self.video_scores(video_query, sub_query, ordinal=True)
             with self._phase("topk_videos"):
                 res.top_video_idx, res.top_video_score = ops.topk_rows(q2c, self.max_n_videos, alpha=self.q2c_alpha,
-                                                                       apply_exp=True)
+                                                                       apply_exp=True, ids=self.score_ids())
         if "VCMR" in tasks:
             with self._phase("pair_lists"):
                 lists = self.span_lists(res.top_video_idx)

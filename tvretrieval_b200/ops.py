@@ -46,6 +46,12 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def _sched_ws(device):
+    """One int of device scratch for the dynamic tile scheduler of a tensor-core kernel (zeroed by the kernel's
+    entry point, on the launch stream)."""
+    return torch.empty(1, device=device, dtype=torch.int32)
+
+
 def add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
     """LayerNorm(x + add[row % add_rows]) over the last dim."""
     x = _f32(x, "x")
@@ -124,7 +130,8 @@ def linear(x, weight, bias=None, residual=None, relu=False):
         w_hi, w_lo = _weight_split(weight, bf16)
         x_hi, x_lo = split_rows(x, kpad=w_hi.shape[1], bf16=bf16)
         rc = _lib.lib().xmlb_linear_tc(_p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo), _p(_f32(bias, "bias")), _p(residual),
-                                       _p(out), rows, out_dim, w_hi.shape[1], int(relu), int(bf16), _stream())
+                                       _p(out), _p(_sched_ws(x.device)), rows, out_dim, w_hi.shape[1], int(relu),
+                                       int(bf16), _stream())
         _lib.check(rc, "xmlb_linear_tc")
         return out
     rc = _lib.lib().xmlb_linear(_p(x), _p(weight), _p(_f32(bias, "bias")), _p(residual), _p(out), rows, out_dim,
@@ -244,26 +251,32 @@ def vr_scores_tc(q_a, c_a, bits_a, n_videos, lp, q_b=None, c_b=None, bits_b=None
     qb = q_b if q_b is not None else (None, None)
     cb = c_b if c_b is not None else (None, None)
     rc = _lib.lib().xmlb_vr_scores_tc(_p(q_a[0]), _p(q_a[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
-                                      _p(cb[1]), _p(bits_a), _p(bits_b), _p(out), nq, n_videos, lp, kpad, int(bf16),
-                                      max_ctas, _stream())
+                                      _p(cb[1]), _p(bits_a), _p(bits_b), _p(out), _p(_sched_ws(out.device)), nq,
+                                      n_videos, lp, kpad, int(bf16), max_ctas, _stream())
     _lib.check(rc, "xmlb_vr_scores_tc")
     return out
 
 
-def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=False, max_ctas=0):
-    """tcgen05 video-level scores on the packed (valid clips only) corpus; `packing` = engine.CorpusPacking."""
+def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=False, max_ctas=0, ordinal=False):
+    """tcgen05 video-level scores on the packed (valid clips only) corpus; `packing` = engine.CorpusPacking.
+    The kernel writes the scores in packed-ordinal order (adjacent columns per tile).  ordinal=True returns that
+    layout, (Nq, Nv) with column o <-> video packing.order_full[o]; ordinal=False re-orders to video ids."""
     nq, kpad = q_a[0].shape
     out = torch.empty(nq, n_videos, device=q_a[0].device, dtype=torch.float32)
     qb = q_b if q_b is not None else (None, None)
     cb = c_b if c_b is not None else (None, None)
     rc = _lib.lib().xmlb_vr_scores_tc_packed(
         _p(q_a[0]), _p(q_a[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]), _p(cb[1]),
-        _p(packing.tile_meta), _p(packing.tile_starts), _p(packing.order), _p(out), nq, n_videos, packing.n_rows,
-        packing.n_tiles, kpad, int(bf16), max_ctas, _stream())
+        _p(packing.tile_meta), _p(packing.tile_starts), _p(out), _p(_sched_ws(out.device)), nq, n_videos,
+        packing.n_rows, packing.n_tiles, kpad, int(bf16), max_ctas, _stream())
     _lib.check(rc, "xmlb_vr_scores_tc_packed")
-    if packing.empty_ids is not None:
-        out[:, packing.empty_ids] = -1e10  # videos without a valid clip (reference: every clip masked -> -1e10)
-    return out
+    if packing.n_packed < n_videos:
+        out[:, packing.n_packed:] = -1e10  # videos without a valid clip (reference: every clip masked -> -1e10)
+    if ordinal:
+        return out
+    by_id = torch.empty_like(out)
+    by_id[:, packing.order_full.long()] = out
+    return by_id
 
 
 class PairLists:
@@ -316,7 +329,7 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
                                        _p(w_st), _p(w_ed), w_st.numel(), int(softmax), n_videos, ctx_len, kcat,
                                        lists.entry_q.numel(), lists.chunk, _p(units),
                                        lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
-                                       _p(st), _p(ed), int(bf16), _stream())
+                                       _p(st), _p(ed), _p(_sched_ws(dev)), int(bf16), _stream())
     _lib.check(rc, "xmlb_span_probs_tc")
     return st, ed
 
@@ -355,12 +368,16 @@ def span_logits(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b=None, feat2_b=None, ma
 
 
 def topk_rows(values, k, alpha=1.0, apply_exp=False, ids=None, tie_desc=False):
-    """-> (idx int32 (R, k), val fp32 (R, k)) ranked by (value desc, id asc)."""
+    """-> (idx int32 (R, k), val fp32 (R, k)) ranked by (value desc, id asc).  ids: None (column index), (R, C)
+    per-row ids or a 1-D (C,) table shared by all rows."""
     values = _f32(values, "values")
     n_rows, n_cols = values.shape
     out_idx = torch.empty(n_rows, k, device=values.device, dtype=torch.int32)
     out_val = torch.empty(n_rows, k, device=values.device, dtype=torch.float32)
-    rc = _lib.lib().xmlb_topk_rows(_p(values), _p(_i32(ids, "ids")), n_rows, n_cols, k, alpha, int(apply_exp),
+    ids = _i32(ids, "ids")
+    shared = ids is not None and ids.dim() == 1
+    assert ids is None or ids.numel() == (n_cols if shared else n_rows * n_cols)
+    rc = _lib.lib().xmlb_topk_rows(_p(values), _p(ids), int(shared), n_rows, n_cols, k, alpha, int(apply_exp),
                                    int(tie_desc), _p(out_idx), _p(out_val), _stream())
     _lib.check(rc, "xmlb_topk_rows")
     return out_idx, out_val
