@@ -305,15 +305,35 @@ class VCMRSearcher:
 
     # ---- host-buffer entry point (the e2e path bench.py times) --------------------------------------
     def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR")):
-        """Pinned host buffers in, numpy arrays out; H2D/D2H copies are part of the call."""
+        """Pinned host buffers in, numpy arrays out; H2D/D2H copies are part of the call.  The query chunks are
+        uploaded on a side stream so that the copy of chunk i+1 overlaps the search of chunk i."""
         dev = self.index.device
-        qf = query_feat_cpu.to(dev, non_blocking=True)
-        qm = query_mask_cpu.to(dev, non_blocking=True)
-        gt = None if gt_video_idx_cpu is None else gt_video_idx_cpu.to(dev, non_blocking=True)
-        res = self.search(qf, qm, gt, tasks)
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        copy = self._copy_stream
+        copy.wait_stream(main)
+        staged = []
+        n = len(query_feat_cpu)
+        for lo in range(0, n, self.query_chunk):
+            hi = min(n, lo + self.query_chunk)
+            with torch.cuda.stream(copy):
+                qf = query_feat_cpu[lo:hi].to(dev, non_blocking=True)
+                qm = query_mask_cpu[lo:hi].to(dev, non_blocking=True)
+                gt = None if gt_video_idx_cpu is None else gt_video_idx_cpu[lo:hi].to(dev, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            staged.append((qf, qm, gt, ready))
+        outs = []
+        for qf, qm, gt, ready in staged:
+            main.wait_event(ready)
+            for t in (qf, qm, gt):
+                if t is not None:
+                    t.record_stream(main)
+            outs.append(self._search_chunk(qf, qm, gt, tasks))
         out = {}
         for s in SearchResult.__slots__:
-            t = getattr(res, s)
-            if t is not None:
+            if getattr(outs[0], s) is not None:
+                t = getattr(outs[0], s) if len(outs) == 1 else torch.cat([getattr(o, s) for o in outs])
                 out[s] = t.cpu().numpy()
         return out
