@@ -245,14 +245,14 @@ def run_ours(args):
 
     with torch.no_grad():
         # ---- device-resident timing ----
+        sampler = ClockSampler(local_rank)
+        sampler.start()  # nvidia-smi needs ~0.2 s to start: begin before the warm-up so short runs get samples
         for _ in range(args.warmup):
             searcher.search(qf, qm)
         timer = PhaseTimer()
         searcher.timer = timer
-        sampler = ClockSampler(local_rank)
         barrier()
         launches0 = _lib.launch_count()
-        sampler.start()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if args.cuda_profiler:
             torch.cuda.profiler.start()

@@ -107,12 +107,15 @@ int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned short* q_lo_a
  * tile's first video, used columns, number of videos (<= 32)}; tile_starts (n_tiles, 8) = 256-bit map of columns
  * where a video starts.  q2c (n_queries, n_videos) is written in PACKED ORDINAL order: column o is the o-th packed
  * video (the caller keeps the ordinal -> video id table and passes it to xmlb_topk_rows as shared ids); columns of
- * videos that are not packed (no valid clip) are not written.  Both modalities share the packing (same masks). */
+ * videos that are not packed (no valid clip) are not written.  Both modalities share the packing (same masks).
+ * hi_only != 0 evaluates only the hi*hi products (1 MMA per k-step): an APPROXIMATE score, |error| <= 2^-11 for
+ * fp16 halves of unit vectors, used as the candidate filter of the two-pass search (xmlb_vr_rescore_tc). */
 int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short* q_lo_a, const unsigned short* q_hi_b,
                              const unsigned short* q_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                              const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* tile_meta,
                              const unsigned int* tile_starts, float* q2c, int* sched_ws, int n_queries, int n_videos,
-                             long long n_packed_rows, int n_tiles, int kpad, int is_bf16, int max_ctas, void* stream);
+                             long long n_packed_rows, int n_tiles, int hi_only, int kpad, int is_bf16, int max_ctas,
+                             void* stream);
 
 /* Tensor-core variant of xmlb_linear (same contract, model_components.py:160-163,278-280,314): x_* (rows, kpad)
  * and w_* (out_dim, kpad) are the 16-bit (hi, lo) halves produced by xmlb_split_rows (normalize = 0).

@@ -49,6 +49,11 @@ def _worker(rank, world, port, use_nccl, precision):
             a, b = getattr(got, name), getattr(want, name)
             assert torch.equal(a, b), "rank %d: %s differs from the single-GPU result" % (rank, name)
         assert (want.span_score[:, 0] > 0).all()
+        # host-buffer entry point: every rank uploads only its query slice
+        host = ShardedSearcher(model, shard, n_videos_total=n_videos, **kw).search_host(qf.cpu(), qm.cpu(), gt.cpu(),
+                                                                                        tasks)
+        for name in ("top_video_idx", "span_flat_idx", "span_score", "svmr_flat_idx"):
+            assert (torch.from_numpy(host[name]) == getattr(want, name).cpu()).all(), name
     finally:
         dist.destroy_process_group()
 

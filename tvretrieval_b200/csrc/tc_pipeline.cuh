@@ -49,6 +49,7 @@ struct Pipe {
   uint32_t smem_base;   // 1024-aligned start of the stage ring
   uint32_t bar_base;
   int stages, stage_bytes, b_tile_bytes;
+  int terms;  // 3: split precision (hi*lo + lo*hi + hi*hi, stage = A_hi|A_lo|B_hi|B_lo); 1: hi*hi only (A_hi|B_hi)
   __device__ uint32_t full_bar(int s) const { return bar_base + 8u * s; }
   __device__ uint32_t empty_bar(int s) const { return bar_base + 8u * (stages + s); }
   __device__ uint32_t tfull_bar(int a) const { return bar_base + 8u * (2 * stages + a); }
@@ -60,22 +61,26 @@ struct Pipe {
   __device__ uint32_t extra() const { return bar_base + PIPE_FIXED_BYTES; }       // kernel-specific scratch
 };
 
-__host__ __device__ inline int pipe_stage_bytes(int block_n) { return 2 * A_TILE_BYTES + 2 * block_n * BLOCK_K * 2; }
+__host__ __device__ inline int pipe_stage_bytes(int block_n, int terms = 3) {
+  return (terms == 3 ? 2 : 1) * (A_TILE_BYTES + block_n * BLOCK_K * 2);
+}
 // number of ring stages that fit next to `extra_bytes` of kernel-specific shared memory
-inline int pipe_stages(int block_n, int extra_bytes) {
-  const int s = (SMEM_LIMIT - 1024 - PIPE_FIXED_BYTES - extra_bytes) / pipe_stage_bytes(block_n);
+inline int pipe_stages(int block_n, int extra_bytes, int terms = 3) {
+  const int s = (SMEM_LIMIT - 1024 - PIPE_FIXED_BYTES - extra_bytes) / pipe_stage_bytes(block_n, terms);
   return s > MAX_STAGES ? MAX_STAGES : s;
 }
-inline size_t pipe_smem_bytes(int block_n, int stages, int extra_bytes) {
-  return 1024 + (size_t)stages * pipe_stage_bytes(block_n) + PIPE_FIXED_BYTES + extra_bytes;
+inline size_t pipe_smem_bytes(int block_n, int stages, int extra_bytes, int terms = 3) {
+  return 1024 + (size_t)stages * pipe_stage_bytes(block_n, terms) + PIPE_FIXED_BYTES + extra_bytes;
 }
 
 // Called by all 192 threads at kernel start.  Returns the TMEM base address.
-__device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw, int stages, int block_n) {
+__device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw, int stages, int block_n,
+                                               int terms = 3) {
   p.smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   p.stages = stages;
+  p.terms = terms;
   p.b_tile_bytes = block_n * BLOCK_K * 2;
-  p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.b_tile_bytes;
+  p.stage_bytes = (terms == 3 ? 2 : 1) * (A_TILE_BYTES + p.b_tile_bytes);
   p.bar_base = p.smem_base + stages * p.stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -144,10 +149,15 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
       mbar_wait(p.empty_bar(stage), phase ^ 1u);
       const uint32_t sa = p.smem_base + stage * p.stage_bytes;
       mbar_expect_tx(p.full_bar(stage), (uint32_t)p.stage_bytes);
-      tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
-      tma_load_2d(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row);
-      tma_load_2d(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
-      tma_load_2d(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+      if (p.terms == 3) {
+        tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+        tma_load_2d(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+        tma_load_2d(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+        tma_load_2d(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+      } else {
+        tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+        tma_load_2d(sa + A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+      }
       if (++stage == p.stages) stage = 0, phase ^= 1u;
     }
   }
@@ -170,15 +180,26 @@ __device__ __forceinline__ void tc_mma_loop(const Pipe& p, uint32_t tmem_base) {
       mbar_wait(p.full_bar(stage), phase);
       fence_after_sync();
       const uint32_t sa = p.smem_base + stage * p.stage_bytes;
-      const uint64_t a_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa), a_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + A_TILE_BYTES);
-      const uint64_t b_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES);
-      const uint64_t b_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES + p.b_tile_bytes);
+      if (p.terms == 3) {
+        const uint64_t a_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa);
+        const uint64_t a_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + A_TILE_BYTES);
+        const uint64_t b_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES);
+        const uint64_t b_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES + p.b_tile_bytes);
 #pragma unroll
-      for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-        const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);  // advance 32 B inside the swizzle row
-        umma_f16(tmem_acc, a_hi + off, b_lo + off, idesc, (kb | k) != 0);
-        umma_f16(tmem_acc, a_lo + off, b_hi + off, idesc, 1u);
-        umma_f16(tmem_acc, a_hi + off, b_hi + off, idesc, 1u);
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);  // advance 32 B inside the swizzle row
+          umma_f16(tmem_acc, a_hi + off, b_lo + off, idesc, (kb | k) != 0);
+          umma_f16(tmem_acc, a_lo + off, b_hi + off, idesc, 1u);
+          umma_f16(tmem_acc, a_hi + off, b_hi + off, idesc, 1u);
+        }
+      } else {
+        const uint64_t a_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa);
+        const uint64_t b_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa + A_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);
+          umma_f16(tmem_acc, a_hi + off, b_hi + off, idesc, (kb | k) != 0);
+        }
       }
       umma_commit(p.empty_bar(stage));  // the smem stage is reusable once these MMAs have read it
       if (++stage == p.stages) stage = 0, phase ^= 1u;

@@ -124,7 +124,7 @@ vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__
 // the TVR length distribution).  Per tile: first packed row, first packed-video ordinal, number of used columns,
 // and a 256-bit map of the columns where a new video starts.  Both modalities share the packing.
 struct VrPackedParams {
-  int n_queries, n_videos, n_tiles, m_tiles, k_blocks, n_mod, stages;
+  int n_queries, n_videos, n_tiles, m_tiles, k_blocks, n_mod, stages, terms;
   const int* tile_meta;          // [n_tiles][4]: row_start, first ordinal, used columns, number of videos
   const unsigned int* tile_starts;  // [n_tiles][8]
   float* out;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(192, 1)
 vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrPackedParams p) {
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, 256);
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, 256, p.terms);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
@@ -469,7 +469,7 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
                                         const unsigned short* c_hi_b, const unsigned short* c_lo_b,
                                         const int* tile_meta, const unsigned int* tile_starts, float* q2c,
                                         int* sched_ws, int n_queries, int n_videos, long long n_packed_rows,
-                                        int n_tiles,
+                                        int n_tiles, int hi_only,
                                         int kpad, int is_bf16, int max_ctas, void* stream) {
   XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && tile_meta && tile_starts && q2c && sched_ws,
                "xmlb_vr_scores_tc_packed: null pointer");
@@ -488,9 +488,10 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   p.tile_counter = sched_ws;
   p.divisor = (float)p.n_mod;
   p.idesc = tc::idesc_f16(BLOCK_M, 256, is_bf16 ? 1 : 0);
-  p.stages = tc::pipe_stages(256, PACKED_EXTRA_SMEM);
+  p.terms = hi_only ? 1 : 3;
+  p.stages = tc::pipe_stages(256, PACKED_EXTRA_SMEM, p.terms);
   XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_scores_tc_packed: tile does not fit in shared memory");
-  const size_t smem = tc::pipe_smem_bytes(256, p.stages, PACKED_EXTRA_SMEM);
+  const size_t smem = tc::pipe_smem_bytes(256, p.stages, PACKED_EXTRA_SMEM, p.terms);
   XMLB_REQUIRE(((uintptr_t)tile_meta & 15) == 0, "xmlb_vr_scores_tc_packed: tile_meta must be 16-byte aligned");
   VrMaps maps;
   const unsigned short* qh[2] = {q_hi_a, q_hi_b};

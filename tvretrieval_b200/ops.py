@@ -257,7 +257,8 @@ def vr_scores_tc(q_a, c_a, bits_a, n_videos, lp, q_b=None, c_b=None, bits_b=None
     return out
 
 
-def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=False, max_ctas=0, ordinal=False):
+def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=False, max_ctas=0, ordinal=False,
+                        hi_only=False):
     """tcgen05 video-level scores on the packed (valid clips only) corpus; `packing` = engine.CorpusPacking.
     The kernel writes the scores in packed-ordinal order (adjacent columns per tile).  ordinal=True returns that
     layout, (Nq, Nv) with column o <-> video packing.order_full[o]; ordinal=False re-orders to video ids."""
@@ -268,7 +269,7 @@ def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=Fa
     rc = _lib.lib().xmlb_vr_scores_tc_packed(
         _p(q_a[0]), _p(q_a[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]), _p(cb[1]),
         _p(packing.tile_meta), _p(packing.tile_starts), _p(out), _p(_sched_ws(out.device)), nq, n_videos,
-        packing.n_rows, packing.n_tiles, kpad, int(bf16), max_ctas, _stream())
+        packing.n_rows, packing.n_tiles, int(hi_only), kpad, int(bf16), max_ctas, _stream())
     _lib.check(rc, "xmlb_vr_scores_tc_packed")
     if packing.n_packed < n_videos:
         out[:, packing.n_packed:] = -1e10  # videos without a valid clip (reference: every clip masked -> -1e10)
