@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--query-chunk", type=int, default=4096)
     ap.add_argument("--precision", default="f16x3", choices=["f16x3", "bf16x3", "f32"],
                     help="video-level score kernel: tcgen05 split-precision (f16x3 / bf16x3) or exact-fp32 SIMT")
+    ap.add_argument("--one-pass", action="store_true",
+                    help="video retrieval with the one-pass split-precision kernel over all pairs (no filter pass)")
     ap.add_argument("--padded-corpus", action="store_true",
                     help="tensor-core VR kernel on the padded (Nv x L) corpus instead of the packed valid clips")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
@@ -222,11 +224,13 @@ def run_ours(args):
     qf_pin, qm_pin = qf_cpu.pin_memory(), qm_cpu.pin_memory()
     qf, qm = qf_pin.to(device), qm_pin.to(device)
 
+    two_pass = False if args.one_pass else None  # None: automatic (on for the packed f16x3 index)
     if world == 1:
-        searcher = VCMRSearcher(model, index, query_chunk=args.query_chunk)
+        searcher = VCMRSearcher(model, index, query_chunk=args.query_chunk, two_pass=two_pass)
     else:
         from tvretrieval_b200.sharding import ShardedSearcher
-        searcher = ShardedSearcher(model, index, n_videos_total=args.n_videos, query_chunk=args.query_chunk)
+        searcher = ShardedSearcher(model, index, n_videos_total=args.n_videos, query_chunk=args.query_chunk,
+                                   two_pass=two_pass)
 
     def barrier():
         torch.cuda.synchronize()
@@ -308,12 +312,20 @@ def run_ours(args):
     achieved = flops_per_step / (vr_ms_per_step / 1e3) / 1e12 if vr_ms_per_step > 0 else 0.0
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     tc_mode = args.precision != "f32"
-    kernel_name = ("vr_scores_tc_kernel (tcgen05 kind::f16, %s split: 3 MMAs per product, fp32 TMEM accumulate)"
-                   % args.precision) if tc_mode else "gemm_simt_kernel (fp32 SIMT, EPI_VRMAX)"
+    mma_per_product = 1 if (searcher.two_pass or not tc_mode) else 3
+    if searcher.two_pass:
+        kernel_name = ("vr_scores_tc_packed_kernel, filter pass of the two-pass search (tcgen05 kind::f16, hi halves "
+                       "only: 1 MMA per product over ALL pairs, fp32 TMEM accumulate; the candidates it leaves are "
+                       "re-scored exactly by vr_rescore_tc_kernel, phases vr_select/vr_rescore)")
+    elif tc_mode:
+        kernel_name = ("vr_scores_tc_packed_kernel (tcgen05 kind::f16, %s split: 3 MMAs per product, fp32 TMEM "
+                       "accumulate)" % args.precision)
+    else:
+        kernel_name = "gemm_simt_kernel (fp32 SIMT, EPI_VRMAX)"
     roofline = {"bound": "tensor", "kernel": kernel_name,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "mma_flops_executed_per_algorithmic": 3 if tc_mode else 1,
-                "frac_of_peak_executed": (3 if tc_mode else 1) * achieved / peak,
+                "mma_flops_executed_per_algorithmic": mma_per_product,
+                "frac_of_peak_executed": mma_per_product * achieved / peak,
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                 "flops_counted": ("algorithmic 2*H*S per modality per query, S = %d valid clips (packed corpus, tile fill "
                                   "%.3f); the padded corpus would be S_pad = %d" % (s_valid, index.packing.fill, s_pad))
@@ -326,7 +338,8 @@ def run_ours(args):
             "vs_baseline": None,
             "dtype": "f32 (corpus contraction: %s)" % ("16-bit hi/lo split tensor-core products, fp32 accumulate"
                                                        if tc_mode else "fp32 FMA"),
-            "data": "synthetic", "config": dict(workload_config(args, world), precision=args.precision),
+            "data": "synthetic", "config": dict(workload_config(args, world), precision=args.precision,
+                                                video_retrieval="two-pass" if searcher.two_pass else "one-pass"),
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
             "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
             "corpus_encode": {"videos_per_s": n_local / t_enc, "seconds": t_enc, "index_gb": index.nbytes() / 1e9}}

@@ -83,12 +83,15 @@ int xmlb_vr_scores_f32(const float* q_video_n, const float* q_sub_n, const float
  * regrouped from groups of group_in (clips of a video) to zero-padded groups of group_out, columns zero-padded
  * to kpad (multiple of 64); normalize != 0 applies F.normalize (model_xml.py:446-447) first.  With row_index
  * (n_groups * group_out ints, group_in = group_out = 1) output row r is taken from source row row_index[r]
- * (negative = zero row): this gathers the valid clips into the packed corpus layout.  Output row r is written at
+ * (negative = output row left untouched): this gathers the valid clips into the packed corpus layout and the
+ * queries into inverted-list order.  Output row r is written at
  * hi/lo[r * out_ld + out_col0 ...] (out_ld >= out_col0 + kpad), which lets two streams be concatenated along K.
+ * hi_err (optional, one float per output row) receives ||x - hi||_2 rounded up: by Cauchy-Schwarz the error of a
+ * product evaluated with the hi halves only is <= hi_err(a) * ||b|| + ||a_hi|| * hi_err(b) (two-pass search).
  * xmlb_mask_bits: mask (n_videos, ctx_len) float {0,1} -> bits (n_videos, lp / 32), bit l%32 of word l/32. */
 int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, int group_in, int group_out, int k,
                     int kpad, int out_ld, int out_col0, int normalize, int is_bf16, unsigned short* hi,
-                    unsigned short* lo, void* stream);
+                    unsigned short* lo, float* hi_err, void* stream);
 int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream);
 
 /* q2c[q][v] = mean over given modalities of max_{l : bit set} q[q] . c[v * lp + l]; same contract as
@@ -108,14 +111,47 @@ int xmlb_vr_scores_tc(const unsigned short* q_hi_a, const unsigned short* q_lo_a
  * where a video starts.  q2c (n_queries, n_videos) is written in PACKED ORDINAL order: column o is the o-th packed
  * video (the caller keeps the ordinal -> video id table and passes it to xmlb_topk_rows as shared ids); columns of
  * videos that are not packed (no valid clip) are not written.  Both modalities share the packing (same masks).
- * hi_only != 0 evaluates only the hi*hi products (1 MMA per k-step): an APPROXIMATE score, |error| <= 2^-11 for
- * fp16 halves of unit vectors, used as the candidate filter of the two-pass search (xmlb_vr_rescore_tc). */
+ * hi_only != 0 evaluates only the hi*hi products (1 MMA per k-step, lo halves not read): an APPROXIMATE score
+ * whose error is bounded by the hi_err outputs of xmlb_split_rows; it is the filter pass of the two-pass search
+ * (xmlb_select_candidates, xmlb_vr_rescore_tc).
+ * m_tile_list / n_m_tiles (both NULL, or device pointers): restricted mode -- only the 128-query tiles
+ * m_tile_list[0 .. *n_m_tiles) are computed (the exact fallback for rows whose candidate list overflowed). */
 int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short* q_lo_a, const unsigned short* q_hi_b,
                              const unsigned short* q_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                              const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* tile_meta,
                              const unsigned int* tile_starts, float* q2c, int* sched_ws, int n_queries, int n_videos,
-                             long long n_packed_rows, int n_tiles, int hi_only, int kpad, int is_bf16, int max_ctas,
-                             void* stream);
+                             long long n_packed_rows, int n_tiles, int hi_only, const int* m_tile_list,
+                             const int* n_m_tiles, int kpad, int is_bf16, int max_ctas, void* stream);
+
+/* ---- two-pass video retrieval: approximate filter, exact re-scoring of the survivors -------------------------
+ * The top-k videos of inference.py:347-348 are found without evaluating all (query, video) pairs at full
+ * precision: pass 1 = xmlb_vr_scores_tc_packed(hi_only = 1) (one third of the tensor-core work); then
+ *
+ * xmlb_select_candidates: per row r of approx (n_rows, n_cols), with error bound
+ *   eps[r] = err_scale * (row_err_a[r] + row_err_b[r]) + err_const        (row_err_b may be NULL)
+ * keeps every column with approx >= (k-th largest approx of the row) - 2 * eps[r] -- a superset of the exact
+ * top-k whenever |approx - exact| <= eps[r].  Outputs (n_rows, max_cand): cand_col = column, cand_id = ids[column]
+ * (ids NULL: column), cand_val = approx value; unused slots are (-1, INT_MAX, -1e10).  A row with more than
+ * max_cand survivors is truncated and FLAGGED in flag_ws (ints, zeroed by the call): [0] = number of flagged row
+ * groups (rows_per_group = 128 = query tile of the scoring kernel), [1, 1+G) group flags, [1+G, 1+2G) list of
+ * flagged groups, [1+2G, 1+2G+n_rows) row flags, G = ceil(n_rows / rows_per_group).  Flagged rows are recomputed
+ * by the restricted modes of xmlb_vr_scores_tc_packed and xmlb_topk_rows (no host round trip).
+ *
+ * xmlb_vr_rescore_tc: exact split-precision scores of the candidate pairs, same value as xmlb_vr_scores_tc_packed.
+ * Pairs are grouped per packed video through xmlb_build_pair_lists(cand_col, chunk = 128) + xmlb_build_span_units;
+ * qg_* (n_entries, kpad) = hi/lo of the normalised queries gathered in list order (xmlb_split_rows with
+ * row_index = entry_q); c_* = packed corpus; row_start (n_packed + 1) = first packed row of each packed video;
+ * cand_val[entry_out[e]] is overwritten for every list entry e.  max_len = longest video (<= 256 clips). */
+int xmlb_select_candidates(const float* approx, const int* ids, int n_rows, int n_cols, int k,
+                           const float* row_err_a, const float* row_err_b, float err_scale, float err_const,
+                           int max_cand, int rows_per_group, int* cand_col, int* cand_id, float* cand_val,
+                           int* flag_ws, void* stream);
+int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a, const unsigned short* qg_hi_b,
+                       const unsigned short* qg_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                       const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
+                       const int* units, const int* n_units, int max_units, const int* entry_out, float* cand_val,
+                       int* sched_ws, long long n_entries, long long n_packed_rows, int max_len, int kpad,
+                       int is_bf16, void* stream);
 
 /* Tensor-core variant of xmlb_linear (same contract, model_components.py:160-163,278-280,314): x_* (rows, kpad)
  * and w_* (out_dim, kpad) are the 16-bit (hi, lo) halves produced by xmlb_split_rows (normalize = 0).
@@ -168,9 +204,10 @@ int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,
 /* Per-row exact top-k, ranked (value desc, id asc | desc).  value = apply_exp ? exp(alpha * x) : x.
  * ids: optional explicit ids (NULL: column index), (n_rows, n_cols) when ids_shared == 0, one (n_cols) table shared
  * by all rows when ids_shared != 0.  Replaces torch.exp + torch.topk of
- * inference.py:317,347-348; returns an error when k > n_cols like torch.topk does.  k <= 1024. */
+ * inference.py:317,347-348; returns an error when k > n_cols like torch.topk does.  k <= 1024.
+ * row_flags (NULL or n_rows ints): restricted mode, rows whose flag is 0 are skipped (outputs left untouched). */
 int xmlb_topk_rows(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k, float alpha,
-                   int apply_exp, int tie_desc, int* out_idx, float* out_val, void* stream);
+                   int apply_exp, int tie_desc, const int* row_flags, int* out_idx, float* out_val, void* stream);
 
 /* Band-limited span scoring + exact top-k, replaces inference.py:370-386 (VCMR) and inference.py:215-224 +
  * utils/tensor_utils.py:133-141 (SVMR, n_slots = 1, video_score = NULL, tie_desc = 1):

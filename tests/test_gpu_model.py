@@ -232,6 +232,31 @@ def test_tvr_shape_video_only_svmr():
     assert (got[..., 3][tail] == 0).all()
 
 
+@pytest.mark.parametrize("precision,max_cand", [("f16x3", None), ("f16x3", 100), ("bf16x3", None)])
+def test_two_pass_search_equals_one_pass(precision, max_cand):
+    """VCMRSearcher(two_pass=True) -- hi-only filter over the corpus, exact re-scoring of the candidates, in-kernel
+    fallback for overflowed rows -- returns bit-identical results to the one-pass split-precision search."""
+    from tvretrieval_b200.engine import CorpusIndex, VCMRSearcher
+    from tvretrieval_b200.synthetic import corpus_batch, corpus_lengths, synthetic_queries
+    cfg, model, weights, ds = tvr_case("video_sub", 4, 4, 256, 64, 3072, seed=3)
+    n_videos, nq = 1300, 300
+    lens = corpus_lengths(n_videos, 64, seed=11)
+    with torch.no_grad():
+        video, sub, mask = corpus_batch(lens, 0, n_videos, 3072, 768, DEV, seed=11, video_split=2048)
+        v1, v2, s1, s2 = model.encode_context(video, mask, sub, mask)
+        index = CorpusIndex(v1, v2, mask, s1, s2, mask, precision=precision)
+        qf, qm = synthetic_queries(nq, 30, 768, seed=12)
+        qf, qm = qf.to(DEV), qm.to(DEV)
+        kw = dict(max_n_videos=100, max_before_nms=200, query_chunk=256)
+        want = VCMRSearcher(model, index, two_pass=False, **kw).search(qf, qm)
+        two = VCMRSearcher(model, index, two_pass=True, max_candidates=max_cand, **kw)
+        assert two.two_pass
+        got = two.search(qf, qm)
+    for name in ("top_video_idx", "top_video_score", "span_flat_idx", "span_score"):
+        assert torch.equal(getattr(got, name), getattr(want, name)), name
+    assert VCMRSearcher(model, index, **kw).two_pass == (precision == "f16x3")  # automatic choice
+
+
 def test_model_rejects_cpu_tensors():
     from tvretrieval_b200._lib import XmlbError
     cfg, model, weights, ds = tvr_case("video", 4, 4, 64, 16, 32, seed=3)

@@ -330,6 +330,119 @@ def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
     assert (got_st[pad_pos] == 0).all()
 
 
+def test_split_rows_hi_err(ops):
+    """hi_err = ||x - hi||_2 (rounded up): the Cauchy-Schwarz error bound of hi-only products holds."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(300, 700, generator=g)
+    x[3] *= 1e-4  # fp16 subnormal range after normalisation
+    for bf16 in (False, True):
+        hi, lo, err = ops.split_rows(x.to(DEV), kpad=704, normalize=True, bf16=bf16, hi_err=True)
+        xn = torch.nn.functional.normalize(x.double(), dim=1)
+        h = hi.view(torch.bfloat16 if bf16 else torch.float16).double().cpu()[:, :700]
+        want = (xn - h).norm(dim=1)
+        got = err.double().cpu()
+        assert (got >= want * (1 - 1e-6)).all() and (got <= want * 1.001 + 1e-9).all()
+        # bound of a hi-only dot product of two unit vectors
+        d_exact = xn[:150] @ xn[150:].T
+        d_hi = h[:150] @ h[150:].T
+        bound = got[:150, None] * 1.0 + 1.001 * got[None, 150:]
+        assert ((d_exact - d_hi).abs() <= bound).all()
+
+
+@pytest.mark.parametrize("rows,cols,k,max_cand", [(5, 300, 10, 64), (130, 2179, 100, 256), (260, 5000, 100, 128)])
+def test_select_candidates(ops, rows, cols, k, max_cand):
+    g = torch.Generator().manual_seed(rows + cols)
+    x = torch.rand(rows, cols, generator=g) * 0.12 + 0.03
+    x[1, :40] = x[1].max()  # ties at the top
+    err_a = torch.rand(rows, generator=g) * 2e-4
+    err_b = torch.rand(rows, generator=g) * 2e-4
+    if rows > 200:
+        err_a[200] = 0.05  # a row whose window holds more than max_cand columns: flagged
+        err_a[7] = 0.05
+    scale, const = 0.5, 1e-4
+    ids = torch.randperm(cols, generator=g).to(torch.int32)
+    cand = ops.select_candidates(x.to(DEV), k, err_a.to(DEV), err_b.to(DEV), scale, const, max_cand, ids=ids.to(DEV))
+    eps = (scale * (err_a + err_b) + const).double()
+    kth = torch.sort(x, dim=1, descending=True)[0][:, k - 1].double()
+    col, cid, val = cand.col.cpu(), cand.ids.cpu(), cand.val.cpu()
+    flags = cand.row_flags.cpu()
+    n_flagged_groups = int(cand.n_flagged.cpu())
+    flagged_groups = set()
+    for r in range(rows):
+        cut = kth[r] - 2 * eps[r]
+        must = set(torch.nonzero(x[r].double() >= cut + 1e-7).flatten().tolist())
+        may = set(torch.nonzero(x[r].double() >= cut - 1e-7).flatten().tolist())
+        got = [c for c in col[r].tolist() if c >= 0]
+        assert len(got) == len(set(got))
+        if len(must) > max_cand:
+            assert flags[r] == 1
+            flagged_groups.add(r // 128)
+            continue
+        if len(may) <= max_cand:
+            assert flags[r] == 0
+        if flags[r] == 0:
+            assert must <= set(got) <= may, r
+            n = len(got)
+            assert (col[r, n:] == -1).all() and (cid[r, n:] == 2 ** 31 - 1).all() and (val[r, n:] == -1e10).all()
+            assert torch.equal(cid[r, :n], ids[col[r, :n].long()]) and torch.equal(val[r, :n], x[r, col[r, :n].long()])
+    if rows > 200:
+        assert flags[200] == 1 and flags[7] == 1
+    assert n_flagged_groups == len(flagged_groups)
+    assert set(cand.flagged_groups.cpu()[:n_flagged_groups].tolist()) == flagged_groups
+
+
+@pytest.mark.parametrize("nq,nv,length,hid,both,k,max_cand", [(300, 900, 64, 256, True, 20, 20),
+                                                             (200, 1500, 128, 768, True, 100, 256),
+                                                             (150, 700, 100, 500, False, 50, 50),
+                                                             (140, 600, 256, 128, True, 30, 40)])
+def test_two_pass_top_videos(ops, nq, nv, length, hid, both, k, max_cand):
+    """hi-only filter + candidate selection + exact re-scoring (+ overflow fallback) returns exactly what the
+    one-pass split-precision kernel + top-k returns."""
+    from tvretrieval_b200.engine import CorpusPacking
+    g = torch.Generator().manual_seed(nq + nv + hid)
+    # clustered scores: a common direction plus noise, so that many videos fall inside the candidate window
+    base = torch.randn(hid, generator=g)
+    mk = lambda *shape: (0.35 * base + torch.randn(*shape, hid, generator=g)).to(DEV)  # noqa: E731
+    qv, qs, fv, fs = mk(nq), mk(nq), mk(nv, length), mk(nv, length)
+    mask = rand_mask(g, nv, length).to(DEV)
+    mask[5] = 0
+    kpad = (hid + 63) // 64 * 64
+    pk = CorpusPacking(mask)
+    ids = pk.order_full + 1000
+    cs = [ops.split_rows(f, kpad=kpad, normalize=True, row_index=pk.src_rows, hi_err=True) for f in (fv, fs)]
+    qsp = [ops.split_rows(q, kpad=kpad, normalize=True, hi_err=True) for q in (qv, qs)]
+    n_mod = 2 if both else 1
+    kw = dict(q_b=qsp[1][:2] if both else None, c_b=cs[1][:2] if both else None, ordinal=True)
+    exact = ops.vr_scores_tc_packed(qsp[0][:2], cs[0][:2], pk, nv, **kw)
+    want_idx, want_val = ops.topk_rows(exact, k, alpha=20.0, apply_exp=True, ids=ids)
+    approx = ops.vr_scores_tc_packed(qsp[0][:2], cs[0][:2], pk, nv, hi_only=True, **kw)
+    scale = 1.001 / n_mod
+    const = scale * sum(float(c[2].max()) for c in cs[:n_mod]) + 4e-5
+    bound = scale * (qsp[0][2] + (qsp[1][2] if both else 0)) + const
+    real = exact > -1e9
+    assert ((approx - exact).abs()[real] <= bound[:, None].expand_as(exact)[real]).all()
+    print("hi-only error: max %.3g, bound min %.3g" % ((approx - exact).abs()[real].max().item(), bound.min().item()))
+    cand = ops.select_candidates(approx, k, qsp[0][2], qsp[1][2] if both else None, scale, const, max_cand, ids=ids)
+    n_cand = (cand.col >= 0).sum(1)
+    print("candidates per query: mean %.1f max %d, flagged rows %d" % (n_cand.float().mean().item(), n_cand.max().item(),
+                                                                     int(cand.row_flags.sum())))
+    ops.vr_rescore_tc(qv, cs[0][:2], pk, cand, kpad, q_fp32_b=qs if both else None, c_b=cs[1][:2] if both else None)
+    ok = cand.col >= 0
+    packed = ok & (cand.col < pk.n_packed)
+    assert torch.equal(cand.val[packed], torch.gather(exact, 1, cand.col.clamp(min=0).long())[packed])
+    idx, val = ops.topk_rows(cand.val, k, alpha=20.0, apply_exp=True, ids=cand.ids)
+    clean = cand.row_flags == 0
+    assert clean.any()
+    assert torch.equal(idx[clean], want_idx[clean]) and torch.equal(val[clean], want_val[clean])
+    # overflowed rows: restricted exact pass + restricted top-k, in place
+    ops.vr_scores_tc_packed(qsp[0][:2], cs[0][:2], pk, nv, out=approx, m_tiles=(cand.flagged_groups, cand.n_flagged),
+                            **kw)
+    ops.topk_rows(approx, k, alpha=20.0, apply_exp=True, ids=ids, row_flags=cand.row_flags, out=(idx, val))
+    assert torch.equal(idx, want_idx) and torch.equal(val, want_val)
+    if max_cand == k:
+        assert int(cand.row_flags.sum()) > 0, "this case is meant to exercise the overflow fallback"
+
+
 @pytest.mark.parametrize("rows,cols,k", [(3, 100, 100), (17, 2179, 100), (4, 21793, 100), (5, 333, 7), (2, 5000, 1000)])
 def test_topk_rows(ops, rows, cols, k):
     g = torch.Generator().manual_seed(rows * cols)

@@ -43,7 +43,9 @@ def _worker(rank, world, port, use_nccl, precision):
             gt = torch.randint(0, n_videos, (nq,), generator=torch.Generator().manual_seed(1)).to(torch.int32).to(dev)
             kw = dict(max_n_videos=k_vid, max_before_nms=k_span, query_chunk=16)
             tasks = ("VCMR", "VR", "SVMR")
-            want = VCMRSearcher(model, full, **kw).search(qf, qm, gt, tasks)
+            want = VCMRSearcher(model, full, two_pass=False, **kw).search(qf, qm, gt, tasks)
+            # the shards additionally use the two-pass (filter + exact re-score) video retrieval
+            kw["two_pass"] = precision != "f32"
             got = ShardedSearcher(model, shard, n_videos_total=n_videos, **kw).search(qf, qm, gt, tasks)
         for name in ("top_video_idx", "top_video_score", "span_flat_idx", "span_score", "svmr_flat_idx", "svmr_score"):
             a, b = getattr(got, name), getattr(want, name)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_invalid_arguments_return_error_codes_not_crashes():
     from tvretrieval_b200 import _lib
     lib = _lib.lib()
-    rc = lib.xmlb_topk_rows(None, None, 0, 1, 10, 5, 1.0, 0, 0, None, None, None)
+    rc = lib.xmlb_topk_rows(None, None, 0, 1, 10, 5, 1.0, 0, 0, None, None, None, None)
     assert rc < 0 and b"null" in lib.xmlb_last_error()
     rc = lib.xmlb_span_topk(None, None, None, None, 1, 1, 8, 2, 16, 5000, 0, 1, None, None, None)
     assert rc < 0

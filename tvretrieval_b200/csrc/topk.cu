@@ -186,11 +186,12 @@ struct RowGen {
 
 __global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__ values, const int* __restrict__ ids,
                                                        int ids_shared, int n_cols, int k, float alpha, int apply_exp,
-                                                       int tie_desc,
+                                                       int tie_desc, const int* __restrict__ row_flags,
                                                        int* __restrict__ out_idx, float* __restrict__ out_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   const long long r = blockIdx.x;
+  if (row_flags && row_flags[r] == 0) return;  // restricted mode: only the flagged rows are (re)computed
   RowGen gen{values + r * n_cols, ids ? ids + (ids_shared ? 0 : r * n_cols) : nullptr, n_cols, alpha, apply_exp,
              tie_desc};
   const int n_out = block_topk(gen, sm, k);
@@ -203,6 +204,63 @@ __global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__
     } else {
       out_idx[r * k + i] = -1;
       out_val[r * k + i] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Candidate filter of the two-pass video retrieval: the scores of a row are approximations with a known error
+// bound eps.  Every column whose exact score can be among the k best satisfies approx >= (k-th largest approx)
+// - 2 eps: k columns have approx >= kth, hence exact >= kth - eps, hence the exact k-th largest is >= kth - eps,
+// and a column with exact >= kth - eps has approx >= kth - 2 eps.
+struct RawRowGen {
+  const float* row;
+  int n;
+  template <class F>
+  __device__ void for_each(F f) const {
+    for (int c = threadIdx.x; c < n; c += NT) f(float_key(__ldg(row + c)), ~(unsigned int)c);
+  }
+};
+
+__global__ void __launch_bounds__(NT) select_candidates_kernel(
+    const float* __restrict__ values, const int* __restrict__ ids, int n_rows, int n_cols, int k,
+    const float* __restrict__ err_a, const float* __restrict__ err_b, float err_scale, float err_const, int max_cand,
+    int rows_per_group, int n_groups, int* __restrict__ cand_col, int* __restrict__ cand_id,
+    float* __restrict__ cand_val, int* __restrict__ flag_ws) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
+  const long long r = blockIdx.x;
+  const float* row = values + r * n_cols;
+  RawRowGen gen{row, n_cols};
+  unsigned int thr = 0;
+  int n_equal, need_equal, n_total;
+  radix_select(gen, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k, thr,
+               n_equal, need_equal, n_total);
+  const float eps = fmaf(err_scale, __ldg(err_a + r) + (err_b ? __ldg(err_b + r) : 0.f), err_const);
+  const float cut = __fmaf_rd(-2.f, eps, key_float(thr));
+  if (threadIdx.x == 0) sm.count = 0;
+  __syncthreads();
+  int* cc = cand_col + r * max_cand;
+  int* ci = cand_id + r * max_cand;
+  float* cv = cand_val + r * max_cand;
+  for (int c = threadIdx.x; c < n_cols; c += NT) {
+    const float x = __ldg(row + c);
+    if (x >= cut) {
+      const int pos = atomicAdd(&sm.count, 1);
+      if (pos < max_cand) cc[pos] = c, ci[pos] = ids ? __ldg(ids + c) : c, cv[pos] = x;
+    }
+  }
+  __syncthreads();
+  const int n = sm.count;
+  for (int i = min(n, max_cand) + threadIdx.x; i < max_cand; i += NT) cc[i] = -1, ci[i] = 0x7fffffff, cv[i] = MASK_FILL;
+  if (threadIdx.x == 0) {
+    // flag_ws: [0] number of flagged groups, [1, 1+G) group flags, [1+G, 1+2G) list of flagged groups,
+    // [1+2G, 1+2G+rows) row flags
+    const bool overflow = n > max_cand;
+    flag_ws[1 + 2 * n_groups + r] = overflow ? 1 : 0;
+    if (overflow) {
+      const int g = (int)(r / rows_per_group);
+      if (atomicExch(flag_ws + 1 + g, 1) == 0) flag_ws[1 + n_groups + atomicAdd(flag_ws, 1)] = g;
     }
   }
 }
@@ -339,15 +397,39 @@ static int check_topk_args(const char* who, int k) {
   return XMLB_OK;
 }
 
+extern "C" int xmlb_select_candidates(const float* approx, const int* ids, int n_rows, int n_cols, int k,
+                                      const float* row_err_a, const float* row_err_b, float err_scale,
+                                      float err_const, int max_cand, int rows_per_group, int* cand_col, int* cand_id,
+                                      float* cand_val, int* flag_ws, void* stream) {
+  XMLB_REQUIRE(approx && row_err_a && cand_col && cand_id && cand_val && flag_ws,
+               "xmlb_select_candidates: null pointer");
+  if (int rc = check_topk_args("xmlb_select_candidates", k)) return rc;
+  XMLB_REQUIRE(n_cols >= k && max_cand >= k, "xmlb_select_candidates: need k <= max_cand and k <= n_cols");
+  XMLB_REQUIRE(rows_per_group >= 1 && err_scale >= 0.f && err_const >= 0.f, "xmlb_select_candidates: bad argument");
+  const int n_groups = ceil_div(n_rows, rows_per_group);
+  XMLB_CUDA(cudaMemsetAsync(flag_ws, 0, sizeof(int) * (size_t)(1 + 2 * n_groups), (cudaStream_t)stream));
+  if (n_rows == 0) return XMLB_OK;
+  XMLB_CUDA(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(SelSmem)));
+  select_candidates_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(
+      approx, ids, n_rows, n_cols, k, row_err_a, row_err_b, err_scale, err_const, max_cand, rows_per_group, n_groups,
+      cand_col, cand_id, cand_val, flag_ws);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
 extern "C" int xmlb_topk_rows(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k,
-                              float alpha, int apply_exp, int tie_desc, int* out_idx, float* out_val, void* stream) {
+                              float alpha, int apply_exp, int tie_desc, const int* row_flags, int* out_idx,
+                              float* out_val, void* stream) {
   XMLB_REQUIRE(values && out_idx && out_val, "xmlb_topk_rows: null pointer");
   if (int rc = check_topk_args("xmlb_topk_rows", k)) return rc;
   XMLB_REQUIRE(n_cols >= k, "xmlb_topk_rows: selected index k out of range (k=%d > %d columns)", k, n_cols);
   if (n_rows == 0) return XMLB_OK;
   XMLB_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
   topk_rows_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(values, ids, ids_shared, n_cols, k, alpha,
-                                                                        apply_exp, tie_desc, out_idx, out_val);
+                                                                        apply_exp, tie_desc, row_flags, out_idx,
+                                                                        out_val);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

@@ -129,6 +129,9 @@ struct VrPackedParams {
   const unsigned int* tile_starts;  // [n_tiles][8]
   float* out;
   int* tile_counter;  // zeroed before the launch
+  // restricted mode (fallback of the two-pass search): only the query tiles m_tile_list[0 .. *n_m_tiles) are computed
+  const int* m_tile_list;
+  const int* n_m_tiles;
   float divisor;
   unsigned int idesc;
 };
@@ -161,19 +164,23 @@ __device__ __forceinline__ float masked_max32(const uint32_t (&r)[32], unsigned 
 struct VrPackedSched {
   const VrMaps* maps;
   const VrPackedParams* p;
-  int tile, mod;
-  __device__ VrPackedSched(const VrMaps* m, const VrPackedParams* pp) : maps(m), p(pp), tile(0), mod(0) {}
+  int m_tiles, m_tile, n_tile, mod;
+  __device__ VrPackedSched(const VrMaps* m, const VrPackedParams* pp)
+      : maps(m), p(pp), m_tiles(pp->m_tile_list ? __ldg(pp->n_m_tiles) : pp->m_tiles), m_tile(0), n_tile(0), mod(0) {}
   __device__ bool next(tc::UnitDesc& u) {
     if (mod == 0) {
-      tile = atomicAdd(p->tile_counter, 1);
-      if (tile >= p->m_tiles * p->n_tiles) return false;
+      if (m_tiles <= 0) return false;
+      const int tile = atomicAdd(p->tile_counter, 1);
+      if (tile >= m_tiles * p->n_tiles) return false;
+      m_tile = tile % m_tiles, n_tile = tile / m_tiles;  // query tile fastest: the corpus tile is shared through L2
+      if (p->m_tile_list) m_tile = __ldg(p->m_tile_list + m_tile);
     }
     u.a_hi = &maps->a_hi[mod], u.a_lo = &maps->a_lo[mod], u.b_hi = &maps->b_hi[mod], u.b_lo = &maps->b_lo[mod];
-    u.a_row = (tile % p->m_tiles) * BLOCK_M;
-    u.b_row = __ldg(p->tile_meta + 4 * (tile / p->m_tiles));
+    u.a_row = m_tile * BLOCK_M;
+    u.b_row = __ldg(p->tile_meta + 4 * n_tile);
     u.k_blocks = p->k_blocks;
     u.idesc = p->idesc;
-    u.tag0 = tile, u.tag1 = mod;
+    u.tag0 = n_tile, u.tag1 = m_tile * 2 + mod;
     if (++mod == p->n_mod) mod = 0;
     return true;
   }
@@ -198,9 +205,9 @@ vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_con
     const uint32_t best_s = pipe.extra();  // float [128][MAX_TILE_VIDEOS + 1]
     const int row = (warp & 3) * 32 + lane;
     const uint32_t my_best = best_s + (uint32_t)row * (MAX_TILE_VIDEOS + 1) * 4;
-    int tile, mod;
-    for (uint32_t unit = 0; tc::epi_next(pipe, unit, tile, mod); ++unit) {
-      const int m_tile = tile % p.m_tiles, n_tile = tile / p.m_tiles;
+    int n_tile, tag1;
+    for (uint32_t unit = 0; tc::epi_next(pipe, unit, n_tile, tag1); ++unit) {
+      const int m_tile = tag1 >> 1, mod = tag1 & 1;
       const int q = m_tile * BLOCK_M + row;
       const bool q_ok = q < p.n_queries;
       const int4 meta = __ldg(reinterpret_cast<const int4*>(p.tile_meta) + n_tile);  // row, first ordinal, used, n videos
@@ -259,6 +266,87 @@ vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Exact (split-precision) re-scoring of the candidate (query, video) pairs of the two-pass search.  Grouped GEMM
+// over inverted lists: one unit = one packed video x up to 128 of the queries that kept it as a candidate, per
+// modality.  A = the queries gathered in list order (xmlb_split_rows with row_index = entry_q), B = the video's
+// clips in the packed corpus (the tile is loaded with a fixed box of block_n rows; columns beyond the video's
+// length belong to the next videos and are ignored).  Same arithmetic per product as the one-pass kernel.
+struct VrRescoreParams {
+  int n_mod, k_blocks, stages, block_n;
+  const int4* units;     // {packed ordinal, first list entry, entries in this chunk, 0}
+  const int* n_units;    // device scalar
+  const int* entry_out;  // [E] slot (row * max_cand + position) of each list entry
+  const int* row_start;  // [n_packed + 1] first packed row of each ordinal
+  float* out;            // candidate scores, indexed by entry_out
+  int* unit_counter;     // zeroed before the launch
+  float divisor;
+  unsigned int idesc;
+};
+
+struct VrRescoreSched {
+  const VrMaps* maps;
+  const VrRescoreParams* p;
+  int n_units, u, mod;
+  int4 m;
+  __device__ VrRescoreSched(const VrMaps* mp, const VrRescoreParams* pp)
+      : maps(mp), p(pp), n_units(__ldg(pp->n_units)), u(0), mod(0) {}
+  __device__ bool next(tc::UnitDesc& d) {
+    if (mod == 0) {
+      u = atomicAdd(p->unit_counter, 1);
+      if (u >= n_units) return false;
+      m = __ldg(p->units + u);
+    }
+    d.a_hi = &maps->a_hi[mod], d.a_lo = &maps->a_lo[mod], d.b_hi = &maps->b_hi[mod], d.b_lo = &maps->b_lo[mod];
+    d.a_row = m.y;
+    d.b_row = __ldg(p->row_start + m.x);
+    d.k_blocks = p->k_blocks;
+    d.idesc = p->idesc;
+    d.tag0 = u, d.tag1 = mod;
+    if (++mod == p->n_mod) mod = 0;
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(192, 1)
+vr_rescore_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrRescoreParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  tc::Pipe pipe;
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (lane == 0) tc::tc_producer_loop(VrRescoreSched(&maps, &p), pipe);
+  } else if (warp == 1) {
+    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+  } else {  // ===================== epilogue warps 2..5: one thread = one listed query =====================
+    const int row = (warp & 3) * 32 + lane;
+    float first = 0.f;
+    int u, mod;
+    for (uint32_t unit = 0; tc::epi_next(pipe, unit, u, mod); ++unit) {
+      const int4 m = __ldg(p.units + u);
+      const int len = __ldg(p.row_start + m.x + 1) - __ldg(p.row_start + m.x);
+      const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
+      float cur = MASK_FILL;
+      for (int c = 0; c * 32 < len; ++c) {  // warp-uniform
+        uint32_t r[32];
+        tc::tmem_ld_32x32(taddr + c * 32, r);
+        tc::tmem_ld_wait();
+        const int n_here = len - c * 32;
+        cur = fmaxf(cur, n_here >= 32 ? max32(r) : masked_max32(r, (1u << n_here) - 1u));
+      }
+      tc::epi_release(pipe, unit);
+      if (mod != p.n_mod - 1) {
+        first = cur;
+      } else if (row < m.z) {
+        const float v = mod != 0 ? __fadd_rn(first, cur) : cur;
+        p.out[__ldg(p.entry_out + m.y + row)] = __fdiv_rn(v, p.divisor);
+      }
+    }
+  }
+  tc::pipe_teardown(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // operand preparation: fp32 rows -> (optionally L2-normalised) hi/lo 16-bit rows, K padded to a multiple of 64,
 // rows regrouped from groups of `gin` to zero-padded groups of `gout` (clips of a video padded to lp).
 // One warp per output row.
@@ -281,7 +369,8 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
                                                          int kpad, int out_ld, int out_col0, int gin, int gout,
                                                          int normalize,
                                                          unsigned short* __restrict__ hi,
-                                                         unsigned short* __restrict__ lo) {
+                                                         unsigned short* __restrict__ lo,
+                                                         float* __restrict__ hi_err) {
   const int lane = threadIdx.x & 31;
   const long long ro = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (ro >= rows_out) return;
@@ -296,7 +385,9 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
     src = l < gin ? g * gin + l : -1;
   }
   if (src < 0) {
+    if (row_index) return;  // gather mode: rows without a source are left untouched (nothing reads them)
     for (int i = lane; i < kpad; i += 32) h[i] = 0, o[i] = 0;
+    if (hi_err && lane == 0) hi_err[ro] = 0.f;
     return;
   }
   const float* xr = x + src * k;
@@ -306,10 +397,20 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
     for (int i = lane; i < k; i += 32) s = fmaf(xr[i], xr[i], s);
     denom = fmaxf(sqrtf(warp_sum(s)), 1e-12f);  // F.normalize eps
   }
+  float err2 = 0.f;
   for (int i = lane; i < kpad; i += 32) {
     unsigned short a = 0, b = 0;
-    if (i < k) split16<BF16>(normalize ? __fdiv_rn(xr[i], denom) : xr[i], a, b);
+    if (i < k) {
+      const float xv = normalize ? __fdiv_rn(xr[i], denom) : xr[i];
+      split16<BF16>(xv, a, b);
+      const float d = xv - (BF16 ? __bfloat162float(__ushort_as_bfloat16(a)) : __half2float(__ushort_as_half(a)));
+      err2 = fmaf(d, d, err2);
+    }
     h[i] = a, o[i] = b;
+  }
+  if (hi_err) {  // ||x - hi||_2, rounded up: the error bound of products that use the hi half only
+    err2 = warp_sum(err2);
+    if (lane == 0) hi_err[ro] = __fmul_ru(__fsqrt_ru(err2), 1.0001f);
   }
 }
 
@@ -365,7 +466,7 @@ int xmlb_make_tmap_2d_u16(CUtensorMap* out, const void* base, unsigned long long
 
 extern "C" int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, int group_in, int group_out,
                                int k, int kpad, int out_ld, int out_col0, int normalize, int is_bf16,
-                               unsigned short* hi, unsigned short* lo, void* stream) {
+                               unsigned short* hi, unsigned short* lo, float* hi_err, void* stream) {
   XMLB_REQUIRE(out_ld >= out_col0 + kpad && out_col0 >= 0, "xmlb_split_rows: need out_col0 + kpad <= out_ld");
   XMLB_REQUIRE(x && hi && lo, "xmlb_split_rows: null pointer");
   XMLB_REQUIRE(k >= 1 && kpad >= k && kpad % 64 == 0, "xmlb_split_rows: kpad must be a multiple of 64 and >= k");
@@ -377,11 +478,11 @@ extern "C" int xmlb_split_rows(const float* x, const int* row_index, long long n
   if (is_bf16)
     split_rows_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, out_ld,
                                                                        out_col0, group_in, group_out, normalize, hi,
-                                                                       lo);
+                                                                       lo, hi_err);
   else
     split_rows_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, row_index, rows_out, k, kpad, out_ld,
                                                                         out_col0, group_in, group_out, normalize, hi,
-                                                                        lo);
+                                                                        lo, hi_err);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
@@ -469,8 +570,8 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
                                         const unsigned short* c_hi_b, const unsigned short* c_lo_b,
                                         const int* tile_meta, const unsigned int* tile_starts, float* q2c,
                                         int* sched_ws, int n_queries, int n_videos, long long n_packed_rows,
-                                        int n_tiles, int hi_only,
-                                        int kpad, int is_bf16, int max_ctas, void* stream) {
+                                        int n_tiles, int hi_only, const int* m_tile_list,
+                                        const int* n_m_tiles, int kpad, int is_bf16, int max_ctas, void* stream) {
   XMLB_REQUIRE(q_hi_a && q_lo_a && c_hi_a && c_lo_a && tile_meta && tile_starts && q2c && sched_ws,
                "xmlb_vr_scores_tc_packed: null pointer");
   const bool two = q_hi_b != nullptr;
@@ -486,6 +587,9 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   p.tile_meta = tile_meta, p.tile_starts = tile_starts;
   p.out = q2c;
   p.tile_counter = sched_ws;
+  XMLB_REQUIRE((m_tile_list == nullptr) == (n_m_tiles == nullptr),
+               "xmlb_vr_scores_tc_packed: m_tile_list and n_m_tiles go together");
+  p.m_tile_list = m_tile_list, p.n_m_tiles = n_m_tiles;
   p.divisor = (float)p.n_mod;
   p.idesc = tc::idesc_f16(BLOCK_M, 256, is_bf16 ? 1 : 0);
   p.terms = hi_only ? 1 : 3;
@@ -518,6 +622,61 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
   XMLB_CUDA(cudaFuncSetAttribute(vr_scores_tc_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   vr_scores_tc_packed_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,
+                                  const unsigned short* qg_hi_b, const unsigned short* qg_lo_b,
+                                  const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                                  const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
+                                  const int* units, const int* n_units, int max_units, const int* entry_out,
+                                  float* cand_val, int* sched_ws, long long n_entries, long long n_packed_rows,
+                                  int max_len, int kpad, int is_bf16, void* stream) {
+  XMLB_REQUIRE(qg_hi_a && qg_lo_a && c_hi_a && c_lo_a && row_start && units && n_units && entry_out && cand_val &&
+                   sched_ws, "xmlb_vr_rescore_tc: null pointer");
+  const bool two = qg_hi_b != nullptr;
+  XMLB_REQUIRE(!two || (qg_lo_b && c_hi_b && c_lo_b), "xmlb_vr_rescore_tc: incomplete second modality");
+  XMLB_REQUIRE(kpad >= 64 && kpad % 64 == 0, "xmlb_vr_rescore_tc: kpad must be a multiple of 64");
+  XMLB_REQUIRE(max_len >= 1 && max_len <= 256, "xmlb_vr_rescore_tc: a video must have at most 256 clips");
+  XMLB_REQUIRE(n_packed_rows > 0 && n_packed_rows < (1ll << 31) && n_entries < (1ll << 31),
+               "xmlb_vr_rescore_tc: bad row count");
+  XMLB_REQUIRE(((uintptr_t)units & 15) == 0, "xmlb_vr_rescore_tc: units must be 16-byte aligned");
+  if (n_entries == 0 || max_units == 0) return XMLB_OK;
+  VrRescoreParams p = {};
+  p.n_mod = two ? 2 : 1;
+  p.k_blocks = kpad / BLOCK_K;
+  p.block_n = max_len <= 64 ? 64 : max_len <= 128 ? 128 : 256;
+  p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out;
+  p.row_start = row_start, p.out = cand_val, p.unit_counter = sched_ws;
+  p.divisor = (float)p.n_mod;
+  p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
+  p.stages = tc::pipe_stages(p.block_n, 0);
+  XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_rescore_tc: tile does not fit in shared memory");
+  const size_t smem = tc::pipe_smem_bytes(p.block_n, p.stages, 0);
+  VrMaps maps;
+  const unsigned short* qh[2] = {qg_hi_a, qg_hi_b};
+  const unsigned short* ql[2] = {qg_lo_a, qg_lo_b};
+  const unsigned short* ch[2] = {c_hi_a, c_hi_b};
+  const unsigned short* cl[2] = {c_lo_a, c_lo_b};
+  for (int m = 0; m < p.n_mod; ++m) {
+    int rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[m], qh[m], n_entries, kpad, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[m], ql[m], n_entries, kpad, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi[m], ch[m], n_packed_rows, kpad, p.block_n, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo[m], cl[m], n_packed_rows, kpad, p.block_n, BLOCK_K))) return rc;
+  }
+  if (!two) {
+    maps.a_hi[1] = maps.a_hi[0], maps.a_lo[1] = maps.a_lo[0], maps.b_hi[1] = maps.b_hi[0], maps.b_lo[1] = maps.b_lo[0];
+  }
+  int dev = 0, sms = 0;
+  XMLB_CUDA(cudaGetDevice(&dev));
+  XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = max_units < sms ? max_units : sms;
+  XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
+  XMLB_CUDA(cudaFuncSetAttribute(vr_rescore_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  vr_rescore_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

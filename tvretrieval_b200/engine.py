@@ -91,6 +91,8 @@ class CorpusPacking:
         self.tile_meta = torch.from_numpy(meta).to(dev)
         self.tile_starts = torch.from_numpy(starts.view(np.int32)).to(dev)
         self.order = torch.from_numpy(order.astype(np.int32)).to(dev)
+        self.row_start = torch.from_numpy(row_start.astype(np.int32)).to(dev)  # (n_packed + 1,)
+        self.max_len = int(olens.max()) if len(olens) else 1
         empty = np.nonzero(lens == 0)[0]
         self.n_packed = len(order)
         # ordinal -> video id for every column of the score matrix (videos without valid clips come last)
@@ -133,10 +135,14 @@ class CorpusIndex:
             bf16 = precision == "bf16x3"
             if packed:
                 self.packing = CorpusPacking(video_mask if video_mask is not None else sub_mask)
-                prep = lambda f: ops.split_rows(f, kpad=self.kpad, normalize=True, bf16=bf16,  # noqa: E731
-                                                row_index=self.packing.src_rows)
-                self.video_tc = prep(video_feat1) if video_feat1 is not None else None
-                self.sub_tc = prep(sub_feat1) if sub_feat1 is not None else None
+                # tc_err[x] = max over clips of ||c - c_hi||_2: error bound of the hi-only filter pass (two-pass search)
+                self.tc_err = {}
+                for name, feat in (("video", video_feat1), ("sub", sub_feat1)):
+                    if feat is not None:
+                        hi, lo, err = ops.split_rows(feat, kpad=self.kpad, normalize=True, bf16=bf16,
+                                                     row_index=self.packing.src_rows, hi_err=True)
+                        setattr(self, name + "_tc", (hi, lo))
+                        self.tc_err[name] = float(err.max()) if err.numel() else 0.0
             else:
                 if video_feat1 is not None:
                     self.video_tc = ops.split_rows(video_feat1, self.ctx_len, self.lp, self.kpad, normalize=True,
@@ -183,9 +189,21 @@ class SearchResult:
 
 
 class VCMRSearcher:
+    # accumulation-order slack of the two-pass error bound: the fp32 TMEM accumulator truncates, <= 1 ulp(1) per
+    # update, 3 * K/16 updates for the exact kernel + K/16 for the filter (K = 768: 192 * 2^-23 = 2.3e-5)
+    TWO_PASS_SLACK = 4e-5
+
     def __init__(self, model, index, q2c_alpha=20.0, min_pred_l=2, max_pred_l=16, max_n_videos=100,
-                 max_before_nms=200, query_chunk=4096):
+                 max_before_nms=200, query_chunk=4096, two_pass=None, max_candidates=None):
+        """two_pass: find the top videos with a hi-only (1 MMA per product) filter pass over the corpus followed by
+        exact re-scoring of the few survivors; same result as the one-pass kernel at a third of the tensor-core
+        work.  None = automatic (packed f16x3 index with at least 4 * max_n_videos videos)."""
         self.model, self.index = model, index
+        auto = index.packing is not None and index.precision == "f16x3" and index.n_videos >= 4 * max_n_videos
+        assert not two_pass or (index.packing is not None and index.precision != "f32"), \
+            "the two-pass search needs the packed tensor-core index"
+        self.two_pass = auto if two_pass is None else bool(two_pass)
+        self.max_candidates = int(max_candidates or max(256, 2 * max_n_videos))
         self.q2c_alpha = float(q2c_alpha)
         self.min_pred_l, self.max_pred_l = int(min_pred_l), int(max_pred_l)
         self.max_n_videos, self.max_before_nms = int(max_n_videos), int(max_before_nms)
@@ -225,6 +243,47 @@ class VCMRSearcher:
             ops.l2norm_rows(video_query) if m.use_video else None, ops.l2norm_rows(sub_query) if m.use_sub else None,
             ix.video_feat1n if m.use_video else None, ix.sub_feat1n if m.use_sub else None,
             ix.video_mask if m.use_video else None, ix.sub_mask if m.use_sub else None)
+
+    def top_videos(self, video_query, sub_query, k):
+        """Exact top-k videos of this index for every query -> (global video ids int32 (Nq, k), exp(alpha * score)),
+        ranked by (score desc, id asc).  Reference: inference.py:317,347-348 on top of model_xml.py:446-452,572-574."""
+        ix, m = self.index, self.model
+        if not (self.two_pass and ix.n_videos >= k):
+            with self._phase("vr_scores"):
+                q2c = self.video_scores(video_query, sub_query, ordinal=True)
+            with self._phase("topk_videos"):
+                ids = self.score_ids()
+                idx, val = ops.topk_rows(q2c, k, alpha=self.q2c_alpha, apply_exp=True, ids=ids)
+                if ids is None and ix.vid_lo:
+                    idx = idx + ix.vid_lo
+            return idx, val
+        bf16 = ix.precision == "bf16x3"
+        pk = ix.packing
+        used = [(q, c, ix.tc_err[name]) for q, c, name, on in ((video_query, ix.video_tc, "video", m.use_video),
+                                                               (sub_query, ix.sub_tc, "sub", m.use_sub)) if on]
+        with self._phase("vr_scores"):  # pass 1: hi halves only
+            split = [ops.split_rows(q, kpad=ix.kpad, normalize=True, bf16=bf16, hi_err=True) for q, _, _ in used]
+            qa, ca = split[0][:2], used[0][1]
+            qb, cb = (split[1][:2], used[1][1]) if len(used) == 2 else (None, None)
+            approx = ops.vr_scores_tc_packed(qa, ca, pk, ix.n_videos, q_b=qb, c_b=cb, bf16=bf16, ordinal=True,
+                                             hi_only=True)
+        with self._phase("vr_select"):
+            # |approx - exact| <= mean over modalities of (||q - q_hi|| * ||c|| + ||q_hi|| * ||c - c_hi||) + slack
+            scale = 1.001 / len(used)
+            const = scale * sum(e for _, _, e in used) + self.TWO_PASS_SLACK
+            cand = ops.select_candidates(approx, k, split[0][2], split[1][2] if len(used) == 2 else None, scale,
+                                         const, self.max_candidates, ids=self.score_ids())
+        with self._phase("vr_rescore"):
+            ops.vr_rescore_tc(used[0][0], ca, pk, cand, ix.kpad, q_fp32_b=used[1][0] if len(used) == 2 else None,
+                              c_b=cb, bf16=bf16)
+        with self._phase("topk_videos"):
+            idx, val = ops.topk_rows(cand.val, k, alpha=self.q2c_alpha, apply_exp=True, ids=cand.ids)
+        with self._phase("vr_fallback"):  # rows whose candidate list overflowed (normally none: both launches idle)
+            ops.vr_scores_tc_packed(qa, ca, pk, ix.n_videos, q_b=qb, c_b=cb, bf16=bf16, ordinal=True, out=approx,
+                                    m_tiles=(cand.flagged_groups, cand.n_flagged))
+            ops.topk_rows(approx, k, alpha=self.q2c_alpha, apply_exp=True, ids=self.score_ids(),
+                          row_flags=cand.row_flags, out=(idx, val))
+        return idx, val
 
     def use_span_tc(self):
         m = self.model
@@ -279,11 +338,7 @@ class VCMRSearcher:
         with self._phase("encode_query"):
             video_query, sub_query = self.encode_queries(query_feat, query_mask)
         if "VR" in tasks or "VCMR" in tasks:
-            with self._phase("vr_scores"):
-                q2c = self.video_scores(video_query, sub_query, ordinal=True)
-            with self._phase("topk_videos"):
-                res.top_video_idx, res.top_video_score = ops.topk_rows(q2c, self.max_n_videos, alpha=self.q2c_alpha,
-                                                                       apply_exp=True, ids=self.score_ids())
+            res.top_video_idx, res.top_video_score = self.top_videos(video_query, sub_query, self.max_n_videos)
         if "VCMR" in tasks:
             with self._phase("pair_lists"):
                 lists = self.span_lists(res.top_video_idx)

@@ -206,10 +206,11 @@ def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, su
 
 
 def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=False, row_index=None, out=None,
-               out_col0=0):
+               out_col0=0, hi_err=False):
     """fp32 rows -> 16-bit (hi, lo) halves with x ~= hi + lo, for the split-precision tensor-core kernels.
     x: (..., k) with rows grouped by `group_in`; output (n_groups * group_out, kpad) int16 tensors (raw bits).
-    With row_index (int32, one source row per output row; negative = zero row) the rows are gathered instead."""
+    With row_index (int32, one source row per output row; negative = zero row) the rows are gathered instead.
+    hi_err=True additionally returns ||x - hi||_2 per output row (error bound of hi-only products)."""
     x = _f32(x, "x")
     k = x.shape[-1]
     rows = x.numel() // k
@@ -226,10 +227,11 @@ def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=Fals
     else:  # write into columns [out_col0, out_col0 + kpad) of preallocated (rows, out_ld) buffers
         hi, lo = out
         assert hi.shape[0] == n_groups * group_out and hi.shape == lo.shape and hi.is_contiguous()
+    err = torch.empty(hi.shape[0], device=x.device, dtype=torch.float32) if hi_err else None
     rc = _lib.lib().xmlb_split_rows(_p(x), _p(row_index), n_groups, group_in, group_out, k, kpad, hi.shape[1],
-                                    out_col0, int(normalize), int(bf16), _p(hi), _p(lo), _stream())
+                                    out_col0, int(normalize), int(bf16), _p(hi), _p(lo), _p(err), _stream())
     _lib.check(rc, "xmlb_split_rows")
-    return hi, lo
+    return (hi, lo, err) if hi_err else (hi, lo)
 
 
 def mask_bits(mask, lp):
@@ -258,26 +260,80 @@ def vr_scores_tc(q_a, c_a, bits_a, n_videos, lp, q_b=None, c_b=None, bits_b=None
 
 
 def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=False, max_ctas=0, ordinal=False,
-                        hi_only=False):
+                        hi_only=False, out=None, m_tiles=None):
     """tcgen05 video-level scores on the packed (valid clips only) corpus; `packing` = engine.CorpusPacking.
     The kernel writes the scores in packed-ordinal order (adjacent columns per tile).  ordinal=True returns that
     layout, (Nq, Nv) with column o <-> video packing.order_full[o]; ordinal=False re-orders to video ids."""
     nq, kpad = q_a[0].shape
-    out = torch.empty(nq, n_videos, device=q_a[0].device, dtype=torch.float32)
+    restricted = m_tiles is not None  # (list, count) device int32 tensors: recompute only these 128-query tiles
+    if out is None:
+        out = torch.empty(nq, n_videos, device=q_a[0].device, dtype=torch.float32)
     qb = q_b if q_b is not None else (None, None)
     cb = c_b if c_b is not None else (None, None)
     rc = _lib.lib().xmlb_vr_scores_tc_packed(
         _p(q_a[0]), _p(q_a[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]), _p(cb[1]),
         _p(packing.tile_meta), _p(packing.tile_starts), _p(out), _p(_sched_ws(out.device)), nq, n_videos,
-        packing.n_rows, packing.n_tiles, int(hi_only), kpad, int(bf16), max_ctas, _stream())
+        packing.n_rows, packing.n_tiles, int(hi_only), _p(m_tiles[0]) if restricted else None,
+        _p(m_tiles[1]) if restricted else None, kpad, int(bf16), max_ctas, _stream())
     _lib.check(rc, "xmlb_vr_scores_tc_packed")
-    if packing.n_packed < n_videos:
+    if packing.n_packed < n_videos and not restricted:
         out[:, packing.n_packed:] = -1e10  # videos without a valid clip (reference: every clip masked -> -1e10)
     if ordinal:
         return out
     by_id = torch.empty_like(out)
     by_id[:, packing.order_full.long()] = out
     return by_id
+
+
+class Candidates:
+    """Output of select_candidates: (R, max_cand) column / id / value tables + the overflow flags."""
+
+    def __init__(self, col, ids, val, flag_ws, n_groups, n_rows):
+        self.col, self.ids, self.val = col, ids, val
+        self.n_flagged = flag_ws[0:1]                          # number of flagged 128-row groups
+        self.flagged_groups = flag_ws[1 + n_groups:1 + 2 * n_groups]
+        self.row_flags = flag_ws[1 + 2 * n_groups:1 + 2 * n_groups + n_rows]
+
+
+def select_candidates(approx, k, row_err_a, row_err_b, err_scale, err_const, max_cand, ids=None, rows_per_group=128):
+    """Columns of `approx` (R, C) that can be among the exact top-k of their row given the error bound
+    eps[r] = err_scale * (row_err_a[r] + row_err_b[r]) + err_const  (see xmlb_select_candidates)."""
+    approx = _f32(approx, "approx")
+    n_rows, n_cols = approx.shape
+    dev = approx.device
+    n_groups = (n_rows + rows_per_group - 1) // rows_per_group
+    col = torch.empty(n_rows, max_cand, device=dev, dtype=torch.int32)
+    cid = torch.empty_like(col)
+    val = torch.empty(n_rows, max_cand, device=dev, dtype=torch.float32)
+    flag_ws = torch.empty(1 + 2 * n_groups + n_rows, device=dev, dtype=torch.int32)
+    rc = _lib.lib().xmlb_select_candidates(_p(approx), _p(_i32(ids, "ids")), n_rows, n_cols, k,
+                                           _p(_f32(row_err_a, "row_err_a")), _p(_f32(row_err_b, "row_err_b")),
+                                           err_scale, err_const, max_cand, rows_per_group, _p(col), _p(cid), _p(val),
+                                           _p(flag_ws), _stream())
+    _lib.check(rc, "xmlb_select_candidates")
+    return Candidates(col, cid, val, flag_ws, n_groups, n_rows)
+
+
+def vr_rescore_tc(q_fp32_a, c_a, packing, cand, kpad, q_fp32_b=None, c_b=None, bf16=False):
+    """Overwrites cand.val with the exact split-precision scores of the candidate (query, packed video) pairs.
+    q_fp32_* (Nq, H) pooled query vectors (normalised here, gathered per video list); c_* packed corpus (hi, lo)."""
+    lists = build_pair_lists(cand.col, packing.n_packed, chunk=128)
+    dev = cand.col.device
+    units = torch.empty(lists.max_chunks * 4 + 4, device=dev, dtype=torch.int32)
+    rc = _lib.lib().xmlb_build_span_units(_p(lists.vid_ptr), _p(lists.chunk_ptr), packing.n_packed, lists.chunk,
+                                          _p(units), _stream())
+    _lib.check(rc, "xmlb_build_span_units")
+    qa = split_rows(q_fp32_a, kpad=kpad, normalize=True, bf16=bf16, row_index=lists.entry_q)
+    qb = split_rows(q_fp32_b, kpad=kpad, normalize=True, bf16=bf16, row_index=lists.entry_q) \
+        if q_fp32_b is not None else (None, None)
+    cb = c_b if c_b is not None else (None, None)
+    rc = _lib.lib().xmlb_vr_rescore_tc(_p(qa[0]), _p(qa[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
+                                       _p(cb[1]), _p(packing.row_start), _p(units),
+                                       lists.chunk_ptr[packing.n_packed:].data_ptr(), lists.max_chunks,
+                                       _p(lists.entry_out), _p(cand.val), _p(_sched_ws(dev)), lists.entry_q.numel(),
+                                       packing.n_rows, packing.max_len, kpad, int(bf16), _stream())
+    _lib.check(rc, "xmlb_vr_rescore_tc")
+    return cand.val
 
 
 class PairLists:
@@ -368,18 +424,24 @@ def span_logits(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b=None, feat2_b=None, ma
     return st, ed
 
 
-def topk_rows(values, k, alpha=1.0, apply_exp=False, ids=None, tie_desc=False):
+def topk_rows(values, k, alpha=1.0, apply_exp=False, ids=None, tie_desc=False, row_flags=None, out=None):
     """-> (idx int32 (R, k), val fp32 (R, k)) ranked by (value desc, id asc).  ids: None (column index), (R, C)
-    per-row ids or a 1-D (C,) table shared by all rows."""
+    per-row ids or a 1-D (C,) table shared by all rows.  row_flags (R,) int32 + out=(idx, val): only the flagged
+    rows are recomputed, in place."""
     values = _f32(values, "values")
     n_rows, n_cols = values.shape
-    out_idx = torch.empty(n_rows, k, device=values.device, dtype=torch.int32)
-    out_val = torch.empty(n_rows, k, device=values.device, dtype=torch.float32)
+    if out is None:
+        assert row_flags is None
+        out_idx = torch.empty(n_rows, k, device=values.device, dtype=torch.int32)
+        out_val = torch.empty(n_rows, k, device=values.device, dtype=torch.float32)
+    else:
+        out_idx, out_val = out
+        assert out_idx.shape == (n_rows, k) and out_idx.is_contiguous() and out_val.is_contiguous()
     ids = _i32(ids, "ids")
     shared = ids is not None and ids.dim() == 1
     assert ids is None or ids.numel() == (n_cols if shared else n_rows * n_cols)
     rc = _lib.lib().xmlb_topk_rows(_p(values), _p(ids), int(shared), n_rows, n_cols, k, alpha, int(apply_exp),
-                                   int(tie_desc), _p(out_idx), _p(out_val), _stream())
+                                   int(tie_desc), _p(row_flags), _p(out_idx), _p(out_val), _stream())
     _lib.check(rc, "xmlb_topk_rows")
     return out_idx, out_val
 

@@ -152,17 +152,11 @@ class ShardedSearcher(VCMRSearcher):
         nq = len(video_query)
         if "VR" in tasks or "VCMR" in tasks:
             k = self.max_n_videos
-            with self._phase("vr_scores"):
-                q2c = self.video_scores(video_query, sub_query, ordinal=True)
-            with self._phase("topk_videos"):
-                k_loc = min(k, ix.n_videos)
-                ids = self.score_ids()  # global video ids of the score columns (None: column = local id)
-                idx, val = ops.topk_rows(q2c, k_loc, alpha=self.q2c_alpha, apply_exp=True, ids=ids)
-                if ids is None:
-                    idx = idx + vid_lo
-                if k_loc < k:  # shard smaller than k: pad so every rank contributes k columns
-                    idx = torch.cat([idx, idx.new_full((nq, k - k_loc), 2 ** 31 - 1)], 1)
-                    val = torch.cat([val, val.new_full((nq, k - k_loc), NEG)], 1)
+            k_loc = min(k, ix.n_videos)
+            idx, val = self.top_videos(video_query, sub_query, k_loc)  # global ids, exp(alpha * score)
+            if k_loc < k:  # shard smaller than k: pad so every rank contributes k columns
+                idx = torch.cat([idx, idx.new_full((nq, k - k_loc), 2 ** 31 - 1)], 1)
+                val = torch.cat([val, val.new_full((nq, k - k_loc), NEG)], 1)
             with self._phase("merge_videos"):
                 g_val, g_idx = all_gather_cat(val, self.group), all_gather_cat(idx, self.group)
                 res.top_video_idx, res.top_video_score = ops.topk_rows(g_val, k, ids=g_idx)
