@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--hidden", type=int, default=768)
     ap.add_argument("--video-dim", type=int, default=3072)
     ap.add_argument("--ctx-bsz", type=int, default=200)
-    ap.add_argument("--query-chunk", type=int, default=4096)
+    ap.add_argument("--query-chunk", type=int, default=16384)
     ap.add_argument("--precision", default="f16x3", choices=["f16x3", "bf16x3", "f32"],
                     help="video-level score kernel: tcgen05 split-precision (f16x3 / bf16x3) or exact-fp32 SIMT")
     ap.add_argument("--one-pass", action="store_true",

@@ -194,7 +194,7 @@ class VCMRSearcher:
     TWO_PASS_SLACK = 4e-5
 
     def __init__(self, model, index, q2c_alpha=20.0, min_pred_l=2, max_pred_l=16, max_n_videos=100,
-                 max_before_nms=200, query_chunk=4096, two_pass=None, max_candidates=None):
+                 max_before_nms=200, query_chunk=16384, two_pass=None, max_candidates=None, encode_chunk=2048):
         """two_pass: find the top videos with a hi-only (1 MMA per product) filter pass over the corpus followed by
         exact re-scoring of the few survivors; same result as the one-pass kernel at a third of the tensor-core
         work.  None = automatic (packed f16x3 index with at least 4 * max_n_videos videos)."""
@@ -207,16 +207,14 @@ class VCMRSearcher:
         self.q2c_alpha = float(q2c_alpha)
         self.min_pred_l, self.max_pred_l = int(min_pred_l), int(max_pred_l)
         self.max_n_videos, self.max_before_nms = int(max_n_videos), int(max_before_nms)
-        self.query_chunk = int(query_chunk)
+        self.query_chunk = int(query_chunk)    # queries searched together (one pass over the corpus per block)
+        self.encode_chunk = int(encode_chunk)  # queries uploaded / encoded per piece inside a block
         self.timer = None  # set to a PhaseTimer to time the phases
 
     def _phase(self, name):
         return self.timer.phase(name) if self.timer is not None else contextlib.nullcontext()
 
     # ---- phases (also used one by one by the sharded searcher) -------------------------------------
-    def encode_queries(self, query_feat, query_mask):
-        return self.model.encode_query(query_feat, query_mask)
-
     def score_ids(self):
         """Column -> (global) video id table of video_scores(ordinal=True), or None when columns are video ids."""
         ix = self.index
@@ -316,13 +314,70 @@ class VCMRSearcher:
                                        ix.sub_mask)
         return ops.span_logits(softmax=True, lists=lists, **args)
 
-    # ---- single-GPU search ------------------------------------------------------------------------
-    def search(self, query_feat, query_mask, gt_video_idx=None, tasks=("VCMR", "VR")):
-        """query_feat (Nq, Lq, Dq), query_mask (Nq, Lq) on the index's device.  gt_video_idx (Nq,) int: corpus
-        position of each query's ground-truth video, needed for SVMR."""
-        outs = [self._search_chunk(query_feat[lo:lo + self.query_chunk], query_mask[lo:lo + self.query_chunk],
-                                   None if gt_video_idx is None else gt_video_idx[lo:lo + self.query_chunk], tasks)
-                for lo in range(0, len(query_feat), self.query_chunk)]
+    # ---- search: encode (pipelined in small chunks) -> one block of queries against the whole index ---------
+    def _my_slice(self, n):
+        """Part [lo, hi) of a block of n queries that THIS process encodes (all of it on one GPU)."""
+        return 0, n
+
+    def _gather_encoded(self, video_query, sub_query, n):
+        """Pooled query vectors of the whole block from the locally encoded slice (identity on one GPU)."""
+        return video_query, sub_query
+
+    def _encode_pieces(self, pieces):
+        """pieces: iterable of (query_feat, query_mask) device tensors -> pooled (video_query, sub_query)."""
+        hid = self.model.config.hidden_size
+        vq, sq = [], []
+        with self._phase("encode_query"):
+            for qf, qm in pieces:
+                a, b = self.model.encode_query(qf, qm)
+                vq.append(a), sq.append(b)
+            if not vq:
+                z = torch.zeros(0, hid, device=self.index.device)
+                return z, z
+            return (vq[0], sq[0]) if len(vq) == 1 else (torch.cat(vq), torch.cat(sq))
+
+    def _device_pieces(self, query_feat, query_mask):
+        for lo in range(0, len(query_feat), self.encode_chunk):
+            yield query_feat[lo:lo + self.encode_chunk], query_mask[lo:lo + self.encode_chunk]
+
+    def _host_pieces(self, query_feat_cpu, query_mask_cpu):
+        """Uploads the pieces on a side stream, so the copy of piece i+1 overlaps the encoding of piece i."""
+        dev = self.index.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        copy = self._copy_stream
+        copy.wait_stream(main)
+        staged = []
+        for lo in range(0, len(query_feat_cpu), self.encode_chunk):
+            with torch.cuda.stream(copy):
+                qf = query_feat_cpu[lo:lo + self.encode_chunk].to(dev, non_blocking=True)
+                qm = query_mask_cpu[lo:lo + self.encode_chunk].to(dev, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            staged.append((qf, qm, ready))
+        for qf, qm, ready in staged:
+            main.wait_event(ready)
+            qf.record_stream(main), qm.record_stream(main)
+            yield qf, qm
+
+    def search(self, query_feat, query_mask, gt_video_idx=None, tasks=("VCMR", "VR"), host=False):
+        """query_feat (Nq, Lq, Dq), query_mask (Nq, Lq) on the index's device (host=True: pinned host tensors, the
+        upload is part of the call).  gt_video_idx (Nq,) int: corpus position of each query's ground-truth video,
+        needed for SVMR.  Queries are processed in blocks of `query_chunk`; inside a block the raw features are
+        uploaded / encoded in pieces of `encode_chunk`, then the whole block is searched at once (each pass over
+        the corpus is shared by all queries of the block)."""
+        outs = []
+        dev = self.index.device
+        for b_lo in range(0, len(query_feat), self.query_chunk):
+            n = min(self.query_chunk, len(query_feat) - b_lo)
+            lo, hi = self._my_slice(n)
+            qf, qm = query_feat[b_lo + lo:b_lo + hi], query_mask[b_lo + lo:b_lo + hi]
+            video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm) if host
+                                                         else self._device_pieces(qf, qm))
+            video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
+            gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
+            outs.append(self._search_encoded(video_query, sub_query, gt, tasks))
         if len(outs) == 1:
             return outs[0]
         res = SearchResult()
@@ -331,12 +386,10 @@ class VCMRSearcher:
                 setattr(res, s, torch.cat([getattr(o, s) for o in outs]))
         return res
 
-    def _search_chunk(self, query_feat, query_mask, gt_video_idx, tasks):
+    def _search_encoded(self, video_query, sub_query, gt_video_idx, tasks):
         ix = self.index
         res = SearchResult()
-        nq = len(query_feat)
-        with self._phase("encode_query"):
-            video_query, sub_query = self.encode_queries(query_feat, query_mask)
+        nq = len(video_query)
         if "VR" in tasks or "VCMR" in tasks:
             res.top_video_idx, res.top_video_score = self.top_videos(video_query, sub_query, self.max_n_videos)
         if "VCMR" in tasks:
@@ -360,35 +413,6 @@ class VCMRSearcher:
 
     # ---- host-buffer entry point (the e2e path bench.py times) --------------------------------------
     def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR")):
-        """Pinned host buffers in, numpy arrays out; H2D/D2H copies are part of the call.  The query chunks are
-        uploaded on a side stream so that the copy of chunk i+1 overlaps the search of chunk i."""
-        dev = self.index.device
-        main = torch.cuda.current_stream(dev)
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(dev)
-        copy = self._copy_stream
-        copy.wait_stream(main)
-        staged = []
-        n = len(query_feat_cpu)
-        for lo in range(0, n, self.query_chunk):
-            hi = min(n, lo + self.query_chunk)
-            with torch.cuda.stream(copy):
-                qf = query_feat_cpu[lo:hi].to(dev, non_blocking=True)
-                qm = query_mask_cpu[lo:hi].to(dev, non_blocking=True)
-                gt = None if gt_video_idx_cpu is None else gt_video_idx_cpu[lo:hi].to(dev, non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(copy)
-            staged.append((qf, qm, gt, ready))
-        outs = []
-        for qf, qm, gt, ready in staged:
-            main.wait_event(ready)
-            for t in (qf, qm, gt):
-                if t is not None:
-                    t.record_stream(main)
-            outs.append(self._search_chunk(qf, qm, gt, tasks))
-        out = {}
-        for s in SearchResult.__slots__:
-            if getattr(outs[0], s) is not None:
-                t = getattr(outs[0], s) if len(outs) == 1 else torch.cat([getattr(o, s) for o in outs])
-                out[s] = t.cpu().numpy()
-        return out
+        """Pinned host buffers in, numpy arrays out; H2D / D2H copies are part of the call."""
+        res = self.search(query_feat_cpu, query_mask_cpu, gt_video_idx_cpu, tasks, host=True)
+        return {s: getattr(res, s).cpu().numpy() for s in SearchResult.__slots__ if getattr(res, s) is not None}

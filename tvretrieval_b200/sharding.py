@@ -105,50 +105,25 @@ class ShardedSearcher(VCMRSearcher):
         lo, hi = self.plan.video_range()
         assert index.vid_lo == lo and index.n_videos == hi - lo, "index does not hold this rank's shard"
 
-    def encode_queries(self, query_feat, query_mask, nq=None):
-        """Each rank encodes its slice of the queries; the pooled vectors are all-gathered.  With nq=None the
-        arguments hold all queries (the slice is taken here), otherwise they already are this rank's slice of nq."""
-        if nq is None:
-            nq = len(query_feat)
-            lo, hi, per = self.plan.query_range(nq)
-            query_feat, query_mask = query_feat[lo:hi], query_mask[lo:hi]
-        else:
-            lo, hi, per = self.plan.query_range(nq)
-            assert len(query_feat) == hi - lo
+    def _my_slice(self, n):
+        lo, hi, _ = self.plan.query_range(n)
+        return lo, hi
+
+    def _gather_encoded(self, video_query, sub_query, n):
+        """Each rank encoded its slice of the block; the pooled vectors are all-gathered (rank-major = query order)."""
+        lo, hi, per = self.plan.query_range(n)
         hid = self.model.config.hidden_size
         packed = torch.zeros(per, 2, hid, device=self.index.device)
         if hi > lo:
-            vq, sq = self.model.encode_query(query_feat, query_mask)
-            packed[:hi - lo, 0], packed[:hi - lo, 1] = vq, sq
-        # rank r contributes queries [r*per, (r+1)*per): rank-major concatenation is query order, padding last
-        allq = all_gather_rows(packed, self.group)[:nq]
+            packed[:hi - lo, 0], packed[:hi - lo, 1] = video_query, sub_query
+        with self._phase("gather_queries"):
+            allq = all_gather_rows(packed, self.group)[:n]
         return allq[:, 0].contiguous(), allq[:, 1].contiguous()
 
-    def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR")):
-        """Host-buffer entry point: every rank uploads only the slice of each query chunk that it encodes."""
-        dev = self.index.device
-        outs = []
-        n = len(query_feat_cpu)
-        for c_lo in range(0, n, self.query_chunk):
-            c_hi = min(n, c_lo + self.query_chunk)
-            lo, hi, _ = self.plan.query_range(c_hi - c_lo)
-            qf = query_feat_cpu[c_lo + lo:c_lo + hi].to(dev, non_blocking=True)
-            qm = query_mask_cpu[c_lo + lo:c_lo + hi].to(dev, non_blocking=True)
-            gt = None if gt_video_idx_cpu is None else gt_video_idx_cpu[c_lo:c_hi].to(dev, non_blocking=True)
-            outs.append(self._search_chunk(qf, qm, gt, tasks, nq=c_hi - c_lo))
-        out = {}
-        for s in SearchResult.__slots__:
-            if getattr(outs[0], s) is not None:
-                t = getattr(outs[0], s) if len(outs) == 1 else torch.cat([getattr(o, s) for o in outs])
-                out[s] = t.cpu().numpy()
-        return out
-
-    def _search_chunk(self, query_feat, query_mask, gt_video_idx, tasks, nq=None):
+    def _search_encoded(self, video_query, sub_query, gt_video_idx, tasks):
         ix = self.index
         res = SearchResult()
         vid_lo, vid_hi = ix.vid_lo, ix.vid_lo + ix.n_videos
-        with self._phase("encode_query"):
-            video_query, sub_query = self.encode_queries(query_feat, query_mask, nq)
         nq = len(video_query)
         if "VR" in tasks or "VCMR" in tasks:
             k = self.max_n_videos
