@@ -257,6 +257,46 @@ def test_two_pass_search_equals_one_pass(precision, max_cand):
     assert VCMRSearcher(model, index, **kw).two_pass == (precision == "f16x3")  # automatic choice
 
 
+@pytest.mark.parametrize("precision", ["f16x3", "f32"])
+def test_index_grows_and_round_trips_through_a_file(precision, tmp_path):
+    """CorpusIndex.add_videos (incremental add) and save / load: searching the grown or reloaded index returns
+    exactly what an index built from all videos at once returns."""
+    from tvretrieval_b200.engine import CorpusIndex, VCMRSearcher
+    from tvretrieval_b200.synthetic import corpus_batch, corpus_lengths, synthetic_queries
+    cfg, model, weights, ds = tvr_case("video_sub", 4, 4, 128, 64, 3072, seed=3)
+    n_videos, n_first, nq = 700, 450, 90
+    lens = corpus_lengths(n_videos, 64, seed=21)
+    lens[5] = 64
+    with torch.no_grad():
+        video, sub, mask = corpus_batch(lens, 0, n_videos, 3072, 768, DEV, seed=21, video_split=2048)
+        feats = model.encode_context(video, mask, sub, mask)
+        parts = lambda lo, hi, w: (feats[0][lo:hi, :w], feats[1][lo:hi, :w], mask[lo:hi, :w], feats[2][lo:hi, :w],  # noqa: E731
+                                   feats[3][lo:hi, :w], mask[lo:hi, :w])
+        full = CorpusIndex(*parts(0, n_videos, 64), precision=precision)
+        grown = CorpusIndex(*parts(0, n_first, 64), precision=precision)
+        w = int(lens[n_first:].max())  # the added batch is narrower than the index, as a later context batch can be
+        grown.add_videos(*[t.contiguous() for t in parts(n_first, n_videos, w)])
+        assert grown.n_videos == n_videos
+        path = grown.save(str(tmp_path / "corpus.xmlb"))
+        loaded = CorpusIndex.load(path, DEV)
+        assert loaded.nbytes() == grown.nbytes()
+        qf, qm = synthetic_queries(nq, 30, 768, seed=22)
+        qf, qm = qf.to(DEV), qm.to(DEV)
+        gt = torch.randint(0, n_videos, (nq,), generator=torch.Generator().manual_seed(2)).to(torch.int32).to(DEV)
+        kw = dict(max_n_videos=100, max_before_nms=200)
+        tasks = ("VCMR", "VR", "SVMR")
+        want = VCMRSearcher(model, full, **kw).search(qf, qm, gt, tasks)
+        for index in (grown, loaded):
+            got = VCMRSearcher(model, index, **kw).search(qf, qm, gt, tasks)
+            for name in ("top_video_idx", "top_video_score", "span_flat_idx", "span_score", "svmr_flat_idx",
+                         "svmr_score"):
+                assert torch.equal(getattr(got, name), getattr(want, name)), name
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.xmlb"
+        bad.write_bytes(b"not an index")
+        CorpusIndex.load(str(bad), DEV)
+
+
 def test_model_rejects_cpu_tensors():
     from tvretrieval_b200._lib import XmlbError
     cfg, model, weights, ds = tvr_case("video", 4, 4, 64, 16, 32, seed=3)

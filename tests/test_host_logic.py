@@ -98,3 +98,44 @@ def test_band_mask_and_collate_match_reference_semantics():
     assert cat.shape == (3, 5, 2) and (cat[:2, 3:] == 0).all()
     with pytest.raises(ValueError):
         I.cat_tensor([torch.ones(2)])
+
+
+def _check_packing(pk, lens):
+    """Invariants of the ragged corpus layout: every video with clips appears once, its rows are contiguous, tiles
+    hold whole videos in <= 256 rows, the start bitmap marks the first column of each video."""
+    order, row_start = pk.order.numpy(), pk.row_start.numpy()
+    meta, starts = pk.tile_meta.numpy(), pk.tile_starts.numpy().view(np.uint32)
+    assert sorted(order.tolist()) == [v for v in range(len(lens)) if lens[v] > 0]
+    assert sorted(pk.empty.tolist()) == [v for v in range(len(lens)) if lens[v] == 0]
+    assert np.array_equal(np.diff(row_start), lens[order]) and row_start[0] == 0
+    assert pk.n_rows == int(lens.sum()) and pk.max_len == int(lens.max())
+    o = 0
+    for t, (row, first, used, nvid) in enumerate(meta):
+        assert first == o and row == row_start[o] and 0 < used <= 256 and 0 < nvid <= 32
+        assert used == row_start[o + nvid] - row_start[o]
+        cols = set((row_start[o:o + nvid] - row).tolist())
+        got = {c for c in range(256) if (starts[t, c // 32] >> (c % 32)) & 1}
+        assert got == cols
+        o += nvid
+    assert o == len(order)
+    assert torch.equal(pk.order_full, torch.cat([pk.order, pk.empty]))
+
+
+def test_corpus_packing_and_incremental_append():
+    from tvretrieval_b200.engine import CorpusPacking
+    g = torch.Generator().manual_seed(0)
+
+    def masks(n, length):
+        lens = torch.randint(0, length + 1, (n,), generator=g)
+        lens[0] = length
+        return (torch.arange(length)[None] < lens[:, None]).float(), lens.numpy()
+
+    m1, l1 = masks(300, 128)
+    m2, l2 = masks(77, 128)
+    pk = CorpusPacking(m1)
+    _check_packing(pk, l1)
+    assert pk.fill > 0.95
+    pk.append(CorpusPacking(m2), 300)
+    _check_packing(pk, np.concatenate([l1, l2]))
+    restored = CorpusPacking.from_state({k: getattr(pk, k) for k in CorpusPacking.STATE}, pk.max_len)
+    _check_packing(restored, np.concatenate([l1, l2]))

@@ -272,6 +272,7 @@ struct SpanGen {
   const float* vr;  // [n_slots] video scores (null -> 1)
   const unsigned char* valid;  // [n_slots] or null
   int n_slots, L, min_l, max_l, tie_desc;
+  unsigned int min_key;  // cells whose score key is below this known lower bound of the k-th best are skipped
   template <class F>
   __device__ void for_each(F f) const {
     const int rows = n_slots * L;
@@ -285,7 +286,7 @@ struct SpanGen {
       const float* e = ed + j * L;
       for (int n = m + min_l; n < n_hi; ++n) {
         const float s = __fmul_rn(a, __ldg(e + n));
-        if (s > 0.f) {
+        if (s > 0.f && float_key(s) >= min_key) {
           const unsigned int id = (unsigned int)(r * L + n);
           f(float_key(s), tie_desc ? id : ~id);
         }
@@ -347,7 +348,21 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   const long long q = blockIdx.x;
   SpanGen gen{st + q * n_slots * L, ed + q * n_slots * L, vr ? vr + q * n_slots : nullptr,
-              slot_valid ? slot_valid + q * n_slots : nullptr, n_slots, L, min_l, max_l, tie_desc};
+              slot_valid ? slot_valid + q * n_slots : nullptr, n_slots, L, min_l, max_l, tie_desc, 0u};
+  // Pre-filter: the k-th best cell of the first few slots (the videos with the largest retrieval scores) is a lower
+  // bound of the k-th best cell overall, so the selection passes over all slots can skip everything below it --
+  // typically > 95 % of the cells, which removes the shared-memory histogram contention of clustered scores.
+  constexpr int SUB_SLOTS = 4;
+  if (n_slots > 2 * SUB_SLOTS) {
+    SpanGen sub = gen;
+    sub.n_slots = SUB_SLOTS;
+    unsigned int thr = 0;
+    int n_equal, need_equal, n_total;
+    if (radix_select(sub, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k,
+                     thr, n_equal, need_equal, n_total))
+      gen.min_key = thr;
+    __syncthreads();
+  }
   const int n_out = block_topk(gen, sm, k);
   int* oi = out_idx + q * k;
   float* ov = out_val + q * k;

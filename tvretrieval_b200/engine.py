@@ -97,7 +97,40 @@ class CorpusPacking:
         self.n_packed = len(order)
         # ordinal -> video id for every column of the score matrix (videos without valid clips come last)
         self.order_full = torch.from_numpy(np.concatenate([order, empty]).astype(np.int32)).to(dev)
+        self.empty = torch.from_numpy(empty.astype(np.int32)).to(dev)
         self.fill = self.n_rows / max(1, self.n_tiles * self.TILE)
+
+    STATE = ("tile_meta", "tile_starts", "order", "row_start", "empty")  # device tensors that define the layout
+
+    @classmethod
+    def from_state(cls, state, max_len):
+        """Rebuild from saved tables (CorpusIndex.load) -- src_rows is only needed while packing new features."""
+        self = cls.__new__(cls)
+        for k in cls.STATE:
+            setattr(self, k, state[k])
+        self.src_rows = None
+        self._refresh(max_len)
+        return self
+
+    def _refresh(self, max_len):
+        self.n_tiles, self.n_packed = len(self.tile_meta), len(self.order)
+        self.n_rows = int(self.row_start[-1]) if len(self.row_start) else 0
+        self.max_len = int(max_len)
+        self.order_full = torch.cat([self.order, self.empty])
+        self.fill = self.n_rows / max(1, self.n_tiles * self.TILE)
+
+    def append(self, other, n_videos_before):
+        """Append the packing of newly added videos (built on their own masks): their tiles, rows and ordinals
+        follow the existing ones; video ids are shifted by the number of videos already in the index."""
+        meta = other.tile_meta.clone()
+        meta[:, 0] += self.n_rows
+        meta[:, 1] += self.n_packed
+        self.tile_meta = torch.cat([self.tile_meta, meta])
+        self.tile_starts = torch.cat([self.tile_starts, other.tile_starts])
+        self.row_start = torch.cat([self.row_start, other.row_start[1:] + self.n_rows])
+        self.order = torch.cat([self.order, other.order + n_videos_before])
+        self.empty = torch.cat([self.empty, other.empty + n_videos_before])
+        self._refresh(max(self.max_len, other.max_len))
 
 
 class CorpusIndex:
@@ -170,6 +203,120 @@ class CorpusIndex:
         return cls(ctx_info.get("video_feat1"), ctx_info.get("video_feat2"), ctx_info.get("video_mask"),
                    ctx_info.get("sub_feat1"), ctx_info.get("sub_feat2"), ctx_info.get("sub_mask"), vid_lo=vid_lo,
                    precision=precision, packed=packed, merged_spans=merged_spans)
+
+    # ---- incremental growth and persistence (the reference re-encodes and keeps the
+    # corpus in Python lists of tensors, inference.py:32-97, and its profiling scenario is "1K videos are added",
+    # baselines/profiling/profile_main.py:1-4) -------------------------------------------------------------------
+    TENSORS = ("video_feat1n", "sub_feat1n", "video_feat2", "sub_feat2", "video_mask", "sub_mask", "video_bits",
+               "sub_bits")
+    PAIRS = ("video_tc", "sub_tc", "f2cat")
+
+    def add_videos(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
+                   sub_mask=None):
+        """Append newly encoded videos (outputs of XML.encode_context, padded to this index's clip width or
+        narrower).  They get the next video ids; existing operand rows are not re-packed.  Searching the grown index
+        gives the same result as an index built from all videos at once."""
+        def widen(t):  # zero-pad the clip axis like cat_tensor does (reference inference.py:71-87)
+            if t is None or t.shape[1] == self.ctx_len:
+                return t
+            assert t.shape[1] < self.ctx_len, "new videos are wider than the index (max_ctx_l)"
+            pad = [0, 0] * (t.dim() - 2) + [0, self.ctx_len - t.shape[1]]
+            return torch.nn.functional.pad(t, pad)
+        args = [widen(t) for t in (video_feat1, video_feat2, video_mask, sub_feat1, sub_feat2, sub_mask)]
+        new = CorpusIndex(*args, vid_lo=self.vid_lo + self.n_videos, precision=self.precision,
+                          packed=self.packing is not None, merged_spans=self.f2cat is not None)
+        assert (new.packing is None) == (self.packing is None) and (new.f2cat is None) == (self.f2cat is None)
+        for name in self.TENSORS:
+            a, b = getattr(self, name), getattr(new, name)
+            assert (a is None) == (b is None), "modalities of the new videos differ from the index: " + name
+            if a is not None:
+                setattr(self, name, torch.cat([a, b]))
+        for name in self.PAIRS:
+            a, b = getattr(self, name), getattr(new, name)
+            if a is not None:
+                setattr(self, name, (torch.cat([a[0], b[0]]), torch.cat([a[1], b[1]])))
+        if self.packing is not None:
+            self.packing.append(new.packing, self.n_videos)
+            self.tc_err = {k: max(v, new.tc_err[k]) for k, v in self.tc_err.items()}
+        self.n_videos += new.n_videos
+        return self
+
+    def save(self, path):
+        """One file: JSON header (shapes, dtypes, offsets) + 4 KiB-aligned raw little-endian tensors, written and
+        read in bounded chunks so that a 44 GB index never needs a host copy of itself."""
+        import json
+        items = {}
+        for name in self.TENSORS:
+            if getattr(self, name) is not None:
+                items[name] = getattr(self, name)
+        for name in self.PAIRS:
+            if getattr(self, name) is not None:
+                items[name + ".hi"], items[name + ".lo"] = getattr(self, name)
+        if self.packing is not None:
+            for k in CorpusPacking.STATE:
+                items["packing." + k] = getattr(self.packing, k)
+        header = dict(format="xmlb200-index", version=1, n_videos=self.n_videos, ctx_len=self.ctx_len,
+                      hidden=self.hidden, vid_lo=self.vid_lo, precision=self.precision,
+                      lp=getattr(self, "lp", None), kpad=getattr(self, "kpad", None),
+                      tc_err=getattr(self, "tc_err", None),
+                      max_len=self.packing.max_len if self.packing is not None else None, tensors={})
+        off = 0
+        for k, t in items.items():
+            header["tensors"][k] = dict(dtype=str(t.dtype).replace("torch.", ""), shape=list(t.shape), offset=off)
+            off += (t.numel() * t.element_size() + 4095) // 4096 * 4096
+        blob = json.dumps(header).encode()
+        head_len = (len(blob) + 16 + 4095) // 4096 * 4096
+        with open(path, "wb") as fh:
+            fh.write(b"XMLB200I" + len(blob).to_bytes(8, "little") + blob)
+            fh.write(b"\0" * (head_len - 16 - len(blob)))
+            for k, t in items.items():
+                flat = t.contiguous().view(-1)
+                step = max(1, (256 << 20) // max(1, t.element_size()))
+                for lo in range(0, flat.numel(), step):
+                    fh.write(flat[lo:lo + step].cpu().numpy().tobytes())
+                pad = -(flat.numel() * t.element_size()) % 4096
+                fh.write(b"\0" * pad)
+        return path
+
+    @classmethod
+    def load(cls, path, device="cuda"):
+        import json
+        with open(path, "rb") as fh:
+            magic = fh.read(8)
+            if magic != b"XMLB200I":
+                raise ValueError("%s is not an xmlb200 index file" % path)
+            n = int.from_bytes(fh.read(8), "little")
+            header = json.loads(fh.read(n))
+        if header.get("version") != 1:
+            raise ValueError("unsupported index file version %r" % header.get("version"))
+        base = (n + 16 + 4095) // 4096 * 4096
+        mm = np.memmap(path, dtype=np.uint8, mode="r")
+        tensors = {}
+        for k, d in header["tensors"].items():
+            dtype = getattr(torch, d["dtype"])
+            t = torch.empty(d["shape"], dtype=dtype, device=device)
+            flat = t.view(-1).view(torch.uint8)
+            nbytes, step = flat.numel(), 256 << 20
+            for lo in range(0, nbytes, step):
+                hi = min(nbytes, lo + step)
+                chunk = torch.from_numpy(np.array(mm[base + d["offset"] + lo:base + d["offset"] + hi]))
+                flat[lo:hi].copy_(chunk)
+            tensors[k] = t
+        self = cls.__new__(cls)
+        self.n_videos, self.ctx_len, self.hidden = header["n_videos"], header["ctx_len"], header["hidden"]
+        self.vid_lo, self.precision, self.device = header["vid_lo"], header["precision"], torch.device(device)
+        if header["lp"] is not None:
+            self.lp, self.kpad = header["lp"], header["kpad"]
+        for name in cls.TENSORS:
+            setattr(self, name, tensors.get(name))
+        for name in cls.PAIRS:
+            setattr(self, name, (tensors[name + ".hi"], tensors[name + ".lo"]) if name + ".hi" in tensors else None)
+        self.packing = None
+        if "packing.order" in tensors:
+            self.packing = CorpusPacking.from_state({k: tensors["packing." + k] for k in CorpusPacking.STATE},
+                                                    header["max_len"])
+            self.tc_err = header["tc_err"]
+        return self
 
     def nbytes(self):
         tensors = [self.video_feat1n, self.sub_feat1n, self.video_feat2, self.sub_feat2, self.video_mask,
