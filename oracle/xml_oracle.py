@@ -228,6 +228,65 @@ def pred_from_raw_query(cfg, w: Weights, query_feat, query_mask, video_feat1, vi
 
 
 # --------------------------------------------------------------------------------------
+# training step: XML.forward + losses (model_xml.py:212-251, 588-637)
+# --------------------------------------------------------------------------------------
+def sampled_negative_scores(scores: Tensor, scores_masked: Tensor, use_hard_negative: bool, hard_pool_size: int):
+    """XML.get_neg_scores, model_xml.py:607-625: per row, one negative drawn uniformly from the ranks
+    [1, 1 + hard_pool_size) (hard negatives) or [1, N) of the row sorted descending with the positive masked to
+    999.  The draw uses torch.randint on the DEFAULT CPU generator exactly like the reference, so that the same
+    torch.manual_seed gives the same negatives."""
+    bsz = len(scores)
+    rows = torch.arange(bsz, device=scores.device)
+    order = torch.sort(scores_masked, descending=True, dim=1)[1]
+    hi = min(1 + hard_pool_size, bsz) if use_hard_negative else bsz
+    pick = torch.randint(1, hi, size=(bsz,)).to(scores.device)
+    return scores[rows, order[rows, pick]]
+
+
+def ranking_loss(cfg, pos: Tensor, neg: Tensor) -> Tensor:
+    """XML.get_ranking_loss, model_xml.py:627-637."""
+    if cfg["ranking_loss_type"] == "hinge":
+        return torch.clamp(cfg["margin"] + neg - pos, min=0).sum() / len(pos)
+    if cfg["ranking_loss_type"] == "lse":
+        return torch.log1p(torch.exp(neg - pos)).sum() / len(pos)
+    raise NotImplementedError("Only support 'hinge' and 'lse'")
+
+
+def video_level_loss(cfg, q2c: Tensor):
+    """XML.get_video_level_loss, model_xml.py:588-605 -> (loss_neg_ctx, loss_neg_q)."""
+    bsz = len(q2c)
+    diag = torch.arange(bsz, device=q2c.device)
+    pos = q2c[diag, diag]
+    masked = q2c.detach().clone()
+    masked[diag, diag] = 999
+    neg_ctx = sampled_negative_scores(q2c, masked, cfg["use_hard_negative"], cfg["hard_pool_size"])
+    neg_q = sampled_negative_scores(q2c.transpose(0, 1), masked.transpose(0, 1), cfg["use_hard_negative"],
+                                    cfg["hard_pool_size"])
+    return ranking_loss(cfg, pos, neg_ctx), ranking_loss(cfg, pos, neg_q)
+
+
+def train_forward(cfg, w: Weights, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask,
+                  st_ed_indices):
+    """XML.forward, model_xml.py:212-251 (eval-mode arithmetic: dropout = identity).  Differentiable w.r.t. the
+    tensors in `w`.  Returns (loss, {loss_st_ed, loss_neg_ctx, loss_neg_q, loss_overall: float})."""
+    v1, v2, s1, s2 = encode_context(cfg, w, video_feat, video_mask, sub_feat, sub_mask)
+    q2c, st, ed = pred_from_raw_query(cfg, w, query_feat, query_mask, v1, v2, video_mask, s1, s2, sub_mask,
+                                      cross=False)
+    loss_st_ed = 0
+    if cfg["lw_st_ed"] != 0:
+        loss_st_ed = F.cross_entropy(st, st_ed_indices[:, 0]) + F.cross_entropy(ed, st_ed_indices[:, 1])
+    loss_neg_ctx = loss_neg_q = 0
+    if cfg["lw_neg_ctx"] != 0 or cfg["lw_neg_q"] != 0:
+        loss_neg_ctx, loss_neg_q = video_level_loss(cfg, q2c)
+    loss_st_ed = cfg["lw_st_ed"] * loss_st_ed
+    loss_neg_ctx = cfg["lw_neg_ctx"] * loss_neg_ctx
+    loss_neg_q = cfg["lw_neg_q"] * loss_neg_q
+    loss = loss_st_ed + loss_neg_ctx + loss_neg_q
+    return loss, {"loss_st_ed": float(loss_st_ed), "loss_neg_ctx": float(loss_neg_ctx),
+                  "loss_neg_q": float(loss_neg_q), "loss_overall": float(loss)}
+
+
+# --------------------------------------------------------------------------------------
 # driver, tensor section (inference.py)
 # --------------------------------------------------------------------------------------
 def cat_padded(tensors):

@@ -180,8 +180,73 @@ def nms_vectors():
     print("wrote", path)
 
 
+TRAIN_VARIANTS = {
+    # reference defaults (hinge, all in-batch negatives)
+    "plain": dict(),
+    # the second training phase: hard negatives from the top of the ranking, lse ranking loss, span loss re-weighted
+    "hard": dict(use_hard_negative=True, hard_pool_size=3, ranking_loss_type="lse", lw_st_ed=0.01, lw_neg_q=0.7),
+}
+TRAIN_SEED = 77
+
+
+def train_batch(case, cfg):
+    """One training batch built from the case's synthetic dataset: item i = (query i, its ground-truth video),
+    padded like start_end_collate (start_end_dataset.py:346-359); st/ed labels are seeded random clip indices."""
+    ds = SyntheticEvalDataset(max_ctx_l=cfg.max_ctx_l, max_desc_l=cfg.max_desc_l,
+                              video_dim=cfg.visual_input_size, sub_dim=cfg.sub_input_size,
+                              query_dim=cfg.query_input_size, ctx_mode=cfg.ctx_mode, min_ctx_l=3, **case["data"])
+    from utils.tensor_utils import pad_sequences_1d
+    gt = [int(q["vid_name"].split("_")[1]) for q in ds.query_data]
+    inputs = {}
+    inputs["query_feat"], inputs["query_mask"] = pad_sequences_1d(list(ds.query_feats), dtype=torch.float32)
+    for name, used, feats in (("video", ds.use_video, ds.video_feats), ("sub", ds.use_sub, ds.sub_feats)):
+        if used:
+            inputs[name + "_feat"], inputs[name + "_mask"] = pad_sequences_1d([feats[v] for v in gt],
+                                                                               dtype=torch.float32)
+        else:
+            inputs[name + "_feat"] = inputs[name + "_mask"] = None
+    inputs["tef_feat"] = inputs["tef_mask"] = None
+    rng = np.random.RandomState(5)
+    lens = np.asarray([ds.ctx_lens[v] for v in gt])
+    st = (rng.rand(len(gt)) * (lens - 1)).astype(np.int64)
+    ed = np.minimum(lens - 1, st + 1 + (rng.rand(len(gt)) * 6).astype(np.int64))
+    inputs["st_ed_indices"] = torch.from_numpy(np.stack([st, ed], 1))
+    return inputs, np.asarray(gt)
+
+
+def train_vectors():
+    """XML.forward + losses + backward (reference model_xml.py:212-251,588-637) with dropout off (eval mode):
+    loss, the four reported floats and the gradient of every parameter."""
+    out = {"seed": np.int64(TRAIN_SEED), "variants_json": json.dumps(TRAIN_VARIANTS)}
+    for name, case in CASES.items():
+        for variant, override in TRAIN_VARIANTS.items():
+            cfg = copy.deepcopy(xml_base_config)
+            cfg.update(case["cfg"])
+            cfg.update(override)
+            torch.manual_seed(2018)
+            model = XML(cfg).eval()
+            inputs, gt = train_batch(case, cfg)
+            torch.manual_seed(TRAIN_SEED)
+            loss, parts = model(**inputs)
+            loss.backward()
+            key = "%s/%s/" % (name, variant)
+            out[key + "loss"] = np.float64(loss.item())
+            out[key + "parts"] = np.asarray([parts[k] for k in ("loss_st_ed", "loss_neg_ctx", "loss_neg_q",
+                                                                "loss_overall")], dtype=np.float64)
+            out[key + "st_ed_indices"] = inputs["st_ed_indices"].numpy()
+            out[key + "gt"] = gt
+            for pname, prm in model.named_parameters():
+                out[key + "g/" + pname] = (prm.grad if prm.grad is not None else torch.zeros_like(prm)).numpy()
+            print(key, "loss %.6f" % loss.item(), parts)
+    path = os.path.join(HERE, "train_step.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    for case_name, case_def in CASES.items():
-        run_case(case_name, case_def)
-    nms_vectors()
+    if "--train-only" not in sys.argv:
+        for case_name, case_def in CASES.items():
+            run_case(case_name, case_def)
+        nms_vectors()
+    train_vectors()

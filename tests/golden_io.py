@@ -66,3 +66,33 @@ class GoldenCase:
         bsz = self.case["q_bsz"]
         for lo in range(0, self.n_queries, bsz):
             yield lo, self.pad(self.query_feats[lo:lo + bsz])
+
+
+TRAIN_VARIANTS = ("plain", "hard")
+
+
+class TrainCase:
+    """One golden training step (tests/golden/train_step.npz): the batch is rebuilt from the case's data --
+    item i = (query i, its ground-truth video) -- and the reference's loss, reported floats and parameter
+    gradients are loaded."""
+
+    def __init__(self, name, variant):
+        import json as _json
+        z = np.load(os.path.join(GOLDEN_DIR, "train_step.npz"))
+        g = GoldenCase(name)
+        key = "%s/%s/" % (name, variant)
+        self.seed = int(z["seed"])
+        self.cfg = dict(g.cfg)
+        self.cfg.update(_json.loads(str(z["variants_json"]))[variant])
+        self.weights = g.weights
+        gt = z[key + "gt"].tolist()
+        self.inputs = dict(query_feat=g.query_feat, query_mask=g.query_mask, tef_feat=None, tef_mask=None,
+                           st_ed_indices=torch.from_numpy(z[key + "st_ed_indices"]))
+        for mod, used, feats in (("video", g.use_video, g.video_feats), ("sub", g.use_sub, g.sub_feats)):
+            if used:
+                self.inputs[mod + "_feat"], self.inputs[mod + "_mask"] = GoldenCase.pad([feats[v] for v in gt])
+            else:
+                self.inputs[mod + "_feat"] = self.inputs[mod + "_mask"] = None
+        self.loss = float(z[key + "loss"])
+        self.parts = dict(zip(("loss_st_ed", "loss_neg_ctx", "loss_neg_q", "loss_overall"), z[key + "parts"].tolist()))
+        self.grads = {k[len(key) + 2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(key + "g/")}

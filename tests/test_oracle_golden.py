@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import xml_oracle as O
-from tests.golden_io import CASE_NAMES, GOLDEN_DIR, GoldenCase
+from tests.golden_io import CASE_NAMES, GOLDEN_DIR, TRAIN_VARIANTS, GoldenCase, TrainCase
 
 RTOL, ATOL = 1e-5, 1e-6  # same torch CPU kernels on both sides -> essentially bit-equal
 
@@ -126,3 +126,24 @@ def test_vcmr_nms(case):
         got = O.vcmr_nms(preds, 0.5, c["max_before_nms"], 20)
         assert len(got) == cnt[q]
         assert np.array_equal(np.asarray(got, dtype=np.float64), ref_out[q, :cnt[q]])
+
+
+@pytest.mark.parametrize("variant", TRAIN_VARIANTS)
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_train_forward_loss_and_gradients(name, variant):
+    """O.train_forward (XML.forward + losses, model_xml.py:212-251,588-637) against the reference's loss, reported
+    floats and the gradient of every parameter (same negative sampling: torch.randint under the same seed)."""
+    tc = TrainCase(name, variant)
+    w = {k: v.clone().requires_grad_(True) for k, v in tc.weights.items()}
+    i = tc.inputs
+    torch.manual_seed(tc.seed)
+    loss, parts = O.train_forward(tc.cfg, w, i["query_feat"], i["query_mask"], i["video_feat"], i["video_mask"],
+                                  i["sub_feat"], i["sub_mask"], i["st_ed_indices"])
+    assert abs(loss.item() - tc.loss) <= 1e-5 * abs(tc.loss)
+    for k, v in tc.parts.items():
+        assert abs(parts[k] - v) <= 1e-5 * max(1e-3, abs(v)), k
+    loss.backward()
+    assert set(tc.grads) == set(w)
+    for k, g in tc.grads.items():
+        got = w[k].grad if w[k].grad is not None else torch.zeros_like(w[k])
+        close(got, g, rtol=1e-4, atol=1e-7)

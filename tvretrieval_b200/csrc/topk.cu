@@ -19,11 +19,13 @@ constexpr int NT = 512;
 constexpr int HIST = 4096;
 constexpr int MAX_K = 1024;
 
+constexpr int LIST_CAP = 3072;  // survivors of the span pre-filter kept in shared memory
+
 struct SelSmem {
   int hist[HIST];
   int warp_tot[NT / 32];
   int sel_bin, sel_above, sel_count, total;
-  int count, count_eq2;
+  int count, count_eq2, n_list;
   unsigned long long buf[MAX_K];
 };
 
@@ -272,12 +274,14 @@ struct SpanGen {
   const float* vr;  // [n_slots] video scores (null -> 1)
   const unsigned char* valid;  // [n_slots] or null
   int n_slots, L, min_l, max_l, tie_desc;
-  unsigned int min_key;  // cells whose score key is below this known lower bound of the k-th best are skipped
+  float min_score;  // cells below this known lower bound of the k-th best score are skipped (0: keep all positive)
   template <class F>
   __device__ void for_each(F f) const {
     const int rows = n_slots * L;
-    for (int r = threadIdx.x; r < rows; r += NT) {
-      const int j = r / L, m = r - j * L;
+    const int dj = NT / L, dm = NT - dj * L;  // row r = j * L + m advances by NT per iteration, without divisions
+    int j = threadIdx.x / L, m = threadIdx.x - j * L;
+    for (int r = threadIdx.x; r < rows; r += NT, j += dj, m += dm) {
+      if (m >= L) m -= L, ++j;
       if (valid && !valid[j]) continue;
       float a = __ldg(st + r);
       if (vr) a = __fmul_rn(a, __ldg(vr + j));  // (st * vr) first: the association torch.einsum uses
@@ -286,11 +290,24 @@ struct SpanGen {
       const float* e = ed + j * L;
       for (int n = m + min_l; n < n_hi; ++n) {
         const float s = __fmul_rn(a, __ldg(e + n));
-        if (s > 0.f && float_key(s) >= min_key) {
+        if (s > 0.f && s >= min_score) {
           const unsigned int id = (unsigned int)(r * L + n);
           f(float_key(s), tie_desc ? id : ~id);
         }
       }
+    }
+  }
+};
+
+// generator over a compact (key, id) list in shared memory
+struct ListGen {
+  const unsigned long long* list;
+  int n;
+  template <class F>
+  __device__ void for_each(F f) const {
+    for (int i = threadIdx.x; i < n; i += NT) {
+      const unsigned long long e = list[i];
+      f((unsigned int)(e >> 32), (unsigned int)(e & 0xffffffffu));
     }
   }
 };
@@ -348,22 +365,36 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   const long long q = blockIdx.x;
   SpanGen gen{st + q * n_slots * L, ed + q * n_slots * L, vr ? vr + q * n_slots : nullptr,
-              slot_valid ? slot_valid + q * n_slots : nullptr, n_slots, L, min_l, max_l, tie_desc, 0u};
+              slot_valid ? slot_valid + q * n_slots : nullptr, n_slots, L, min_l, max_l, tie_desc, 0.f};
   // Pre-filter: the k-th best cell of the first few slots (the videos with the largest retrieval scores) is a lower
-  // bound of the k-th best cell overall, so the selection passes over all slots can skip everything below it --
-  // typically > 95 % of the cells, which removes the shared-memory histogram contention of clustered scores.
-  constexpr int SUB_SLOTS = 4;
+  // bound of the k-th best cell overall.  ONE pass over all slots then collects the few cells at or above it into
+  // shared memory and the exact selection runs on that list (instead of 4 passes over ~180K cells per query).
+  constexpr int SUB_SLOTS = 8;
+  unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(SelSmem));
+  int n_out = -1;
   if (n_slots > 2 * SUB_SLOTS) {
     SpanGen sub = gen;
     sub.n_slots = SUB_SLOTS;
     unsigned int thr = 0;
     int n_equal, need_equal, n_total;
-    if (radix_select(sub, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k,
-                     thr, n_equal, need_equal, n_total))
-      gen.min_key = thr;
+    const bool full = radix_select(sub, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; },
+                                   sm, k, thr, n_equal, need_equal, n_total);
     __syncthreads();
+    if (full) {
+      gen.min_score = key_float(thr);
+      if (threadIdx.x == 0) sm.n_list = 0;
+      __syncthreads();
+      gen.for_each([&](unsigned int key, unsigned int idk) {
+        const int pos = atomicAdd(&sm.n_list, 1);
+        if (pos < LIST_CAP) list[pos] = ((unsigned long long)key << 32) | idk;
+      });
+      __syncthreads();
+      const int n_list = sm.n_list;
+      __syncthreads();
+      if (n_list <= LIST_CAP) n_out = block_topk(ListGen{list, n_list}, sm, k);
+    }
   }
-  const int n_out = block_topk(gen, sm, k);
+  if (n_out < 0) n_out = block_topk(gen, sm, k);
   int* oi = out_idx + q * k;
   float* ov = out_val + q * k;
   for (int i = threadIdx.x; i < k; i += NT) {
@@ -460,8 +491,9 @@ extern "C" int xmlb_span_topk(const float* st_prob, const float* ed_prob, const 
                "xmlb_span_topk: n_slots*L*L must fit in int32");
   XMLB_REQUIRE(min_l >= 0 && max_l > min_l, "xmlb_span_topk: need 0 <= min_l < max_l");
   if (n_queries == 0) return XMLB_OK;
-  XMLB_CUDA(cudaFuncSetAttribute(span_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
-  span_topk_kernel<<<n_queries, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(
+  const size_t smem = sizeof(SelSmem) + (size_t)LIST_CAP * sizeof(unsigned long long);
+  XMLB_CUDA(cudaFuncSetAttribute(span_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  span_topk_kernel<<<n_queries, NT, smem, (cudaStream_t)stream>>>(
       st_prob, ed_prob, video_score, slot_valid, n_slots, ctx_len, min_l, max_l, k, tie_desc, zero_fill_missing,
       out_flat_idx, out_score);
   xmlb_count_launch(1);
