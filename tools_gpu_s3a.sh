@@ -1,0 +1,11 @@
+#!/bin/bash
+# session-3 call A: full GPU test suite, default bench, launch list, ncu --set full of the VR filter kernel
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -2 > gpurun_out/bench_s3a.log
+tail -c 3000 gpurun_out/bench_s3a.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_s3a.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --cuda-profiler > gpurun_out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"vr_scores_tc_packed" -c 1 -o gpurun_out/prof_vr_filter_s3a -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --cuda-profiler > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log | cut -c1-300
+ls -la gpurun_out
