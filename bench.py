@@ -187,6 +187,18 @@ def cpu_baseline(args, cfg, weights, ctx_dev, query_feat, query_mask):
                       % (nq, n_sub, n_total, t, n_sub, n_total)}
 
 
+def ncu_traffic(args, world, searcher):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed
+    ncu --set full capture (profiles/ncu_traffic.json); only valid for the shape and mode it was captured at."""
+    try:
+        t = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return None
+    same = (world == 1 and searcher.two_pass and args.precision == t.get("precision")
+            and [args.n_videos, args.n_queries, args.max_ctx_l, args.hidden] == t.get("shape"))
+    return t.get("dram_bytes_per_launch") if same else None
+
+
 def run_ours(args):
     from tvretrieval_b200 import _lib
     from tvretrieval_b200.engine import CorpusIndex, PhaseTimer, VCMRSearcher
@@ -314,9 +326,10 @@ def run_ours(args):
     tc_mode = args.precision != "f32"
     mma_per_product = 1 if (searcher.two_pass or not tc_mode) else 3
     if searcher.two_pass:
-        kernel_name = ("vr_scores_tc_packed_kernel, filter pass of the two-pass search (tcgen05 kind::f16, hi halves "
-                       "only: 1 MMA per product over ALL pairs, fp32 TMEM accumulate; the candidates it leaves are "
-                       "re-scored exactly by vr_rescore_tc_kernel, phases vr_select/vr_rescore)")
+        kernel_name = ("vr_filter_pair_kernel, filter pass of the two-pass search (tcgen05 cta_group::2 kind::f16 on CTA "
+                       "pairs, M=256 x N=256 tiles, hi halves only: 1 MMA per product over ALL pairs, fp32 TMEM "
+                       "accumulate; the candidates it leaves are re-scored exactly by vr_rescore_tc_kernel, phases "
+                       "vr_select/vr_rescore)")
     elif tc_mode:
         kernel_name = ("vr_scores_tc_packed_kernel (tcgen05 kind::f16, %s split: 3 MMAs per product, fp32 TMEM "
                        "accumulate)" % args.precision)
@@ -326,7 +339,7 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "mma_flops_executed_per_algorithmic": mma_per_product,
                 "frac_of_peak_executed": mma_per_product * achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                "traffic": ncu_traffic(args, world, searcher), "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                 "flops_counted": ("algorithmic 2*H*S per modality per query, S = %d valid clips (packed corpus, tile fill "
                                   "%.3f); the padded corpus would be S_pad = %d" % (s_valid, index.packing.fill, s_pad))
                 if packed else "algorithmic 2*H*S_pad per modality per query, S_pad = n_videos*L = %d padded clips" % s_pad,

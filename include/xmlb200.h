@@ -201,6 +201,15 @@ int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,
                        int block_n, const int* units, const int* n_units, int max_units, const int* entry_out,
                        float* out_st, float* out_ed, int* sched_ws, int is_bf16, void* stream);
 
+/* Filter pass of the two-pass video retrieval on CTA pairs (tcgen05 cta_group::2, M = 256): the hi-only
+ * (1 MMA per product) scores of xmlb_vr_scores_tc_packed(hi_only = 1) for all (query, video) pairs, same packed
+ * corpus, tile tables and packed-ordinal output layout; approximates model_xml.py:446-452,572-574 to within the
+ * bound that xmlb_select_candidates uses.  q_hi_b / c_hi_b NULL = one modality. */
+int xmlb_vr_filter_pair(const unsigned short* q_hi_a, const unsigned short* q_hi_b, const unsigned short* c_hi_a,
+                        const unsigned short* c_hi_b, const int* tile_meta, const unsigned int* tile_starts,
+                        float* q2c, int* sched_ws, int n_queries, int n_videos, long long n_packed_rows, int n_tiles,
+                        int kpad, int is_bf16, void* stream);
+
 /* Per-row exact top-k, ranked (value desc, id asc | desc).  value = apply_exp ? exp(alpha * x) : x.
  * ids: optional explicit ids (NULL: column index), (n_rows, n_cols) when ids_shared == 0, one (n_cols) table shared
  * by all rows when ids_shared != 0.  Replaces torch.exp + torch.topk of
@@ -230,6 +239,30 @@ int xmlb_span_zero_fill(int* flat_idx, float* score, int n_queries, int k, long 
 int xmlb_temporal_nms(const int* video_idx, const float* st, const float* ed, const float* score,
                       const int* n_valid, int n_queries, int n_in, double iou_thd, int max_per_group, int max_out,
                       int* out_idx, int* out_count, void* stream);
+
+/* ---------------------------------------------------------------- training step (config #4) -------- */
+
+/* out[i] = keep(seed, index0 + i) ? x[i] / (1 - p) : 0 -- nn.Dropout in train mode (model_components.py:77,152,
+ * 263,311).  The mask is a pure function of (seed, element index), so the backward pass calls this again with the
+ * same seed instead of storing a mask.  x NULL = ones (returns the scaled mask itself); in-place allowed. */
+int xmlb_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
+                 unsigned long long index0, void* stream);
+
+/* xmlb_attention with dropout on the attention probabilities (model_components.py:296; train mode).  The mask of
+ * probability element e (flat index in (batch, n_heads, len_q, len_k)) is keep(seed, index0 + e). */
+int xmlb_attention_train(const float* q, const float* k, const float* v, const float* mask,
+                         long long mask_batch_stride, long long mask_q_stride, float* out, float* scores_ws,
+                         int batch, int len_q, int len_k, int hidden, int n_heads, float dropout_p,
+                         unsigned long long seed, unsigned long long index0, void* stream);
+
+/* One BertAdam.step (optimization.py:273-338) over all parameter tensors in two launches.
+ * chunk_table: n_chunks rows of 6 x int64 {param*, grad*, m*, v* (offset to the chunk), elements, tensor id};
+ * tensor_table: n_tensors rows of {int first_chunk, int n_chunks, float lr_scheduled, float weight_decay};
+ * partial_ws: n_chunks floats.  Per tensor: g *= min(1, max_grad_norm / (||g|| + 1e-6)) (written back, like
+ * clip_grad_norm_); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g g; p -= lr (m / (sqrt(v) + eps) + wd p).
+ * max_grad_norm <= 0 disables clipping.  No bias correction (as the reference). */
+int xmlb_bert_adam_step(const long long* chunk_table, int n_chunks, const int* tensor_table, int n_tensors,
+                        float* partial_ws, float b1, float b2, float eps, float max_grad_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,10 @@
+#!/bin/bash
+# session-3 call B: GPU test suite + default bench + launch list + ncu --set full of the pair filter kernel
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --timeout 600 -x 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -2 > gpurun_out/bench_s3b.log
+tail -c 3000 gpurun_out/bench_s3b.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_s3b.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --cuda-profiler > gpurun_out/ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"vr_filter_pair" -c 1 -o gpurun_out/prof_vr_filter_pair_s3b -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --cuda-profiler > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log | cut -c1-300

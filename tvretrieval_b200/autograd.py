@@ -112,6 +112,23 @@ def linear(kernel_fn, x, weight, bias, residual, relu):
     return _Linear.apply(kernel_fn, x, weight, bias, residual, relu)
 
 
+class Dropout(torch.autograd.Function):
+    """Forward and backward are the same kernel call: the mask is a function of (seed, element index)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, index0):
+        from . import ops
+        ctx.args = (p, seed, index0)
+        with torch.no_grad():
+            return ops.dropout(x, p, seed, index0)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        with torch.no_grad():
+            return ops.dropout(g.contiguous(), *ctx.args), None, None, None
+
+
 # ------------------------------------------------------------------------------------------------ torch twins
 def t_add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
     dim = x.shape[-1]
@@ -122,7 +139,7 @@ def t_add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
     return F.layer_norm(x, (dim,), gamma, beta, eps)
 
 
-def t_attention(q, k, v, mask3, n_heads, max_batch=8192, dropout_p=0.0):
+def t_attention(q, k, v, mask3, n_heads, max_batch=8192, dropout_p=0.0, seed=0):
     """reference model_components.py:277-303 after the projections."""
     n, lq, hid = q.shape
     dh = hid // n_heads
@@ -130,8 +147,9 @@ def t_attention(q, k, v, mask3, n_heads, max_batch=8192, dropout_p=0.0):
     scores = torch.matmul(heads(q), heads(k).transpose(-1, -2)) / (dh ** 0.5)
     scores = scores + (1.0 - mask3.unsqueeze(1)) * ATT_MASK_FILL
     probs = torch.softmax(scores, dim=-1)
-    if dropout_p > 0:
-        probs = F.dropout(probs, dropout_p, training=True)
+    if dropout_p > 0:  # the very mask the forward kernel applied
+        from . import ops
+        probs = probs * ops.dropout_mask(probs.shape, dropout_p, seed, probs.device)
     return torch.matmul(probs, heads(v)).permute(0, 2, 1, 3).reshape(n, lq, hid)
 
 
@@ -142,7 +160,7 @@ def t_mask_logits(x, m):
 def t_modular_pool(encoded, mask, w_mod):
     att = torch.softmax(t_mask_logits(F.linear(encoded, w_mod), mask.unsqueeze(2)), dim=1)
     pooled = torch.einsum("blm,bld->bmd", att, encoded)
-    return (pooled[:, 0], pooled[:, 1]) if pooled.shape[1] == 2 else (pooled[:, 0], pooled[:, 0])
+    return tuple(pooled[:, m] for m in range(pooled.shape[1]))
 
 
 def t_l2norm_rows(x, eps=1e-12):

@@ -8,10 +8,13 @@
 
 extern "C" int xmlb_softmax_rows(const float* x, float* out, long long rows, int dim, void* stream);
 
-extern "C" int xmlb_attention(const float* q, const float* k, const float* v, const float* mask,
-                              long long mask_batch_stride, long long mask_q_stride, float* out,
-                              float* scores_ws, int batch, int len_q, int len_k, int hidden, int n_heads,
-                              void* stream_) {
+extern "C" int xmlb_dropout(const float* x, float* out, long long n, float p, unsigned long long seed,
+                            unsigned long long index0, void* stream);
+
+static int attention_impl(const float* q, const float* k, const float* v, const float* mask,
+                          long long mask_batch_stride, long long mask_q_stride, float* out, float* scores_ws,
+                          int batch, int len_q, int len_k, int hidden, int n_heads, float dropout_p,
+                          unsigned long long seed, unsigned long long index0, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   XMLB_REQUIRE(q && k && v && mask && out && scores_ws, "xmlb_attention: null pointer");
   XMLB_REQUIRE(n_heads > 0 && hidden % n_heads == 0, "xmlb_attention: hidden %% n_heads != 0");
@@ -35,6 +38,11 @@ extern "C" int xmlb_attention(const float* q, const float* k, const float* v, co
   // 2) softmax over keys, in place
   rc = xmlb_softmax_rows(scores_ws, scores_ws, (long long)batch * n_heads * len_q, len_k, stream_);
   if (rc) return rc;
+  if (dropout_p > 0.f) {  // train mode: dropout on the probabilities (model_components.py:296)
+    rc = xmlb_dropout(scores_ws, scores_ws, (long long)batch * n_heads * len_q * len_k, dropout_p, seed, index0,
+                      stream_);
+    if (rc) return rc;
+  }
   // 3) out[b][:, h*dh:(h+1)*dh] = P_h V_h
   GemmParams o = {};
   o.A = scores_ws, o.B = v, o.C = out;
@@ -46,6 +54,24 @@ extern "C" int xmlb_attention(const float* q, const float* k, const float* v, co
   o.sC0 = (long long)len_q * hidden, o.sC1 = dh;
   o.epilogue = EPI_STORE;
   return xmlb_gemm_launch(o, batch, stream);
+}
+
+extern "C" int xmlb_attention(const float* q, const float* k, const float* v, const float* mask,
+                              long long mask_batch_stride, long long mask_q_stride, float* out,
+                              float* scores_ws, int batch, int len_q, int len_k, int hidden, int n_heads,
+                              void* stream) {
+  return attention_impl(q, k, v, mask, mask_batch_stride, mask_q_stride, out, scores_ws, batch, len_q, len_k,
+                        hidden, n_heads, 0.f, 0ull, 0ull, stream);
+}
+
+extern "C" int xmlb_attention_train(const float* q, const float* k, const float* v, const float* mask,
+                                    long long mask_batch_stride, long long mask_q_stride, float* out,
+                                    float* scores_ws, int batch, int len_q, int len_k, int hidden, int n_heads,
+                                    float dropout_p, unsigned long long seed, unsigned long long index0,
+                                    void* stream) {
+  XMLB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "xmlb_attention_train: dropout_p must be in [0, 1)");
+  return attention_impl(q, k, v, mask, mask_batch_stride, mask_q_stride, out, scores_ws, batch, len_q, len_k,
+                        hidden, n_heads, dropout_p, seed, index0, stream);
 }
 
 // One CTA (128 threads) per query.  smem: att[len][n_mod]

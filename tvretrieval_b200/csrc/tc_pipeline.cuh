@@ -49,6 +49,7 @@ struct Pipe {
   uint32_t smem_base;   // 1024-aligned start of the stage ring
   uint32_t bar_base;
   int stages, stage_bytes, b_tile_bytes;
+  int probe;  // limiter experiments (XMLB_VR_PROBE): bit 1 = the producer skips the B tiles
   int terms;  // 3: split precision (hi*lo + lo*hi + hi*hi, stage = A_hi|A_lo|B_hi|B_lo); 1: hi*hi only (A_hi|B_hi)
   __device__ uint32_t full_bar(int s) const { return bar_base + 8u * s; }
   __device__ uint32_t empty_bar(int s) const { return bar_base + 8u * (stages + s); }
@@ -79,6 +80,7 @@ __device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw,
   p.smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   p.stages = stages;
   p.terms = terms;
+  p.probe = 0;
   p.b_tile_bytes = block_n * BLOCK_K * 2;
   p.stage_bytes = (terms == 3 ? 2 : 1) * (A_TILE_BYTES + p.b_tile_bytes);
   p.bar_base = p.smem_base + stages * p.stage_bytes;
@@ -148,12 +150,14 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
     for (int kb = 0; kb < u.k_blocks; ++kb) {
       mbar_wait(p.empty_bar(stage), phase ^ 1u);
       const uint32_t sa = p.smem_base + stage * p.stage_bytes;
-      mbar_expect_tx(p.full_bar(stage), (uint32_t)p.stage_bytes);
+      mbar_expect_tx(p.full_bar(stage), (p.probe & 2) ? (uint32_t)A_TILE_BYTES : (uint32_t)p.stage_bytes);
       if (p.terms == 3) {
         tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
         tma_load_2d(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row);
         tma_load_2d(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
         tma_load_2d(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+      } else if (p.probe & 2) {
+        tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
       } else {
         tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
         tma_load_2d(sa + A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);

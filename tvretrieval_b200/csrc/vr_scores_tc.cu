@@ -15,9 +15,11 @@
 //               (one thread = one query row, no shuffles), combine the two modalities, store q2c
 // The two modalities of a tile alternate between the two TMEM accumulators, so the epilogue of one overlaps the
 // MMAs of the other.
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "tc_pipeline.cuh"
+#include "vr_common.cuh"
 #include "xmlb200.h"
 
 namespace {
@@ -25,8 +27,8 @@ namespace {
 using tc::BLOCK_K;
 using tc::BLOCK_M;
 constexpr int MAX_VPT = 8;  // videos per tile (BLOCK_N = vpt * lp <= 256, lp multiple of 32)
-constexpr int MAX_TILE_VIDEOS = 32;  // packed layout: at most this many videos share a tile
-constexpr int PACKED_EXTRA_SMEM = 128 * (MAX_TILE_VIDEOS + 1) * 4;
+using vr::MAX_TILE_VIDEOS;
+using vr::PACKED_EXTRA_SMEM;
 
 struct VrMaps {
   CUtensorMap a_hi[2], a_lo[2], b_hi[2], b_lo[2];
@@ -134,32 +136,8 @@ struct VrPackedParams {
   const int* n_m_tiles;
   float divisor;
   unsigned int idesc;
+  int probe;  // XMLB_VR_PROBE (limiter experiments): bit 0 = epilogue only waits and releases, bit 1 = no B loads
 };
-
-__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
-  float m[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) m[i] = fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 16]));
-#pragma unroll
-  for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-    for (int i = 0; i < w; ++i) m[i] = fmaxf(m[i], m[i + w]);
-  return m[0];
-}
-__device__ __forceinline__ float masked_max32(const uint32_t (&r)[32], unsigned int mask) {
-  float m[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float a = (mask >> i) & 1u ? __uint_as_float(r[i]) : MASK_FILL;
-    const float b = (mask >> (i + 16)) & 1u ? __uint_as_float(r[i + 16]) : MASK_FILL;
-    m[i] = fmaxf(a, b);
-  }
-#pragma unroll
-  for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-    for (int i = 0; i < w; ++i) m[i] = fmaxf(m[i], m[i + w]);
-  return m[0];
-}
 
 struct VrPackedSched {
   const VrMaps* maps;
@@ -191,6 +169,7 @@ vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_con
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
   const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, 256, p.terms);
+  pipe.probe = p.probe;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
@@ -211,55 +190,15 @@ vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_con
       const int q = m_tile * BLOCK_M + row;
       const bool q_ok = q < p.n_queries;
       const int4 meta = __ldg(reinterpret_cast<const int4*>(p.tile_meta) + n_tile);  // row, first ordinal, used, n videos
-      const int used = meta.z;
       float* __restrict__ out_row = p.out + (long long)q * p.n_videos + meta.y;
       const unsigned int* __restrict__ starts = p.tile_starts + 8 * n_tile;
       const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
-      const bool last = mod == p.n_mod - 1;
-      int j = -1;
-      float cur = MASK_FILL;
-      auto flush = [&]() {
-        if (j < 0) return;
-        if (!last) {
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(my_best + 4u * j), "f"(cur) : "memory");
-        } else {
-          float v = cur;
-          if (mod != 0) {
-            float first;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(first) : "r"(my_best + 4u * j) : "memory");
-            v = __fadd_rn(first, cur);
-          }
-          if (q_ok) out_row[j] = __fdiv_rn(v, p.divisor);
-        }
-      };
-      for (int c = 0; c < 8 && c * 32 < used; ++c) {  // warp-uniform
-        uint32_t r[32];
-        tc::tmem_ld_32x32(taddr + c * 32, r);
-        tc::tmem_ld_wait();
-        const int n_here = min(32, used - c * 32);
-        const unsigned int valid = n_here == 32 ? 0xffffffffu : (1u << n_here) - 1u;
-        unsigned int sb = __ldg(starts + c) & valid;
-        if (sb == 0u && n_here == 32) {  // the whole chunk continues the current video: branch-free max tree
-          cur = fmaxf(cur, max32(r));
-        } else {  // walk the video segments of this chunk (all conditions are uniform over the CTA)
-          int pos = 0;
-          while (true) {
-            const int nxt = sb ? __ffs(sb) - 1 : n_here;  // next video start, or end of the used columns
-            if (nxt > pos) {
-              const unsigned int seg = (nxt == 32 ? 0xffffffffu : (1u << nxt) - 1u) & ~((1u << pos) - 1u);
-              cur = fmaxf(cur, masked_max32(r, seg));
-            }
-            if (nxt >= n_here) break;
-            flush();  // a new video starts at column nxt
-            ++j;
-            cur = MASK_FILL;
-            pos = nxt;
-            sb &= sb - 1u;
-          }
-        }
+      if (p.probe & 1) {
+        tc::epi_release(pipe, unit);
+        continue;
       }
-      tc::epi_release(pipe, unit);  // all TMEM reads of this accumulator are done
-      flush();
+      vr::packed_epilogue(taddr, meta.z, starts, out_row, q_ok, mod, p.n_mod, p.divisor, my_best,
+                          [&]() { tc::epi_release(pipe, unit); });
     }
   }
   tc::pipe_teardown(tmem_base);
@@ -332,7 +271,7 @@ vr_rescore_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant_
         tc::tmem_ld_32x32(taddr + c * 32, r);
         tc::tmem_ld_wait();
         const int n_here = len - c * 32;
-        cur = fmaxf(cur, n_here >= 32 ? max32(r) : masked_max32(r, (1u << n_here) - 1u));
+        cur = fmaxf(cur, n_here >= 32 ? vr::max32(r) : vr::masked_max32(r, (1u << n_here) - 1u));
       }
       tc::epi_release(pipe, unit);
       if (mod != p.n_mod - 1) {
@@ -594,6 +533,8 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   p.idesc = tc::idesc_f16(BLOCK_M, 256, is_bf16 ? 1 : 0);
   p.terms = hi_only ? 1 : 3;
   p.stages = tc::pipe_stages(256, PACKED_EXTRA_SMEM, p.terms);
+  if (const char* e = getenv("XMLB_VR_PROBE")) p.probe = atoi(e);
+  if (const char* e = getenv("XMLB_VR_STAGES")) p.stages = atoi(e) < p.stages ? atoi(e) : p.stages;
   XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_scores_tc_packed: tile does not fit in shared memory");
   const size_t smem = tc::pipe_smem_bytes(256, p.stages, PACKED_EXTRA_SMEM, p.terms);
   XMLB_REQUIRE(((uintptr_t)tile_meta & 15) == 0, "xmlb_vr_scores_tc_packed: tile_meta must be 16-byte aligned");

@@ -3,11 +3,21 @@
 They mirror the reference module tree (reference baselines/crossmodal_moment_localization/
 model_components.py:67-89,141-163,201-216,244-317) only as far as checkpoint compatibility requires: identical
 attribute names, parameter shapes and `state_dict` keys.  The arithmetic itself is in
-tvretrieval_b200/csrc/*.cu.  Inference only (eval semantics: dropout is the identity).
+tvretrieval_b200/csrc/*.cu.  In train mode (`module.training`, dropout p > 0) the reference's nn.Dropout layers are
+applied by the counter-based xmlb_dropout kernel (ops.dropout) at the same places; in eval mode they are the
+identity, exactly like the reference.
 """
 import torch.nn as nn
 
 from . import ops
+
+
+def _drop(module, x):
+    """module.dropout (an nn.Dropout, kept for its `p` and for state_dict/attribute parity) applied by ops.dropout."""
+    p = module.p
+    if not module.training or p <= 0:
+        return x
+    return ops.dropout(x, p, ops.new_seed())
 
 
 class TrainablePositionalEncoding(nn.Module):
@@ -24,8 +34,9 @@ class TrainablePositionalEncoding(nn.Module):
         if seq_len > self.position_embeddings.num_embeddings:
             raise IndexError("sequence length %d exceeds the %d learned positions"
                              % (seq_len, self.position_embeddings.num_embeddings))
-        return ops.add_layernorm(input_feat, self.LayerNorm.weight, self.LayerNorm.bias,
-                                 add=self.position_embeddings.weight, add_rows=seq_len, eps=self.LayerNorm.eps)
+        out = ops.add_layernorm(input_feat, self.LayerNorm.weight, self.LayerNorm.bias,
+                                add=self.position_embeddings.weight, add_rows=seq_len, eps=self.LayerNorm.eps)
+        return _drop(self.dropout, out)
 
 
 class LinearLayer(nn.Module):
@@ -43,7 +54,7 @@ class LinearLayer(nn.Module):
         if self.layer_norm:
             x = ops.add_layernorm(x, self.LayerNorm.weight, self.LayerNorm.bias, eps=self.LayerNorm.eps)
         fc = self.net[1]
-        return ops.linear(x, fc.weight, fc.bias, relu=self.relu)
+        return ops.linear(_drop(self.net[0], x), fc.weight, fc.bias, relu=self.relu)
 
 
 class BertSelfAttention(nn.Module):
@@ -67,7 +78,9 @@ class BertSelfAttention(nn.Module):
         q = ops.linear(query_states, self.query.weight, self.query.bias)
         k = ops.linear(key_states, self.key.weight, self.key.bias)
         v = ops.linear(value_states, self.value.weight, self.value.bias)
-        return ops.attention(q, k, v, attention_mask, self.num_attention_heads)
+        p = self.dropout.p if self.training else 0.0
+        return ops.attention(q, k, v, attention_mask, self.num_attention_heads, dropout_p=p,
+                             seed=ops.new_seed() if p > 0 else 0)
 
 
 class BertSelfOutput(nn.Module):
@@ -80,6 +93,10 @@ class BertSelfOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
     def forward(self, hidden_states, input_tensor):
+        if self.training and self.dropout.p > 0:  # dense -> dropout -> + residual -> LN
+            h = _drop(self.dropout, ops.linear(hidden_states, self.dense.weight, self.dense.bias))
+            return ops.add_layernorm(h, self.LayerNorm.weight, self.LayerNorm.bias, add=input_tensor,
+                                     eps=self.LayerNorm.eps)
         h = ops.linear(hidden_states, self.dense.weight, self.dense.bias, residual=input_tensor)
         return ops.add_layernorm(h, self.LayerNorm.weight, self.LayerNorm.bias, eps=self.LayerNorm.eps)
 

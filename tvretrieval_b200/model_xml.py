@@ -5,7 +5,8 @@ Mirror of the public surface of reference baselines/crossmodal_moment_localizati
 and method signatures (`encode_context`, `encode_query`, `encode_input`, `get_modularized_queries`,
 `get_video_level_scores`, `get_merged_st_ed_prob`, `get_st_ed_prob`, `get_pred_from_raw_query`, ...), so the
 reference drivers and `baselines/profiling/profile_main.py` can use it unchanged.  Tensors must live on a CUDA
-device: there is no CPU or PyTorch-eager fallback.  Only `encoder_type="transformer"` with
+device: there is no CPU or PyTorch-eager fallback.  `forward` (the training step) runs the same kernels and
+differentiates them through tvretrieval_b200/autograd.py.  Only `encoder_type="transformer"` with
 `span_predictor_type="conv"` (the shipped configuration) is implemented.
 """
 import copy
@@ -13,7 +14,7 @@ import copy
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import autograd, ops
 from .model_components import BertAttention, BertSelfAttention, LinearLayer, TrainablePositionalEncoding
 
 
@@ -136,9 +137,63 @@ class XML(nn.Module):
 
     def forward(self, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask, tef_feat, tef_mask,
                 st_ed_indices):
-        raise NotImplementedError(
-            "XML.forward is the training step (reference model_xml.py:212-251); this package covers the "
-            "inference hot path only (SURVEY.md section 8f lists training as a later row)")
+        """The training step, reference model_xml.py:212-251: encode the batch's contexts and queries, in-batch
+        video-level scores (N, N) and span logits of each query on its own video (N, L) -> weighted sum of the
+        start/end cross-entropy and the two sampled-negative ranking losses.
+        -> (loss: 0-dim tensor with grad, {"loss_st_ed", "loss_neg_ctx", "loss_neg_q", "loss_overall": float}).
+        Forward values come from the CUDA kernels; gradients flow through tvretrieval_b200/autograd.py.
+        tef_feat / tef_mask are accepted and ignored like in the reference."""
+        cfg = self.config
+        video_feat1, video_feat2, sub_feat1, sub_feat2 = self.encode_context(video_feat, video_mask, sub_feat,
+                                                                             sub_mask)
+        q2c, st_logits, ed_logits = self.get_pred_from_raw_query(
+            query_feat, query_mask, video_feat1, video_feat2, video_mask, sub_feat1, sub_feat2, sub_mask, cross=False)
+        loss_st_ed = 0
+        if cfg.lw_st_ed != 0:
+            loss_st_ed = self.temporal_criterion(st_logits, st_ed_indices[:, 0]) + \
+                self.temporal_criterion(ed_logits, st_ed_indices[:, 1])
+        loss_neg_ctx = loss_neg_q = 0
+        if cfg.lw_neg_ctx != 0 or cfg.lw_neg_q != 0:
+            loss_neg_ctx, loss_neg_q = self.get_video_level_loss(q2c)
+        loss_st_ed = cfg.lw_st_ed * loss_st_ed
+        loss_neg_ctx = cfg.lw_neg_ctx * loss_neg_ctx
+        loss_neg_q = cfg.lw_neg_q * loss_neg_q
+        loss = loss_st_ed + loss_neg_ctx + loss_neg_q
+        return loss, {"loss_st_ed": float(loss_st_ed), "loss_neg_ctx": float(loss_neg_ctx),
+                      "loss_neg_q": float(loss_neg_q), "loss_overall": float(loss)}
+
+    # ------------------------------------------------------------------ losses (tiny (N, N) / (N,) tensors)
+    def get_video_level_loss(self, query_context_scores):
+        """reference model_xml.py:588-605: ranking losses of each positive pair (the diagonal) against one sampled
+        negative video per query (rows) and one sampled negative query per video (columns)."""
+        n = len(query_context_scores)
+        diag = torch.arange(n, device=query_context_scores.device)
+        pos = query_context_scores[diag, diag]
+        masked = query_context_scores.detach().clone()
+        masked[diag, diag] = 999  # the positive sorts first and is skipped by the sampler
+        neg_ctx = self.get_neg_scores(query_context_scores, masked)
+        neg_q = self.get_neg_scores(query_context_scores.transpose(0, 1), masked.transpose(0, 1))
+        return self.get_ranking_loss(pos, neg_ctx), self.get_ranking_loss(pos, neg_q)
+
+    def get_neg_scores(self, scores, scores_masked):
+        """reference model_xml.py:607-625: per row one negative drawn uniformly from ranks [1, 1 + hard_pool_size)
+        (hard negatives) or [1, N) of the row sorted descending; the draw is torch.randint on the default CPU
+        generator, as in the reference, so torch.manual_seed reproduces its sampling."""
+        n = len(scores)
+        rows = torch.arange(n, device=scores.device)
+        order = torch.sort(scores_masked, descending=True, dim=1)[1]
+        hi = min(1 + self.config.hard_pool_size, n) if self.config.use_hard_negative else n
+        pick = torch.randint(1, hi, size=(n,)).to(scores.device)
+        return scores[rows, order[rows, pick]]
+
+    def get_ranking_loss(self, pos_score, neg_score):
+        """reference model_xml.py:627-637."""
+        kind = self.config.ranking_loss_type
+        if kind == "hinge":
+            return torch.clamp(self.config.margin + neg_score - pos_score, min=0).sum() / len(pos_score)
+        if kind == "lse":
+            return torch.log1p(torch.exp(neg_score - pos_score)).sum() / len(pos_score)
+        raise NotImplementedError("Only support 'hinge' and 'lse'")
 
     # ------------------------------------------------------------------ encoders
     def encode_input(self, feat, mask, input_proj_layer, encoder_layer, pos_embed_layer):
@@ -211,6 +266,8 @@ class XML(nn.Module):
     def _normalized_corpus(self, feat1):
         """The reference re-normalises the whole corpus tensor on every call (model_xml.py:447); the result only
         depends on the tensor, so it is cached per (storage, version)."""
+        if autograd.recording(feat1):  # training: differentiable, never cached
+            return ops.l2norm_rows(feat1)
         key = (feat1.data_ptr(), tuple(feat1.shape), feat1._version)
         hit = self._norm_cache.get(key)
         if hit is None:

@@ -5,7 +5,7 @@ import weakref
 
 import torch
 
-from . import _lib
+from . import _lib, autograd
 
 
 def _stream():
@@ -54,6 +54,9 @@ def _sched_ws(device):
 
 def add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
     """LayerNorm(x + add[row % add_rows]) over the last dim."""
+    if autograd.recording(x, gamma, beta, add):
+        return autograd.recompute_op(add_layernorm, autograd.t_add_layernorm, (x, gamma, beta),
+                                     dict(add=add, add_rows=add_rows, eps=eps))
     x = _f32(x, "x")
     dim = x.shape[-1]
     rows = x.numel() // dim
@@ -116,6 +119,8 @@ def _weight_split(weight, bf16):
 
 
 def linear(x, weight, bias=None, residual=None, relu=False):
+    if autograd.recording(x, weight, bias, residual):
+        return autograd.linear(linear, x, weight, bias, residual, relu)
     x = _f32(x, "x")
     weight = _f32(weight, "weight")
     out_dim, in_dim = weight.shape
@@ -140,8 +145,12 @@ def linear(x, weight, bias=None, residual=None, relu=False):
     return out
 
 
-def attention(q, k, v, mask3, n_heads, max_batch=8192):
-    """q (N, Lq, H), k/v (N, Lk, H), mask3 (N, 1 or Lq, Lk) float {0,1} -> (N, Lq, H)."""
+def attention(q, k, v, mask3, n_heads, max_batch=8192, dropout_p=0.0, seed=0):
+    """q (N, Lq, H), k/v (N, Lk, H), mask3 (N, 1 or Lq, Lk) float {0,1} -> (N, Lq, H).
+    dropout_p > 0 (train mode): dropout on the attention probabilities with the counter-based mask of `seed`."""
+    if autograd.recording(q, k, v):
+        return autograd.recompute_op(attention, autograd.t_attention, (q, k, v, mask3, n_heads),
+                                     dict(max_batch=max_batch, dropout_p=dropout_p, seed=seed))
     q, k, v, mask3 = _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(mask3, "mask")
     n, lq, hid = q.shape
     lk = k.shape[1]
@@ -152,14 +161,20 @@ def attention(q, k, v, mask3, n_heads, max_batch=8192):
     mq = 0 if mask3.shape[1] == 1 else lk
     for lo in range(0, n, step):
         hi = min(n, lo + step)
-        rc = _lib.lib().xmlb_attention(_p(q[lo:hi]), _p(k[lo:hi]), _p(v[lo:hi]), _p(mask3[lo:hi]),
-                                       mask3.shape[1] * lk, mq, _p(out[lo:hi]), _p(ws), hi - lo, lq, lk, hid,
-                                       n_heads, _stream())
+        if dropout_p > 0:
+            rc = _lib.lib().xmlb_attention_train(_p(q[lo:hi]), _p(k[lo:hi]), _p(v[lo:hi]), _p(mask3[lo:hi]),
+                                                 mask3.shape[1] * lk, mq, _p(out[lo:hi]), _p(ws), hi - lo, lq, lk,
+                                                 hid, n_heads, dropout_p, seed, lo * n_heads * lq * lk, _stream())
+        else:
+            rc = _lib.lib().xmlb_attention(_p(q[lo:hi]), _p(k[lo:hi]), _p(v[lo:hi]), _p(mask3[lo:hi]),
+                                           mask3.shape[1] * lk, mq, _p(out[lo:hi]), _p(ws), hi - lo, lq, lk, hid,
+                                           n_heads, _stream())
         _lib.check(rc, "xmlb_attention")
     return out
 
 
-def modular_pool(encoded, mask, w_mod):
+def _modular_pool_outputs(encoded, mask, w_mod):
+    """-> tuple of n_mod pooled (N, H) tensors."""
     encoded, mask, w_mod = _f32(encoded, "encoded"), _f32(mask, "mask"), _f32(w_mod, "w_mod")
     n, length, hid = encoded.shape
     n_mod = w_mod.shape[0]
@@ -168,10 +183,48 @@ def modular_pool(encoded, mask, w_mod):
     rc = _lib.lib().xmlb_modular_pool(_p(encoded), _p(mask), _p(w_mod), _p(out0), _p(out1), n, length, hid, n_mod,
                                       _stream())
     _lib.check(rc, "xmlb_modular_pool")
-    return (out0, out1) if n_mod == 2 else (out0, out0)
+    return (out0, out1) if n_mod == 2 else (out0,)
+
+
+def dropout(x, p, seed, index0=0):
+    """x * keep / (1 - p) with the counter-based mask keep(seed, index0 + i) -- nn.Dropout in train mode.  The
+    backward pass applies the same mask to the gradient (nothing is stored)."""
+    if p <= 0:
+        return x
+    if autograd.recording(x):
+        return autograd.Dropout.apply(x, p, seed, index0)
+    x = _f32(x, "x")
+    out = torch.empty_like(x)
+    rc = _lib.lib().xmlb_dropout(_p(x), _p(out), x.numel(), p, seed, index0, _stream())
+    _lib.check(rc, "xmlb_dropout")
+    return out
+
+
+def dropout_mask(shape, p, seed, device, index0=0):
+    """The scaled keep mask itself: keep / (1 - p)."""
+    out = torch.empty(shape, device=device, dtype=torch.float32)
+    rc = _lib.lib().xmlb_dropout(None, _p(out), out.numel(), p, seed, index0, _stream())
+    _lib.check(rc, "xmlb_dropout")
+    return out
+
+
+def new_seed():
+    """Dropout seed drawn from torch's default CPU generator (follows torch.manual_seed)."""
+    return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+
+def modular_pool(encoded, mask, w_mod):
+    """-> (video_query, sub_query); the same vector twice for a single-modality model (model_xml.py:420-423)."""
+    if autograd.recording(encoded, w_mod):
+        outs = autograd.recompute_op(_modular_pool_outputs, autograd.t_modular_pool, (encoded, mask, w_mod), {})
+    else:
+        outs = _modular_pool_outputs(encoded, mask, w_mod)
+    return (outs[0], outs[1]) if len(outs) == 2 else (outs[0], outs[0])
 
 
 def l2norm_rows(x, eps=1e-12):
+    if autograd.recording(x):
+        return autograd.recompute_op(l2norm_rows, autograd.t_l2norm_rows, (x,), dict(eps=eps))
     x = _f32(x, "x")
     out = torch.empty_like(x)
     dim = x.shape[-1]
@@ -191,6 +244,9 @@ def softmax_rows(x):
 
 def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask):
     """-> q2c (Nq, Nv).  Inputs already L2-normalised; a modality is skipped when None."""
+    if autograd.recording(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n):
+        return autograd.recompute_op(vr_scores_f32, autograd.t_vr_scores,
+                                     (q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask), {})
     ref_q = q_video_n if q_video_n is not None else q_sub_n
     ref_c = feat1_video_n if feat1_video_n is not None else feat1_sub_n
     nq, hid = ref_q.shape
@@ -270,13 +326,27 @@ def vr_scores_tc_packed(q_a, c_a, packing, n_videos, q_b=None, c_b=None, bf16=Fa
         out = torch.empty(nq, n_videos, device=q_a[0].device, dtype=torch.float32)
     qb = q_b if q_b is not None else (None, None)
     cb = c_b if c_b is not None else (None, None)
+    if hi_only and not restricted and max_ctas == 0 and FILTER_ON_CTA_PAIRS:
+        # the filter pass of the two-pass search: CTA pairs (tcgen05 cta_group::2) halve the operand traffic per SM
+        rc = _lib.lib().xmlb_vr_filter_pair(_p(q_a[0]), _p(qb[0]), _p(c_a[0]), _p(cb[0]), _p(packing.tile_meta),
+                                            _p(packing.tile_starts), _p(out), _p(_sched_ws(out.device)), nq, n_videos,
+                                            packing.n_rows, packing.n_tiles, kpad, int(bf16), _stream())
+        _lib.check(rc, "xmlb_vr_filter_pair")
+        return _vr_packed_finish(out, packing, n_videos, ordinal)
     rc = _lib.lib().xmlb_vr_scores_tc_packed(
         _p(q_a[0]), _p(q_a[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]), _p(cb[1]),
         _p(packing.tile_meta), _p(packing.tile_starts), _p(out), _p(_sched_ws(out.device)), nq, n_videos,
         packing.n_rows, packing.n_tiles, int(hi_only), _p(m_tiles[0]) if restricted else None,
         _p(m_tiles[1]) if restricted else None, kpad, int(bf16), max_ctas, _stream())
     _lib.check(rc, "xmlb_vr_scores_tc_packed")
-    if packing.n_packed < n_videos and not restricted:
+    return _vr_packed_finish(out, packing, n_videos, ordinal, fill=not restricted)
+
+
+FILTER_ON_CTA_PAIRS = True  # False: run the hi-only pass on the single-CTA kernel (kept for A/B measurements)
+
+
+def _vr_packed_finish(out, packing, n_videos, ordinal, fill=True):
+    if fill and packing.n_packed < n_videos:
         out[:, packing.n_packed:] = -1e10  # videos without a valid clip (reference: every clip masked -> -1e10)
     if ordinal:
         return out
@@ -394,12 +464,18 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
 def diagonal_pair_lists(n, device):
     """Lists for the in-batch (cross=False) case: query i <-> video i."""
     ar = torch.arange(n + 1, device=device, dtype=torch.int32)
-    return PairLists(ar, ar, ar[:n], ar[:n], n, n)
+    lists = PairLists(ar, ar, ar[:n], ar[:n], n, n)
+    lists.diagonal = True  # autograd.t_span_logits differentiates this case (the training step) only
+    return lists
 
 
 def span_logits(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b=None, feat2_b=None, mask_b=None, w_st_b=None, w_ed_b=None,
                 merged=False, softmax=False, lists=None, out_rows=None):
     """Dense (lists=None): -> st, ed of shape (Nq, Nv, L).  List mode: -> (out_rows, L) each."""
+    if autograd.recording(q_a, feat2_a, w_st_a, w_ed_a, q_b, feat2_b, w_st_b, w_ed_b):
+        return autograd.recompute_op(span_logits, autograd.t_span_logits, (q_a, feat2_a, mask_a, w_st_a, w_ed_a),
+                                     dict(q_b=q_b, feat2_b=feat2_b, mask_b=mask_b, w_st_b=w_st_b, w_ed_b=w_ed_b,
+                                          merged=merged, softmax=softmax, lists=lists, out_rows=out_rows))
     q_a, feat2_a = _f32(q_a, "q_a"), _f32(feat2_a, "feat2_a")
     nq, hid = q_a.shape
     nv, length, _ = feat2_a.shape
