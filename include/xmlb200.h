@@ -262,7 +262,7 @@ int xmlb_attention_train(const float* q, const float* k, const float* v, const f
  * clip_grad_norm_); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g g; p -= lr (m / (sqrt(v) + eps) + wd p).
  * max_grad_norm <= 0 disables clipping.  No bias correction (as the reference). */
 int xmlb_bert_adam_step(const long long* chunk_table, int n_chunks, const int* tensor_table, int n_tensors,
-                        float* partial_ws, float b1, float b2, float eps, float max_grad_norm, void* stream);
+                        float* partial_ws, double b1, double b2, double eps, double max_grad_norm, void* stream);
 
 #ifdef __cplusplus
 }

@@ -287,6 +287,48 @@ def train_forward(cfg, w: Weights, query_feat, query_mask, video_feat, video_mas
 
 
 # --------------------------------------------------------------------------------------
+# optimizer: BertAdam.step (optimization.py:273-338) and the warm-up schedules (:31-170)
+# --------------------------------------------------------------------------------------
+def lr_multiplier(schedule: str, warmup: float, t_total: float, step: int) -> float:
+    """_LRSchedule.get_lr, optimization.py:51-66, for ConstantLR / WarmupConstantSchedule / WarmupLinearSchedule /
+    WarmupCosineSchedule (cycles = 0.5)."""
+    if t_total < 0 or schedule in (None, "none"):
+        return 1.0
+    warmup = max(warmup, 0.0)
+    progress = float(step) / t_total
+    if progress < warmup:
+        return progress / warmup
+    if schedule == "warmup_constant":
+        return 1.0
+    if schedule == "warmup_linear":
+        return max((progress - 1.0) / (warmup - 1.0), 0.0)
+    if schedule == "warmup_cosine":
+        return 0.5 * (1.0 + math.cos(math.pi * (progress - warmup) / (1 - warmup)))
+    raise ValueError(schedule)
+
+
+def bert_adam_step(param: Tensor, grad: Tensor, state: dict, *, lr: float, weight_decay: float, schedule: str,
+                   warmup: float, t_total: float, b1: float, b2: float, e: float, max_grad_norm: float) -> None:
+    """One BertAdam update of one parameter, in place (param, grad, state = {step, next_m, next_v}).
+    optimization.py:296-330: clip_grad_norm_(p, max_grad_norm) rescales the stored gradient by
+    max_norm / (||g||_2 + 1e-6) when that is < 1; moments without bias correction; weight decay added to the
+    update (decoupled); lr scaled by the schedule at the parameter's own step count."""
+    if not state:
+        state.update(step=0, next_m=torch.zeros_like(param), next_v=torch.zeros_like(param))
+    if max_grad_norm > 0:
+        coef = max_grad_norm / (float(torch.linalg.vector_norm(grad.double())) + 1e-6)
+        if coef < 1:
+            grad.mul_(coef)
+    state["next_m"].mul_(b1).add_(grad, alpha=1 - b1)
+    state["next_v"].mul_(b2).addcmul_(grad, grad, value=1 - b2)
+    update = state["next_m"] / (state["next_v"].sqrt() + e)
+    if weight_decay > 0.0:
+        update = update + weight_decay * param
+    param.sub_(lr * lr_multiplier(schedule, warmup, t_total, state["step"]) * update)
+    state["step"] += 1
+
+
+# --------------------------------------------------------------------------------------
 # driver, tensor section (inference.py)
 # --------------------------------------------------------------------------------------
 def cat_padded(tensors):

@@ -243,10 +243,60 @@ def train_vectors():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+ADAM_SHAPES = {"enc.weight": (24, 16), "enc.bias": (24,), "enc.LayerNorm.weight": (24,), "big.weight": (130, 70),
+               "conv.weight": (1, 1, 5)}
+ADAM_HYPER = dict(lr=1e-2, warmup=0.25, t_total=8, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6,
+                  max_grad_norm=1.0)
+ADAM_STEPS = 5
+
+
+def bert_adam_vectors():
+    """BertAdam.step (reference optimization.py:273-338) for a few steps on seeded parameters / gradients with the
+    two parameter groups of train.py:151-156 (weight decay 0.01 / 0.0) and the warmup_linear schedule.  Gradients
+    of some tensors exceed max_grad_norm (clipped), others do not; "conv.weight" gets no gradient at step 2."""
+    from baselines.crossmodal_moment_localization.optimization import BertAdam
+    g = torch.Generator().manual_seed(99)
+    params = {k: torch.nn.Parameter(torch.randn(*shp, generator=g) * 0.5) for k, shp in ADAM_SHAPES.items()}
+    no_decay = ["bias", "LayerNorm.bias", "LayerNorm.weight"]
+    groups = [{"params": [p for n, p in params.items() if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+              {"params": [p for n, p in params.items() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+    opt = BertAdam(groups, **ADAM_HYPER)
+    out = {"hyper_json": json.dumps(ADAM_HYPER), "shapes_json": json.dumps(ADAM_SHAPES), "n_steps": np.int64(ADAM_STEPS)}
+    for k, p in params.items():
+        out["p0/" + k] = p.detach().numpy().copy()
+    for step in range(ADAM_STEPS):
+        for k, p in params.items():
+            scale = {"enc.weight": 0.01, "big.weight": 0.05}.get(k, 1.0)  # small-norm and large-norm gradients
+            grad = torch.randn(*p.shape, generator=g) * scale
+            if k == "conv.weight" and step == 2:
+                p.grad = None
+                out["has_grad/%d/%s" % (step, k)] = np.int64(0)
+                continue
+            out["has_grad/%d/%s" % (step, k)] = np.int64(1)
+            out["g/%d/%s" % (step, k)] = grad.numpy().copy()
+            p.grad = grad.clone()
+        opt.step()
+        for k, p in params.items():
+            out["p/%d/%s" % (step, k)] = p.detach().numpy().copy()
+            if p.grad is not None:
+                out["g_after/%d/%s" % (step, k)] = p.grad.numpy().copy()
+        out["lr/%d" % step] = np.asarray(opt.get_lr(), dtype=np.float64)
+    for k, p in params.items():
+        out["m/" + k] = opt.state[p]["next_m"].numpy().copy()
+        out["v/" + k] = opt.state[p]["next_v"].numpy().copy()
+    path = os.path.join(HERE, "bert_adam.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
+    if "--adam-only" in sys.argv:
+        bert_adam_vectors()
+        sys.exit(0)
     if "--train-only" not in sys.argv:
         for case_name, case_def in CASES.items():
             run_case(case_name, case_def)
         nms_vectors()
     train_vectors()
+    bert_adam_vectors()

@@ -96,3 +96,29 @@ class TrainCase:
         self.loss = float(z[key + "loss"])
         self.parts = dict(zip(("loss_st_ed", "loss_neg_ctx", "loss_neg_q", "loss_overall"), z[key + "parts"].tolist()))
         self.grads = {k[len(key) + 2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(key + "g/")}
+
+
+class AdamCase:
+    """tests/golden/bert_adam.npz: the reference BertAdam run for a few steps (make_golden.bert_adam_vectors)."""
+    NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")  # reference train.py:152
+
+    def __init__(self):
+        import json as _json
+        self.z = z = np.load(os.path.join(GOLDEN_DIR, "bert_adam.npz"))
+        self.hyper = _json.loads(str(z["hyper_json"]))
+        self.names = list(_json.loads(str(z["shapes_json"])))
+        self.n_steps = int(z["n_steps"])
+
+    def weight_decay(self, name):
+        return 0.0 if any(nd in name for nd in self.NO_DECAY) else 0.01
+
+    def initial(self):
+        return {k: torch.from_numpy(self.z["p0/" + k]).clone() for k in self.names}
+
+    def grad(self, step, name):
+        if not int(self.z["has_grad/%d/%s" % (step, name)]):
+            return None
+        return torch.from_numpy(self.z["g/%d/%s" % (step, name)]).clone()
+
+    def t(self, key):
+        return torch.from_numpy(self.z[key])

@@ -64,8 +64,37 @@ def test_model_has_no_cpu_fallback():
     model = XML(AttrDict(g.cfg)).eval()
     with pytest.raises(XmlbError):
         model.encode_query(g.query_feat, g.query_mask)
-    with pytest.raises(NotImplementedError):
-        model(None, None, None, None, None, None, None, None, None)
+    with torch.no_grad(), pytest.raises(XmlbError):
+        model.encode_query(g.query_feat, g.query_mask)
+    # the training step has no CPU path either (golden batch on CPU tensors)
+    from tests.golden_io import TrainCase
+    tc = TrainCase("video_only_svmr", "plain")
+    with pytest.raises(XmlbError):
+        model(**tc.inputs)
+
+
+def test_bert_adam_surface_and_schedules():
+    """Constructor validation, schedules and get_lr() of the fused optimizer mirror reference optimization.py
+    (no GPU needed: step() itself is covered by tests/test_gpu_train.py)."""
+    from oracle import xml_oracle as O
+    from tvretrieval_b200._lib import XmlbError
+    from tvretrieval_b200.optimization import SCHEDULES, BertAdam
+    p = torch.nn.Parameter(torch.zeros(3))
+    for bad in (dict(lr=-1.0), dict(lr=1e-3, schedule="nope"), dict(lr=1e-3, b1=1.0), dict(lr=1e-3, b2=-0.1),
+                dict(lr=1e-3, e=-1.0), dict(lr=1e-3, warmup=1.5)):
+        with pytest.raises(ValueError):
+            BertAdam([p], **bad)
+    for name in ("warmup_linear", "warmup_constant", "warmup_cosine", "none"):
+        sched = SCHEDULES[name](warmup=0.1, t_total=50)
+        for step in (0, 1, 4, 5, 6, 25, 49, 50, 60):
+            assert abs(sched.get_lr(step) - O.lr_multiplier(name, 0.1, 50, step)) < 1e-12, (name, step)
+    assert SCHEDULES["warmup_linear"](warmup=0.1, t_total=-1).get_lr(7) == 1.0
+    opt = BertAdam([p], lr=1e-3, warmup=0.1, t_total=50)
+    assert opt.get_lr() == [0]
+    opt.step()  # no gradients: nothing to do, no GPU touched
+    p.grad = torch.ones(3)
+    with pytest.raises(XmlbError):  # CPU parameters: no fallback
+        opt.step()
 
 
 def test_unsupported_variants_fail_loudly():

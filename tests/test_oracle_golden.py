@@ -147,3 +147,30 @@ def test_train_forward_loss_and_gradients(name, variant):
     for k, g in tc.grads.items():
         got = w[k].grad if w[k].grad is not None else torch.zeros_like(w[k])
         close(got, g, rtol=1e-4, atol=1e-7)
+
+
+def test_bert_adam_steps():
+    """O.bert_adam_step (optimization.py:273-338) against the reference optimizer: parameters and clipped gradients
+    after every step, final moments, scheduled learning rates."""
+    from tests.golden_io import AdamCase
+    ac = AdamCase()
+    h = ac.hyper
+    params, states = ac.initial(), {k: {} for k in ac.names}
+    for step in range(ac.n_steps):
+        for k in ac.names:
+            g = ac.grad(step, k)
+            if g is None:
+                continue
+            O.bert_adam_step(params[k], g, states[k], lr=h["lr"], weight_decay=ac.weight_decay(k),
+                             schedule=h["schedule"], warmup=h["warmup"], t_total=h["t_total"], b1=h["b1"], b2=h["b2"],
+                             e=h["e"], max_grad_norm=h["max_grad_norm"])
+            close(g, ac.t("g_after/%d/%s" % (step, k)), rtol=1e-5, atol=1e-8)
+        for k in ac.names:
+            close(params[k], ac.t("p/%d/%s" % (step, k)), rtol=1e-5, atol=1e-7)  # 1-ulp differences of the update
+    for k in ac.names:
+        close(states[k]["next_m"], ac.t("m/" + k), rtol=1e-5, atol=1e-8)
+        close(states[k]["next_v"], ac.t("v/" + k), rtol=1e-5, atol=1e-10)
+    # get_lr() after the last step: lr * multiplier(step count) per parameter, in parameter-group order
+    order = [k for k in ac.names if ac.weight_decay(k) > 0] + [k for k in ac.names if ac.weight_decay(k) == 0]
+    want = [h["lr"] * O.lr_multiplier(h["schedule"], h["warmup"], h["t_total"], states[k]["step"]) for k in order]
+    np.testing.assert_allclose(ac.z["lr/%d" % (ac.n_steps - 1)], want, rtol=1e-12)

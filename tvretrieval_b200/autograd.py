@@ -79,9 +79,11 @@ def recompute_op(kernel_fn, torch_fn, args, kwargs):
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, kernel_fn, x, weight, bias, residual, relu):
+        from . import ops
         with torch.no_grad():
             out = kernel_fn(x, weight, bias, residual, relu)
         ctx.kernel_fn, ctx.relu = kernel_fn, relu
+        ctx.precision = ops.get_linear_precision()  # the backward GEMMs run in the precision of the forward one
         ctx.save_for_backward(x, weight, out if relu else None)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         return out
@@ -96,7 +98,8 @@ class _Linear(torch.autograd.Function):
         out_dim, in_dim = weight.shape
         g2, x2 = g.reshape(-1, out_dim), x.reshape(-1, in_dim)
         dx = dw = db = dres = None
-        with torch.no_grad():
+        from . import ops
+        with torch.no_grad(), ops.linear_precision(ctx.precision):
             if ctx.needs_input_grad[1]:
                 dx = lin(g2, weight.t().contiguous(), None, None, False).view(x.shape)      # dY . W
             if ctx.needs_input_grad[2]:

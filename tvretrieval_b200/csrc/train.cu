@@ -100,7 +100,8 @@ struct BaTensor {
 
 __global__ void __launch_bounds__(256) bert_adam_update_kernel(const BaChunk* __restrict__ chunks,
                                                                const BaTensor* __restrict__ tensors,
-                                                               const float* __restrict__ partial, float b1, float b2,
+                                                               const float* __restrict__ partial, float b1,
+                                                               float one_minus_b1, float b2, float one_minus_b2,
                                                                float eps, float max_grad_norm) {
   __shared__ float clip_s;
   const BaChunk c = chunks[blockIdx.x];
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(256) bert_adam_update_kernel(const BaChunk* __
       g *= clip;
       c.g[i] = g;  // clip_grad_norm_ rescales the stored gradient in place
     }
-    const float m = __fadd_rn(__fmul_rn(c.m[i], b1), __fmul_rn(1.f - b1, g));
-    const float v = __fadd_rn(__fmul_rn(c.v[i], b2), __fmul_rn(__fmul_rn(1.f - b2, g), g));
+    const float m = __fadd_rn(__fmul_rn(c.m[i], b1), __fmul_rn(one_minus_b1, g));
+    const float v = __fadd_rn(__fmul_rn(c.v[i], b2), __fmul_rn(__fmul_rn(one_minus_b2, g), g));
     float update = __fdiv_rn(m, __fadd_rn(sqrtf(v), eps));
     const float p = c.p[i];
     if (t.weight_decay > 0.f) update = __fadd_rn(update, __fmul_rn(t.weight_decay, p));
@@ -136,21 +137,24 @@ __global__ void __launch_bounds__(256) bert_adam_update_kernel(const BaChunk* __
 }
 
 extern "C" int xmlb_bert_adam_step(const long long* chunk_table, int n_chunks, const int* tensor_table,
-                                   int n_tensors, float* partial_ws, float b1, float b2, float eps,
-                                   float max_grad_norm, void* stream) {
+                                   int n_tensors, float* partial_ws, double b1, double b2, double eps,
+                                   double max_grad_norm, void* stream) {
   XMLB_REQUIRE(chunk_table && tensor_table && partial_ws, "xmlb_bert_adam_step: null pointer");
   XMLB_REQUIRE(n_chunks >= 0 && n_tensors >= 0, "xmlb_bert_adam_step: negative count");
-  XMLB_REQUIRE(b1 >= 0.f && b1 < 1.f && b2 >= 0.f && b2 < 1.f && eps >= 0.f, "xmlb_bert_adam_step: bad hyper-parameter");
+  XMLB_REQUIRE(b1 >= 0. && b1 < 1. && b2 >= 0. && b2 < 1. && eps >= 0., "xmlb_bert_adam_step: bad hyper-parameter");
   if (n_chunks == 0) return XMLB_OK;
   const BaChunk* chunks = reinterpret_cast<const BaChunk*>(chunk_table);
   const BaTensor* tensors = reinterpret_cast<const BaTensor*>(tensor_table);
   int launches = 1;
-  if (max_grad_norm > 0.f) {
+  if (max_grad_norm > 0.) {
     bert_adam_sqnorm_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(chunks, partial_ws);
     ++launches;
   }
-  bert_adam_update_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(chunks, tensors, partial_ws, b1, b2, eps,
-                                                                      max_grad_norm);
+  // hyper-parameters arrive as doubles and are rounded to fp32 ONCE each, like the Python scalars of the reference
+  // (1 - b2 evaluated in fp32 from 0.999f would be off by 4.7e-5 relative)
+  bert_adam_update_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(chunks, tensors, partial_ws, (float)b1,
+                                                                      (float)(1.0 - b1), (float)b2, (float)(1.0 - b2),
+                                                                      (float)eps, (float)max_grad_norm);
   xmlb_count_launch(launches);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

@@ -135,6 +135,11 @@ class XML(nn.Module):
     def set_train_st_ed(self, lw_st_ed):
         self.config.lw_st_ed = lw_st_ed
 
+    # Linear-layer kernels of the training step (forward and the dX / dW GEMMs of the backward pass): "f32" = exact
+    # SIMT FMA (default: gradients then match the reference to ~1e-4), "f16x3" / "bf16x3" = split-precision tcgen05
+    # (several times faster; its truncating accumulator costs ~1e-2 relative on the long-K dW sums).
+    train_precision = "f32"
+
     def forward(self, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask, tef_feat, tef_mask,
                 st_ed_indices):
         """The training step, reference model_xml.py:212-251: encode the batch's contexts and queries, in-batch
@@ -144,10 +149,12 @@ class XML(nn.Module):
         Forward values come from the CUDA kernels; gradients flow through tvretrieval_b200/autograd.py.
         tef_feat / tef_mask are accepted and ignored like in the reference."""
         cfg = self.config
-        video_feat1, video_feat2, sub_feat1, sub_feat2 = self.encode_context(video_feat, video_mask, sub_feat,
-                                                                             sub_mask)
-        q2c, st_logits, ed_logits = self.get_pred_from_raw_query(
-            query_feat, query_mask, video_feat1, video_feat2, video_mask, sub_feat1, sub_feat2, sub_mask, cross=False)
+        with ops.linear_precision(self.train_precision):
+            video_feat1, video_feat2, sub_feat1, sub_feat2 = self._encode_context(video_feat, video_mask, sub_feat,
+                                                                                  sub_mask)
+            q2c, st_logits, ed_logits = self.get_pred_from_raw_query(
+                query_feat, query_mask, video_feat1, video_feat2, video_mask, sub_feat1, sub_feat2, sub_mask,
+                cross=False)
         loss_st_ed = 0
         if cfg.lw_st_ed != 0:
             loss_st_ed = self.temporal_criterion(st_logits, st_ed_indices[:, 0]) + \

@@ -83,8 +83,7 @@ _WEIGHT_SPLITS = {}
 def set_linear_precision(precision):
     global _LINEAR_PRECISION
     assert precision in ("f16x3", "bf16x3", "f32"), precision
-    _LINEAR_PRECISION = precision
-    _WEIGHT_SPLITS.clear()
+    _LINEAR_PRECISION = precision  # (the weight-split cache is keyed by the 16-bit format: nothing to drop)
 
 
 def get_linear_precision():
@@ -105,8 +104,17 @@ class linear_precision:
         set_linear_precision(self.saved)
 
 
+def invalidate_weight_caches():
+    """Drop the cached (hi, lo) weight splits: called after kernels that write parameters in place without going
+    through torch (BertAdam.step), which leaves tensor._version unchanged."""
+    _WEIGHT_SPLITS.clear()
+
+
 def _weight_split(weight, bf16):
-    """(hi, lo) of a weight matrix, cached per (tensor, version)."""
+    """(hi, lo) of a weight matrix, cached per (tensor, version) for module parameters (not for the transposed
+    temporaries of the backward pass)."""
+    if not isinstance(weight, torch.nn.Parameter):
+        return split_rows(weight.detach(), bf16=bf16)
     key = (weight.data_ptr(), tuple(weight.shape), bf16)
     hit = _WEIGHT_SPLITS.get(key)
     if hit is not None and hit[0]() is weight and hit[1] == weight._version:
