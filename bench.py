@@ -77,52 +77,57 @@ def workload_config(args, n_gpus):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the run by a thread polling NVML every 5 ms (an
+    `nvidia-smi -lms` child needs longer to start than a short multi-GPU run lasts)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(suffix=".csv")
-        self.gpu_index = gpu_index
-        self.proc = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis and all(v.strip().isdigit() for v in vis.split(",")) and gpu_index < len(vis.split(",")):
+            gpu_index = int(vis.split(",")[gpu_index])
+        self.gpu_index, self.thread, self.stop_flag, self.samples, self.err = gpu_index, None, False, [], None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), smax,
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(get_reasons(h))))
+                time.sleep(0.005)
+        except Exception as exc:  # reported in the JSON line, never fatal
+            self.err = "%s: %s" % (type(exc).__name__, exc)
 
     def start(self):
-        try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
-                                         stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        import threading
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def mark(self):
+        """Samples taken before this call (model warm-up) are dropped if enough remain afterwards."""
+        self.mark_at = len(self.samples)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.fh.close()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in open(self.path):
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])), smax.append(float(f[2])), power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        samples = self.samples
+        if getattr(self, "mark_at", 0) and len(samples) - self.mark_at >= 3:
+            samples = samples[self.mark_at:]
+        if not samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        sm = sorted(x[0] for x in samples)
+        bits = 0
+        for x in samples:
+            bits |= x[3]
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(samples[0][1]),
+                "reasons": sorted(name for bit, name in self.REASONS if bits & bit),
+                "power_w_max": max(x[2] for x in samples), "samples": len(samples)}
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -262,9 +267,11 @@ def run_ours(args):
     with torch.no_grad():
         # ---- device-resident timing ----
         sampler = ClockSampler(local_rank)
-        sampler.start()  # nvidia-smi needs ~0.2 s to start: begin before the warm-up so short runs get samples
+        sampler.start()  # begins before the warm-up so that very short runs still get samples under load
         for _ in range(args.warmup):
             searcher.search(qf, qm)
+        torch.cuda.synchronize()
+        sampler.mark()
         timer = PhaseTimer()
         searcher.timer = timer
         barrier()

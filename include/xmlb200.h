@@ -130,7 +130,9 @@ int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short*
  * xmlb_select_candidates: per row r of approx (n_rows, n_cols), with error bound
  *   eps[r] = err_scale * (row_err_a[r] + row_err_b[r]) + err_const        (row_err_b may be NULL)
  * keeps every column with approx >= (k-th largest approx of the row) - 2 * eps[r] -- a superset of the exact
- * top-k whenever |approx - exact| <= eps[r].  Outputs (n_rows, max_cand): cand_col = column, cand_id = ids[column]
+ * top-k whenever |approx - exact| <= eps[r].  row_kth (NULL, or n_rows floats): the k-th largest approx value
+ * supplied by the caller instead -- for a corpus sharded over GPUs it is taken over ALL shards (one small
+ * all-gather), so each shard keeps only its part of the GLOBAL candidate set (n_cols < k is then allowed).  Outputs (n_rows, max_cand): cand_col = column, cand_id = ids[column]
  * (ids NULL: column), cand_val = approx value; unused slots are (-1, INT_MAX, -1e10).  A row with more than
  * max_cand survivors is truncated and FLAGGED in flag_ws (ints, zeroed by the call): [0] = number of flagged row
  * groups (rows_per_group = 128 = query tile of the scoring kernel), [1, 1+G) group flags, [1+G, 1+2G) list of
@@ -144,8 +146,8 @@ int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short*
  * cand_val[entry_out[e]] is overwritten for every list entry e.  max_len = longest video (<= 256 clips). */
 int xmlb_select_candidates(const float* approx, const int* ids, int n_rows, int n_cols, int k,
                            const float* row_err_a, const float* row_err_b, float err_scale, float err_const,
-                           int max_cand, int rows_per_group, int* cand_col, int* cand_id, float* cand_val,
-                           int* flag_ws, void* stream);
+                           const float* row_kth, int max_cand, int rows_per_group, int* cand_col, int* cand_id,
+                           float* cand_val, int* flag_ws, void* stream);
 int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a, const unsigned short* qg_hi_b,
                        const unsigned short* qg_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                        const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,

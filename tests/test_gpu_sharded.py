@@ -60,8 +60,9 @@ def _worker(rank, world, port, use_nccl, precision):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("precision", ["f32", "f16x3"])
-def test_sharded_search_equals_single_gpu(precision):
-    use_nccl = torch.cuda.device_count() >= 2
-    port = 29500 + (os.getpid() * 7 + len(precision)) % 2000
-    mp.spawn(_worker, args=(2, port, use_nccl, precision), nprocs=2, join=True)
+def test_sharded_search_equals_single_gpu(precision, world):
+    use_nccl = torch.cuda.device_count() >= world
+    port = 29500 + (os.getpid() * 7 + len(precision) + 13 * world) % 2000
+    mp.spawn(_worker, args=(world, port, use_nccl, precision), nprocs=world, join=True)

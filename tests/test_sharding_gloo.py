@@ -40,6 +40,14 @@ def _worker(rank, world, port, n_videos, nq, k):
         assert torch.equal(mine.bool(), plan.owner_of(merged) == rank)
         counts = all_gather_rows(mine.sum(1, keepdim=True).to(torch.int64))
         assert (counts.view(world, nq).sum(0) == k).all()  # every selected video has exactly one owner
+        # owner exchange: each query's per-rank lists meet on the rank that owns the query; gathering the owners'
+        # slices restores what a plain all-gather delivers
+        from tvretrieval_b200.sharding import exchange_to_owners, gather_from_owners
+        o_val, o_idx = exchange_to_owners(val, idx)
+        q_lo, q_hi, per = plan.query_range(nq)
+        assert o_val.shape == (per, world * k) and o_idx.dtype == torch.int32
+        assert torch.equal(o_val[:q_hi - q_lo], g_val[q_lo:q_hi]) and torch.equal(o_idx[:q_hi - q_lo], g_idx[q_lo:q_hi])
+        assert torch.equal(gather_from_owners(o_val, nq), g_val) and torch.equal(gather_from_owners(o_idx, nq), g_idx)
         # query split: rank-major concatenation restores query order
         q_lo, q_hi, per = plan.query_range(nq)
         packed = torch.full((per, 3), -1.0)

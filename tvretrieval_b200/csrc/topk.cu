@@ -226,20 +226,26 @@ struct RawRowGen {
 
 __global__ void __launch_bounds__(NT) select_candidates_kernel(
     const float* __restrict__ values, const int* __restrict__ ids, int n_rows, int n_cols, int k,
-    const float* __restrict__ err_a, const float* __restrict__ err_b, float err_scale, float err_const, int max_cand,
-    int rows_per_group, int n_groups, int* __restrict__ cand_col, int* __restrict__ cand_id,
-    float* __restrict__ cand_val, int* __restrict__ flag_ws) {
+    const float* __restrict__ err_a, const float* __restrict__ err_b, float err_scale, float err_const,
+    const float* __restrict__ row_kth, int max_cand, int rows_per_group, int n_groups, int* __restrict__ cand_col,
+    int* __restrict__ cand_id, float* __restrict__ cand_val, int* __restrict__ flag_ws) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   const long long r = blockIdx.x;
   const float* row = values + r * n_cols;
   RawRowGen gen{row, n_cols};
-  unsigned int thr = 0;
-  int n_equal, need_equal, n_total;
-  radix_select(gen, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k, thr,
-               n_equal, need_equal, n_total);
+  float kth;
+  if (row_kth) {  // k-th largest approximate score over a LARGER set of columns (all shards of a sharded corpus)
+    kth = __ldg(row_kth + r);
+  } else {
+    unsigned int thr = 0;
+    int n_equal, need_equal, n_total;
+    radix_select(gen, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k, thr,
+                 n_equal, need_equal, n_total);
+    kth = key_float(thr);
+  }
   const float eps = fmaf(err_scale, __ldg(err_a + r) + (err_b ? __ldg(err_b + r) : 0.f), err_const);
-  const float cut = __fmaf_rd(-2.f, eps, key_float(thr));
+  const float cut = __fmaf_rd(-2.f, eps, kth);
   if (threadIdx.x == 0) sm.count = 0;
   __syncthreads();
   int* cc = cand_col + r * max_cand;
@@ -375,6 +381,20 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
   if (n_slots > 2 * SUB_SLOTS) {
     SpanGen sub = gen;
     sub.n_slots = SUB_SLOTS;
+    if (gen.valid) {  // sharded search: most slots belong to other ranks -- take the first SUB_SLOTS VALID ones
+      __shared__ int sub_slots_s;
+      if (threadIdx.x == 0) {
+        int seen = 0, n = n_slots;
+        for (int j = 0; j < n_slots; ++j)
+          if (gen.valid[j] && ++seen == SUB_SLOTS) {
+            n = j + 1;
+            break;
+          }
+        sub_slots_s = n;
+      }
+      __syncthreads();
+      sub.n_slots = sub_slots_s;
+    }
     unsigned int thr = 0;
     int n_equal, need_equal, n_total;
     const bool full = radix_select(sub, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; },
@@ -445,12 +465,13 @@ static int check_topk_args(const char* who, int k) {
 
 extern "C" int xmlb_select_candidates(const float* approx, const int* ids, int n_rows, int n_cols, int k,
                                       const float* row_err_a, const float* row_err_b, float err_scale,
-                                      float err_const, int max_cand, int rows_per_group, int* cand_col, int* cand_id,
-                                      float* cand_val, int* flag_ws, void* stream) {
+                                      float err_const, const float* row_kth, int max_cand, int rows_per_group,
+                                      int* cand_col, int* cand_id, float* cand_val, int* flag_ws, void* stream) {
   XMLB_REQUIRE(approx && row_err_a && cand_col && cand_id && cand_val && flag_ws,
                "xmlb_select_candidates: null pointer");
   if (int rc = check_topk_args("xmlb_select_candidates", k)) return rc;
-  XMLB_REQUIRE(n_cols >= k && max_cand >= k, "xmlb_select_candidates: need k <= max_cand and k <= n_cols");
+  XMLB_REQUIRE(max_cand >= 1 && (row_kth || (n_cols >= k && max_cand >= k)),
+               "xmlb_select_candidates: need k <= max_cand and k <= n_cols (unless row_kth is given)");
   XMLB_REQUIRE(rows_per_group >= 1 && err_scale >= 0.f && err_const >= 0.f, "xmlb_select_candidates: bad argument");
   const int n_groups = ceil_div(n_rows, rows_per_group);
   XMLB_CUDA(cudaMemsetAsync(flag_ws, 0, sizeof(int) * (size_t)(1 + 2 * n_groups), (cudaStream_t)stream));
@@ -458,8 +479,8 @@ extern "C" int xmlb_select_candidates(const float* approx, const int* ids, int n
   XMLB_CUDA(cudaFuncSetAttribute(select_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(SelSmem)));
   select_candidates_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(
-      approx, ids, n_rows, n_cols, k, row_err_a, row_err_b, err_scale, err_const, max_cand, rows_per_group, n_groups,
-      cand_col, cand_id, cand_val, flag_ws);
+      approx, ids, n_rows, n_cols, k, row_err_a, row_err_b, err_scale, err_const, row_kth, max_cand, rows_per_group,
+      n_groups, cand_col, cand_id, cand_val, flag_ws);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

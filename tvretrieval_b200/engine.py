@@ -140,6 +140,7 @@ class CorpusIndex:
 
     PRECISIONS = ("f16x3", "bf16x3", "f32")
 
+    @torch.no_grad()
     def __init__(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
                  sub_mask=None, vid_lo=0, precision="f16x3", packed=True, merged_spans=True):
         """precision selects the video-level-score kernel: "f16x3" / "bf16x3" = tcgen05 tensor cores with
@@ -211,6 +212,7 @@ class CorpusIndex:
                "sub_bits")
     PAIRS = ("video_tc", "sub_tc", "f2cat")
 
+    @torch.no_grad()
     def add_videos(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
                    sub_mask=None):
         """Append newly encoded videos (outputs of XML.encode_context, padded to this index's clip width or
@@ -389,9 +391,16 @@ class VCMRSearcher:
             ix.video_feat1n if m.use_video else None, ix.sub_feat1n if m.use_sub else None,
             ix.video_mask if m.use_video else None, ix.sub_mask if m.use_sub else None)
 
-    def top_videos(self, video_query, sub_query, k):
+    def _global_kth(self, approx, k):
+        """k-th largest approximate score of each query over the WHOLE corpus when this index is one shard of it
+        (ShardedSearcher overrides this); None = the index is the whole corpus."""
+        return None
+
+    def top_videos(self, video_query, sub_query, k, k_global=None):
         """Exact top-k videos of this index for every query -> (global video ids int32 (Nq, k), exp(alpha * score)),
-        ranked by (score desc, id asc).  Reference: inference.py:317,347-348 on top of model_xml.py:446-452,572-574."""
+        ranked by (score desc, id asc).  Reference: inference.py:317,347-348 on top of model_xml.py:446-452,572-574.
+        k_global (sharded search): the k of the final, corpus-wide selection -- the candidate filter then keeps only
+        this shard's part of the global candidate set, and entries that did not make it come back as (INT_MAX, 0)."""
         ix, m = self.index, self.model
         if not (self.two_pass and ix.n_videos >= k):
             with self._phase("vr_scores"):
@@ -417,7 +426,8 @@ class VCMRSearcher:
             scale = 1.001 / len(used)
             const = scale * sum(e for _, _, e in used) + self.TWO_PASS_SLACK
             cand = ops.select_candidates(approx, k, split[0][2], split[1][2] if len(used) == 2 else None, scale,
-                                         const, self.max_candidates, ids=self.score_ids())
+                                         const, self.max_candidates, ids=self.score_ids(),
+                                         row_kth=self._global_kth(approx, k_global or k))
         with self._phase("vr_rescore"):
             ops.vr_rescore_tc(used[0][0], ca, pk, cand, ix.kpad, q_fp32_b=used[1][0] if len(used) == 2 else None,
                               c_b=cb, bf16=bf16)
@@ -508,6 +518,7 @@ class VCMRSearcher:
             qf.record_stream(main), qm.record_stream(main)
             yield qf, qm
 
+    @torch.no_grad()  # inference only: the kernels must never record an autograd graph here
     def search(self, query_feat, query_mask, gt_video_idx=None, tasks=("VCMR", "VR"), host=False):
         """query_feat (Nq, Lq, Dq), query_mask (Nq, Lq) on the index's device (host=True: pinned host tensors, the
         upload is part of the call).  gt_video_idx (Nq,) int: corpus position of each query's ground-truth video,
@@ -559,6 +570,7 @@ class VCMRSearcher:
         return res
 
     # ---- host-buffer entry point (the e2e path bench.py times) --------------------------------------
+    @torch.no_grad()
     def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR")):
         """Pinned host buffers in, numpy arrays out; H2D / D2H copies are part of the call."""
         res = self.search(query_feat_cpu, query_mask_cpu, gt_video_idx_cpu, tasks, host=True)

@@ -373,9 +373,11 @@ class Candidates:
         self.row_flags = flag_ws[1 + 2 * n_groups:1 + 2 * n_groups + n_rows]
 
 
-def select_candidates(approx, k, row_err_a, row_err_b, err_scale, err_const, max_cand, ids=None, rows_per_group=128):
+def select_candidates(approx, k, row_err_a, row_err_b, err_scale, err_const, max_cand, ids=None, rows_per_group=128,
+                      row_kth=None):
     """Columns of `approx` (R, C) that can be among the exact top-k of their row given the error bound
-    eps[r] = err_scale * (row_err_a[r] + row_err_b[r]) + err_const  (see xmlb_select_candidates)."""
+    eps[r] = err_scale * (row_err_a[r] + row_err_b[r]) + err_const  (see xmlb_select_candidates).
+    row_kth (R,): the k-th largest approximate score of each row over a larger column set (all shards)."""
     approx = _f32(approx, "approx")
     n_rows, n_cols = approx.shape
     dev = approx.device
@@ -386,8 +388,8 @@ def select_candidates(approx, k, row_err_a, row_err_b, err_scale, err_const, max
     flag_ws = torch.empty(1 + 2 * n_groups + n_rows, device=dev, dtype=torch.int32)
     rc = _lib.lib().xmlb_select_candidates(_p(approx), _p(_i32(ids, "ids")), n_rows, n_cols, k,
                                            _p(_f32(row_err_a, "row_err_a")), _p(_f32(row_err_b, "row_err_b")),
-                                           err_scale, err_const, max_cand, rows_per_group, _p(col), _p(cid), _p(val),
-                                           _p(flag_ws), _stream())
+                                           err_scale, err_const, _p(_f32(row_kth, "row_kth")), max_cand,
+                                           rows_per_group, _p(col), _p(cid), _p(val), _p(flag_ws), _stream())
     _lib.check(rc, "xmlb_select_candidates")
     return Candidates(col, cid, val, flag_ws, n_groups, n_rows)
 
