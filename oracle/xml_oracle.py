@@ -395,10 +395,10 @@ def query_batch_tensor_section(cfg, w: Weights, ctx: dict, query_feat, query_mas
         top_idx, top_sc = order, torch.gather(q2c, 1, order)
     else:
         top_sc, top_idx = torch.topk(q2c, max_n_videos, dim=1, largest=True)  # inference.py:347-348
-    rows = torch.arange(len(st)).unsqueeze(1)
+    rows = torch.arange(len(st), device=st.device).unsqueeze(1)
     st_sel, ed_sel = st[rows, top_idx], ed[rows, top_idx]  # inference.py:365-367
     span = torch.einsum("qvm,qv,qvn->qvmn", st_sel, top_sc, ed_sel)  # inference.py:370
-    span = span * torch.from_numpy(band_mask(span.shape[-1], min_pred_l, max_pred_l))  # :371-374
+    span = span * torch.from_numpy(band_mask(span.shape[-1], min_pred_l, max_pred_l)).to(span.device)  # :371-374
     flat = span.reshape(len(span), -1)
     if canonical_ties:
         order = stable_desc_order(flat)[:, :max_before_nms]

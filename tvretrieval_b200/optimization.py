@@ -114,8 +114,7 @@ class BertAdam(Optimizer):
         return loss
 
     def _step_group(self, group):
-        chunks, tensors = [], []
-        dev = None
+        live, lrs = [], []
         for p in group["params"]:
             if p.grad is None:
                 continue
@@ -125,33 +124,52 @@ class BertAdam(Optimizer):
                 raise _lib.XmlbError("BertAdam: parameters must be contiguous CUDA float32 tensors (no CPU path)")
             if not p.grad.is_contiguous():
                 p.grad = p.grad.contiguous()
-            dev = p.device
             state = self.state[p]
             if len(state) == 0:
                 state["step"] = 0
                 state["next_m"] = torch.zeros_like(p)
                 state["next_v"] = torch.zeros_like(p)
-            n = p.numel()
-            lr = group["lr"] * group["schedule"].get_lr(state["step"])
-            t = len(tensors)
-            first = len(chunks)
-            ptrs = (p.data_ptr(), p.grad.data_ptr(), state["next_m"].data_ptr(), state["next_v"].data_ptr())
-            for off in range(0, n, CHUNK):
-                chunks.append((ptrs[0] + 4 * off, ptrs[1] + 4 * off, ptrs[2] + 4 * off, ptrs[3] + 4 * off,
-                               min(CHUNK, n - off), t))
-            tensors.append((first, len(chunks) - first, lr, group["weight_decay"]))
+            live.append(p)
+            lrs.append(group["lr"] * group["schedule"].get_lr(state["step"]))
             state["step"] += 1
-        if not chunks:
+        if not live:
             return
-        chunk_np = np.asarray(chunks, dtype=np.int64)
-        tens_np = np.zeros((len(tensors), 4), dtype=np.int32)
-        tens_np[:, 0] = [t[0] for t in tensors]
-        tens_np[:, 1] = [t[1] for t in tensors]
-        tens_np[:, 2:] = np.asarray([[t[2], t[3]] for t in tensors], dtype=np.float32).view(np.int32)
-        chunk_dev = torch.from_numpy(chunk_np).to(dev, non_blocking=True)
-        tens_dev = torch.from_numpy(tens_np).to(dev, non_blocking=True)
-        partial = torch.empty(len(chunks), device=dev, dtype=torch.float32)
-        rc = _lib.lib().xmlb_bert_adam_step(chunk_dev.data_ptr(), len(chunks), tens_dev.data_ptr(), len(tensors),
-                                            partial.data_ptr(), group["b1"], group["b2"], group["e"],
-                                            group["max_grad_norm"], torch.cuda.current_stream().cuda_stream)
+        dev = live[0].device
+        # The chunk table only depends on the buffer addresses, which stay the same from step to step when
+        # zero_grad() keeps the gradient buffers: build and upload it once, then refresh only the per-tensor
+        # (lr, weight decay) rows -- a few hundred bytes -- every step.
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), p.numel()) for p in live)
+        tables = self.__dict__.setdefault("_xmlb_tables", {})  # not in param_groups: state_dict() stays reference-like
+        cache = tables.get(id(group))
+        if cache is None or cache["key"] != key:
+            chunks, spans = [], []
+            for t, p in enumerate(live):
+                st = self.state[p]
+                ptrs = (p.data_ptr(), p.grad.data_ptr(), st["next_m"].data_ptr(), st["next_v"].data_ptr())
+                n, first = p.numel(), len(chunks)
+                for off in range(0, n, CHUNK):
+                    chunks.append((ptrs[0] + 4 * off, ptrs[1] + 4 * off, ptrs[2] + 4 * off, ptrs[3] + 4 * off,
+                                   min(CHUNK, n - off), t))
+                spans.append((first, len(chunks) - first))
+            tens_np = np.zeros((len(live), 4), dtype=np.int32)
+            tens_np[:, :2] = np.asarray(spans, dtype=np.int32)
+            cache = dict(key=key, n_chunks=len(chunks), tens_np=tens_np,
+                         chunk_dev=torch.from_numpy(np.asarray(chunks, dtype=np.int64)).to(dev),
+                         tens_host=torch.empty((len(live), 4), dtype=torch.int32).pin_memory(),
+                         tens_dev=torch.empty((len(live), 4), dtype=torch.int32, device=dev),
+                         partial=torch.empty(len(chunks), device=dev, dtype=torch.float32), copied=None)
+            tables[id(group)] = cache
+        tens_np = cache["tens_np"]
+        tens_np[:, 2] = np.asarray(lrs, dtype=np.float32).view(np.int32)
+        tens_np[:, 3] = np.float32(group["weight_decay"]).view(np.int32)
+        if cache["copied"] is not None:
+            cache["copied"].synchronize()  # the previous step's upload has left the pinned staging buffer
+        cache["tens_host"].numpy()[:] = tens_np
+        cache["tens_dev"].copy_(cache["tens_host"], non_blocking=True)
+        cache["copied"] = torch.cuda.Event()
+        cache["copied"].record(torch.cuda.current_stream(dev))
+        rc = _lib.lib().xmlb_bert_adam_step(cache["chunk_dev"].data_ptr(), cache["n_chunks"],
+                                            cache["tens_dev"].data_ptr(), len(live), cache["partial"].data_ptr(),
+                                            group["b1"], group["b2"], group["e"], group["max_grad_norm"],
+                                            torch.cuda.current_stream(dev).cuda_stream)
         _lib.check(rc, "xmlb_bert_adam_step")
