@@ -93,6 +93,11 @@ int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, in
                     int kpad, int out_ld, int out_col0, int normalize, int is_bf16, unsigned short* hi,
                     unsigned short* lo, float* hi_err, void* stream);
 int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream);
+/* dst_{hi,lo}[r] = src_{hi,lo}[row_index[r]] for rows of kpad 16-bit elements (negative index: row left untouched):
+ * brings operands that were split once (queries of a block) into inverted-list order for xmlb_vr_rescore_tc and
+ * xmlb_span_probs_tc -- same bits as xmlb_split_rows with row_index, without re-reading the fp32 rows. */
+int xmlb_gather_rows16(const unsigned short* src_hi, const unsigned short* src_lo, const int* row_index,
+                       long long rows_out, int kpad, unsigned short* dst_hi, unsigned short* dst_lo, void* stream);
 
 /* q2c[q][v] = mean over given modalities of max_{l : bit set} q[q] . c[v * lp + l]; same contract as
  * xmlb_vr_scores_f32 (model_xml.py:446-452, 572-574) on prepared operands: q_* (n_queries, kpad),

@@ -243,6 +243,48 @@ def train_vectors():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def external_vr_vectors():
+    """compute_query2ctx_info with --external_inference_vr_res_path (reference inference.py:264-273,349-355) on the
+    video_sub_vcmr case: the VCMR video lists come from another system's VR submission instead of the model's own
+    video retrieval.  The "external" submission is synthetic: per query, a seeded random set of videos with seeded
+    cosine-like scores in descending order."""
+    import tempfile
+    name = "video_sub_vcmr"
+    case = CASES[name]
+    cfg = copy.deepcopy(xml_base_config)
+    cfg.update(case["cfg"])
+    torch.manual_seed(2018)
+    model = XML(cfg).eval()
+    ds = SyntheticEvalDataset(max_ctx_l=cfg.max_ctx_l, max_desc_l=cfg.max_desc_l,
+                              video_dim=cfg.visual_input_size, sub_dim=cfg.sub_input_size,
+                              query_dim=cfg.query_input_size, ctx_mode=cfg.ctx_mode, min_ctx_l=3, **case["data"])
+    opt = make_opt(case, cfg)
+    rng = np.random.RandomState(3)
+    k = case["max_n_videos"]
+    video_ids = [ds.video2idx[v["vid_name"]] for v in ds.video_data]
+    vr = []
+    for q in ds.query_data:
+        vids = rng.permutation(video_ids)[:k + 2]  # two more than needed: get_submission_top_n truncates
+        scores = np.sort(rng.uniform(-0.2, 0.6, size=k + 2))[::-1]
+        vr.append(dict(desc_id=q["desc_id"], desc=q["desc"],
+                       predictions=[[int(v), 0, 0, float(s)] for v, s in zip(vids, scores)]))
+    submission = dict(video2idx=ds.video2idx, VR=vr)
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+        json.dump(submission, fh)
+    opt.external_inference_vr_res_path = fh.name
+    with torch.no_grad():
+        ctx = ref_inf.compute_context_info(model, ds, opt)
+        res = ref_inf.compute_query2ctx_info(model, ds, opt, ctx, max_before_nms=case["max_before_nms"],
+                                             max_n_videos=k, tasks=("VCMR", "VR"))
+    os.unlink(fh.name)
+    out = {"case": name, "submission_json": json.dumps(submission)}
+    for task, lst in res.items():
+        out["res/%s" % task] = preds_to_array(lst)[0]
+    path = os.path.join(HERE, "external_vr.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 ADAM_SHAPES = {"enc.weight": (24, 16), "enc.bias": (24,), "enc.LayerNorm.weight": (24,), "big.weight": (130, 70),
                "conv.weight": (1, 1, 5)}
 ADAM_HYPER = dict(lr=1e-2, warmup=0.25, t_total=8, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6,
@@ -294,9 +336,13 @@ if __name__ == "__main__":
     if "--adam-only" in sys.argv:
         bert_adam_vectors()
         sys.exit(0)
+    if "--external-vr-only" in sys.argv:
+        external_vr_vectors()
+        sys.exit(0)
     if "--train-only" not in sys.argv:
         for case_name, case_def in CASES.items():
             run_case(case_name, case_def)
         nms_vectors()
     train_vectors()
     bert_adam_vectors()
+    external_vr_vectors()

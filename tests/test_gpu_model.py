@@ -144,6 +144,37 @@ def test_golden_driver(golden):
         assert np.array_equal(preds_array(top[task]), golden.z["top7/" + task])
 
 
+def test_golden_external_vr_lists(tmp_path):
+    """--external_inference_vr_res_path (reference inference.py:264-273,349-355): the VCMR video lists come from
+    another system's VR submission; compared with the reference's own output for the same submission file
+    (tests/golden/external_vr.npz)."""
+    import json
+    import os
+    from tests.golden_io import GOLDEN_DIR
+    from tvretrieval_b200 import inference as I
+    from tvretrieval_b200.synthetic import SyntheticEvalDataset
+    z = np.load(os.path.join(GOLDEN_DIR, "external_vr.npz"))
+    g = GoldenCase(str(z["case"]))
+    ds = SyntheticEvalDataset(max_ctx_l=g.cfg["max_ctx_l"], max_desc_l=g.cfg["max_desc_l"],
+                              video_dim=g.cfg["visual_input_size"], sub_dim=g.cfg["sub_input_size"],
+                              query_dim=g.cfg["query_input_size"], ctx_mode=g.cfg["ctx_mode"], min_ctx_l=3,
+                              **g.case["data"])
+    model = build_model(g.cfg, g.weights)
+    opt = Opt(g.case, g.cfg)
+    path = tmp_path / "external_vr.json"
+    path.write_text(str(z["submission_json"]))
+    opt.external_inference_vr_res_path = str(path)
+    ctx = I.compute_context_info(model, ds, opt)
+    res = I.compute_query2ctx_info(model, ds, opt, ctx, max_before_nms=g.case["max_before_nms"],
+                                   max_n_videos=g.case["max_n_videos"], tasks=("VCMR", "VR"))
+    sub = json.loads(str(z["submission_json"]))
+    k = g.case["max_n_videos"]
+    for e, want in zip(res["VR"], sub["VR"]):  # VR output = the external lists, scores exponentiated
+        assert [p[0] for p in e["predictions"]] == [p[0] for p in want["predictions"][:k]]
+    close(preds_array(res["VR"])[..., 3], z["res/VR"][..., 3], rtol=1e-6, atol=0)
+    assert assert_ranked_equal(preds_array(res["VCMR"]), z["res/VCMR"]) == 0
+
+
 # ---------------------------------------------------------------------------------------------------------
 # TVR-shaped comparison against the oracle (BASELINE.json configs[1] dims, fewer videos so the CPU finishes fast)
 # ---------------------------------------------------------------------------------------------------------

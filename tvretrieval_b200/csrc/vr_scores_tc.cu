@@ -427,6 +427,45 @@ extern "C" int xmlb_split_rows(const float* x, const int* row_index, long long n
   return XMLB_OK;
 }
 
+// Row gather of already split operands: dst_{hi,lo}[r] = src_{hi,lo}[row_index[r]] (16-byte copies, one warp per
+// row; rows with a negative index are left untouched).  The queries of a block are split ONCE and then only copied
+// into inverted-list order for the grouped kernels (re-scoring, span similarity).
+__global__ void __launch_bounds__(256) gather_rows16_kernel(const uint4* __restrict__ src_hi, const uint4* __restrict__ src_lo,
+                                                            const int* __restrict__ row_index, long long rows_out,
+                                                            int vec_per_row, uint4* __restrict__ dst_hi,
+                                                            uint4* __restrict__ dst_lo) {
+  const int lane = threadIdx.x & 31;
+  const long long ro = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (ro >= rows_out) return;
+  const long long src = row_index[ro];
+  if (src < 0) return;
+  const uint4* sh = src_hi + src * vec_per_row;
+  const uint4* sl = src_lo + src * vec_per_row;
+  uint4* dh = dst_hi + ro * vec_per_row;
+  uint4* dl = dst_lo + ro * vec_per_row;
+  for (int i = lane; i < vec_per_row; i += 32) {
+    const uint4 a = __ldg(sh + i), b = __ldg(sl + i);
+    dh[i] = a, dl[i] = b;
+  }
+}
+
+extern "C" int xmlb_gather_rows16(const unsigned short* src_hi, const unsigned short* src_lo, const int* row_index,
+                                  long long rows_out, int kpad, unsigned short* dst_hi, unsigned short* dst_lo,
+                                  void* stream) {
+  XMLB_REQUIRE(src_hi && src_lo && row_index && dst_hi && dst_lo, "xmlb_gather_rows16: null pointer");
+  XMLB_REQUIRE(kpad >= 8 && kpad % 8 == 0, "xmlb_gather_rows16: kpad must be a multiple of 8 (16-byte copies)");
+  XMLB_REQUIRE((((uintptr_t)src_hi | (uintptr_t)src_lo | (uintptr_t)dst_hi | (uintptr_t)dst_lo) & 15) == 0,
+               "xmlb_gather_rows16: buffers must be 16-byte aligned");
+  if (rows_out == 0) return XMLB_OK;
+  XMLB_REQUIRE(rows_out / 8 + 1 < (1ll << 31), "xmlb_gather_rows16: too many rows");
+  gather_rows16_kernel<<<ceil_div(rows_out, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(src_hi), reinterpret_cast<const uint4*>(src_lo), row_index, rows_out, kpad / 8,
+      reinterpret_cast<uint4*>(dst_hi), reinterpret_cast<uint4*>(dst_lo));
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
 extern "C" int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream) {
   XMLB_REQUIRE(mask && bits, "xmlb_mask_bits: null pointer");
   XMLB_REQUIRE(lp % 32 == 0 && lp >= ctx_len && ctx_len >= 1, "xmlb_mask_bits: lp must be a multiple of 32, >= ctx_len");

@@ -359,6 +359,7 @@ class VCMRSearcher:
         self.query_chunk = int(query_chunk)    # queries searched together (one pass over the corpus per block)
         self.encode_chunk = int(encode_chunk)  # queries uploaded / encoded per piece inside a block
         self.timer = None  # set to a PhaseTimer to time the phases
+        self._external = None  # (video positions, exp-scores) of the current block when external lists are given
 
     def _phase(self, name):
         return self.timer.phase(name) if self.timer is not None else contextlib.nullcontext()
@@ -430,7 +431,7 @@ class VCMRSearcher:
                                          row_kth=self._global_kth(approx, k_global or k))
         with self._phase("vr_rescore"):
             ops.vr_rescore_tc(used[0][0], ca, pk, cand, ix.kpad, q_fp32_b=used[1][0] if len(used) == 2 else None,
-                              c_b=cb, bf16=bf16)
+                              c_b=cb, bf16=bf16, q_split_a=qa, q_split_b=qb)
         with self._phase("topk_videos"):
             idx, val = ops.topk_rows(cand.val, k, alpha=self.q2c_alpha, apply_exp=True, ids=cand.ids)
         with self._phase("vr_fallback"):  # rows whose candidate list overflowed (normally none: both launches idle)
@@ -452,7 +453,10 @@ class VCMRSearcher:
         if self.use_span_tc():
             avg = top_idx.numel() / max(1, ix.n_videos)
             chunk = 128 if avg >= 96 else 64 if avg >= 40 else 32
-        return ops.build_pair_lists(top_idx, ix.n_videos, vid_lo=ix.vid_lo, slot_valid=slot_valid, chunk=chunk)
+        lists = ops.build_pair_lists(top_idx, ix.n_videos, vid_lo=ix.vid_lo, slot_valid=slot_valid, chunk=chunk)
+        # selected videos of a single-GPU search all live in this index: every output row will be written
+        lists.complete = slot_valid is None and ix.vid_lo == 0 and not hasattr(self, "plan")
+        return lists
 
     def span_probs(self, video_query, sub_query, lists):
         """softmax-normalised start/end distributions for the listed (query, video) pairs -> (rows, L) x 2."""
@@ -519,10 +523,13 @@ class VCMRSearcher:
             yield qf, qm
 
     @torch.no_grad()  # inference only: the kernels must never record an autograd graph here
-    def search(self, query_feat, query_mask, gt_video_idx=None, tasks=("VCMR", "VR"), host=False):
+    def search(self, query_feat, query_mask, gt_video_idx=None, tasks=("VCMR", "VR"), host=False,
+               external_topk=None):
         """query_feat (Nq, Lq, Dq), query_mask (Nq, Lq) on the index's device (host=True: pinned host tensors, the
         upload is part of the call).  gt_video_idx (Nq,) int: corpus position of each query's ground-truth video,
-        needed for SVMR.  Queries are processed in blocks of `query_chunk`; inside a block the raw features are
+        needed for SVMR.  external_topk = (video positions int (Nq, max_n_videos), raw scores (Nq, max_n_videos)):
+        the video lists of another retrieval system replace this model's own video retrieval (reference
+        inference.py:349-355, --external_inference_vr_res_path); their scores enter as exp(q2c_alpha * score).  Queries are processed in blocks of `query_chunk`; inside a block the raw features are
         uploaded / encoded in pieces of `encode_chunk`, then the whole block is searched at once (each pass over
         the corpus is shared by all queries of the block)."""
         outs = []
@@ -535,7 +542,15 @@ class VCMRSearcher:
                                                          else self._device_pieces(qf, qm))
             video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
             gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
+            self._external = None
+            if external_topk is not None:
+                ext_idx = external_topk[0][b_lo:b_lo + n].to(dev).to(torch.int32).contiguous()
+                ext_val = torch.exp(self.q2c_alpha * external_topk[1][b_lo:b_lo + n].to(dev).float()).contiguous()
+                assert ext_idx.shape == (n, self.max_n_videos) == ext_val.shape, \
+                    "external video lists must hold max_n_videos entries per query"
+                self._external = (ext_idx, ext_val)
             outs.append(self._search_encoded(video_query, sub_query, gt, tasks))
+            self._external = None
         if len(outs) == 1:
             return outs[0]
         res = SearchResult()
@@ -548,7 +563,9 @@ class VCMRSearcher:
         ix = self.index
         res = SearchResult()
         nq = len(video_query)
-        if "VR" in tasks or "VCMR" in tasks:
+        if ("VR" in tasks or "VCMR" in tasks) and self._external is not None:
+            res.top_video_idx, res.top_video_score = self._external
+        elif "VR" in tasks or "VCMR" in tasks:
             res.top_video_idx, res.top_video_score = self.top_videos(video_query, sub_query, self.max_n_videos)
         if "VCMR" in tasks:
             with self._phase("pair_lists"):
@@ -571,7 +588,9 @@ class VCMRSearcher:
 
     # ---- host-buffer entry point (the e2e path bench.py times) --------------------------------------
     @torch.no_grad()
-    def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR")):
+    def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR"),
+                    external_topk=None):
         """Pinned host buffers in, numpy arrays out; H2D / D2H copies are part of the call."""
-        res = self.search(query_feat_cpu, query_mask_cpu, gt_video_idx_cpu, tasks, host=True)
+        res = self.search(query_feat_cpu, query_mask_cpu, gt_video_idx_cpu, tasks, host=True,
+                          external_topk=external_topk)
         return {s: getattr(res, s).cpu().numpy() for s in SearchResult.__slots__ if getattr(res, s) is not None}

@@ -163,16 +163,32 @@ def get_svmr_res_from_st_ed_probs(svmr_gt_st_probs, svmr_gt_ed_probs, query_meta
                              clip_length)
 
 
+def load_external_vr_res2(external_vr_res_path, top_n_vr_videos=5):
+    """reference inference.py:244-249: desc_id -> top retrieved [video_idx, 0, 0, score] rows of a VR submission."""
+    import json
+    with open(external_vr_res_path) as fh:
+        external_vr_res = json.load(fh)
+    external_vr_res = get_submission_top_n(external_vr_res, top_n=top_n_vr_videos)["VR"]
+    return {e["desc_id"]: e["predictions"] for e in external_vr_res}
+
+
 def compute_query2ctx_info(model, eval_dataset, opt, ctx_info, max_before_nms=1000, max_n_videos=100,
                            tasks=("SVMR",)):
     """reference inference.py:252-445 -> {"SVMR"/"VCMR"/"VR": [...]} (keys with empty results dropped)."""
     is_svmr, is_vr, is_vcmr = "SVMR" in tasks, "VR" in tasks, "VCMR" in tasks
-    if getattr(opt, "external_inference_vr_res_path", None) is not None:
-        raise NotImplementedError("external VR results (--external_inference_vr_res_path) are not supported yet")
     video2idx = eval_dataset.video2idx
     video_metas = ctx_info["video_metas"]
     model.eval()
     query_metas, qfeat, qmask = _gather_queries(eval_dataset, opt, is_svmr)
+    external = None
+    if getattr(opt, "external_inference_vr_res_path", None) is not None:
+        # reference inference.py:264-273,349-355: the top videos of every query come from another system's VR
+        # submission (dataset video ids -> positions in video_metas; raw scores, exponentiated by the search)
+        query2video = load_external_vr_res2(opt.external_inference_vr_res_path, top_n_vr_videos=max_n_videos)
+        video_idx2meta_idx = {video2idx[m["vid_name"]]: i for i, m in enumerate(video_metas)}
+        rows = [query2video[m["desc_id"]] for m in query_metas]
+        external = (torch.tensor([[video_idx2meta_idx[e[0]] for e in r] for r in rows], dtype=torch.int32),
+                    torch.tensor([[e[3] for e in r] for r in rows], dtype=torch.float32))
     searcher = _searcher(model, opt, ctx_info, max_before_nms, max_n_videos)
     gt = None
     if is_svmr:
@@ -180,7 +196,7 @@ def compute_query2ctx_info(model, eval_dataset, opt, ctx_info, max_before_nms=10
         gt = torch.tensor([meta_idx[m["vid_name"]] for m in query_metas], dtype=torch.int32)
     run_tasks = tuple(t for t in ("VCMR", "VR", "SVMR") if t in tasks)
     with torch.no_grad():
-        out = searcher.search_host(qfeat, qmask, gt, run_tasks)
+        out = searcher.search_host(qfeat, qmask, gt, run_tasks, external_topk=external)
 
     # ---- host section (reference inference.py:391-445), vectorised ----
     ctx_len = searcher.index.ctx_len

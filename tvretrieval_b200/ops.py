@@ -298,6 +298,18 @@ def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=Fals
     return (hi, lo, err) if hi_err else (hi, lo)
 
 
+def gather_rows16(src, row_index):
+    """src = (hi, lo) int16 (rows, kpad) -> (hi, lo) gathered at row_index (int32; negative = row left unwritten)."""
+    row_index = _i32(row_index, "row_index")
+    kpad = src[0].shape[1]
+    hi = torch.empty(row_index.numel(), kpad, device=src[0].device, dtype=torch.int16)
+    lo = torch.empty_like(hi)
+    rc = _lib.lib().xmlb_gather_rows16(_p(src[0]), _p(src[1]), _p(row_index), row_index.numel(), kpad, _p(hi), _p(lo),
+                                       _stream())
+    _lib.check(rc, "xmlb_gather_rows16")
+    return hi, lo
+
+
 def mask_bits(mask, lp):
     """(Nv, L) float {0,1} -> (Nv, lp // 32) int32 bit masks."""
     mask = _f32(mask, "mask")
@@ -394,18 +406,23 @@ def select_candidates(approx, k, row_err_a, row_err_b, err_scale, err_const, max
     return Candidates(col, cid, val, flag_ws, n_groups, n_rows)
 
 
-def vr_rescore_tc(q_fp32_a, c_a, packing, cand, kpad, q_fp32_b=None, c_b=None, bf16=False):
+def vr_rescore_tc(q_fp32_a, c_a, packing, cand, kpad, q_fp32_b=None, c_b=None, bf16=False, q_split_a=None,
+                  q_split_b=None):
     """Overwrites cand.val with the exact split-precision scores of the candidate (query, packed video) pairs.
-    q_fp32_* (Nq, H) pooled query vectors (normalised here, gathered per video list); c_* packed corpus (hi, lo)."""
+    q_fp32_* (Nq, H) pooled query vectors (normalised here, gathered per video list); c_* packed corpus (hi, lo).
+    q_split_* = (hi, lo) of the normalised queries when the caller already has them (then only copied)."""
     lists = build_pair_lists(cand.col, packing.n_packed, chunk=128)
     dev = cand.col.device
     units = torch.empty(lists.max_chunks * 4 + 4, device=dev, dtype=torch.int32)
     rc = _lib.lib().xmlb_build_span_units(_p(lists.vid_ptr), _p(lists.chunk_ptr), packing.n_packed, lists.chunk,
                                           _p(units), _stream())
     _lib.check(rc, "xmlb_build_span_units")
-    qa = split_rows(q_fp32_a, kpad=kpad, normalize=True, bf16=bf16, row_index=lists.entry_q)
-    qb = split_rows(q_fp32_b, kpad=kpad, normalize=True, bf16=bf16, row_index=lists.entry_q) \
-        if q_fp32_b is not None else (None, None)
+    def gathered(q_fp32, q_split):
+        if q_split is not None:
+            return gather_rows16(q_split, lists.entry_q)
+        return split_rows(q_fp32, kpad=kpad, normalize=True, bf16=bf16, row_index=lists.entry_q)
+    qa = gathered(q_fp32_a, q_split_a)
+    qb = gathered(q_fp32_b, q_split_b) if (q_fp32_b is not None or q_split_b is not None) else (None, None)
     cb = c_b if c_b is not None else (None, None)
     rc = _lib.lib().xmlb_vr_rescore_tc(_p(qa[0]), _p(qa[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
                                        _p(cb[1]), _p(packing.row_start), _p(units),
@@ -442,7 +459,9 @@ def build_pair_lists(top_idx, n_videos, vid_lo=0, slot_valid=None, chunk=32):
                                           _p(entry_q), _p(entry_out), _stream())
     _lib.check(rc, "xmlb_build_pair_lists")
     max_chunks = (n_pairs + chunk - 1) // chunk + min(n_videos, n_pairs)
-    return PairLists(vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_pairs, chunk)
+    lists = PairLists(vid_ptr, chunk_ptr, entry_q, entry_out, max_chunks, n_pairs, chunk)
+    lists.complete = False  # set by the caller when it knows that EVERY pair is listed (no -1 / foreign ids)
+    return lists
 
 
 def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, bf16=False, out_rows=None):
@@ -457,10 +476,13 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
     rc = _lib.lib().xmlb_build_span_units(_p(lists.vid_ptr), _p(lists.chunk_ptr), n_videos, lists.chunk, _p(units),
                                           _stream())
     _lib.check(rc, "xmlb_build_span_units")
-    qg = split_rows(q_cat, kpad=kcat, bf16=bf16, row_index=lists.entry_q)  # queries gathered in list order
+    # queries: split once, then copied into list order
+    qg = gather_rows16(split_rows(q_cat, kpad=kcat, bf16=bf16), lists.entry_q)
     rows = lists.n_rows if out_rows is None else out_rows
-    st = torch.zeros(rows, ctx_len, device=dev, dtype=torch.float32)
-    ed = torch.zeros_like(st)
+    # rows that no list entry covers (videos of other shards) must read as zeros
+    alloc = torch.empty if (out_rows is None and getattr(lists, "complete", False)) else torch.zeros
+    st = alloc(rows, ctx_len, device=dev, dtype=torch.float32)
+    ed = alloc(rows, ctx_len, device=dev, dtype=torch.float32)
     w_st, w_ed = _f32(w_st.reshape(-1), "w_st"), _f32(w_ed.reshape(-1), "w_ed")
     rc = _lib.lib().xmlb_span_probs_tc(_p(f2cat[0]), _p(f2cat[1]), _p(qg[0]), _p(qg[1]), _p(_f32(mask, "mask")),
                                        _p(w_st), _p(w_ed), w_st.numel(), int(softmax), n_videos, ctx_len, kcat,

@@ -193,8 +193,10 @@ class ShardedSearcher(VCMRSearcher):
         res = SearchResult()
         vid_lo, vid_hi = ix.vid_lo, ix.vid_lo + ix.n_videos
         nq = len(video_query)
-        if "VR" in tasks or "VCMR" in tasks:
-            k = self.max_n_videos
+        k = self.max_n_videos
+        if ("VR" in tasks or "VCMR" in tasks) and self._external is not None:
+            res.top_video_idx, res.top_video_score = self._external  # the same lists on every rank: nothing to merge
+        elif "VR" in tasks or "VCMR" in tasks:
             k_loc = min(k, ix.n_videos)
             idx, val = self.top_videos(video_query, sub_query, k_loc, k_global=k)  # global ids, exp(alpha * score)
             if k_loc < k:  # shard smaller than k: pad so every rank contributes k columns
