@@ -2,8 +2,12 @@
 """Accuracy of the training-step gradients at TVR dims (H=768, Dv=3072, L<=128, bsz=32): the kernels (exact-fp32
 linears) and torch's own fp32 CPU evaluation of the same arithmetic, both against a float64 evaluation.
 Test infrastructure (it imports the oracle): run on the GPU box, output kept in profiles/r01_train_grad_accuracy.txt."""
-import sys, torch
-sys.path.insert(0, '.')
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import xml_oracle as O
 from tvretrieval_b200.model_xml import XML, AttrDict, xml_base_config
 cfg = dict(xml_base_config, hidden_size=768, visual_input_size=3072, max_ctx_l=128, max_desc_l=30,
