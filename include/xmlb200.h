@@ -247,6 +247,27 @@ int xmlb_temporal_nms(const int* video_idx, const float* st, const float* ed, co
                       const int* n_valid, int n_queries, int n_in, double iou_thd, int max_per_group, int max_out,
                       int* out_idx, int* out_count, void* stream);
 
+/* ---------------------------------------------------------------- packed (ragged) query encoder -------- */
+/* The query encoder on a PACKED token layout: only the valid tokens of each query are stored, sequence s owns rows
+ * [cu_seqlens[s], cu_seqlens[s+1]) of every (T, hidden) activation.  Padded tokens have exactly zero weight as
+ * attention keys (exp(-10000 - max) == 0 in fp32) and in the modular pooling (softmax of -1e10), and their own rows
+ * are never read, so the pooled query vectors equal those of the padded computation (model_xml.py:291-295,377-423)
+ * at the work of the valid tokens only.  Row-wise ops (xmlb_linear*, xmlb_split_rows, xmlb_add_layernorm) run on the
+ * packed rows unchanged; the three below are the sequence-aware pieces.
+ *
+ * xmlb_add_layernorm_indexed: out[r] = LayerNorm(x[r] + add[add_index[r]]) -- TrainablePositionalEncoding
+ *   (model_components.py:81-88) with the position of every packed row given explicitly.
+ * xmlb_attention_ragged: fused softmax(Q_h K_h^T / sqrt(dh)) V_h per (sequence, head), sequences of <= 32 tokens,
+ *   head size a multiple of 4; q / k / v / out (T, hidden), no workspace (model_components.py:277-303).
+ * xmlb_modular_pool_ragged: xmlb_modular_pool on packed rows (model_xml.py:410-423). */
+int xmlb_add_layernorm_indexed(const float* x, const float* add, const int* add_index, long long add_rows,
+                               const float* gamma, const float* beta, float* out, long long rows, int dim, float eps,
+                               void* stream);
+int xmlb_attention_ragged(const float* q, const float* k, const float* v, const int* cu_seqlens, float* out,
+                          int n_seqs, int max_len, int hidden, int n_heads, void* stream);
+int xmlb_modular_pool_ragged(const float* encoded, const int* cu_seqlens, const float* w_mod, float* out0, float* out1,
+                             int n_queries, int max_len, int hidden, int n_mod, void* stream);
+
 /* ---------------------------------------------------------------- training step (config #4) -------- */
 
 /* out[i] = keep(seed, index0 + i) ? x[i] / (1 - p) : 0 -- nn.Dropout in train mode (model_components.py:77,152,

@@ -542,3 +542,58 @@ def test_temporal_nms_known_answers(ops):
         kept, cnt = ops.temporal_nms(p[None, :, 0], p[None, :, 1], p[None, :, 2], float(z["thd/%d" % i]), 100)
         got = preds[order][kept[0, :int(cnt[0])].cpu().numpy()]
         assert np.array_equal(got, z["out/%d" % i]), i
+
+
+# ---------------------------------------------------------------------------------------------------------
+# packed (ragged) query encoder
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hid,heads", [(768, 4), (64, 2), (256, 1), (64, 4), (40, 2)])
+def test_attention_ragged_vs_padded_reference(hid, heads):
+    """xmlb_attention_ragged on packed tokens == the reference attention (model_components.py:277-303) of the padded
+    batch at every valid token (padded keys have probability exactly 0 there)."""
+    from tvretrieval_b200 import autograd, ops
+    g = torch.Generator().manual_seed(5)
+    n, width = 37, 30
+    lens = torch.randint(1, width + 1, (n,), generator=g)
+    lens[0], lens[1] = width, 1
+    mask = (torch.arange(width)[None] < lens[:, None]).float()
+    q, k, v = (torch.randn(n, width, hid, generator=g) for _ in range(3))
+    want = autograd.t_attention(q.double(), k.double(), v.double(), mask.double().unsqueeze(1), heads)
+    valid = mask.bool()
+    cu = torch.zeros(n + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(lens, 0)
+    got = ops.attention_ragged(q[valid].to(DEV), k[valid].to(DEV), v[valid].to(DEV), cu.to(DEV), int(lens.max()), heads)
+    torch.testing.assert_close(got.cpu().double(), want[valid], rtol=1e-5, atol=1e-6)
+    # and the padded kernel path agrees with it to rounding
+    padded = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), mask.unsqueeze(1).to(DEV), heads)
+    torch.testing.assert_close(got, padded[valid.to(DEV)], rtol=1e-5, atol=1e-6)
+
+
+def test_ragged_attention_argument_checks():
+    from tvretrieval_b200 import ops
+    from tvretrieval_b200._lib import XmlbError
+    x = torch.zeros(40, 64, device=DEV)
+    cu = torch.tensor([0, 40], dtype=torch.int32, device=DEV)
+    with pytest.raises(XmlbError):
+        ops.attention_ragged(x, x, x, cu, 40, 2)       # longer than 32 tokens
+    y = x[:, :12].contiguous()
+    with pytest.raises(XmlbError):
+        ops.attention_ragged(y, y, y, cu, 8, 2)        # head size 6: not a multiple of 4
+
+
+@pytest.mark.parametrize("name", ["video_sub_vcmr", "video_only_svmr"])
+def test_packed_query_encoder_equals_padded(name):
+    """XML.encode_query_packed (valid tokens only) returns the pooled vectors of XML.encode_query."""
+    from tests.golden_io import GoldenCase
+    from tvretrieval_b200.model_xml import XML, AttrDict
+    g = GoldenCase(name)
+    model = XML(AttrDict(g.cfg))
+    model.load_state_dict(g.weights)
+    model = model.to(DEV).eval()
+    qf, qm = g.query_feat.to(DEV), g.query_mask.to(DEV)
+    with torch.no_grad():
+        want = model.encode_query(qf, qm)
+        got = model.encode_query_packed(qf, g.query_mask.sum(1).long().numpy())
+    for a, b, key in zip(got, want, ("video_query", "sub_query")):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(a.cpu(), g.t(key), rtol=1e-4, atol=1e-5)  # and the reference's own vectors

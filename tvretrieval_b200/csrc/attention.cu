@@ -77,10 +77,16 @@ extern "C" int xmlb_attention_train(const float* q, const float* k, const float*
 // One CTA (128 threads) per query.  smem: att[len][n_mod]
 __global__ void __launch_bounds__(128) modular_pool_kernel(const float* __restrict__ enc, const float* __restrict__ mask,
                                                            const float* __restrict__ w_mod, float* __restrict__ out0,
-                                                           float* __restrict__ out1, int len, int hidden, int n_mod) {
+                                                           float* __restrict__ out1, int len, int hidden, int n_mod,
+                                                           const int* __restrict__ cu_seqlens) {
   extern __shared__ float att[];  // [len][2]
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* e = enc + (long long)n * len * hidden;
+  if (cu_seqlens) {  // packed tokens: sequence n owns rows [cu[n], cu[n+1]), all valid
+    const int r0 = __ldg(cu_seqlens + n);
+    e = enc + (long long)r0 * hidden;
+    len = min(len, __ldg(cu_seqlens + n + 1) - r0);
+  }
   for (int t = warp; t < len; t += 4) {
     float s0 = 0.f, s1 = 0.f;
     for (int d = lane; d < hidden; d += 32) {
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(128) modular_pool_kernel(const float* __restri
     }
     s0 = warp_sum(s0), s1 = warp_sum(s1);
     if (lane == 0) {
-      const float m = mask[(long long)n * len + t];
+      const float m = cu_seqlens ? 1.f : mask[(long long)n * len + t];
       att[t * 2 + 0] = mask_logit(s0, m);
       att[t * 2 + 1] = mask_logit(s1, m);
     }
@@ -118,15 +124,29 @@ __global__ void __launch_bounds__(128) modular_pool_kernel(const float* __restri
   }
 }
 
-extern "C" int xmlb_modular_pool(const float* encoded, const float* mask, const float* w_mod, float* out0,
-                                 float* out1, int n_queries, int len, int hidden, int n_mod, void* stream) {
-  XMLB_REQUIRE(encoded && mask && w_mod && out0, "xmlb_modular_pool: null pointer");
+static int modular_pool_launch(const float* encoded, const float* mask, const int* cu_seqlens, const float* w_mod,
+                               float* out0, float* out1, int n_queries, int len, int hidden, int n_mod, void* stream) {
+  XMLB_REQUIRE(encoded && (mask || cu_seqlens) && w_mod && out0, "xmlb_modular_pool: null pointer");
   XMLB_REQUIRE(n_mod == 1 || (n_mod == 2 && out1), "xmlb_modular_pool: n_mod must be 1 or 2 (with out1)");
   XMLB_REQUIRE(len > 0 && len <= 4096, "xmlb_modular_pool: len out of range");
   if (n_queries == 0) return XMLB_OK;
   modular_pool_kernel<<<n_queries, 128, len * 2 * sizeof(float), (cudaStream_t)stream>>>(
-      encoded, mask, w_mod, out0, out1, len, hidden, n_mod);
+      encoded, mask, w_mod, out0, out1, len, hidden, n_mod, cu_seqlens);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
+}
+
+extern "C" int xmlb_modular_pool(const float* encoded, const float* mask, const float* w_mod, float* out0,
+                                 float* out1, int n_queries, int len, int hidden, int n_mod, void* stream) {
+  XMLB_REQUIRE(mask, "xmlb_modular_pool: null pointer");
+  return modular_pool_launch(encoded, mask, nullptr, w_mod, out0, out1, n_queries, len, hidden, n_mod, stream);
+}
+
+extern "C" int xmlb_modular_pool_ragged(const float* encoded, const int* cu_seqlens, const float* w_mod, float* out0,
+                                        float* out1, int n_queries, int max_len, int hidden, int n_mod,
+                                        void* stream) {
+  XMLB_REQUIRE(cu_seqlens, "xmlb_modular_pool_ragged: null pointer");
+  return modular_pool_launch(encoded, nullptr, cu_seqlens, w_mod, out0, out1, n_queries, max_len, hidden, n_mod,
+                             stream);
 }

@@ -9,14 +9,15 @@
 #include "xmlb200.h"
 
 __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add,
-                                                            long long add_rows, const float* __restrict__ gamma,
+                                                            long long add_rows, const int* __restrict__ add_index,
+                                                            const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ out,
                                                             long long rows, int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = x + row * dim;
-  const float* ar = add ? add + (row % add_rows) * dim : nullptr;
+  const float* ar = add ? add + (add_index ? (long long)__ldg(add_index + row) : row % add_rows) * dim : nullptr;
   float s = 0.f;
   for (int i = lane; i < dim; i += 32) s += ar ? xr[i] + ar[i] : xr[i];
   const float mean = warp_sum(s) / (float)dim;
@@ -33,16 +34,29 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   }
 }
 
-extern "C" int xmlb_add_layernorm(const float* x, const float* add, long long add_rows, const float* gamma,
-                                  const float* beta, float* out, long long rows, int dim, float eps, void* stream) {
+static int add_layernorm_launch(const float* x, const float* add, long long add_rows, const int* add_index,
+                                const float* gamma, const float* beta, float* out, long long rows, int dim, float eps,
+                                void* stream) {
   XMLB_REQUIRE(x && gamma && beta && out && dim > 0 && rows >= 0, "xmlb_add_layernorm: bad argument");
   XMLB_REQUIRE(!add || add_rows > 0, "xmlb_add_layernorm: add_rows must be > 0 when add is given");
   if (rows == 0) return XMLB_OK;
-  add_layernorm_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, add, add_rows, gamma, beta, out,
-                                                                           rows, dim, eps);
+  add_layernorm_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, add, add_rows, add_index, gamma, beta,
+                                                                           out, rows, dim, eps);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
+}
+
+extern "C" int xmlb_add_layernorm(const float* x, const float* add, long long add_rows, const float* gamma,
+                                  const float* beta, float* out, long long rows, int dim, float eps, void* stream) {
+  return add_layernorm_launch(x, add, add_rows, nullptr, gamma, beta, out, rows, dim, eps, stream);
+}
+
+extern "C" int xmlb_add_layernorm_indexed(const float* x, const float* add, const int* add_index, long long add_rows,
+                                          const float* gamma, const float* beta, float* out, long long rows, int dim,
+                                          float eps, void* stream) {
+  XMLB_REQUIRE(add && add_index, "xmlb_add_layernorm_indexed: add and add_index are required");
+  return add_layernorm_launch(x, add, add_rows, add_index, gamma, beta, out, rows, dim, eps, stream);
 }
 
 __global__ void __launch_bounds__(256) l2norm_rows_kernel(const float* __restrict__ x, float* __restrict__ out,

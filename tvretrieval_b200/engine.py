@@ -10,6 +10,7 @@ instead of materialising (Nq, Nv, L) logits and sorting 100*L*L cells per query.
 reference's (same arithmetic per cell; ranking = score desc, index asc).
 """
 import contextlib
+import os
 
 import numpy as np
 import torch
@@ -484,13 +485,29 @@ class VCMRSearcher:
         """Pooled query vectors of the whole block from the locally encoded slice (identity on one GPU)."""
         return video_query, sub_query
 
-    def _encode_pieces(self, pieces):
-        """pieces: iterable of (query_feat, query_mask) device tensors -> pooled (video_query, sub_query)."""
+    # Encode only the valid query tokens (XML.encode_query_packed): same pooled vectors, ~40 % fewer rows through the
+    # encoder for TVR's query lengths.  False = the padded reference layout (XML.encode_query).
+    packed_queries = os.environ.get("XMLB_PACKED_QUERIES", "1") != "0"
+
+    def _encode_pieces(self, pieces, lens_cpu=None):
+        """pieces: iterable of (query_feat, query_mask) device tensors -> pooled (video_query, sub_query).
+        lens_cpu: host int tensor, valid tokens of every query in piece order (None: padded encoding)."""
         hid = self.model.config.hidden_size
         vq, sq = [], []
         with self._phase("encode_query"):
-            for qf, qm in pieces:
-                a, b = self.model.encode_query(qf, qm)
+            tables = None
+            if lens_cpu is not None:
+                # the (small) index tables of every piece go to the device FIRST: `pieces` is lazy, and once it has
+                # enqueued its bulk uploads a later H2D copy would wait behind all of them
+                lens = lens_cpu.numpy()
+                tables = [self.model.packed_query_tables(lens[lo:lo + self.encode_chunk], self._piece_width,
+                                                         self.index.device)
+                          for lo in range(0, len(lens), self.encode_chunk)]
+            for i, (qf, qm) in enumerate(pieces):
+                if tables is not None:
+                    a, b = self.model.encode_query_packed(qf, tables=tables[i])
+                else:
+                    a, b = self.model.encode_query(qf, qm)
                 vq.append(a), sq.append(b)
             if not vq:
                 z = torch.zeros(0, hid, device=self.index.device)
@@ -538,8 +555,13 @@ class VCMRSearcher:
             n = min(self.query_chunk, len(query_feat) - b_lo)
             lo, hi = self._my_slice(n)
             qf, qm = query_feat[b_lo + lo:b_lo + hi], query_mask[b_lo + lo:b_lo + hi]
+            lens = None
+            self._piece_width = qm.shape[1]
+            if self.packed_queries and hi > lo and qm.shape[1] <= self.model.PACKED_MAX_LEN:
+                # valid tokens per query (masks are prefix masks); one small D2H when the masks live on the device
+                lens = (qm != 0).sum(1).to(torch.int64).cpu()
             video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm) if host
-                                                         else self._device_pieces(qf, qm))
+                                                         else self._device_pieces(qf, qm), lens)
             video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
             gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
             self._external = None

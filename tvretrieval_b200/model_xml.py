@@ -213,6 +213,69 @@ class XML(nn.Module):
                                     self.query_pos_embed)
         return self.get_modularized_queries(encoded, query_mask)
 
+    PACKED_MAX_LEN = 32  # longest query the packed encoder handles (xmlb_attention_ragged)
+
+    def _upload_ints(self, arr, dev):
+        """Small host int32 table -> device through a ring of reusable pinned staging buffers (a pageable source makes
+        the copy synchronous with the stream, and pinning a fresh buffer per call costs more than the encoder)."""
+        ring = self.__dict__.setdefault("_pin_ring", {"slots": [None] * 8, "next": 0})
+        i = ring["next"]
+        ring["next"] = (i + 1) % len(ring["slots"])
+        slot = ring["slots"][i]
+        if slot is None or slot[0].numel() < arr.size:
+            slot = [torch.empty(max(arr.size, 1 << 17), dtype=torch.int32).pin_memory(), None]
+            ring["slots"][i] = slot
+        if slot[1] is not None:
+            slot[1].synchronize()  # the copy issued 8 uploads ago has long left this buffer
+        slot[0][:arr.size].numpy()[:] = arr
+        out = slot[0][:arr.size].to(dev, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(dev))
+        return out
+
+    def packed_query_tables(self, lens_cpu, width, dev):
+        """Index tables of the packed layout for queries with `lens_cpu` valid tokens out of `width` padded ones:
+        (row of every packed token in the padded (N * width, Dq) layout, its position in its query, cu_seqlens,
+        longest query), uploaded through pinned staging.  Callers that also stream the query features from the host
+        create the tables BEFORE enqueueing those big copies (the H2D engine serves copies in issue order)."""
+        import numpy as np
+        lens = np.minimum(np.asarray(lens_cpu, dtype=np.int64), width)
+        n = len(lens)
+        assert lens.max(initial=0) <= self.PACKED_MAX_LEN
+        cu = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=cu[1:])
+        pos = np.arange(cu[-1]) - np.repeat(cu[:-1], lens)
+        rows = pos + np.repeat(np.arange(n) * width, lens)
+        t = self._upload_ints(np.concatenate([rows, pos, cu]).astype(np.int32), dev)
+        return t[:len(rows)], t[len(rows):2 * len(rows)], t[2 * len(rows):], int(max(1, lens.max(initial=1)))
+
+    @torch.no_grad()
+    def encode_query_packed(self, query_feat, lens_cpu=None, tables=None):
+        """encode_query (reference model_xml.py:291-295) on the VALID tokens only: query_feat (N, Lq, Dq) padded
+        features on the device, lens_cpu (N,) host ints = valid tokens per query (masks are prefix masks,
+        utils/tensor_utils.py:5-53), or `tables` = packed_query_tables(...) made earlier.  The tokens are packed into
+        (T, Dq) rows, every row-wise layer runs on T instead of N * Lq rows, attention and pooling are
+        sequence-aware kernels.  Same pooled vectors as encode_query (padded tokens carry exactly zero weight
+        there); inference only."""
+        n, width = query_feat.shape[:2]
+        if tables is None:
+            tables = self.packed_query_tables(lens_cpu, width, query_feat.device)
+        rows_d, pos_d, cu_d, max_len = tables
+        assert cu_d.numel() == n + 1
+        x = query_feat.reshape(n * width, -1).index_select(0, rows_d)
+        h = self.query_input_proj(x)
+        pe = self.query_pos_embed
+        h = ops.add_layernorm_indexed(h, pe.LayerNorm.weight, pe.LayerNorm.bias, pe.position_embeddings.weight, pos_d,
+                                      eps=pe.LayerNorm.eps)
+        att, outp = self.query_encoder.self, self.query_encoder.output
+        q = ops.linear(h, att.query.weight, att.query.bias)
+        k = ops.linear(h, att.key.weight, att.key.bias)
+        v = ops.linear(h, att.value.weight, att.value.bias)
+        ctx = ops.attention_ragged(q, k, v, cu_d, max_len, att.num_attention_heads)
+        o = ops.linear(ctx, outp.dense.weight, outp.dense.bias, residual=h)
+        o = ops.add_layernorm(o, outp.LayerNorm.weight, outp.LayerNorm.bias, eps=outp.LayerNorm.eps)
+        return ops.modular_pool_ragged(o, cu_d, self.PACKED_MAX_LEN, self.modular_vector_mapping.weight)
+
     def get_modularized_queries(self, encoded_query, query_mask, return_modular_att=False):
         """reference model_xml.py:399-423."""
         if self.config.no_modular:

@@ -194,6 +194,40 @@ def _modular_pool_outputs(encoded, mask, w_mod):
     return (out0, out1) if n_mod == 2 else (out0,)
 
 
+def add_layernorm_indexed(x, gamma, beta, add, add_index, eps=1e-5):
+    """LayerNorm(x[r] + add[add_index[r]]): the position encoding of packed (ragged) token rows."""
+    x, add = _f32(x, "x"), _f32(add, "add")
+    dim = x.shape[-1]
+    out = torch.empty_like(x)
+    rc = _lib.lib().xmlb_add_layernorm_indexed(_p(x), _p(add), _p(_i32(add_index, "add_index")), add.numel() // dim,
+                                               _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(out),
+                                               x.numel() // dim, dim, eps, _stream())
+    _lib.check(rc, "xmlb_add_layernorm_indexed")
+    return out
+
+
+def attention_ragged(q, k, v, cu_seqlens, max_len, n_heads):
+    """Fused self-attention over packed sequences: q / k / v (T, H), sequence s = rows [cu[s], cu[s+1]), <= 32 tokens."""
+    q, k, v = _f32(q, "q"), _f32(k, "k"), _f32(v, "v")
+    out = torch.empty_like(q)
+    rc = _lib.lib().xmlb_attention_ragged(_p(q), _p(k), _p(v), _p(_i32(cu_seqlens, "cu_seqlens")), _p(out),
+                                          cu_seqlens.numel() - 1, max_len, q.shape[-1], n_heads, _stream())
+    _lib.check(rc, "xmlb_attention_ragged")
+    return out
+
+
+def modular_pool_ragged(encoded, cu_seqlens, max_len, w_mod):
+    """modular_pool on packed token rows -> (video_query, sub_query), each (n_sequences, H)."""
+    encoded, w_mod = _f32(encoded, "encoded"), _f32(w_mod, "w_mod")
+    n, hid, n_mod = cu_seqlens.numel() - 1, encoded.shape[-1], w_mod.shape[0]
+    out0 = torch.empty(n, hid, device=encoded.device, dtype=torch.float32)
+    out1 = torch.empty_like(out0) if n_mod == 2 else None
+    rc = _lib.lib().xmlb_modular_pool_ragged(_p(encoded), _p(_i32(cu_seqlens, "cu_seqlens")), _p(w_mod), _p(out0),
+                                             _p(out1), n, max_len, hid, n_mod, _stream())
+    _lib.check(rc, "xmlb_modular_pool_ragged")
+    return (out0, out1) if n_mod == 2 else (out0, out0)
+
+
 def dropout(x, p, seed, index0=0):
     """x * keep / (1 - p) with the counter-based mask keep(seed, index0 + i) -- nn.Dropout in train mode.  The
     backward pass applies the same mask to the gradient (nothing is stored)."""
