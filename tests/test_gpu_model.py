@@ -225,7 +225,10 @@ def test_tvr_shape_video_sub_vcmr():
     v2i = np.asarray([ds.video2idx[v["vid_name"]] for v in ds.video_data])
     want_vcmr = O.decode_vcmr(o["span_flat_idx"].numpy(), o["span_score"].numpy(), o["top_video_idx"].numpy(), v2i,
                               k_vid, 128, 1.5)
-    swapped = assert_ranked_equal(preds_array(res["VCMR"]), want_vcmr, score_rtol=1e-3)
+    # final VCMR scores carry ~5e-5 relative error here (split-precision tensor-core encoders + span similarity,
+    # exp(20 q2c) on top): neighbours closer than 2e-4 relative are ties no fp32 implementation pair agrees on --
+    # whether such a pair swaps even depends on the last bits of the CPU oracle's own threaded reductions
+    swapped = assert_ranked_equal(preds_array(res["VCMR"]), want_vcmr, score_rtol=1e-3, tie_rtol=2e-4)
     assert swapped <= 8  # of 24 x 200 ranked moments
     want_vr = np.zeros((n_queries, k_vid, 4))
     want_vr[..., 0] = v2i[o["top_video_idx"].numpy()]

@@ -20,6 +20,7 @@ constexpr int HIST = 4096;
 constexpr int MAX_K = 1024;
 
 constexpr int LIST_CAP = 3072;  // survivors of the span pre-filter kept in shared memory
+constexpr int SORT_CAP = 2048;  // rows up to this length are sorted whole (HIST ints = SORT_CAP 64-bit entries)
 
 struct SelSmem {
   int hist[HIST];
@@ -196,10 +197,30 @@ __global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__
   if (row_flags && row_flags[r] == 0) return;  // restricted mode: only the flagged rows are (re)computed
   RowGen gen{values + r * n_cols, ids ? ids + (ids_shared ? 0 : r * n_cols) : nullptr, n_cols, alpha, apply_exp,
              tie_desc};
-  const int n_out = block_topk(gen, sm, k);
+  // Short rows (candidate tables, merges of per-GPU lists): sort the whole row in shared memory -- the radix select
+  // spends most of its time clearing and scanning 4096-bin histograms that such rows barely touch.
+  unsigned long long* sorted = sm.buf;
+  int n_out;
+  if (n_cols <= SORT_CAP) {
+    sorted = reinterpret_cast<unsigned long long*>(smem_raw);  // SORT_CAP entries over hist[] (same 16 KB)
+    int pow2 = 32;
+    while (pow2 < n_cols) pow2 <<= 1;
+    for (int i = n_cols + threadIdx.x; i < pow2; i += NT) sorted[i] = 0ull;  // below every real (key, id) pair
+    for (int c = threadIdx.x; c < n_cols; c += NT) {
+      const float x = __ldg(gen.row + c);
+      const float e = apply_exp ? expf(alpha * x) : x;
+      const unsigned int id = gen.ids ? (unsigned int)__ldg(gen.ids + c) : (unsigned int)c;
+      sorted[c] = ((unsigned long long)float_key(e) << 32) | (tie_desc ? id : ~id);
+    }
+    __syncthreads();
+    bitonic_sort_desc(sorted, pow2);
+    n_out = min(n_cols, k);
+  } else {
+    n_out = block_topk(gen, sm, k);
+  }
   for (int i = threadIdx.x; i < k; i += NT) {
     if (i < n_out) {
-      const unsigned long long e = sm.buf[i];
+      const unsigned long long e = sorted[i];
       const unsigned int idk = (unsigned int)(e & 0xffffffffu);
       out_idx[r * k + i] = (int)(tie_desc ? idk : ~idk);
       out_val[r * k + i] = key_float((unsigned int)(e >> 32));
