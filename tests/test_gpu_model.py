@@ -144,6 +144,36 @@ def test_golden_driver(golden):
         assert np.array_equal(preds_array(top[task]), golden.z["top7/" + task])
 
 
+def test_search_with_packed_query_encoder_equals_padded():
+    """The engine switches to XML.encode_query_packed for large query blocks; forced on here, the search must return
+    the ranks of the padded encoder (scores to rounding: the fused attention sums in a different order)."""
+    from tvretrieval_b200.engine import CorpusIndex, VCMRSearcher
+    from tvretrieval_b200.inference import cat_tensor
+    g = GoldenCase("video_sub_vcmr")
+    model = build_model(g.cfg, g.weights)
+    with torch.no_grad():
+        acc = {k: [] for k in ("video_feat1", "video_feat2", "video_mask", "sub_feat1", "sub_feat2", "sub_mask")}
+        for b in g.context_batches():
+            b = {k: v.to(DEV) for k, v in b.items()}
+            v1, v2, s1, s2 = model.encode_context(b["video_feat"], b["video_mask"], b["sub_feat"], b["sub_mask"])
+            for k, v in zip(acc, (v1, v2, b["video_mask"], s1, s2, b["sub_mask"])):
+                acc[k].append(v)
+        index = CorpusIndex.from_ctx_info({k: cat_tensor(v) for k, v in acc.items()})
+    kw = dict(max_n_videos=g.case["max_n_videos"], max_before_nms=g.case["max_before_nms"])
+    qf, qm = g.query_feat.to(DEV), g.query_mask.to(DEV)
+    gt = torch.as_tensor(g.query_gt_meta_idx, dtype=torch.int32, device=DEV)
+    padded, packed = VCMRSearcher(model, index, **kw), VCMRSearcher(model, index, **kw)
+    padded.packed_queries, packed.packed_min_queries = False, 0
+    want = padded.search(qf, qm, gt, tasks=("VCMR", "VR", "SVMR"))
+    for got in (packed.search(qf, qm, gt, tasks=("VCMR", "VR", "SVMR")),
+                packed.search(g.query_feat.pin_memory(), g.query_mask.pin_memory(), gt.cpu(),
+                              tasks=("VCMR", "VR", "SVMR"), host=True)):
+        for name in ("top_video_idx", "span_flat_idx", "svmr_flat_idx"):
+            assert torch.equal(getattr(got, name), getattr(want, name)), name
+        for name in ("top_video_score", "span_score", "svmr_score"):
+            torch.testing.assert_close(getattr(got, name), getattr(want, name), rtol=2e-5, atol=1e-12)
+
+
 def test_golden_external_vr_lists(tmp_path):
     """--external_inference_vr_res_path (reference inference.py:264-273,349-355): the VCMR video lists come from
     another system's VR submission; compared with the reference's own output for the same submission file
