@@ -162,7 +162,8 @@ def test_search_with_packed_query_encoder_equals_padded():
     kw = dict(max_n_videos=g.case["max_n_videos"], max_before_nms=g.case["max_before_nms"])
     qf, qm = g.query_feat.to(DEV), g.query_mask.to(DEV)
     gt = torch.as_tensor(g.query_gt_meta_idx, dtype=torch.int32, device=DEV)
-    padded, packed = VCMRSearcher(model, index, **kw), VCMRSearcher(model, index, **kw)
+    # `packed` also runs the two-pass retrieval, in host mode with its filter pass pipelined over 3 uploaded pieces
+    padded, packed = VCMRSearcher(model, index, **kw), VCMRSearcher(model, index, two_pass=True, encode_chunk=5, **kw)
     padded.packed_queries, packed.packed_min_queries = False, 0
     want = padded.search(qf, qm, gt, tasks=("VCMR", "VR", "SVMR"))
     for got in (packed.search(qf, qm, gt, tasks=("VCMR", "VR", "SVMR")),

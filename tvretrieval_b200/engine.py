@@ -329,6 +329,35 @@ class CorpusIndex:
         return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
 
+class _Prefilter:
+    """Pass 1 of the two-pass video retrieval for one block of queries: hi/lo splits of the normalised pooled
+    queries (+ the hi-only error bounds) and the approximate (Nq, Nv) scores, filled for row ranges [lo, hi)."""
+
+    def __init__(self, searcher, n):
+        ix, m = searcher.index, searcher.model
+        self.s, self.bf16 = searcher, ix.precision == "bf16x3"
+        dev = ix.device
+        self.corpus = [c for c, on in ((ix.video_tc, m.use_video), (ix.sub_tc, m.use_sub)) if on]
+        self.which = [i for i, on in enumerate((m.use_video, m.use_sub)) if on]
+        self.split = [(torch.empty(n, ix.kpad, device=dev, dtype=torch.int16),
+                       torch.empty(n, ix.kpad, device=dev, dtype=torch.int16),
+                       torch.empty(n, device=dev, dtype=torch.float32)) for _ in self.corpus]
+        self.approx = torch.empty(n, ix.n_videos, device=dev, dtype=torch.float32)
+
+    def run(self, lo, hi, video_query, sub_query):
+        ix = self.s.index
+        qs = [(video_query, sub_query)[i] for i in self.which]
+        with self.s._phase("vr_scores"):
+            for q, (h, l, e) in zip(qs, self.split):
+                ops.split_rows(q, kpad=ix.kpad, normalize=True, bf16=self.bf16, hi_err=True, out=(h[lo:hi], l[lo:hi]),
+                               err_out=e[lo:hi])
+            parts = [(h[lo:hi], l[lo:hi]) for h, l, _ in self.split]
+            ops.vr_scores_tc_packed(parts[0], self.corpus[0], ix.packing, ix.n_videos,
+                                    q_b=parts[1] if len(parts) == 2 else None,
+                                    c_b=self.corpus[1] if len(parts) == 2 else None, bf16=self.bf16, ordinal=True,
+                                    hi_only=True, out=self.approx[lo:hi])
+
+
 class SearchResult:
     """Device tensors for one batch of queries."""
     __slots__ = ("top_video_idx", "top_video_score", "span_flat_idx", "span_score", "svmr_flat_idx", "svmr_score")
@@ -361,6 +390,7 @@ class VCMRSearcher:
         self.encode_chunk = int(encode_chunk)  # queries uploaded / encoded per piece inside a block
         self.timer = None  # set to a PhaseTimer to time the phases
         self._external = None  # (video positions, exp-scores) of the current block when external lists are given
+        self._prefilter = None  # pass-1 state of the current block when it was filled piece by piece
 
     def _phase(self, name):
         return self.timer.phase(name) if self.timer is not None else contextlib.nullcontext()
@@ -417,12 +447,13 @@ class VCMRSearcher:
         pk = ix.packing
         used = [(q, c, ix.tc_err[name]) for q, c, name, on in ((video_query, ix.video_tc, "video", m.use_video),
                                                                (sub_query, ix.sub_tc, "sub", m.use_sub)) if on]
-        with self._phase("vr_scores"):  # pass 1: hi halves only
-            split = [ops.split_rows(q, kpad=ix.kpad, normalize=True, bf16=bf16, hi_err=True) for q, _, _ in used]
-            qa, ca = split[0][:2], used[0][1]
-            qb, cb = (split[1][:2], used[1][1]) if len(used) == 2 else (None, None)
-            approx = ops.vr_scores_tc_packed(qa, ca, pk, ix.n_videos, q_b=qb, c_b=cb, bf16=bf16, ordinal=True,
-                                             hi_only=True)
+        pre, self._prefilter = self._prefilter, None
+        if pre is None:  # pass 1 over the whole block now (otherwise it ran piece by piece behind the uploads)
+            pre = _Prefilter(self, len(video_query))
+            pre.run(0, len(video_query), video_query, sub_query)
+        split, approx = pre.split, pre.approx
+        qa, ca = split[0][:2], used[0][1]
+        qb, cb = (split[1][:2], used[1][1]) if len(used) == 2 else (None, None)
         with self._phase("vr_select"):
             # |approx - exact| <= mean over modalities of (||q - q_hi|| * ||c|| + ||q_hi|| * ||c - c_hi||) + slack
             scale = 1.001 / len(used)
@@ -493,9 +524,10 @@ class VCMRSearcher:
     # 8 GPUs, 1,250 queries per rank: 2.1 ms packed vs 1.6 ms padded)
     packed_min_queries = 4096
 
-    def _encode_pieces(self, pieces, lens_cpu=None):
+    def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None):
         """pieces: iterable of (query_feat, query_mask) device tensors -> pooled (video_query, sub_query).
-        lens_cpu: host int tensor, valid tokens of every query in piece order (None: padded encoding)."""
+        lens_cpu: host int tensor, valid tokens of every query in piece order (None: padded encoding).
+        on_piece(lo, hi, video_query, sub_query): called after each piece is encoded (pipelined filter pass)."""
         hid = self.model.config.hidden_size
         vq, sq = [], []
         with self._phase("encode_query"):
@@ -507,16 +539,25 @@ class VCMRSearcher:
                 tables = [self.model.packed_query_tables(lens[lo:lo + self.encode_chunk], self._piece_width,
                                                          self.index.device)
                           for lo in range(0, len(lens), self.encode_chunk)]
+            off = 0
             for i, (qf, qm) in enumerate(pieces):
                 if tables is not None:
                     a, b = self.model.encode_query_packed(qf, tables=tables[i])
                 else:
                     a, b = self.model.encode_query(qf, qm)
                 vq.append(a), sq.append(b)
+                if on_piece is not None:
+                    on_piece(off, off + len(a), a, b)
+                off += len(a)
             if not vq:
                 z = torch.zeros(0, hid, device=self.index.device)
                 return z, z
             return (vq[0], sq[0]) if len(vq) == 1 else (torch.cat(vq), torch.cat(sq))
+
+    # Host-buffer searches run the filter pass of the video retrieval per uploaded piece (5 launches over the corpus
+    # instead of 1: ~20 GB more L2->HBM traffic, hidden under the tensor-core work) so that only the first piece's
+    # upload is exposed instead of the whole 0.9 GB.
+    pipelined_filter = True
 
     def _device_pieces(self, query_feat, query_mask):
         for lo in range(0, len(query_feat), self.encode_chunk):
@@ -565,8 +606,15 @@ class VCMRSearcher:
                     and qm.shape[1] <= self.model.PACKED_MAX_LEN):
                 # valid tokens per query (masks are prefix masks); one small D2H when the masks live on the device
                 lens = (qm != 0).sum(1).to(torch.int64).cpu()
+            on_piece = None
+            self._prefilter = None
+            if (host and self.pipelined_filter and external_topk is None and ("VR" in tasks or "VCMR" in tasks)
+                    and self.two_pass and self.index.n_videos >= self.max_n_videos and lo == 0 and hi == n):
+                # host buffers: the filter pass of piece i runs while piece i+1 is still being uploaded
+                self._prefilter = _Prefilter(self, n)
+                on_piece = self._prefilter.run
             video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm) if host
-                                                         else self._device_pieces(qf, qm), lens)
+                                                         else self._device_pieces(qf, qm), lens, on_piece)
             video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
             gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
             self._external = None

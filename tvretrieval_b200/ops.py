@@ -304,7 +304,7 @@ def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, su
 
 
 def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=False, row_index=None, out=None,
-               out_col0=0, hi_err=False):
+               out_col0=0, hi_err=False, err_out=None):
     """fp32 rows -> 16-bit (hi, lo) halves with x ~= hi + lo, for the split-precision tensor-core kernels.
     x: (..., k) with rows grouped by `group_in`; output (n_groups * group_out, kpad) int16 tensors (raw bits).
     With row_index (int32, one source row per output row; negative = zero row) the rows are gathered instead.
@@ -325,7 +325,10 @@ def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=Fals
     else:  # write into columns [out_col0, out_col0 + kpad) of preallocated (rows, out_ld) buffers
         hi, lo = out
         assert hi.shape[0] == n_groups * group_out and hi.shape == lo.shape and hi.is_contiguous()
-    err = torch.empty(hi.shape[0], device=x.device, dtype=torch.float32) if hi_err else None
+    err = None
+    if hi_err:
+        err = err_out if err_out is not None else torch.empty(hi.shape[0], device=x.device, dtype=torch.float32)
+        assert err.numel() == hi.shape[0] and err.is_contiguous()
     rc = _lib.lib().xmlb_split_rows(_p(x), _p(row_index), n_groups, group_in, group_out, k, kpad, hi.shape[1],
                                     out_col0, int(normalize), int(bf16), _p(hi), _p(lo), _p(err), _stream())
     _lib.check(rc, "xmlb_split_rows")
