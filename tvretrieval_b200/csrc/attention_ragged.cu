@@ -47,29 +47,34 @@ __global__ void __launch_bounds__(128) attention_ragged_kernel(const float* __re
     *reinterpret_cast<float4*>(Vs + r * dh + c) = d;
   }
   __syncthreads();
-  // ---- S = Q K^T: thread (ti, tj) owns rows {2 ti, 2 ti + 1} x columns {tj, tj + 8, tj + 16, tj + 24} ----
+  // ---- S = Q K^T: thread (ti, tj) owns rows {2 ti, 2 ti + 1} x columns {tj, tj + 8, tj + 16, tj + 24}; rows and
+  // columns beyond the sequence are skipped (a warp covers rows 8 w .. 8 w + 7: whole warps drop out for short queries)
   const int ti = tid >> 3, tj = tid & 7;
-  {
+  if (2 * ti < len) {
     float acc[2][4] = {};
     const float* q0 = Qs + (2 * ti) * ld;
     const float* q1 = q0 + ld;
+    const int nc = (len - tj + 7) >> 3;  // columns tj + 8 c < len  <=>  c < nc  (0 when tj >= len)
     for (int d = 0; d < dh; d += 4) {
       const float4 a0 = *reinterpret_cast<const float4*>(q0 + d);
       const float4 a1 = *reinterpret_cast<const float4*>(q1 + d);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float4 b = *reinterpret_cast<const float4*>(Ks + (tj + 8 * c) * ld + d);
-        acc[0][c] = fmaf(a0.x, b.x, acc[0][c]), acc[0][c] = fmaf(a0.y, b.y, acc[0][c]);
-        acc[0][c] = fmaf(a0.z, b.z, acc[0][c]), acc[0][c] = fmaf(a0.w, b.w, acc[0][c]);
-        acc[1][c] = fmaf(a1.x, b.x, acc[1][c]), acc[1][c] = fmaf(a1.y, b.y, acc[1][c]);
-        acc[1][c] = fmaf(a1.z, b.z, acc[1][c]), acc[1][c] = fmaf(a1.w, b.w, acc[1][c]);
+        if (c < nc) {
+          const float4 b = *reinterpret_cast<const float4*>(Ks + (tj + 8 * c) * ld + d);
+          acc[0][c] = fmaf(a0.x, b.x, acc[0][c]), acc[0][c] = fmaf(a0.y, b.y, acc[0][c]);
+          acc[0][c] = fmaf(a0.z, b.z, acc[0][c]), acc[0][c] = fmaf(a0.w, b.w, acc[0][c]);
+          acc[1][c] = fmaf(a1.x, b.x, acc[1][c]), acc[1][c] = fmaf(a1.y, b.y, acc[1][c]);
+          acc[1][c] = fmaf(a1.z, b.z, acc[1][c]), acc[1][c] = fmaf(a1.w, b.w, acc[1][c]);
+        }
       }
     }
     const float div = sqrtf((float)dh);
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) Ps[(2 * ti + r) * (RL + 1) + tj + 8 * c] = __fdiv_rn(acc[r][c], div);
+      for (int c = 0; c < 4; ++c)
+        if (c < nc) Ps[(2 * ti + r) * (RL + 1) + tj + 8 * c] = __fdiv_rn(acc[r][c], div);
   }
   __syncthreads();
   // ---- softmax over the valid keys: warp w handles rows 8 w .. 8 w + 7, lane = key ----

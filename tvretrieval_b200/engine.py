@@ -524,25 +524,29 @@ class VCMRSearcher:
     # 8 GPUs, 1,250 queries per rank: 2.1 ms packed vs 1.6 ms padded)
     packed_min_queries = 4096
 
-    def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None):
+    def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None, tables_first=False):
         """pieces: iterable of (query_feat, query_mask) device tensors -> pooled (video_query, sub_query).
         lens_cpu: host int tensor, valid tokens of every query in piece order (None: padded encoding).
-        on_piece(lo, hi, video_query, sub_query): called after each piece is encoded (pipelined filter pass)."""
+        on_piece(lo, hi, video_query, sub_query): called after each piece is encoded (pipelined filter pass).
+        tables_first: build and upload the packed-layout tables of ALL pieces before touching `pieces` -- needed when
+        `pieces` streams the features from the host: once it has enqueued its bulk uploads, a later small H2D copy
+        would wait behind all of them.  Otherwise each piece's tables are built just before its launches, while
+        the GPU is still busy with the previous piece."""
         hid = self.model.config.hidden_size
         vq, sq = [], []
         with self._phase("encode_query"):
+            lens = lens_cpu.numpy() if lens_cpu is not None else None
+
+            def piece_tables(lo):
+                return self.model.packed_query_tables(lens[lo:lo + self.encode_chunk], self._piece_width,
+                                                      self.index.device)
             tables = None
-            if lens_cpu is not None:
-                # the (small) index tables of every piece go to the device FIRST: `pieces` is lazy, and once it has
-                # enqueued its bulk uploads a later H2D copy would wait behind all of them
-                lens = lens_cpu.numpy()
-                tables = [self.model.packed_query_tables(lens[lo:lo + self.encode_chunk], self._piece_width,
-                                                         self.index.device)
-                          for lo in range(0, len(lens), self.encode_chunk)]
+            if lens is not None and tables_first:
+                tables = [piece_tables(lo) for lo in range(0, len(lens), self.encode_chunk)]
             off = 0
             for i, (qf, qm) in enumerate(pieces):
-                if tables is not None:
-                    a, b = self.model.encode_query_packed(qf, tables=tables[i])
+                if lens is not None:
+                    a, b = self.model.encode_query_packed(qf, tables=tables[i] if tables else piece_tables(off))
                 else:
                     a, b = self.model.encode_query(qf, qm)
                 vq.append(a), sq.append(b)
@@ -614,7 +618,8 @@ class VCMRSearcher:
                 self._prefilter = _Prefilter(self, n)
                 on_piece = self._prefilter.run
             video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm) if host
-                                                         else self._device_pieces(qf, qm), lens, on_piece)
+                                                         else self._device_pieces(qf, qm), lens, on_piece,
+                                                         tables_first=host)
             video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
             gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
             self._external = None
