@@ -168,3 +168,17 @@ def test_corpus_packing_and_incremental_append():
     _check_packing(pk, np.concatenate([l1, l2]))
     restored = CorpusPacking.from_state({k: getattr(pk, k) for k in CorpusPacking.STATE}, pk.max_len)
     _check_packing(restored, np.concatenate([l1, l2]))
+
+
+def test_packed_query_layout():
+    """Index tables of the packed query encoder (XML.encode_query_packed): valid tokens in query order."""
+    from tvretrieval_b200.model_xml import packed_layout
+    lens, width = [3, 0, 5, 1, 9], 5
+    rows, pos, cu, max_len = packed_layout(lens, width)
+    assert cu.tolist() == [0, 3, 3, 8, 9, 14] and max_len == 5  # 9 is clamped to the padded width
+    assert pos.tolist() == [0, 1, 2, 0, 1, 2, 3, 4, 0, 0, 1, 2, 3, 4]
+    assert rows.tolist() == [0, 1, 2, 10, 11, 12, 13, 14, 15, 20, 21, 22, 23, 24]
+    mask = (np.arange(width)[None] < np.minimum(lens, width)[:, None])
+    assert np.array_equal(np.flatnonzero(mask.reshape(-1)), rows)  # == boolean-mask gather of the padded layout
+    rows, pos, cu, max_len = packed_layout([], 5)
+    assert len(rows) == 0 and cu.tolist() == [0] and max_len == 1

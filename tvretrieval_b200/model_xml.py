@@ -54,6 +54,20 @@ def mask_logits(target, mask):
     return target * mask + (1 - mask) * (-1e10)
 
 
+def packed_layout(lens, width):
+    """Index arithmetic of the packed (ragged) token layout: queries with `lens[i]` valid tokens (clamped to `width`,
+    the padded length) -> (rows, pos, cu_seqlens, max_len): for every packed token its row in the padded
+    (N * width) layout and its position inside its query; cu_seqlens[i] = first packed row of query i."""
+    import numpy as np
+    lens = np.minimum(np.asarray(lens, dtype=np.int64), width)
+    n = len(lens)
+    cu = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=cu[1:])
+    pos = np.arange(cu[-1]) - np.repeat(cu[:-1], lens)
+    rows = pos + np.repeat(np.arange(n) * width, lens)
+    return rows, pos, cu, int(max(1, lens.max(initial=1)))
+
+
 class XML(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -239,15 +253,10 @@ class XML(nn.Module):
         longest query), uploaded through pinned staging.  Callers that also stream the query features from the host
         create the tables BEFORE enqueueing those big copies (the H2D engine serves copies in issue order)."""
         import numpy as np
-        lens = np.minimum(np.asarray(lens_cpu, dtype=np.int64), width)
-        n = len(lens)
-        assert lens.max(initial=0) <= self.PACKED_MAX_LEN
-        cu = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(lens, out=cu[1:])
-        pos = np.arange(cu[-1]) - np.repeat(cu[:-1], lens)
-        rows = pos + np.repeat(np.arange(n) * width, lens)
+        rows, pos, cu, max_len = packed_layout(lens_cpu, width)
+        assert max_len <= self.PACKED_MAX_LEN
         t = self._upload_ints(np.concatenate([rows, pos, cu]).astype(np.int32), dev)
-        return t[:len(rows)], t[len(rows):2 * len(rows)], t[2 * len(rows):], int(max(1, lens.max(initial=1)))
+        return t[:len(rows)], t[len(rows):2 * len(rows)], t[2 * len(rows):], max_len
 
     @torch.no_grad()
     def encode_query_packed(self, query_feat, lens_cpu=None, tables=None):
