@@ -227,6 +227,22 @@ def pred_from_raw_query(cfg, w: Weights, query_feat, query_mask, video_feat1, vi
     return q2c, st, ed
 
 
+def visualization_data(cfg, w: Weights, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask):
+    """XML.get_visualization_data, model_xml.py:253-289 (tensors before the per-example cut to valid lengths):
+    modular token attention (N, Lq, 2), masked start / end logits, merged / video / subtitle similarity (N, L)."""
+    _, v2, _, s2 = encode_context(cfg, w, video_feat, video_mask, sub_feat, sub_mask)
+    e = encode_input(query_feat, query_mask, w, "query_input_proj", "query_encoder", "query_pos_embed", cfg["n_heads"])
+    att = torch.softmax(mask_logits(F.linear(e, w["modular_vector_mapping.weight"]), query_mask.unsqueeze(2)), dim=1)
+    vq, sq = modular_queries(e, query_mask, w)
+    st, ed = merged_st_ed_logits(w, vq, v2, sq, s2, video_mask, cross=False)
+    qv = F.linear(vq, w["video_query_linear.weight"], w["video_query_linear.bias"])
+    qs = F.linear(sq, w["sub_query_linear.weight"], w["sub_query_linear.bias"])
+    v_sim = torch.einsum("bd,bld->bl", qv, v2)
+    s_sim = torch.einsum("bd,bld->bl", qs, s2)
+    return dict(modular_att_scores=att, st_prob=st, ed_prob=ed, similarity_scores=(v_sim + s_sim) / 2,
+                video_similarity=v_sim, sub_similarity=s_sim)
+
+
 # --------------------------------------------------------------------------------------
 # training step: XML.forward + losses (model_xml.py:212-251, 588-637)
 # --------------------------------------------------------------------------------------

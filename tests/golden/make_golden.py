@@ -285,6 +285,26 @@ def external_vr_vectors():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def visualization_vectors():
+    """XML.get_visualization_data (reference model_xml.py:253-289) on the video_sub_vcmr training batch."""
+    name = "video_sub_vcmr"
+    case = CASES[name]
+    cfg = copy.deepcopy(xml_base_config)
+    cfg.update(case["cfg"])
+    torch.manual_seed(2018)
+    model = XML(cfg).eval()
+    inputs, _ = train_batch(case, cfg)
+    with torch.no_grad():
+        data = model.get_visualization_data(**inputs)
+    out = {"case": name, "n": np.int64(len(data))}
+    for i, d in enumerate(data):
+        for k, v in d.items():
+            out["%d/%s" % (i, k)] = np.asarray(v)
+    path = os.path.join(HERE, "visualization.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 ADAM_SHAPES = {"enc.weight": (24, 16), "enc.bias": (24,), "enc.LayerNorm.weight": (24,), "big.weight": (130, 70),
                "conv.weight": (1, 1, 5)}
 ADAM_HYPER = dict(lr=1e-2, warmup=0.25, t_total=8, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6,
@@ -336,6 +356,9 @@ if __name__ == "__main__":
     if "--adam-only" in sys.argv:
         bert_adam_vectors()
         sys.exit(0)
+    if "--visualization-only" in sys.argv:
+        visualization_vectors()
+        sys.exit(0)
     if "--external-vr-only" in sys.argv:
         external_vr_vectors()
         sys.exit(0)
@@ -346,3 +369,4 @@ if __name__ == "__main__":
     train_vectors()
     bert_adam_vectors()
     external_vr_vectors()
+    visualization_vectors()

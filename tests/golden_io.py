@@ -122,3 +122,29 @@ class AdamCase:
 
     def t(self, key):
         return torch.from_numpy(self.z[key])
+
+
+class VisualizationCase:
+    """tests/golden/visualization.npz: XML.get_visualization_data of the reference on a training batch."""
+    KEYS = ("modular_att_scores", "st_prob", "ed_prob", "similarity_scores", "video_similarity", "sub_similarity")
+
+    def __init__(self):
+        z = np.load(os.path.join(GOLDEN_DIR, "visualization.npz"))
+        self.train = TrainCase(str(z["case"]), "plain")
+        self.items = [{k: z["%d/%s" % (i, k)] for k in self.KEYS + ("st_ed_indices",)} for i in range(int(z["n"]))]
+
+    def check(self, got, rtol, atol):
+        """got: list of per-example dicts (the product) or dict of full tensors (the oracle)."""
+        i = self.train.inputs
+        q_len = i["query_mask"].sum(1).long().tolist()
+        c_len = i["video_mask"].sum(1).long().tolist()
+        assert len(self.items) == len(q_len)
+        for n, want in enumerate(self.items):
+            for k in self.KEYS:
+                if isinstance(got, dict):
+                    g = got[k][n][:(q_len[n] if k == "modular_att_scores" else c_len[n])]
+                else:
+                    g = got[n][k]
+                g = torch.as_tensor(np.asarray(g.detach().cpu() if torch.is_tensor(g) else g))
+                assert tuple(g.shape) == want[k].shape, (n, k, g.shape, want[k].shape)
+                torch.testing.assert_close(g.double(), torch.from_numpy(want[k]).double(), rtol=rtol, atol=atol)

@@ -175,6 +175,21 @@ def test_search_with_packed_query_encoder_equals_padded():
             torch.testing.assert_close(getattr(got, name), getattr(want, name), rtol=2e-5, atol=1e-12)
 
 
+def test_golden_visualization_data():
+    """XML.get_visualization_data / return_modular_att / return_similaity (reference model_xml.py:253-289,410-416,
+    498-500) against the reference's own output."""
+    from tests.golden_io import VisualizationCase
+    vc = VisualizationCase()
+    tc = vc.train
+    model = build_model(tc.cfg, tc.weights)
+    inputs = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in tc.inputs.items()}
+    got = model.get_visualization_data(**inputs)
+    assert len(got) == len(vc.items) and set(got[0]) == set(vc.items[0])
+    for g, w in zip(got, vc.items):
+        assert np.array_equal(g["st_ed_indices"], w["st_ed_indices"])
+    vc.check(got, rtol=1e-4, atol=1e-5)
+
+
 def test_golden_external_vr_lists(tmp_path):
     """--external_inference_vr_res_path (reference inference.py:264-273,349-355): the VCMR video lists come from
     another system's VR submission; compared with the reference's own output for the same submission file

@@ -174,3 +174,15 @@ def test_bert_adam_steps():
     order = [k for k in ac.names if ac.weight_decay(k) > 0] + [k for k in ac.names if ac.weight_decay(k) == 0]
     want = [h["lr"] * O.lr_multiplier(h["schedule"], h["warmup"], h["t_total"], states[k]["step"]) for k in order]
     np.testing.assert_allclose(ac.z["lr/%d" % (ac.n_steps - 1)], want, rtol=1e-12)
+
+
+def test_visualization_data():
+    """O.visualization_data (XML.get_visualization_data, model_xml.py:253-289) against the reference's output."""
+    from tests.golden_io import VisualizationCase
+    vc = VisualizationCase()
+    tc = vc.train
+    i = tc.inputs
+    with torch.no_grad():
+        got = O.visualization_data(tc.cfg, tc.weights, i["query_feat"], i["query_mask"], i["video_feat"],
+                                   i["video_mask"], i["sub_feat"], i["sub_mask"])
+    vc.check(got, RTOL, ATOL)

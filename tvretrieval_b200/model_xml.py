@@ -183,6 +183,26 @@ class XML(nn.Module):
         return loss, {"loss_st_ed": float(loss_st_ed), "loss_neg_ctx": float(loss_neg_ctx),
                       "loss_neg_q": float(loss_neg_q), "loss_overall": float(loss)}
 
+    @torch.no_grad()
+    def get_visualization_data(self, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask, tef_feat,
+                               tef_mask, st_ed_indices):
+        """reference model_xml.py:253-289: per example the modular token attention, start / end logits and the
+        similarity curves of the query on its own video, cut to the valid lengths -> list of N dicts of numpy arrays."""
+        assert self.config.merge_two_stream and self.use_video and self.use_sub and not self.config.no_modular
+        _, video_feat2, _, sub_feat2 = self.encode_context(video_feat, video_mask, sub_feat, sub_mask)
+        encoded_query = self.encode_input(query_feat, query_mask, self.query_input_proj, self.query_encoder,
+                                          self.query_pos_embed)
+        video_query, sub_query, att = self.get_modularized_queries(encoded_query, query_mask, return_modular_att=True)
+        st, ed, sim, v_sim, s_sim = self.get_merged_st_ed_prob(video_query, video_feat2, sub_query, sub_feat2,
+                                                               video_mask, cross=False, return_similaity=True)
+        data = dict(modular_att_scores=att, st_prob=st, ed_prob=ed, similarity_scores=sim, video_similarity=v_sim,
+                    sub_similarity=s_sim, st_ed_indices=st_ed_indices)
+        data = {k: v.cpu().numpy() for k, v in data.items()}
+        q_len = query_mask.sum(1).to(torch.long).cpu().tolist()
+        c_len = video_mask.sum(1).to(torch.long).cpu().tolist()
+        return [{k: v[i][:(q_len[i] if k == "modular_att_scores" else c_len[i])] for k, v in data.items()}
+                for i in range(len(q_len))]
+
     # ------------------------------------------------------------------ losses (tiny (N, N) / (N,) tensors)
     def get_video_level_loss(self, query_context_scores):
         """reference model_xml.py:588-605: ranking losses of each positive pair (the diagonal) against one sampled
@@ -289,9 +309,16 @@ class XML(nn.Module):
         """reference model_xml.py:399-423."""
         if self.config.no_modular:
             raise NotImplementedError("no_modular=True is not supported")
-        if return_modular_att:
-            raise NotImplementedError("return_modular_att (visualisation only) is not supported")
-        return ops.modular_pool(encoded_query, query_mask, self.modular_vector_mapping.weight)
+        pooled = ops.modular_pool(encoded_query, query_mask, self.modular_vector_mapping.weight)
+        if not return_modular_att:
+            return pooled
+        # visualisation path (reference model_xml.py:410-416): the token attention itself, (N, Lq, 2)
+        assert self.modular_vector_mapping.weight.shape[0] == 2
+        with ops.linear_precision("f32"):  # 2 output features: not a tensor-core shape
+            logits = ops.linear(encoded_query, self.modular_vector_mapping.weight)      # (N, Lq, 2)
+        logits = mask_logits(logits, query_mask.unsqueeze(2)).transpose(1, 2).contiguous()  # (N, 2, Lq)
+        att = ops.softmax_rows(logits).transpose(1, 2).contiguous()
+        return pooled[0], pooled[1], att
 
     def cross_context_encoder(self, main_context_feat, main_context_mask, side_context_feat, side_context_mask,
                               cross_att_layer, norm_layer, self_att_layer):
@@ -365,14 +392,24 @@ class XML(nn.Module):
                               return_similaity=False):
         """reference model_xml.py:455-502 -> masked st/ed logits."""
         assert self.use_video and self.use_sub and self.config.span_predictor_type == "conv"
-        if return_similaity:
-            raise NotImplementedError("return_similaity (visualisation only) is not supported")
         qv = ops.linear(video_query, self.video_query_linear.weight, self.video_query_linear.bias)
         qs = ops.linear(sub_query, self.sub_query_linear.weight, self.sub_query_linear.bias)
         lists = None if cross else ops.diagonal_pair_lists(len(qv), qv.device)
-        return ops.span_logits(qv, video_feat, context_mask, self.merged_st_predictor.weight,
-                               self.merged_ed_predictor.weight, q_b=qs, feat2_b=sub_feat, mask_b=context_mask,
-                               merged=True, lists=lists)
+        st, ed = ops.span_logits(qv, video_feat, context_mask, self.merged_st_predictor.weight,
+                                 self.merged_ed_predictor.weight, q_b=qs, feat2_b=sub_feat, mask_b=context_mask,
+                                 merged=True, lists=lists)
+        if not return_similaity:
+            return st, ed
+        # visualisation path (reference model_xml.py:484-485,498-500): the similarity curves themselves = the same
+        # kernel with an identity "convolution" (one tap of 1.0) and an all-ones mask
+        assert not cross
+        one = torch.ones(1, device=qv.device)
+        ones = torch.ones_like(context_mask)
+        sim = ops.span_logits(qv, video_feat, ones, one, one, q_b=qs, feat2_b=sub_feat, mask_b=ones, merged=True,
+                              lists=lists)[0]
+        v_sim = ops.span_logits(qv, video_feat, ones, one, one, lists=lists)[0]
+        s_sim = ops.span_logits(qs, sub_feat, ones, one, one, lists=lists)[0]
+        return st, ed, sim, v_sim, s_sim
 
     def get_st_ed_prob(self, modularied_query, context_feat2, context_mask, module_name="video", cross=False):
         """reference model_xml.py:504-551 (single stream)."""
