@@ -76,3 +76,29 @@ def test_shard_plan_covers_corpus():
             assert (owner[lo:hi] == r).all()
         qs = [ShardPlan(n, g, r).query_range(1003) for r in range(g)]
         assert qs[0][0] == 0 and max(q[1] for q in qs) == 1003
+
+
+def _ddp_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tvretrieval_b200.sharding import all_reduce_gradients
+        g = torch.Generator().manual_seed(3)
+        shapes = [(5, 4), (7,), (1, 1, 5), (3,)]
+        params = [torch.nn.Parameter(torch.zeros(*s)) for s in shapes]
+        grads = [[torch.randn(*s, generator=g) for s in shapes] for _ in range(world)]  # same on every rank
+        for i, p in enumerate(params):
+            p.grad = grads[rank][i].clone()
+        params[3].grad = None if rank == 1 else params[3].grad  # a parameter unused on one rank
+        frozen = torch.nn.Parameter(torch.ones(2), requires_grad=False)
+        all_reduce_gradients(params + [frozen])
+        for i, p in enumerate(params):
+            want = sum(grads[r][i] for r in range(world) if not (i == 3 and r == 1)) / world
+            assert torch.allclose(p.grad, want, atol=1e-7), i
+        assert frozen.grad is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_average():
+    mp.spawn(_ddp_worker, args=(2, 29500 + (os.getpid() + 977) % 2000), nprocs=2, join=True)

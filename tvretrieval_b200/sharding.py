@@ -238,3 +238,27 @@ class ShardedSearcher(VCMRSearcher):
                 val, idx, m, self.group, tie_desc=True,
                 finish=lambda i, v: ops.span_zero_fill(i, v, cells, tie_desc=True))
         return res
+
+
+# ------------------------------------------------------------------------------------------------ data-parallel training
+def all_reduce_gradients(parameters, group=None):
+    """Data-parallel training step (BASELINE config #4 on several GPUs; SURVEY.md section 8e "Training"): every rank
+    ran XML.forward / backward on its own mini-batch (in-batch negatives stay per rank, like the reference under
+    DataParallel); the gradients of all parameters are averaged with ONE all-reduce over a flat buffer (81 MB for the
+    20.2 M-parameter video_sub model) and written back in place, after which every rank applies the same
+    BertAdam.step().  Parameters without a gradient on this rank contribute zeros."""
+    params = [p for p in parameters if p.requires_grad]
+    if not params:
+        return
+    world = dist.get_world_size(group)
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    dist.all_reduce(flat, group=group)
+    flat /= world
+    off = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is None:
+            p.grad = flat[off:off + n].view_as(p).clone()
+        else:
+            p.grad.copy_(flat[off:off + n].view_as(p))
+        off += n
