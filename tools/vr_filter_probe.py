@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Limiter experiments on the hi-only (filter) pass of the packed tcgen05 VR kernel at the bench shape.
-XMLB_VR_PROBE bit 0: epilogue only waits/releases; bit 1: producer loads no B tiles; XMLB_VR_STAGES: ring depth."""
+XMLB_VR_PROBE bit 0: epilogue only waits/releases; bit 1: producer loads no B tiles; XMLB_VR_STAGES: ring depth.
+Needs a library built with the probe knobs compiled in:  python -m tvretrieval_b200.build --force --probes
+(and a plain `python -m tvretrieval_b200.build --force` afterwards)."""
 import os
 import sys
 import torch

@@ -1,6 +1,6 @@
 """Build libxmlb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-    python -m tvretrieval_b200.build [--force]
+    python -m tvretrieval_b200.build [--force] [--probes]
 
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
@@ -35,12 +35,15 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    digest = _digest()
+def build(force=False, verbose=False, probes=False):
+    """probes=True compiles the limiter-experiment knobs of the VR kernels in (XMLB_VR_PROBE / XMLB_VR_STAGES env
+    variables, used by tools/vr_filter_probe.py); the default library ignores them."""
+    digest = _digest() + ("+probes" if probes else "")
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP) and open(STAMP).read() == digest:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + (["-DXMLB_ENABLE_PROBES"] if probes else []) + \
+        ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(HERE, "build.log"), "w") as fh:
@@ -55,5 +58,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, probes="--probes" in sys.argv)
     print("built", path)

@@ -572,8 +572,10 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   p.idesc = tc::idesc_f16(BLOCK_M, 256, is_bf16 ? 1 : 0);
   p.terms = hi_only ? 1 : 3;
   p.stages = tc::pipe_stages(256, PACKED_EXTRA_SMEM, p.terms);
+#ifdef XMLB_ENABLE_PROBES  // limiter experiments only (python -m tvretrieval_b200.build --probes; tools/vr_filter_probe.py)
   if (const char* e = getenv("XMLB_VR_PROBE")) p.probe = atoi(e);
   if (const char* e = getenv("XMLB_VR_STAGES")) p.stages = atoi(e) < p.stages ? atoi(e) : p.stages;
+#endif
   XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_scores_tc_packed: tile does not fit in shared memory");
   const size_t smem = tc::pipe_smem_bytes(256, p.stages, PACKED_EXTRA_SMEM, p.terms);
   XMLB_REQUIRE(((uintptr_t)tile_meta & 15) == 0, "xmlb_vr_scores_tc_packed: tile_meta must be 16-byte aligned");
