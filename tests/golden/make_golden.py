@@ -305,6 +305,60 @@ def visualization_vectors():
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def eval_metric_vectors():
+    """standalone_eval.eval.eval_retrieval (reference standalone_eval/eval.py:255-276) on a synthetic submission:
+    variable numbers of predictions per query (some beyond the 100 that are evaluated), predictions engineered to hit
+    the IoU thresholds from both sides, TVR-style single ground-truth spans and DiDeMo-style multi-annotation ones."""
+    from standalone_eval.eval import eval_retrieval
+    rng = np.random.RandomState(21)
+    n_videos, n_desc = 30, 80
+    video2idx = {"vid_%d" % i: 100 + 3 * i for i in range(n_videos)}
+    names = list(video2idx)
+    gts, sub = [], dict(video2idx=video2idx, VCMR=[], SVMR=[], VR=[])
+    for d in range(n_desc):
+        vid = names[rng.randint(n_videos)]
+        st = float(np.round(rng.uniform(0, 60), 1))
+        ed = st + float(np.round(rng.uniform(3, 20), 1))
+        multi = d % 9 == 4
+        ts = [[st + float(rng.choice([-3, 0, 1.5])), ed + float(rng.choice([-1.5, 0, 3]))] for _ in range(4 + d % 2)] \
+            if multi else [st, ed]
+        gts.append(dict(desc_id=1000 + d, desc="q%d" % d, type=["v", "t", "vt"][rng.randint(3)], vid_name=vid, ts=ts))
+
+        def spans(n):
+            out = []
+            for _ in range(n):
+                kind = rng.randint(4)
+                if kind == 0:    # near the ground truth: IoU around the thresholds
+                    a = st + rng.choice([-4.5, -3, -1.5, 0, 1.5, 3])
+                    b = ed + rng.choice([-4.5, -3, -1.5, 0, 1.5, 3])
+                    b = max(b, a + 1.5)
+                else:
+                    a = float(np.floor(rng.uniform(0, 80) / 1.5) * 1.5)
+                    b = a + 1.5 * rng.randint(2, 17)
+                out.append((float(a), float(b)))
+            return out
+        n_vcmr = int(rng.choice([1, 3, 40, 100, 130])) if d % 7 else 100  # (the reference cannot take 0)
+        sub["VCMR"].append(dict(desc_id=1000 + d, desc="q%d" % d, predictions=[
+            [video2idx[vid] if rng.rand() < 0.3 else video2idx[names[rng.randint(n_videos)]], a, b, float(rng.rand())]
+            for a, b in spans(n_vcmr)]))
+        sub["SVMR"].append(dict(desc_id=1000 + d, desc="q%d" % d, predictions=[
+            [video2idx[vid], a, b, float(rng.rand())] for a, b in spans(int(rng.choice([1, 12, 100, 120])))]))
+        order = rng.permutation(n_videos)[:int(rng.choice([5, 30]))]
+        sub["VR"].append(dict(desc_id=1000 + d, desc="q%d" % d, predictions=[
+            [video2idx[names[v]], 0, 0, float(rng.rand())] for v in order]))
+    out = dict(submission=sub, ground_truth=gts, expected={})
+    for use_type in (True, False):
+        for thds in ((0.5, 0.7), (0.3,)):
+            res = eval_retrieval(copy.deepcopy(sub), copy.deepcopy(gts), iou_thds=thds, verbose=False,
+                                 use_desc_type=use_type)
+            out["expected"]["%s/%s" % (use_type, ",".join(map(str, thds)))] = \
+                [[task, list(m.items())] for task, m in res.items()]
+    path = os.path.join(HERE, "eval_metrics.json")
+    with open(path, "w") as fh:
+        json.dump(out, fh)
+    print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 ADAM_SHAPES = {"enc.weight": (24, 16), "enc.bias": (24,), "enc.LayerNorm.weight": (24,), "big.weight": (130, 70),
                "conv.weight": (1, 1, 5)}
 ADAM_HYPER = dict(lr=1e-2, warmup=0.25, t_total=8, schedule="warmup_linear", b1=0.9, b2=0.999, e=1e-6,
@@ -356,6 +410,10 @@ if __name__ == "__main__":
     if "--adam-only" in sys.argv:
         bert_adam_vectors()
         sys.exit(0)
+    if "--eval-only" in sys.argv:
+        np.bool = bool  # standalone_eval/eval.py uses the removed alias (numpy < 1.24)
+        eval_metric_vectors()
+        sys.exit(0)
     if "--visualization-only" in sys.argv:
         visualization_vectors()
         sys.exit(0)
@@ -370,3 +428,5 @@ if __name__ == "__main__":
     bert_adam_vectors()
     external_vr_vectors()
     visualization_vectors()
+    np.bool = bool  # standalone_eval/eval.py uses the removed alias (numpy < 1.24)
+    eval_metric_vectors()

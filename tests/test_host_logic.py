@@ -182,3 +182,24 @@ def test_packed_query_layout():
     assert np.array_equal(np.flatnonzero(mask.reshape(-1)), rows)  # == boolean-mask gather of the padded layout
     rows, pos, cu, max_len = packed_layout([], 5)
     assert len(rows) == 0 and cu.tolist() == [0] and max_len == 1
+
+
+def test_eval_retrieval_matches_reference_evaluator():
+    """tvretrieval_b200.eval_metrics.eval_retrieval == standalone_eval.eval.eval_retrieval (reference
+    standalone_eval/eval.py:83-276) on the golden submission: same keys in the same order, same rounded values."""
+    import json
+    from tests.golden_io import GOLDEN_DIR
+    from tvretrieval_b200.eval_metrics import eval_retrieval
+    z = json.load(open(os.path.join(GOLDEN_DIR, "eval_metrics.json")))
+    for key, want in z["expected"].items():
+        use_type, thds = key.split("/")
+        got = eval_retrieval(copy.deepcopy(z["submission"]), copy.deepcopy(z["ground_truth"]),
+                             iou_thds=tuple(float(t) for t in thds.split(",")), verbose=False,
+                             use_desc_type=use_type == "True")
+        got = [[task, [[k, v] for k, v in m.items()]] for task, m in got.items()]
+        assert got == want, key
+    # a query without predictions (the reference cannot evaluate it) simply never hits
+    sub = copy.deepcopy(z["submission"])
+    sub["VCMR"][0]["predictions"] = []
+    m = eval_retrieval(sub, z["ground_truth"], verbose=False)
+    assert set(m) == {"VCMR", "SVMR", "VR", "VCMR_by_type", "SVMR_by_type", "VR_by_type"}
