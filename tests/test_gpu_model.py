@@ -4,6 +4,7 @@
 Floating point: north_star tolerance 1e-3 relative (the asserts below use tighter bounds where they hold);
 ranked indices: exact wherever the oracle's own neighbouring scores differ by more than 5e-5 relative."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -173,6 +174,35 @@ def test_search_with_packed_query_encoder_equals_padded():
             assert torch.equal(getattr(got, name), getattr(want, name)), name
         for name in ("top_video_score", "span_score", "svmr_score"):
             torch.testing.assert_close(getattr(got, name), getattr(want, name), rtol=2e-5, atol=1e-12)
+
+
+def test_eval_epoch_writes_submission_and_metrics(tmp_path):
+    """eval_epoch (reference inference.py:472-531): submission + metrics files before and after NMS; the metrics are
+    those of the reference evaluator on the written submission."""
+    import json
+    from tvretrieval_b200 import inference as I
+    from tvretrieval_b200.eval_metrics import eval_retrieval
+    from tvretrieval_b200.synthetic import SyntheticEvalDataset
+    g = GoldenCase("video_sub_vcmr")
+    ds = SyntheticEvalDataset(max_ctx_l=g.cfg["max_ctx_l"], max_desc_l=g.cfg["max_desc_l"],
+                              video_dim=g.cfg["visual_input_size"], sub_dim=g.cfg["sub_input_size"],
+                              query_dim=g.cfg["query_input_size"], ctx_mode=g.cfg["ctx_mode"], min_ctx_l=3,
+                              **g.case["data"])
+    model = build_model(g.cfg, g.weights)
+    opt = Opt(g.case, g.cfg)
+    opt.results_dir, opt.eval_split_name, opt.dset_name, opt.nms_thd = str(tmp_path), "val", "tvr", 0.5
+    metrics, metrics_nms, paths = I.eval_epoch(model, ds, opt, "sub.json", tasks=("VCMR", "SVMR", "VR"),
+                                               max_after_nms=20)
+    assert [os.path.basename(p) for p in paths] == ["sub.json", "sub_metrics.json", "sub_nms_thd_0.5.json",
+                                                    "sub_nms_thd_0.5_metrics.json"]
+    sub = json.load(open(paths[0]))
+    assert set(sub) == {"video2idx", "VCMR", "SVMR", "VR"} and all(len(e["predictions"]) <= 20 for e in sub["VCMR"])
+    again = eval_retrieval(sub, ds.query_data, verbose=False)
+    assert json.load(open(paths[1])) == json.loads(json.dumps(again)) == json.loads(json.dumps(metrics))
+    assert set(metrics_nms) == {"VCMR", "SVMR", "VCMR_by_type", "SVMR_by_type"}
+    assert metrics["SVMR"]["0.5-r100"] >= metrics["SVMR"]["0.5-r1"]
+    after = json.load(open(paths[2]))
+    assert set(after) == {"video2idx", "VCMR", "SVMR"}
 
 
 def test_golden_visualization_data():

@@ -297,3 +297,57 @@ def post_processing_vcmr_nms(vcmr_res, nms_thd=0.6, max_before_nms=1000, max_aft
 def post_processing_svmr_nms(svmr_res, nms_thd=0.6, max_before_nms=1000, max_after_nms=100):
     """reference baselines/clip_alignment_with_language/inference.py:247-265."""
     return _nms_lists(svmr_res, nms_thd, max_before_nms, max_after_nms, per_video=False)
+
+
+# ------------------------------------------------------------------------------------------------ per-epoch evaluation
+POST_PROCESSING_MMS_FUNC = {"SVMR": post_processing_svmr_nms, "VCMR": post_processing_vcmr_nms}
+
+
+def _save_json(data, path, pretty=False):
+    import json
+    with open(path, "w") as fh:
+        if pretty:
+            json.dump(data, fh, indent=4, sort_keys=False)
+        else:
+            json.dump(data, fh)
+
+
+def eval_epoch(model, eval_dataset, opt, save_submission_filename, tasks=("SVMR",), max_after_nms=100):
+    """reference inference.py:472-531: run the retrieval drivers, write the top-`max_after_nms` submission (and, on the
+    validation split, its metrics) under opt.results_dir; with opt.nms_thd != -1 repeat after temporal NMS.
+    -> (metrics, metrics_nms, written file paths).  opt fields read here: results_dir, eval_split_name, debug,
+    dset_name, nms_thd, max_before_nms (plus those of the drivers)."""
+    import os
+    from .eval_metrics import eval_retrieval
+    model.eval()
+    raw = get_eval_res(model, eval_dataset, opt, tasks, max_after_nms=max_after_nms)
+    iou_thds = (0.5, 0.7)
+    submission_path = os.path.join(opt.results_dir, save_submission_filename)
+    submission = get_submission_top_n(raw, top_n=max_after_nms)
+    _save_json(submission, submission_path)
+    metrics = metrics_nms = None
+    paths = [submission_path]
+    on_val = opt.eval_split_name == "val"  # test_public has no ground truth
+    if on_val:
+        metrics = eval_retrieval(submission, eval_dataset.query_data, iou_thds=iou_thds, match_number=not opt.debug,
+                                 verbose=opt.debug, use_desc_type=opt.dset_name == "tvr")
+        metrics_path = submission_path.replace(".json", "_metrics.json")
+        _save_json(metrics, metrics_path, pretty=True)
+        paths.append(metrics_path)
+    if opt.nms_thd != -1:
+        after = dict(video2idx=raw["video2idx"])
+        for task, nms in POST_PROCESSING_MMS_FUNC.items():
+            if task in raw:
+                after[task] = nms(raw[task], nms_thd=opt.nms_thd, max_before_nms=opt.max_before_nms,
+                                  max_after_nms=max_after_nms)
+        nms_path = submission_path.replace(".json", "_nms_thd_{}.json".format(opt.nms_thd))
+        _save_json(after, nms_path)
+        if on_val:
+            metrics_nms = eval_retrieval(after, eval_dataset.query_data, iou_thds=iou_thds,
+                                         match_number=not opt.debug, verbose=opt.debug)
+            nms_metrics_path = nms_path.replace(".json", "_metrics.json")
+            _save_json(metrics_nms, nms_metrics_path, pretty=True)
+            paths += [nms_path, nms_metrics_path]
+        else:
+            paths = [nms_path]
+    return metrics, metrics_nms, paths
