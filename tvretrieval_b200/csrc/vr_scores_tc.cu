@@ -443,9 +443,19 @@ __global__ void __launch_bounds__(256) gather_rows16_kernel(const uint4* __restr
   const uint4* sl = src_lo + src * vec_per_row;
   uint4* dh = dst_hi + ro * vec_per_row;
   uint4* dl = dst_lo + ro * vec_per_row;
-  for (int i = lane; i < vec_per_row; i += 32) {
-    const uint4 a = __ldg(sh + i), b = __ldg(sl + i);
-    dh[i] = a, dl[i] = b;
+  // up to 4 x 2 independent 16-byte loads in flight per lane before the first store (a 768-wide row is 3 iterations)
+  for (int i0 = lane; i0 < vec_per_row; i0 += 128) {
+    uint4 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < vec_per_row) a[u] = __ldg(sh + i), b[u] = __ldg(sl + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < vec_per_row) dh[i] = a[u], dl[i] = b[u];
+    }
   }
 }
 
