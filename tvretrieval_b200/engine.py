@@ -524,9 +524,10 @@ class VCMRSearcher:
     # 8 GPUs, 1,250 queries per rank: 2.1 ms packed vs 1.6 ms padded)
     packed_min_queries = 4096
 
-    def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None, tables_first=False):
+    def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None, tables_first=False, width=None):
         """pieces: iterable of (query_feat, query_mask) device tensors -> pooled (video_query, sub_query).
-        lens_cpu: host int tensor, valid tokens of every query in piece order (None: padded encoding).
+        lens_cpu: host int tensor, valid tokens of every query in piece order (None: padded encoding); `width` is
+        the padded token count of the pieces.
         on_piece(lo, hi, video_query, sub_query): called after each piece is encoded (pipelined filter pass).
         tables_first: build and upload the packed-layout tables of ALL pieces before touching `pieces` -- needed when
         `pieces` streams the features from the host: once it has enqueued its bulk uploads, a later small H2D copy
@@ -538,8 +539,7 @@ class VCMRSearcher:
             lens = lens_cpu.numpy() if lens_cpu is not None else None
 
             def piece_tables(lo):
-                return self.model.packed_query_tables(lens[lo:lo + self.encode_chunk], self._piece_width,
-                                                      self.index.device)
+                return self.model.packed_query_tables(lens[lo:lo + self.encode_chunk], width, self.index.device)
             tables = None
             if lens is not None and tables_first:
                 tables = [piece_tables(lo) for lo in range(0, len(lens), self.encode_chunk)]
@@ -605,7 +605,6 @@ class VCMRSearcher:
             lo, hi = self._my_slice(n)
             qf, qm = query_feat[b_lo + lo:b_lo + hi], query_mask[b_lo + lo:b_lo + hi]
             lens = None
-            self._piece_width = qm.shape[1]
             if (self.packed_queries and hi - lo >= self.packed_min_queries
                     and qm.shape[1] <= self.model.PACKED_MAX_LEN):
                 # valid tokens per query (masks are prefix masks); one small D2H when the masks live on the device
@@ -619,7 +618,7 @@ class VCMRSearcher:
                 on_piece = self._prefilter.run
             video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm) if host
                                                          else self._device_pieces(qf, qm), lens, on_piece,
-                                                         tables_first=host)
+                                                         tables_first=host, width=qm.shape[1])
             video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
             gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
             self._external = None
