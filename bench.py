@@ -30,12 +30,14 @@ if REPO not in sys.path:
 METRIC = "queries/sec full-corpus VCMR (21.8K-video shape)"
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"],
+                    help="ours = the CUDA kernels; reference = the reference's own code on the host CPU cores; "
+                         "torch_gpu = the reference's own code through PyTorch on the same GPU")
     ap.add_argument("--n-videos", type=int, default=21793)
     ap.add_argument("--n-queries", type=int, default=10000)
     ap.add_argument("--max-ctx-l", type=int, default=128)
@@ -52,9 +54,12 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the float64 parity check after the timed region")
+    ap.add_argument("--no-gpu-reference", action="store_true",
+                    help="skip timing the reference through PyTorch on the same GPU (gpu_reference in the JSON line)")
     ap.add_argument("--cuda-profiler", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 def model_config(args):
@@ -156,28 +161,92 @@ def encode_corpus_shard(model, args, lens, vid_lo, vid_hi, device):
     return out, time.perf_counter() - t0
 
 
+# ------------------------------------------------------------------------------------------------ reference legs
+def _reference_opt(ref_ns, cfg, device, bsz, max_ctx_l):
+    return ref_ns.EasyDict(eval_query_bsz=bsz, eval_context_bsz=200, num_workers=0, pin_memory=False, device=device,
+                           ctx_mode=cfg["ctx_mode"], external_inference_vr_res_path=None, q2c_alpha=20.0,
+                           min_pred_l=2, max_pred_l=16, max_ctx_l=max_ctx_l, clip_length=1.5, debug=False)
+
+
+def reference_query_path(ref_ns, model, cfg, ctx, qf, qm, bsz, device, sync=None):
+    """One run of the reference's UNMODIFIED compute_query2ctx_info(tasks=VCMR+VR) (baseline/_ref, reference
+    inference.py:252-445) over the given queries in batches of `bsz` against the encoded corpus `ctx` (tensors on
+    `device`).  -> (seconds in total, seconds in the tensor section :302-389, result dict).  The split comes from
+    replacing the module's tqdm progress bar by a timer (tests/reference_loader.SectionTimer)."""
+    from tests import reference_loader as RL
+    nv, L = ctx["video_mask"].shape
+    ds = RL.QueryDataset(qf, qm, nv, L)
+    info = dict(video_metas=[{"vid_name": "vid_%05d" % i} for i in range(nv)], **{k: ctx[k] for k in CTX_KEYS})
+    timer = RL.SectionTimer(sync)
+    ref_ns.inference.tqdm = timer
+    opt = _reference_opt(ref_ns, cfg, device, bsz, L)
+    if sync:
+        sync()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        res = ref_ns.inference.compute_query2ctx_info(model, ds, opt, info, max_before_nms=200,
+                                                      max_n_videos=min(100, nv), tasks=("VCMR", "VR"))
+    if sync:
+        sync()
+    return time.perf_counter() - t0, timer.seconds.get("Computing q embedding", float("nan")), res
+
+
+CTX_KEYS = ("video_feat1", "video_feat2", "video_mask", "sub_feat1", "sub_feat2", "sub_mask")
+
+
+def reference_model(cfg, weights, device):
+    """The reference's own XML (baseline/_ref) with the given weights, or None when baseline/_ref is not vendored."""
+    from tests import reference_loader as RL
+    if not RL.available():
+        return None, None
+    ref_ns = RL.load()
+    model = ref_ns.XML(ref_ns.EasyDict(dict(cfg)))
+    model.load_state_dict(weights)
+    return ref_ns, model.to(device).eval()
+
+
+def extrapolate_seconds(n_a, t_a, n_b, t_b, n_total):
+    """Seconds per pass at n_total videos from two timed corpus sizes: t(n) = fixed + per_video * n (the fixed part --
+    query encoding, loader, host lists -- must not be scaled with the corpus, or the CPU arm would look slower than it
+    is).  -> (seconds, description)."""
+    if n_b > n_a and t_b > t_a:
+        per_video = (t_b - t_a) / (n_b - n_a)
+        fixed = max(0.0, t_a - per_video * n_a)
+    else:
+        per_video, fixed = t_b / n_b, 0.0
+    return fixed + per_video * n_total, ("extrapolated to %d videos as fixed %.3f s + %.3e s/video (from passes over %d "
+                                         "and %d videos)" % (n_total, fixed, per_video, n_a, n_b))
+
+
 def cpu_baseline(args, cfg, weights, ctx_dev, query_feat, query_mask):
-    """Oracle port of the reference's query path timed on the host cores, on a bounded sample: Q=50 queries (the
-    reference's eval_query_bsz) against the first Nv_s videos of the same encoded corpus; Nv_s is calibrated so the
-    sample takes about --cpu-seconds.  queries/sec is extrapolated linearly in Nv_s / Nv."""
-    from oracle import xml_oracle as O
+    """The reference's query path timed on the host cores, on a bounded sample: Q=50 queries (the reference's
+    eval_query_bsz) against the first Nv_s videos of the same encoded corpus; Nv_s is calibrated so the sample
+    takes about --cpu-seconds.  queries/sec is extrapolated linearly in Nv_s / Nv.
+    kind "reference" = the unmodified reference from baseline/_ref; "port" = oracle/xml_oracle.py when the
+    vendored copy is absent."""
     n_thr = os.cpu_count() or 1
     torch.set_num_threads(n_thr)
     nq = min(50, len(query_feat))
     qf, qm = query_feat[:nq].cpu(), query_mask[:nq].cpu()
     n_total = ctx_dev["video_feat1"].shape[0]
-    k_vid = min(100, n_total)
+    ref_ns, ref_model = reference_model(cfg, weights, "cpu")
+    kind = "reference" if ref_model is not None else "port"
 
     def run(n_sub, reps):
-        ctx = {k: ctx_dev[k][:n_sub].cpu() for k in ("video_feat1", "video_feat2", "video_mask", "sub_feat1",
-                                                     "sub_feat2", "sub_mask")}
+        ctx = {k: ctx_dev[k][:n_sub].cpu() for k in CTX_KEYS}
         best = float("inf")
-        with torch.no_grad():
-            for _ in range(reps):
+        for _ in range(reps):
+            if ref_model is not None:
+                t, _, _ = reference_query_path(ref_ns, ref_model, cfg, ctx, qf, qm, nq, torch.device("cpu"))
+            else:
+                from oracle import xml_oracle as O
                 t0 = time.perf_counter()
-                O.query_batch_tensor_section(cfg, weights, ctx, qf, qm, q2c_alpha=20.0, max_n_videos=min(k_vid, n_sub),
-                                             max_before_nms=200, min_pred_l=2, max_pred_l=16, canonical_ties=False)
-                best = min(best, time.perf_counter() - t0)
+                with torch.no_grad():
+                    O.query_batch_tensor_section(dict(cfg), weights, ctx, qf, qm, q2c_alpha=20.0,
+                                                 max_n_videos=min(100, n_sub), max_before_nms=200, min_pred_l=2,
+                                                 max_pred_l=16, canonical_ties=False)
+                t = time.perf_counter() - t0
+            best = min(best, t)
         return best
 
     n_cal = min(n_total, 400)
@@ -185,11 +254,81 @@ def cpu_baseline(args, cfg, weights, ctx_dev, query_feat, query_mask):
     t_cal = run(n_cal, 1)
     n_sub = int(min(n_total, max(n_cal, n_cal * (args.cpu_seconds / 3.0) / max(t_cal, 1e-3))))
     t = run(n_sub, 2)
-    qps_sample = nq / t
-    return {"value": qps_sample * n_sub / n_total, "unit": "queries/s", "cores": n_thr, "kind": "port",
-            "sample": "%d queries x first %d of %d videos (%.2f s per pass, best of 2), oracle port of the reference "
-                      "query path incl. full sort, torch CPU fp32; scaled by %d/%d to the full corpus"
-                      % (nq, n_sub, n_total, t, n_sub, n_total)}
+    t_full, fit = extrapolate_seconds(n_cal, t_cal, n_sub, t, n_total)
+    what = ("the unmodified reference compute_query2ctx_info (baseline/_ref, model + driver incl. full sort and host "
+            "lists), torch CPU fp32" if kind == "reference" else
+            "oracle port of the reference query path incl. full sort, torch CPU fp32")
+    return {"value": nq / t_full, "unit": "queries/s", "cores": n_thr, "kind": kind,
+            "sample": "%d queries x first %d of %d videos (%.2f s per pass, best of 2), %s; %s"
+                      % (nq, n_sub, n_total, t, what, fit)}
+
+
+def gpu_reference(args, cfg, weights, ctx, qf_cpu, qm_cpu, device):
+    """The reference single-GPU PyTorch path on the SAME B200 and the SAME encoded corpus: the unmodified reference
+    model + compute_query2ctx_info (baseline/_ref) on cuda, fp32 with TF32 off and on, at the reference's query batch
+    (50) and at a large one.  queries/s over the whole call (tensor section + host lists) and over the tensor section
+    alone (reference inference.py:302-389)."""
+    ref_ns, model = reference_model(cfg, weights, device)
+    if model is None:
+        return {"unavailable": "baseline/_ref not vendored (tools/vendor_reference.py)"}
+    out = {"api": "baseline/_ref baselines.crossmodal_moment_localization.inference.compute_query2ctx_info "
+                  "(unmodified), reference XML on cuda, tasks VCMR+VR, top-100 videos, top-200 moments",
+           "runs": []}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for tf32, bsz, nq in ((False, 50, 250), (True, 50, 250), (True, 400, 800), (False, 400, 800)):
+            nq = min(nq, len(qf_cpu))
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = tf32
+            run = {"tf32": tf32, "query_batch": bsz, "n_queries": nq}
+            try:
+                reference_query_path(ref_ns, model, cfg, ctx, qf_cpu[:min(bsz, nq)], qm_cpu[:min(bsz, nq)], bsz,
+                                     device, torch.cuda.synchronize)  # warm-up: one batch
+                t, t_tensor, _ = reference_query_path(ref_ns, model, cfg, ctx, qf_cpu[:nq], qm_cpu[:nq], bsz, device,
+                                                      torch.cuda.synchronize)
+                run.update(queries_per_s=nq / t, queries_per_s_tensor_section=nq / t_tensor, seconds=t)
+            except torch.cuda.OutOfMemoryError:
+                run["error"] = "out of memory"
+            torch.cuda.empty_cache()
+            out["runs"].append(run)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    ok = [r for r in out["runs"] if "queries_per_s" in r]
+    if ok:
+        out["best_queries_per_s"] = max(r["queries_per_s"] for r in ok)
+        out["best_queries_per_s_tensor_section"] = max(r["queries_per_s_tensor_section"] for r in ok)
+    return out
+
+
+def parity_check(args, cfg, weights, ctx, res, qf_cpu, qm_cpu, device, n_sample=32, tau=1e-4):
+    """After the timed region: the lists the timed search returned for `n_sample` of its queries against the reference
+    arithmetic evaluated in float64 over the whole corpus (tests/rank_check.py; oracle/ used as the checker only)."""
+    from tests import rank_check as R
+    nq = len(qf_cpu)
+    sample = torch.arange(0, nq, max(1, nq // n_sample))[:n_sample]
+    vr64, st64, ed64 = R.fp64_scores(dict(cfg), weights, ctx, qf_cpu[sample], qm_cpu[sample], device=device, chunk=512)
+    sd = sample.to(device)
+    stats = R.check_search_result(vr64, st64, ed64, res.top_video_idx[sd], res.top_video_score[sd],
+                                  res.span_flat_idx[sd], res.span_score[sd], args.max_ctx_l)
+    worst = max(v for st_ in stats.values() for k, v in st_.items() if k != "positions_off")
+    return {"parity_checked": bool(worst <= tau),
+            "parity": {"against": "reference arithmetic in float64 (oracle/xml_oracle.py) over all %d videos"
+                                  % ctx["video_mask"].shape[0], "n_queries": int(len(sample)), "tau": tau,
+                       "worst_relative_deviation": worst, "stats": stats}}
+
+
+def host_postprocess_ms(out, n_videos, ctx_len):
+    """a18 (reference inference.py:391-445): building the VR + VCMR prediction lists of ALL queries from the numpy
+    arrays search_host returned (vectorised host section of tvretrieval_b200.inference), milliseconds."""
+    from tvretrieval_b200.inference import host_section
+    nq = len(out["top_video_idx"])
+    video_metas = [{"vid_name": "vid_%05d" % i} for i in range(n_videos)]
+    video2idx = {m["vid_name"]: i for i, m in enumerate(video_metas)}
+    metas = [dict(desc_id=i, desc="q%d" % i) for i in range(nq)]
+    t0 = time.perf_counter()
+    res = host_section(out, metas, video_metas, video2idx, ctx_len, 1.5, ("VCMR", "VR"))
+    dt = time.perf_counter() - t0
+    assert len(res["VCMR"]) == nq and len(res["VCMR"][0]["predictions"]) == out["span_flat_idx"].shape[1]
+    return 1e3 * dt
 
 
 def ncu_traffic(args, world, searcher):
@@ -232,7 +371,8 @@ def run_ours(args):
     vid_hi = (rank + 1) * args.n_videos // world
     ctx, t_enc = encode_corpus_shard(model, args, lens, vid_lo, vid_hi, device)
     index = CorpusIndex.from_ctx_info(ctx, vid_lo=vid_lo, precision=args.precision, packed=not args.padded_corpus)
-    keep_ctx = ctx if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    keep_ctx = ctx if (rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_parity
+                                                          and args.no_gpu_reference)) else None
     if keep_ctx is None:
         del ctx
     torch.cuda.empty_cache()
@@ -365,6 +505,18 @@ def run_ours(args):
             "corpus_encode": {"videos_per_s": n_local / t_enc, "seconds": t_enc, "index_gb": index.nbytes() / 1e9}}
     if e2e is not None:
         line["e2e"] = e2e
+    if e2e is not None:
+        line["host_postprocess_ms"] = host_postprocess_ms(out, args.n_videos, args.max_ctx_l)
+    if rank == 0 and world == 1 and not args.no_parity:
+        line.update(parity_check(args, cfg, weights_cpu, keep_ctx, res, qf_cpu, qm_cpu, device))
+    else:
+        line["parity_checked"] = False
+        line["parity"] = {"skipped": "run at N=1 (sharded results are bit-equal to N=1: tests/test_gpu_sharded.py)"
+                          if world > 1 else "--no-parity"}
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        del searcher, index
+        torch.cuda.empty_cache()
+        line["gpu_reference"] = gpu_reference(args, cfg, weights_cpu, keep_ctx, qf_cpu, qm_cpu, device)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, cfg, weights_cpu, keep_ctx, qf_cpu, qm_cpu)
     if rank == 0:
@@ -375,60 +527,126 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
+# ------------------------------------------------------------------------------------------------ reference arms
+def _synthetic_encoded_corpus(n, L, H, gen):
+    """Random stand-in for an encoded corpus (the query path's cost does not depend on the values)."""
+    lens = torch.randint(L // 8, L + 1, (n,), generator=gen)
+    lens[0] = L
+    mask = (torch.arange(L)[None] < lens[:, None]).float()
+    ctx = {"video_mask": mask, "sub_mask": mask}
+    for k in ("video_feat1", "video_feat2", "sub_feat1", "sub_feat2"):
+        ctx[k] = torch.randn(n, L, H, generator=gen)
+    return ctx
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the reference's own query path (no kernels, models or engine of this repo)."""
+    """CPU arm: the reference's own query path on the host cores -- the UNMODIFIED reference model + driver from
+    baseline/_ref (kind "reference"), or the oracle port when the vendored copy is absent (kind "port").  None of this
+    repo's kernels, models or engine are on this path.  Each step = 50 queries (reference eval_query_bsz) against a
+    bounded sample of the corpus; queries/s scaled linearly to the full corpus."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import xml_oracle as O
     n_thr = os.cpu_count() or 1
     torch.set_num_threads(n_thr)
     cfg = dict(model_config(args))
-    w = O.init_weights(cfg)
+    from tvretrieval_b200.synthetic import synthetic_queries
     nq = min(50, args.n_queries)
-    gen = torch.Generator().manual_seed(4321)
-    qlen = torch.randint(5, 31, (nq,), generator=gen)
-    qm = (torch.arange(30)[None] < qlen[:, None]).float()
-    qf = torch.nn.functional.normalize(torch.randn(nq, 30, 768, generator=gen), dim=-1) * qm.unsqueeze(2)
+    qf, qm = synthetic_queries(nq, 30, 768)
     L, H = args.max_ctx_l, args.hidden
+    gen = torch.Generator().manual_seed(4321)
+    from tests import reference_loader as RL
+    if RL.available():
+        torch.manual_seed(2018)
+        ref_ns = RL.load()
+        model = ref_ns.XML(ref_ns.EasyDict(cfg)).eval()
+        kind = "reference"
 
-    def make_ctx(n):
-        lens = torch.randint(L // 8, L + 1, (n,), generator=gen)
-        lens[0] = L
-        mask = (torch.arange(L)[None] < lens[:, None]).float()
-        ctx = {"video_mask": mask, "sub_mask": mask}
-        for k in ("video_feat1", "video_feat2", "sub_feat1", "sub_feat2"):
-            ctx[k] = torch.randn(n, L, H, generator=gen)
-        return ctx
+        def one_pass(ctx):
+            return reference_query_path(ref_ns, model, cfg, ctx, qf, qm, nq, torch.device("cpu"))[0]
+    else:
+        from oracle import xml_oracle as O
+        w = O.init_weights(cfg)
+        kind = "port"
 
-    def one_pass(ctx):
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            O.query_batch_tensor_section(cfg, w, ctx, qf, qm, q2c_alpha=20.0, max_n_videos=min(100, len(ctx["video_mask"])),
-                                         max_before_nms=200, min_pred_l=2, max_pred_l=16, canonical_ties=False)
-        return time.perf_counter() - t0
+        def one_pass(ctx):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                O.query_batch_tensor_section(cfg, w, ctx, qf, qm, q2c_alpha=20.0,
+                                             max_n_videos=min(100, len(ctx["video_mask"])), max_before_nms=200,
+                                             min_pred_l=2, max_pred_l=16, canonical_ties=False)
+            return time.perf_counter() - t0
 
     n_cal = min(args.n_videos, 400)
-    cal = make_ctx(n_cal)
+    cal = _synthetic_encoded_corpus(n_cal, L, H, gen)
     one_pass(cal)
     t_cal = one_pass(cal)
     budget = 150.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
     n_sub = int(min(args.n_videos, max(n_cal, n_cal * min(budget, args.cpu_seconds) / 3.0 / max(t_cal, 1e-3))))
-    ctx = make_ctx(n_sub)
+    ctx = _synthetic_encoded_corpus(n_sub, L, H, gen)
     for _ in range(args.warmup):
         one_pass(ctx)
     times = [one_pass(ctx) for _ in range(args.steps)]
     t = sum(times) / len(times)
-    value = nq / t * n_sub / args.n_videos
+    t_full, fit = extrapolate_seconds(n_cal, t_cal, n_sub, t, args.n_videos)
+    value = nq / t_full
+    what = ("the UNMODIFIED reference (baseline/_ref): XML.get_pred_from_raw_query(cross=True) inside "
+            "inference.compute_query2ctx_info incl. full sort and host lists" if kind == "reference" else
+            "oracle port of get_pred_from_raw_query(cross=True) + exp/softmax/topk/gather/einsum/band mask/full sort")
     sample = ("each step = %d queries (reference eval_query_bsz) x %d of %d videos, synthetic encoded corpus, torch CPU "
-              "fp32 oracle port of get_pred_from_raw_query(cross=True) + exp/softmax/topk/gather/einsum/band mask/"
-              "full sort; queries/s scaled by %d/%d to the full corpus" % (nq, n_sub, args.n_videos, n_sub, args.n_videos))
+              "fp32, %s; %s" % (nq, n_sub, args.n_videos, what, fit))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": n_thr, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "queries/s", "cores": n_thr, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_torch_gpu(args):
+    """The "reference single-GPU PyTorch path" of north_star on cuda:0: the UNMODIFIED reference (baseline/_ref) encodes
+    the synthetic corpus with its own XML.encode_context and answers the queries with its own compute_query2ctx_info;
+    no kernel, model or engine of this repo is on this path (tvretrieval_b200.synthetic only generates the inputs)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from tests import reference_loader as RL
+    if not RL.available():
+        print(json.dumps({"impl": "torch_gpu", "unavailable": "baseline/_ref not vendored"}))
+        return
+    from tvretrieval_b200.synthetic import corpus_batch, corpus_lengths, synthetic_queries
+    device = torch.device("cuda", 0)
+    torch.cuda.set_device(device)
+    cfg = dict(model_config(args))
+    torch.manual_seed(2018)
+    ref_ns = RL.load()
+    model = ref_ns.XML(ref_ns.EasyDict(cfg)).to(device).eval()
+    lens = corpus_lengths(args.n_videos, args.max_ctx_l)
+    L, H = args.max_ctx_l, args.hidden
+    ctx = {k: torch.zeros(args.n_videos, L, H, device=device) for k in ("video_feat1", "video_feat2", "sub_feat1",
+                                                                          "sub_feat2")}
+    mask = torch.zeros(args.n_videos, L, device=device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for b in range((args.n_videos + args.ctx_bsz - 1) // args.ctx_bsz):
+            video, sub, m = corpus_batch(lens, b, args.ctx_bsz, args.video_dim, 768, device)
+            outs = model.encode_context(video, m, sub, m)
+            lo, w = b * args.ctx_bsz, m.shape[1]
+            for k, t in zip(("video_feat1", "video_feat2", "sub_feat1", "sub_feat2"), outs):
+                ctx[k][lo:lo + len(m), :w] = t
+            mask[lo:lo + len(m), :w] = m
+    torch.cuda.synchronize()
+    t_enc = time.perf_counter() - t0
+    ctx["video_mask"] = ctx["sub_mask"] = mask
+    qf, qm = synthetic_queries(args.n_queries, 30, 768)
+    weights = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    del model
+    g = gpu_reference(args, cfg, weights, ctx, qf, qm, device)
+    best = g.get("best_queries_per_s", 0.0)
+    line = {"impl": "torch_gpu", "metric": METRIC, "value": best, "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, 1), "gpu_reference": g,
+            "corpus_encode": {"videos_per_s": args.n_videos / t_enc, "seconds": t_enc}}
     print(json.dumps(line))
 
 
@@ -436,5 +654,7 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "torch_gpu":
+        run_torch_gpu(a)
     else:
         run_ours(a)

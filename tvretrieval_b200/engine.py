@@ -391,6 +391,9 @@ class VCMRSearcher:
         self.timer = None  # set to a PhaseTimer to time the phases
         self._external = None  # (video positions, exp-scores) of the current block when external lists are given
         self._prefilter = None  # pass-1 state of the current block when it was filled piece by piece
+        # tests / bench parity leg: set to a dict to receive the two-pass candidate tables of the last block
+        # ("cand": ops.Candidates after exact re-scoring)
+        self.debug = None
 
     def _phase(self, name):
         return self.timer.phase(name) if self.timer is not None else contextlib.nullcontext()
@@ -464,6 +467,8 @@ class VCMRSearcher:
         with self._phase("vr_rescore"):
             ops.vr_rescore_tc(used[0][0], ca, pk, cand, ix.kpad, q_fp32_b=used[1][0] if len(used) == 2 else None,
                               c_b=cb, bf16=bf16, q_split_a=qa, q_split_b=qb)
+        if self.debug is not None:
+            self.debug["cand"] = cand
         with self._phase("topk_videos"):
             idx, val = ops.topk_rows(cand.val, k, alpha=self.q2c_alpha, apply_exp=True, ids=cand.ids)
         with self._phase("vr_fallback"):  # rows whose candidate list overflowed (normally none: both launches idle)

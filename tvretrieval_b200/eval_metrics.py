@@ -48,8 +48,9 @@ def _recall(hit, topks, prefix, select=None):
         if select is None:
             out["{}r{}".format(prefix, k)] = get_rounded_percentage(np.mean(any_k))
         else:
-            out["{}r{}".format(prefix, k)] = get_rounded_percentage(1.0 * np.sum(np.logical_and(any_k, select[0]))
-                                                                    / select[1])
+            with np.errstate(invalid="ignore", divide="ignore"):  # a type without queries gives nan, as the reference
+                out["{}r{}".format(prefix, k)] = get_rounded_percentage(
+                    1.0 * np.sum(np.logical_and(any_k, select[0])) / select[1])
     return out
 
 

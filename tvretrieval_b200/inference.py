@@ -198,10 +198,16 @@ def compute_query2ctx_info(model, eval_dataset, opt, ctx_info, max_before_nms=10
     with torch.no_grad():
         out = searcher.search_host(qfeat, qmask, gt, run_tasks, external_topk=external)
 
-    # ---- host section (reference inference.py:391-445), vectorised ----
-    ctx_len = searcher.index.ctx_len
+    return host_section(out, query_metas, video_metas, video2idx, searcher.index.ctx_len, opt.clip_length, tasks)
+
+
+def host_section(out, query_metas, video_metas, video2idx, ctx_len, clip_length, tasks):
+    """Host section of compute_query2ctx_info (reference inference.py:391-445), vectorised: the numpy result arrays
+    of VCMRSearcher.search_host -> {"SVMR"/"VCMR"/"VR": [{desc_id, desc, predictions}]} in the reference's format
+    (flat index -> (rank, st, ed); rank -> position in video_metas -> dataset video id; clip indices -> seconds)."""
+    is_svmr, is_vr, is_vcmr = "SVMR" in tasks, "VR" in tasks, "VCMR" in tasks
     meta_to_video_idx = np.asarray([video2idx[m["vid_name"]] for m in video_metas], dtype=np.int64)
-    clip = opt.clip_length
+    clip = clip_length
     res = {}
     if is_svmr:
         res["SVMR"] = _svmr_predictions(out["svmr_flat_idx"], out["svmr_score"], query_metas, video2idx, ctx_len, clip)

@@ -10,6 +10,7 @@ differentiates them through tvretrieval_b200/autograd.py.  Only `encoder_type="t
 `span_predictor_type="conv"` (the shipped configuration) is implemented.
 """
 import copy
+import weakref
 
 import torch
 import torch.nn as nn
@@ -141,6 +142,11 @@ class XML(nn.Module):
                 m.bias.data.zero_()
 
         self.apply(init)
+        ops.invalidate_weight_caches()  # .data writes do not bump tensor._version
+
+    def _load_from_state_dict(self, *args, **kw):
+        super()._load_from_state_dict(*args, **kw)
+        ops.invalidate_weight_caches()
 
     def set_hard_negative(self, use_hard_negative, hard_pool_size):
         self.config.use_hard_negative = use_hard_negative
@@ -180,8 +186,10 @@ class XML(nn.Module):
         loss_neg_ctx = cfg.lw_neg_ctx * loss_neg_ctx
         loss_neg_q = cfg.lw_neg_q * loss_neg_q
         loss = loss_st_ed + loss_neg_ctx + loss_neg_q
-        return loss, {"loss_st_ed": float(loss_st_ed), "loss_neg_ctx": float(loss_neg_ctx),
-                      "loss_neg_q": float(loss_neg_q), "loss_overall": float(loss)}
+        def scalar(x):
+            return float(x.detach()) if torch.is_tensor(x) else float(x)
+        return loss, {"loss_st_ed": scalar(loss_st_ed), "loss_neg_ctx": scalar(loss_neg_ctx),
+                      "loss_neg_q": scalar(loss_neg_q), "loss_overall": scalar(loss)}
 
     @torch.no_grad()
     def get_visualization_data(self, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask, tef_feat,
@@ -374,14 +382,18 @@ class XML(nn.Module):
         depends on the tensor, so it is cached per (storage, version)."""
         if autograd.recording(feat1):  # training: differentiable, never cached
             return ops.l2norm_rows(feat1)
+        # Entries are valid only for the very tensor object they were made from: kernel-written tensors all have
+        # _version 0 and the caching allocator re-uses addresses, so (data_ptr, shape, version) alone would serve
+        # the normalisation of a freed corpus to a new one of the same shape.
         key = (feat1.data_ptr(), tuple(feat1.shape), feat1._version)
         hit = self._norm_cache.get(key)
-        if hit is None:
-            if len(self._norm_cache) > 8:
-                self._norm_cache.clear()
-            hit = ops.l2norm_rows(feat1)
-            self._norm_cache[key] = hit
-        return hit
+        if hit is not None and hit[0]() is feat1:
+            return hit[1]
+        if len(self._norm_cache) > 4:
+            self._norm_cache.clear()
+        out = ops.l2norm_rows(feat1)
+        self._norm_cache[key] = (weakref.ref(feat1), out)
+        return out
 
     def get_video_level_scores(self, modularied_query, context_feat1, context_mask):
         """reference model_xml.py:436-453 -> (Nq, Nv)."""
