@@ -167,6 +167,45 @@ int xmlb_linear_tc(const unsigned short* x_hi, const unsigned short* x_lo, const
                    const unsigned short* w_lo, const float* bias, const float* residual, float* out, int* sched_ws,
                    long long rows, int out_dim, int kpad, int relu, int is_bf16, void* stream);
 
+/* xmlb_linear_tc with K-chunked accumulation made explicit and fused output formats (any subset of the three):
+ *   out                   fp32 (rows, out_dim), as xmlb_linear_tc;
+ *   out_hi / out_lo       the 16-bit (hi, lo) split of output columns [0, out16_cols), rows of out16_ld elements
+ *                         (columns beyond out16_cols are not written): the operand of the next xmlb_linear_tc /
+ *                         the Q and K operands of xmlb_attention_tc;
+ *   vt_hi / vt_lo         the split of output columns [vt_col0, out_dim) TRANSPOSED per sequence of vt_seq rows:
+ *                         vt[(b * (out_dim - vt_col0) + c) * vt_ld + l] = out[b * vt_seq + l][vt_col0 + c] -- the V^T
+ *                         operand of xmlb_attention_tc (positions l >= vt_seq are not written: zero them once).
+ * k_chunk (multiple of 32; 0 = 128): elements of K summed by the tensor core between two round-to-nearest fp32
+ * additions in registers -- the TMEM accumulator truncates, so its error grows with the number of updates. */
+int xmlb_linear_tc_ex(const unsigned short* x_hi, const unsigned short* x_lo, const unsigned short* w_hi,
+                      const unsigned short* w_lo, const float* bias, const float* residual, float* out,
+                      unsigned short* out_hi, unsigned short* out_lo, int out16_ld, int out16_cols,
+                      unsigned short* vt_hi, unsigned short* vt_lo, int vt_col0, int vt_seq, int vt_ld, int* sched_ws,
+                      long long rows, int out_dim, int kpad, int relu, int is_bf16, int k_chunk, void* stream);
+
+/* xmlb_add_layernorm (add_index NULL) / xmlb_add_layernorm_indexed that also (or only: out NULL) writes the 16-bit
+ * (hi, lo) split of the normalised rows, kpad >= dim elements per row, zero padded -- the operand format of the
+ * xmlb_linear_tc that follows every LayerNorm of the encoders (model_components.py:158-163, 81-88, 316). */
+int xmlb_add_layernorm_split(const float* x, const float* add, long long add_rows, const int* add_index,
+                             const float* gamma, const float* beta, float* out, unsigned short* out_hi,
+                             unsigned short* out_lo, int kpad, int is_bf16, long long rows, int dim, float eps,
+                             void* stream);
+
+/* Fused multi-head attention core on the tensor cores, same function as xmlb_attention (model_components.py:277-303)
+ * without the (batch, heads, len_q, len_k) workspace: S = Q K^T in TMEM, scale + additive -10000 mask + softmax in
+ * registers, P written back to shared memory as (hi, lo) halves, O = P V in TMEM.  Operands are the split outputs of
+ * xmlb_linear_tc_ex: q_* (batch * len_q, q_ld) with head h at columns q_col0 + h * dh, k_* (batch * len_k, k_ld)
+ * likewise, vt_* (batch * hidden, vt_ld) = V transposed per sequence (row b * hidden + c, column = key position;
+ * vt_ld >= max(len_k, 64), multiple of 8, columns >= len_k zero).  mask as in xmlb_attention.  Outputs: out fp32
+ * (batch * len_q, hidden) and / or its (hi, lo) split with rows of out16_ld elements.  len_k <= 256,
+ * head size in {64, 128, 192, 256}. */
+int xmlb_attention_tc(const unsigned short* q_hi, const unsigned short* q_lo, int q_ld, int q_col0,
+                      const unsigned short* k_hi, const unsigned short* k_lo, int k_ld, int k_col0,
+                      const unsigned short* vt_hi, const unsigned short* vt_lo, int vt_ld, const float* mask,
+                      long long mask_batch_stride, long long mask_q_stride, float* out, unsigned short* out_hi,
+                      unsigned short* out_lo, int out16_ld, int batch, int len_q, int len_k, int hidden, int n_heads,
+                      int is_bf16, void* stream);
+
 /* Similarity curves + ConvSE + mask (+ softmax), replaces XML.get_merged_st_ed_prob (model_xml.py:455-502),
  * XML._get_st_ed_prob (:512-551) and the driver's softmax over clips (inference.py:321-322).
  *   sim_x[q][v][l] = q_x[q] . feat2_x[v][l]                       for stream x in {a, b}
@@ -224,6 +263,32 @@ int xmlb_vr_filter_pair(const unsigned short* q_hi_a, const unsigned short* q_hi
  * row_flags (NULL or n_rows ints): restricted mode, rows whose flag is 0 are skipped (outputs left untouched). */
 int xmlb_topk_rows(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k, float alpha,
                    int apply_exp, int tie_desc, const int* row_flags, int* out_idx, float* out_val, void* stream);
+
+/* ---- peer-memory output of the ranking kernels (video-sharded search over NVLink, no counterpart in the reference) ----
+ * The *_ex variants write their ranked lists through PEER POINTERS into the symmetric workspaces of the other GPUs
+ * (addresses obtained from torch.distributed._symmetric_memory; host arrays of `world` <= 8 entries, 0 = skip):
+ *   peer_mode 0: local out_idx / out_val only (the plain entry points);
+ *   peer_mode 1 "to owner": row r belongs to rank o = r / per and is stored on rank o at row self_rank * per + r % per;
+ *   peer_mode 2 "to all"  : row r (an owned query) is stored on EVERY rank at row self_rank * per + r.
+ * xmlb_topk_rows_ex extras: seg_k > 0 reads the row as per-rank lists laid out [source rank][row][seg_k] with
+ * seg_stride elements between source ranks (what a mode-1 exchange leaves on the owner); missing_neg treats entries
+ * with negative ids as absent (returned as (-1, 0)); only ranks [out_first, out_first + out_count) of each list are
+ * written, followed by (pad_idx, pad_val) up to pad_to entries per row (row pitch = max(out_count, pad_to)).
+ * xmlb_peer_copy: src[0 .. bytes) -> the same bytes at peer_dst[p] for every p (16-byte granularity). */
+int xmlb_topk_rows_ex(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k, float alpha,
+                      int apply_exp, int tie_desc, const int* row_flags, int seg_k, long long seg_stride,
+                      int missing_neg, int out_first, int out_count, int pad_to, int pad_idx, float pad_val,
+                      int* out_idx, float* out_val, const long long* peer_idx, const long long* peer_val, int world,
+                      int peer_mode, int per, int self_rank, void* stream);
+int xmlb_span_topk_ex(const float* st_prob, const float* ed_prob, const float* video_score,
+                      const unsigned char* slot_valid, int n_queries, int n_slots, int ctx_len, int min_l, int max_l,
+                      int k, int tie_desc, int zero_fill_missing, int* out_flat_idx, float* out_score,
+                      const long long* peer_idx, const long long* peer_val, int world, int peer_mode, int per,
+                      int self_rank, void* stream);
+int xmlb_span_zero_fill_ex(int* flat_idx, float* score, int n_queries, int k, long long total_cells, int tie_desc,
+                           const long long* peer_idx, const long long* peer_val, int world, int peer_mode, int per,
+                           int self_rank, void* stream);
+int xmlb_peer_copy(const void* src, long long bytes, const long long* peer_dst, int world, void* stream);
 
 /* Band-limited span scoring + exact top-k, replaces inference.py:370-386 (VCMR) and inference.py:215-224 +
  * utils/tensor_utils.py:133-141 (SVMR, n_slots = 1, video_score = NULL, tie_desc = 1):

@@ -44,11 +44,7 @@ def test_add_layernorm(ops, rows, dim):
 @pytest.mark.parametrize("rows,out_dim,in_dim", [(1, 8, 8), (50, 64, 48), (257, 130, 70), (1000, 768, 3072),
                                                  (129, 768, 768), (64, 500, 500)])
 def test_linear(ops, rows, out_dim, in_dim):
-    ops.set_linear_precision("f32")
-    try:
-        _check_linear(ops, rows, out_dim, in_dim, 1.0)
-    finally:
-        ops.set_linear_precision("f16x3")
+    _check_linear(ops, rows, out_dim, in_dim, 1.0, precision="f32")
 
 
 @pytest.mark.parametrize("rows,out_dim,in_dim", [(256, 64, 48), (257, 130, 70), (1000, 768, 3072), (6000, 768, 768),
@@ -56,14 +52,10 @@ def test_linear(ops, rows, out_dim, in_dim):
 @pytest.mark.parametrize("precision", ["f16x3", "bf16x3"])
 def test_linear_tc(ops, rows, out_dim, in_dim, precision):
     """tcgen05 split-precision Linear vs float64; error budget a few fp32 ulps of the accumulated magnitude."""
-    ops.set_linear_precision(precision)
-    try:
-        _check_linear(ops, rows, out_dim, in_dim, 1.0 if precision == "f16x3" else 4.0, fp64=True)
-    finally:
-        ops.set_linear_precision("f16x3")
+    _check_linear(ops, rows, out_dim, in_dim, 1.0 if precision == "f16x3" else 4.0, fp64=True, precision=precision)
 
 
-def _check_linear(ops, rows, out_dim, in_dim, slack, fp64=False):
+def _check_linear(ops, rows, out_dim, in_dim, slack, fp64=False, precision="f32"):
     g = torch.Generator().manual_seed(rows + out_dim)
     x = torch.randn(rows, in_dim, generator=g)
     w = torch.randn(out_dim, in_dim, generator=g) * 0.05
@@ -72,12 +64,15 @@ def _check_linear(ops, rows, out_dim, in_dim, slack, fp64=False):
     tol = dict(rtol=1e-4, atol=slack * 1e-5 * max(1.0, in_dim / 256))
     lin = torch.nn.functional.linear
     ref = (lambda *a: lin(*[t.double() for t in a])) if fp64 else lin
-    close(ops.linear(x.to(DEV), w.to(DEV), b.to(DEV)), ref(x, w, b), **tol)
-    close(ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), relu=True), torch.relu(ref(x, w, b)), **tol)
-    close(ops.linear(x.to(DEV), w.to(DEV), None, residual=r.to(DEV)), ref(x, w) + r, **tol)
+    close(ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), precision=precision), ref(x, w, b), **tol)
+    close(ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), relu=True, precision=precision), torch.relu(ref(x, w, b)), **tol)
+    close(ops.linear(x.to(DEV), w.to(DEV), None, residual=r.to(DEV), precision=precision), ref(x, w) + r, **tol)
     if fp64:
-        err = (ops.linear(x.to(DEV), w.to(DEV), b.to(DEV)).cpu().double() - ref(x, w, b)).abs().max().item()
-        print("linear_tc %s rows=%d K=%d: max abs err vs fp64 = %.3g" % (ops.get_linear_precision(), rows, in_dim, err))
+        got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), precision=precision).cpu().double()
+        err = (got - ref(x, w, b)).abs().max().item()
+        err32 = (lin(x, w, b).double() - ref(x, w, b)).abs().max().item()
+        print("linear_tc %s rows=%d K=%d: max abs err vs fp64 = %.3g (torch CPU fp32: %.3g)"
+              % (precision, rows, in_dim, err, err32))
 
 
 @pytest.mark.parametrize("n,lq,lk,hid,nh,full_mask", [(3, 12, 12, 64, 4, False), (5, 30, 30, 768, 4, False),

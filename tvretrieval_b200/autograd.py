@@ -78,12 +78,11 @@ def recompute_op(kernel_fn, torch_fn, args, kwargs):
 # ------------------------------------------------------------------------------------------------ linear
 class _Linear(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, kernel_fn, x, weight, bias, residual, relu):
-        from . import ops
+    def forward(ctx, kernel_fn, x, weight, bias, residual, relu, precision):
         with torch.no_grad():
-            out = kernel_fn(x, weight, bias, residual, relu)
+            out = kernel_fn(x, weight, bias, residual, relu, precision)
         ctx.kernel_fn, ctx.relu = kernel_fn, relu
-        ctx.precision = ops.get_linear_precision()  # the backward GEMMs run in the precision of the forward one
+        ctx.precision = precision  # the backward GEMMs run in the precision of the forward one
         ctx.save_for_backward(x, weight, out if relu else None)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         return out
@@ -98,21 +97,21 @@ class _Linear(torch.autograd.Function):
         out_dim, in_dim = weight.shape
         g2, x2 = g.reshape(-1, out_dim), x.reshape(-1, in_dim)
         dx = dw = db = dres = None
-        from . import ops
-        with torch.no_grad(), ops.linear_precision(ctx.precision):
+        prec = ctx.precision
+        with torch.no_grad():
             if ctx.needs_input_grad[1]:
-                dx = lin(g2, weight.t().contiguous(), None, None, False).view(x.shape)      # dY . W
+                dx = lin(g2, weight.t().contiguous(), None, None, False, prec).view(x.shape)      # dY . W
             if ctx.needs_input_grad[2]:
-                dw = lin(g2.t().contiguous(), x2.t().contiguous(), None, None, False)       # dY^T . X
+                dw = lin(g2.t().contiguous(), x2.t().contiguous(), None, None, False, prec)       # dY^T . X
             if ctx.has_bias and ctx.needs_input_grad[3]:
                 db = g2.sum(0)
             if ctx.has_res and ctx.needs_input_grad[4]:
                 dres = g
-        return None, dx, dw, db, dres, None
+        return None, dx, dw, db, dres, None, None
 
 
-def linear(kernel_fn, x, weight, bias, residual, relu):
-    return _Linear.apply(kernel_fn, x, weight, bias, residual, relu)
+def linear(kernel_fn, x, weight, bias, residual, relu, precision):
+    return _Linear.apply(kernel_fn, x, weight, bias, residual, relu, precision)
 
 
 class Dropout(torch.autograd.Function):

@@ -39,7 +39,8 @@ struct UnitDesc {
   const CUtensorMap* b_hi;
   const CUtensorMap* b_lo;
   int a_row, b_row;   // first row of the A / B tile in their tensor maps
-  int k_blocks;       // number of 64-wide k-blocks to accumulate (> 0)
+  int k_blocks;       // number of BLOCK_K-wide k-blocks to accumulate (> 0)
+  int k_block0;       // first k-block (K-chunked accumulation: a unit may cover only a slice of K); 0 by default
   uint32_t idesc;     // instruction descriptor (carries N of this unit)
   int tag0, tag1;     // kernel-specific payload handed to the epilogue (tile index, modality, ...)
 };
@@ -50,6 +51,7 @@ struct Pipe {
   uint32_t bar_base;
   int stages, stage_bytes, b_tile_bytes;
   int probe;  // limiter experiments (XMLB_VR_PROBE): bit 1 = the producer skips the B tiles
+  int epi_warps;  // epilogue warps that consume every unit (4, or 8 when two warps share a TMEM lane quadrant)
   int terms;  // 3: split precision (hi*lo + lo*hi + hi*hi, stage = A_hi|A_lo|B_hi|B_lo); 1: hi*hi only (A_hi|B_hi)
   __device__ uint32_t full_bar(int s) const { return bar_base + 8u * s; }
   __device__ uint32_t empty_bar(int s) const { return bar_base + 8u * (stages + s); }
@@ -74,13 +76,14 @@ inline size_t pipe_smem_bytes(int block_n, int stages, int extra_bytes, int term
   return 1024 + (size_t)stages * pipe_stage_bytes(block_n, terms) + PIPE_FIXED_BYTES + extra_bytes;
 }
 
-// Called by all 192 threads at kernel start.  Returns the TMEM base address.
+// Called by all threads (64 + 32 * epi_warps) at kernel start.  Returns the TMEM base address.
 __device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw, int stages, int block_n,
-                                               int terms = 3) {
+                                               int terms = 3, int epi_warps = 4) {
   p.smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   p.stages = stages;
   p.terms = terms;
   p.probe = 0;
+  p.epi_warps = epi_warps;
   p.b_tile_bytes = block_n * BLOCK_K * 2;
   p.stage_bytes = (terms == 3 ? 2 : 1) * (A_TILE_BYTES + p.b_tile_bytes);
   p.bar_base = p.smem_base + stages * p.stage_bytes;
@@ -92,11 +95,11 @@ __device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(p.tfull_bar(a), 1);
-      mbar_init(p.tempty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(p.tempty_bar(a), epi_warps);  // one arrival per epilogue warp
     }
     for (int i = 0; i < QUEUE_DEPTH; ++i) {
       mbar_init(p.qfull_bar(i), 1);
-      mbar_init(p.qempty_bar(i), 5);  // MMA thread + one arrival per epilogue warp
+      mbar_init(p.qempty_bar(i), 1 + epi_warps);  // MMA thread + one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -145,9 +148,10 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
   int stage = 0;
   uint32_t phase = 0, n = 0;
   UnitDesc u;
+  u.k_block0 = 0;
   while (sched.next(u)) {
     queue_push(p, n++, u.tag0, u.tag1, u.k_blocks, u.idesc);
-    for (int kb = 0; kb < u.k_blocks; ++kb) {
+    for (int kb = u.k_block0; kb < u.k_block0 + u.k_blocks; ++kb) {
       mbar_wait(p.empty_bar(stage), phase ^ 1u);
       const uint32_t sa = p.smem_base + stage * p.stage_bytes;
       mbar_expect_tx(p.full_bar(stage), (p.probe & 2) ? (uint32_t)A_TILE_BYTES : (uint32_t)p.stage_bytes);

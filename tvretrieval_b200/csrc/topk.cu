@@ -170,6 +170,44 @@ __device__ int block_topk(const Gen& gen, SelSmem& sm, int k) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Where a kernel writes its ranked lists.  mode 0: the caller's local buffers.  Modes 1 / 2 write through peer
+// pointers into the symmetric workspaces of the other GPUs of a video-sharded search (NVLink stores issued by the
+// kernel that produced the list -- no collective call, no staging copy; tvretrieval_b200/sharding.py):
+//   mode 1 "to owner": row r (a query of the block) belongs to rank o = r / per; it lands in rank o's buffer at row
+//                      self_rank * per + (r - o * per)  -> each owner ends up with [source rank][owned query] lists
+//   mode 2 "to all"  : row r (an owned query) lands in EVERY rank's buffer at row self_rank * per + r
+struct PeerOut {
+  long long idx_ptr[8];
+  long long val_ptr[8];
+  int world, mode, per, self_rank;
+};
+
+struct OutSpec {
+  int first, count;    // only ranks [first, first + count) of each list are written, at positions 0 .. count - 1
+  int pad_to;          // positions [count, pad_to) are filled with (pad_idx, pad_val); row pitch = max(count, pad_to)
+  int pad_idx;
+  float pad_val;
+};
+
+__device__ __forceinline__ void out_store(const PeerOut& po, int* __restrict__ out_idx, float* __restrict__ out_val,
+                                          long long row, int pitch, int pos, int idx, float val) {
+  if (po.mode == 0) {
+    if (out_idx) out_idx[row * pitch + pos] = idx;
+    if (out_val) out_val[row * pitch + pos] = val;
+  } else if (po.mode == 1) {
+    const int o = (int)(row / po.per);
+    const long long at = ((long long)po.self_rank * po.per + (row - (long long)o * po.per)) * pitch + pos;
+    if (po.idx_ptr[o]) reinterpret_cast<int*>(po.idx_ptr[o])[at] = idx;
+    if (po.val_ptr[o]) reinterpret_cast<float*>(po.val_ptr[o])[at] = val;
+  } else {
+    const long long at = ((long long)po.self_rank * po.per + row) * pitch + pos;
+    for (int p = 0; p < po.world; ++p) {
+      if (po.idx_ptr[p]) reinterpret_cast<int*>(po.idx_ptr[p])[at] = idx;
+      if (po.val_ptr[p]) reinterpret_cast<float*>(po.val_ptr[p])[at] = val;
+    }
+  }
+}
+
 struct RowGen {
   const float* row;
   const int* ids;
@@ -187,10 +225,15 @@ struct RowGen {
   }
 };
 
+// seg_k > 0: the row is the concatenation of per-rank ranked lists stored as [source rank][row][seg_k] (the owner's
+// side of a mode-1 exchange): column c lives at (c / seg_k) * seg_stride + r * seg_k + c % seg_k.  missing_neg: entries
+// with a negative id are absent (they rank below every real entry and come out as (-1, 0)).
 __global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__ values, const int* __restrict__ ids,
                                                        int ids_shared, int n_cols, int k, float alpha, int apply_exp,
-                                                       int tie_desc, const int* __restrict__ row_flags,
-                                                       int* __restrict__ out_idx, float* __restrict__ out_val) {
+                                                       int tie_desc, const int* __restrict__ row_flags, int seg_k,
+                                                       long long seg_stride, int missing_neg, OutSpec os,
+                                                       int* __restrict__ out_idx, float* __restrict__ out_val,
+                                                       const __grid_constant__ PeerOut po) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   const long long r = blockIdx.x;
@@ -201,15 +244,21 @@ __global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__
   // spends most of its time clearing and scanning 4096-bin histograms that such rows barely touch.
   unsigned long long* sorted = sm.buf;
   int n_out;
-  if (n_cols <= SORT_CAP) {
+  if (n_cols <= SORT_CAP || seg_k > 0) {
     sorted = reinterpret_cast<unsigned long long*>(smem_raw);  // SORT_CAP entries over hist[] (same 16 KB)
     int pow2 = 32;
     while (pow2 < n_cols) pow2 <<= 1;
     for (int i = n_cols + threadIdx.x; i < pow2; i += NT) sorted[i] = 0ull;  // below every real (key, id) pair
     for (int c = threadIdx.x; c < n_cols; c += NT) {
-      const float x = __ldg(gen.row + c);
-      const float e = apply_exp ? expf(alpha * x) : x;
-      const unsigned int id = gen.ids ? (unsigned int)__ldg(gen.ids + c) : (unsigned int)c;
+      long long at = c;
+      if (seg_k > 0) {
+        const int sgm = c / seg_k;
+        at = sgm * seg_stride + r * seg_k + (c - sgm * seg_k) - r * n_cols;  // relative to gen.row / gen.ids
+      }
+      const float x = __ldg(gen.row + at);
+      float e = apply_exp ? expf(alpha * x) : x;
+      unsigned int id = gen.ids ? (unsigned int)__ldg(gen.ids + at) : (unsigned int)c;
+      if (missing_neg && (int)id < 0) e = -1.f, id = (unsigned int)(-1 - c);  // absent entry: distinct id, last rank
       sorted[c] = ((unsigned long long)float_key(e) << 32) | (tie_desc ? id : ~id);
     }
     __syncthreads();
@@ -218,16 +267,22 @@ __global__ void __launch_bounds__(NT) topk_rows_kernel(const float* __restrict__
   } else {
     n_out = block_topk(gen, sm, k);
   }
-  for (int i = threadIdx.x; i < k; i += NT) {
-    if (i < n_out) {
-      const unsigned long long e = sorted[i];
-      const unsigned int idk = (unsigned int)(e & 0xffffffffu);
-      out_idx[r * k + i] = (int)(tie_desc ? idk : ~idk);
-      out_val[r * k + i] = key_float((unsigned int)(e >> 32));
-    } else {
-      out_idx[r * k + i] = -1;
-      out_val[r * k + i] = 0.f;
+  const int pitch = max(os.count, os.pad_to);
+  for (int i = threadIdx.x; i < pitch; i += NT) {
+    int idx = os.pad_idx;
+    float val = os.pad_val;
+    if (i < os.count) {
+      const int src = os.first + i;
+      idx = -1, val = 0.f;
+      if (src < n_out) {
+        const unsigned long long e = sorted[src];
+        const unsigned int idk = (unsigned int)(e & 0xffffffffu);
+        idx = (int)(tie_desc ? idk : ~idk);
+        val = key_float((unsigned int)(e >> 32));
+        if (missing_neg && idx < 0) idx = -1, val = 0.f;
+      }
     }
+    out_store(po, out_idx, out_val, r, pitch, i, idx, val);
   }
 }
 
@@ -387,7 +442,8 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
                                                        const unsigned char* __restrict__ slot_valid, int n_slots,
                                                        int L, int min_l, int max_l, int k, int tie_desc,
                                                        int do_zero_fill, int* __restrict__ out_idx,
-                                                       float* __restrict__ out_val) {
+                                                       float* __restrict__ out_val,
+                                                       const __grid_constant__ PeerOut po) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   const long long q = blockIdx.x;
@@ -436,6 +492,19 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
     }
   }
   if (n_out < 0) n_out = block_topk(gen, sm, k);
+  if (po.mode != 0) {  // sharded search: this rank's list goes straight to the rank that owns the query
+    for (int i = threadIdx.x; i < k; i += NT) {
+      int idx = -1;
+      float val = 0.f;
+      if (i < n_out) {
+        const unsigned long long e = sm.buf[i];
+        const unsigned int idk = (unsigned int)(e & 0xffffffffu);
+        idx = (int)(tie_desc ? idk : ~idk), val = key_float((unsigned int)(e >> 32));
+      }
+      out_store(po, nullptr, nullptr, q, k, i, idx, val);
+    }
+    return;
+  }
   int* oi = out_idx + q * k;
   float* ov = out_val + q * k;
   for (int i = threadIdx.x; i < k; i += NT) {
@@ -458,7 +527,8 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
 // Zero fill for an already ranked list (multi-GPU merge): the first n_pos[r] entries of a row are the positive
 // cells, the rest is replaced by the zero-score cells in canonical flat-index order.
 __global__ void __launch_bounds__(NT) span_zero_fill_kernel(int* __restrict__ idx, float* __restrict__ val, int k,
-                                                            long long total_cells, int tie_desc) {
+                                                            long long total_cells, int tie_desc,
+                                                            const __grid_constant__ PeerOut po) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
   __shared__ int n_pos_s;
@@ -475,6 +545,10 @@ __global__ void __launch_bounds__(NT) span_zero_fill_kernel(int* __restrict__ id
   __syncthreads();
   const int n_pos = n_pos_s;
   if (n_pos < k) zero_fill(sm, n_pos, k, total_cells, tie_desc, oi, ov);
+  if (po.mode != 0) {  // publish the completed row to the other ranks (zero_fill's writes are this block's own)
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += NT) out_store(po, nullptr, nullptr, blockIdx.x, k, i, oi[i], ov[i]);
+  }
 }
 
 }  // namespace
@@ -507,17 +581,75 @@ extern "C" int xmlb_select_candidates(const float* approx, const int* ids, int n
   return XMLB_OK;
 }
 
+static int make_peer_out(PeerOut& po, const long long* peer_idx, const long long* peer_val, int world, int peer_mode,
+                         int per, int self_rank, const char* who) {
+  po = PeerOut{};
+  po.mode = peer_mode;
+  if (peer_mode == 0) return XMLB_OK;
+  XMLB_REQUIRE(peer_mode == 1 || peer_mode == 2, "%s: peer_mode must be 0, 1 or 2", who);
+  XMLB_REQUIRE(world >= 1 && world <= 8 && per >= 1 && self_rank >= 0 && self_rank < world && (peer_idx || peer_val),
+               "%s: bad peer arguments (world <= 8)", who);
+  for (int p = 0; p < world; ++p) {
+    po.idx_ptr[p] = peer_idx ? peer_idx[p] : 0;
+    po.val_ptr[p] = peer_val ? peer_val[p] : 0;
+  }
+  po.world = world, po.per = per, po.self_rank = self_rank;
+  return XMLB_OK;
+}
+
+extern "C" int xmlb_topk_rows_ex(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k,
+                                 float alpha, int apply_exp, int tie_desc, const int* row_flags, int seg_k,
+                                 long long seg_stride, int missing_neg, int out_first, int out_count, int pad_to,
+                                 int pad_idx, float pad_val, int* out_idx, float* out_val, const long long* peer_idx,
+                                 const long long* peer_val, int world, int peer_mode, int per, int self_rank,
+                                 void* stream) {
+  XMLB_REQUIRE(values && (peer_mode != 0 || out_idx || out_val), "xmlb_topk_rows: null pointer");
+  if (int rc = check_topk_args("xmlb_topk_rows", k)) return rc;
+  XMLB_REQUIRE(n_cols >= k, "xmlb_topk_rows: selected index k out of range (k=%d > %d columns)", k, n_cols);
+  XMLB_REQUIRE(out_first >= 0 && out_count >= 1 && out_first + out_count <= k && (pad_to == 0 || pad_to >= out_count),
+               "xmlb_topk_rows: bad output slice");
+  XMLB_REQUIRE(seg_k == 0 || (n_cols % seg_k == 0 && n_cols <= SORT_CAP),
+               "xmlb_topk_rows: segmented rows must hold a whole number of segments and at most %d entries", SORT_CAP);
+  PeerOut po;
+  if (int rc = make_peer_out(po, peer_idx, peer_val, world, peer_mode, per, self_rank, "xmlb_topk_rows")) return rc;
+  if (n_rows == 0) return XMLB_OK;
+  OutSpec os{out_first, out_count, pad_to, pad_idx, pad_val};
+  XMLB_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
+  topk_rows_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(
+      values, ids, ids_shared, n_cols, k, alpha, apply_exp, tie_desc, row_flags, seg_k, seg_stride, missing_neg, os,
+      out_idx, out_val, po);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
 extern "C" int xmlb_topk_rows(const float* values, const int* ids, int ids_shared, int n_rows, int n_cols, int k,
                               float alpha, int apply_exp, int tie_desc, const int* row_flags, int* out_idx,
                               float* out_val, void* stream) {
-  XMLB_REQUIRE(values && out_idx && out_val, "xmlb_topk_rows: null pointer");
-  if (int rc = check_topk_args("xmlb_topk_rows", k)) return rc;
-  XMLB_REQUIRE(n_cols >= k, "xmlb_topk_rows: selected index k out of range (k=%d > %d columns)", k, n_cols);
-  if (n_rows == 0) return XMLB_OK;
-  XMLB_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelSmem)));
-  topk_rows_kernel<<<n_rows, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(values, ids, ids_shared, n_cols, k, alpha,
-                                                                        apply_exp, tie_desc, row_flags, out_idx,
-                                                                        out_val);
+  XMLB_REQUIRE(out_idx && out_val, "xmlb_topk_rows: null pointer");
+  return xmlb_topk_rows_ex(values, ids, ids_shared, n_rows, n_cols, k, alpha, apply_exp, tie_desc, row_flags, 0, 0, 0, 0,
+                           k, 0, 0, 0.f, out_idx, out_val, nullptr, nullptr, 0, 0, 0, 0, stream);
+}
+
+extern "C" int xmlb_span_topk_ex(const float* st_prob, const float* ed_prob, const float* video_score,
+                                 const unsigned char* slot_valid, int n_queries, int n_slots, int ctx_len, int min_l,
+                                 int max_l, int k, int tie_desc, int zero_fill_missing, int* out_flat_idx,
+                                 float* out_score, const long long* peer_idx, const long long* peer_val, int world,
+                                 int peer_mode, int per, int self_rank, void* stream) {
+  XMLB_REQUIRE(st_prob && ed_prob && (peer_mode != 0 || (out_flat_idx && out_score)), "xmlb_span_topk: null pointer");
+  if (int rc = check_topk_args("xmlb_span_topk", k)) return rc;
+  XMLB_REQUIRE(n_slots >= 1 && ctx_len >= 1 && (long long)n_slots * ctx_len * ctx_len < (1ll << 31),
+               "xmlb_span_topk: n_slots*L*L must fit in int32");
+  XMLB_REQUIRE(min_l >= 0 && max_l > min_l, "xmlb_span_topk: need 0 <= min_l < max_l");
+  XMLB_REQUIRE(peer_mode == 0 || !zero_fill_missing, "xmlb_span_topk: peer output carries unfilled lists only");
+  PeerOut po;
+  if (int rc = make_peer_out(po, peer_idx, peer_val, world, peer_mode, per, self_rank, "xmlb_span_topk")) return rc;
+  if (n_queries == 0) return XMLB_OK;
+  const size_t smem = sizeof(SelSmem) + (size_t)LIST_CAP * sizeof(unsigned long long);
+  XMLB_CUDA(cudaFuncSetAttribute(span_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  span_topk_kernel<<<n_queries, NT, smem, (cudaStream_t)stream>>>(
+      st_prob, ed_prob, video_score, slot_valid, n_slots, ctx_len, min_l, max_l, k, tie_desc, zero_fill_missing,
+      out_flat_idx, out_score, po);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
@@ -527,17 +659,20 @@ extern "C" int xmlb_span_topk(const float* st_prob, const float* ed_prob, const 
                               const unsigned char* slot_valid, int n_queries, int n_slots, int ctx_len, int min_l,
                               int max_l, int k, int tie_desc, int zero_fill_missing, int* out_flat_idx,
                               float* out_score, void* stream) {
-  XMLB_REQUIRE(st_prob && ed_prob && out_flat_idx && out_score, "xmlb_span_topk: null pointer");
-  if (int rc = check_topk_args("xmlb_span_topk", k)) return rc;
-  XMLB_REQUIRE(n_slots >= 1 && ctx_len >= 1 && (long long)n_slots * ctx_len * ctx_len < (1ll << 31),
-               "xmlb_span_topk: n_slots*L*L must fit in int32");
-  XMLB_REQUIRE(min_l >= 0 && max_l > min_l, "xmlb_span_topk: need 0 <= min_l < max_l");
+  return xmlb_span_topk_ex(st_prob, ed_prob, video_score, slot_valid, n_queries, n_slots, ctx_len, min_l, max_l, k,
+                           tie_desc, zero_fill_missing, out_flat_idx, out_score, nullptr, nullptr, 0, 0, 0, 0, stream);
+}
+
+extern "C" int xmlb_span_zero_fill_ex(int* flat_idx, float* score, int n_queries, int k, long long total_cells,
+                                      int tie_desc, const long long* peer_idx, const long long* peer_val, int world,
+                                      int peer_mode, int per, int self_rank, void* stream) {
+  XMLB_REQUIRE(flat_idx && score, "xmlb_span_zero_fill: null pointer");
+  if (int rc = check_topk_args("xmlb_span_zero_fill", k)) return rc;
+  PeerOut po;
+  if (int rc = make_peer_out(po, peer_idx, peer_val, world, peer_mode, per, self_rank, "xmlb_span_zero_fill")) return rc;
   if (n_queries == 0) return XMLB_OK;
-  const size_t smem = sizeof(SelSmem) + (size_t)LIST_CAP * sizeof(unsigned long long);
-  XMLB_CUDA(cudaFuncSetAttribute(span_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  span_topk_kernel<<<n_queries, NT, smem, (cudaStream_t)stream>>>(
-      st_prob, ed_prob, video_score, slot_valid, n_slots, ctx_len, min_l, max_l, k, tie_desc, zero_fill_missing,
-      out_flat_idx, out_score);
+  span_zero_fill_kernel<<<n_queries, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(flat_idx, score, k, total_cells,
+                                                                                 tie_desc, po);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
@@ -545,11 +680,33 @@ extern "C" int xmlb_span_topk(const float* st_prob, const float* ed_prob, const 
 
 extern "C" int xmlb_span_zero_fill(int* flat_idx, float* score, int n_queries, int k, long long total_cells,
                                    int tie_desc, void* stream) {
-  XMLB_REQUIRE(flat_idx && score, "xmlb_span_zero_fill: null pointer");
-  if (int rc = check_topk_args("xmlb_span_zero_fill", k)) return rc;
-  if (n_queries == 0) return XMLB_OK;
-  span_zero_fill_kernel<<<n_queries, NT, sizeof(SelSmem), (cudaStream_t)stream>>>(flat_idx, score, k, total_cells,
-                                                                                 tie_desc);
+  return xmlb_span_zero_fill_ex(flat_idx, score, n_queries, k, total_cells, tie_desc, nullptr, nullptr, 0, 0, 0, 0,
+                                stream);
+}
+
+// Plain copy of `bytes` bytes (multiple of 16, 16-byte aligned) from a local buffer into the same offset of every
+// peer's symmetric workspace (mode "to all" for payloads no selection kernel produces: the pooled query vectors).
+__global__ void __launch_bounds__(256) peer_copy_kernel(const uint4* __restrict__ src, long long n_vec,
+                                                        const __grid_constant__ PeerOut po) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n_vec; i += (long long)gridDim.x * 256) {
+    const uint4 v = __ldg(src + i);
+    for (int p = 0; p < po.world; ++p) reinterpret_cast<uint4*>(po.val_ptr[p])[i] = v;
+  }
+}
+
+extern "C" int xmlb_peer_copy(const void* src, long long bytes, const long long* peer_dst, int world, void* stream) {
+  XMLB_REQUIRE(src && peer_dst && world >= 1 && world <= 8, "xmlb_peer_copy: bad argument (world <= 8)");
+  XMLB_REQUIRE(bytes >= 0 && bytes % 16 == 0 && ((uintptr_t)src & 15) == 0, "xmlb_peer_copy: 16-byte granularity");
+  if (bytes == 0) return XMLB_OK;
+  PeerOut po = {};
+  po.world = world;
+  for (int p = 0; p < world; ++p) {
+    XMLB_REQUIRE((peer_dst[p] & 15) == 0, "xmlb_peer_copy: destination must be 16-byte aligned");
+    po.val_ptr[p] = peer_dst[p];
+  }
+  const long long n_vec = bytes / 16;
+  const int blocks = (int)((n_vec + 255) / 256 < 1184 ? (n_vec + 255) / 256 : 1184);
+  peer_copy_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(src), n_vec, po);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

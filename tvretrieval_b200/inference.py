@@ -134,9 +134,14 @@ def _searcher(model, opt, ctx_info, max_before_nms, max_n_videos):
 
 
 def _rows_to_predictions(video_idx, st_sec, ed_sec, score):
-    """(K,) arrays -> [[int, float, float, float], ...] like the reference's float() boxing."""
-    return [[int(v), float(s), float(e), float(c)] for v, s, e, c in
-            zip(video_idx.tolist(), st_sec.tolist(), ed_sec.tolist(), score.tolist())]
+    """(..., K) arrays -> nested lists of [int, float, float, float] rows like the reference's float() boxing
+    (inference.py:436-438); the boxing runs in numpy's C loops (object arrays), not in a Python loop per row."""
+    rows = np.empty(np.shape(video_idx) + (4,), dtype=object)
+    rows[..., 0] = np.asarray(video_idx, dtype=np.int64).astype(object)
+    rows[..., 1] = np.asarray(st_sec, dtype=np.float64).astype(object)  # float32 -> double, exactly like float()
+    rows[..., 2] = np.asarray(ed_sec, dtype=np.float64).astype(object)
+    rows[..., 3] = np.asarray(score, dtype=np.float64).astype(object)
+    return rows.tolist()
 
 
 def _svmr_predictions(flat_idx, score, query_metas, video2idx, ctx_len, clip_length):
@@ -213,9 +218,12 @@ def host_section(out, query_metas, video_metas, video2idx, ctx_len, clip_length,
         res["SVMR"] = _svmr_predictions(out["svmr_flat_idx"], out["svmr_score"], query_metas, video2idx, ctx_len, clip)
     if is_vr:
         top_idx, top_sc = out["top_video_idx"][:, :100], out["top_video_score"][:, :100]
-        res["VR"] = [dict(desc_id=m["desc_id"], desc=m["desc"],
-                          predictions=[[int(v), 0, 0, float(s)] for v, s in
-                                       zip(meta_to_video_idx[top_idx[i]].tolist(), top_sc[i].tolist())])
+        vr_rows = np.empty(top_idx.shape + (4,), dtype=object)
+        vr_rows[..., 0] = meta_to_video_idx[top_idx].astype(object)
+        vr_rows[..., 1] = vr_rows[..., 2] = 0
+        vr_rows[..., 3] = top_sc.astype(np.float64).astype(object)
+        vr_rows = vr_rows.tolist()
+        res["VR"] = [dict(desc_id=m["desc_id"], desc=m["desc"], predictions=vr_rows[i])
                      for i, m in enumerate(query_metas)]
     if is_vcmr:
         flat = out["span_flat_idx"].astype(np.int64)
@@ -227,8 +235,8 @@ def host_section(out, query_metas, video_metas, video2idx, ctx_len, clip_length,
         vid = meta_to_video_idx[meta]
         st_sec = st_i.astype(np.float32) * clip
         ed_sec = ed_i.astype(np.float32) * clip + clip
-        res["VCMR"] = [dict(desc_id=m["desc_id"], desc=m["desc"],
-                            predictions=_rows_to_predictions(vid[i], st_sec[i], ed_sec[i], out["span_score"][i]))
+        vcmr_rows = _rows_to_predictions(vid, st_sec, ed_sec, out["span_score"])
+        res["VCMR"] = [dict(desc_id=m["desc_id"], desc=m["desc"], predictions=vcmr_rows[i])
                        for i, m in enumerate(query_metas)]
     return {k: v for k, v in res.items() if len(v) != 0}
 

@@ -50,11 +50,11 @@ class LinearLayer(nn.Module):
             self.LayerNorm = nn.LayerNorm(in_hsz)
         self.net = nn.Sequential(nn.Dropout(dropout), nn.Linear(in_hsz, out_hsz))
 
-    def forward(self, x):
+    def forward(self, x, precision=ops.DEFAULT_PRECISION):
         if self.layer_norm:
             x = ops.add_layernorm(x, self.LayerNorm.weight, self.LayerNorm.bias, eps=self.LayerNorm.eps)
         fc = self.net[1]
-        return ops.linear(_drop(self.net[0], x), fc.weight, fc.bias, relu=self.relu)
+        return ops.linear(_drop(self.net[0], x), fc.weight, fc.bias, relu=self.relu, precision=precision)
 
 
 class BertSelfAttention(nn.Module):
@@ -73,11 +73,11 @@ class BertSelfAttention(nn.Module):
         self.value = nn.Linear(config.hidden_size, self.all_head_size)
         self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
 
-    def forward(self, query_states, key_states, value_states, attention_mask):
+    def forward(self, query_states, key_states, value_states, attention_mask, precision=ops.DEFAULT_PRECISION):
         """attention_mask: (N, Lq or 1, L) float, 1 = attend."""
-        q = ops.linear(query_states, self.query.weight, self.query.bias)
-        k = ops.linear(key_states, self.key.weight, self.key.bias)
-        v = ops.linear(value_states, self.value.weight, self.value.bias)
+        q = ops.linear(query_states, self.query.weight, self.query.bias, precision=precision)
+        k = ops.linear(key_states, self.key.weight, self.key.bias, precision=precision)
+        v = ops.linear(value_states, self.value.weight, self.value.bias, precision=precision)
         p = self.dropout.p if self.training else 0.0
         return ops.attention(q, k, v, attention_mask, self.num_attention_heads, dropout_p=p,
                              seed=ops.new_seed() if p > 0 else 0)
@@ -92,12 +92,13 @@ class BertSelfOutput(nn.Module):
         self.LayerNorm = nn.LayerNorm(config.hidden_size)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
-    def forward(self, hidden_states, input_tensor):
+    def forward(self, hidden_states, input_tensor, precision=ops.DEFAULT_PRECISION):
         if self.training and self.dropout.p > 0:  # dense -> dropout -> + residual -> LN
-            h = _drop(self.dropout, ops.linear(hidden_states, self.dense.weight, self.dense.bias))
+            h = _drop(self.dropout, ops.linear(hidden_states, self.dense.weight, self.dense.bias,
+                                               precision=precision))
             return ops.add_layernorm(h, self.LayerNorm.weight, self.LayerNorm.bias, add=input_tensor,
                                      eps=self.LayerNorm.eps)
-        h = ops.linear(hidden_states, self.dense.weight, self.dense.bias, residual=input_tensor)
+        h = ops.linear(hidden_states, self.dense.weight, self.dense.bias, residual=input_tensor, precision=precision)
         return ops.add_layernorm(h, self.LayerNorm.weight, self.LayerNorm.bias, eps=self.LayerNorm.eps)
 
 
@@ -109,6 +110,6 @@ class BertAttention(nn.Module):
         self.self = BertSelfAttention(config)
         self.output = BertSelfOutput(config)
 
-    def forward(self, input_tensor, attention_mask):
-        att = self.self(input_tensor, input_tensor, input_tensor, attention_mask)
-        return self.output(att, input_tensor)
+    def forward(self, input_tensor, attention_mask, precision=ops.DEFAULT_PRECISION):
+        att = self.self(input_tensor, input_tensor, input_tensor, attention_mask, precision=precision)
+        return self.output(att, input_tensor, precision=precision)

@@ -169,12 +169,12 @@ class XML(nn.Module):
         Forward values come from the CUDA kernels; gradients flow through tvretrieval_b200/autograd.py.
         tef_feat / tef_mask are accepted and ignored like in the reference."""
         cfg = self.config
-        with ops.linear_precision(self.train_precision):
-            video_feat1, video_feat2, sub_feat1, sub_feat2 = self._encode_context(video_feat, video_mask, sub_feat,
-                                                                                  sub_mask)
-            q2c, st_logits, ed_logits = self.get_pred_from_raw_query(
-                query_feat, query_mask, video_feat1, video_feat2, video_mask, sub_feat1, sub_feat2, sub_mask,
-                cross=False)
+        prec = self.train_precision
+        video_feat1, video_feat2, sub_feat1, sub_feat2 = self._encode_context(video_feat, video_mask, sub_feat,
+                                                                              sub_mask, prec)
+        q2c, st_logits, ed_logits = self.get_pred_from_raw_query(
+            query_feat, query_mask, video_feat1, video_feat2, video_mask, sub_feat1, sub_feat2, sub_mask,
+            cross=False, precision=prec)
         loss_st_ed = 0
         if cfg.lw_st_ed != 0:
             loss_st_ed = self.temporal_criterion(st_logits, st_ed_indices[:, 0]) + \
@@ -245,14 +245,15 @@ class XML(nn.Module):
         raise NotImplementedError("Only support 'hinge' and 'lse'")
 
     # ------------------------------------------------------------------ encoders
-    def encode_input(self, feat, mask, input_proj_layer, encoder_layer, pos_embed_layer):
+    def encode_input(self, feat, mask, input_proj_layer, encoder_layer, pos_embed_layer,
+                     precision=ops.DEFAULT_PRECISION):
         """reference model_xml.py:377-392: projection -> position + LN -> self-attention block."""
-        feat = pos_embed_layer(input_proj_layer(feat))
-        return encoder_layer(feat, mask.unsqueeze(1))
+        feat = pos_embed_layer(input_proj_layer(feat, precision=precision))
+        return encoder_layer(feat, mask.unsqueeze(1), precision=precision)
 
-    def encode_query(self, query_feat, query_mask):
+    def encode_query(self, query_feat, query_mask, precision=ops.DEFAULT_PRECISION):
         encoded = self.encode_input(query_feat, query_mask, self.query_input_proj, self.query_encoder,
-                                    self.query_pos_embed)
+                                    self.query_pos_embed, precision=precision)
         return self.get_modularized_queries(encoded, query_mask)
 
     PACKED_MAX_LEN = 32  # longest query the packed encoder handles (xmlb_attention_ragged)
@@ -322,59 +323,152 @@ class XML(nn.Module):
             return pooled
         # visualisation path (reference model_xml.py:410-416): the token attention itself, (N, Lq, 2)
         assert self.modular_vector_mapping.weight.shape[0] == 2
-        with ops.linear_precision("f32"):  # 2 output features: not a tensor-core shape
-            logits = ops.linear(encoded_query, self.modular_vector_mapping.weight)      # (N, Lq, 2)
+        # 2 output features: not a tensor-core shape
+        logits = ops.linear(encoded_query, self.modular_vector_mapping.weight, precision="f32")      # (N, Lq, 2)
         logits = mask_logits(logits, query_mask.unsqueeze(2)).transpose(1, 2).contiguous()  # (N, 2, Lq)
         att = ops.softmax_rows(logits).transpose(1, 2).contiguous()
         return pooled[0], pooled[1], att
 
     def cross_context_encoder(self, main_context_feat, main_context_mask, side_context_feat, side_context_mask,
-                              cross_att_layer, norm_layer, self_att_layer):
+                              cross_att_layer, norm_layer, self_att_layer, precision=ops.DEFAULT_PRECISION):
         """reference model_xml.py:357-373."""
         cross_mask = main_context_mask.unsqueeze(2) * side_context_mask.unsqueeze(1)  # (N, Lq, Lk) {0,1}
-        cross_out = cross_att_layer(main_context_feat, side_context_feat, side_context_feat, cross_mask)
+        cross_out = cross_att_layer(main_context_feat, side_context_feat, side_context_feat, cross_mask,
+                                    precision=precision)
         residual_out = ops.add_layernorm(cross_out, norm_layer.weight, norm_layer.bias, add=main_context_feat,
                                          eps=norm_layer.eps)
-        return self_att_layer(residual_out, main_context_mask.unsqueeze(1))
+        return self_att_layer(residual_out, main_context_mask.unsqueeze(1), precision=precision)
 
-    def cross_encode_context(self, video_feat, video_mask, sub_feat, sub_mask):
+    def cross_encode_context(self, video_feat, video_mask, sub_feat, sub_mask, precision=ops.DEFAULT_PRECISION):
         """reference model_xml.py:344-355."""
-        v1 = self.encode_input(video_feat, video_mask, self.video_input_proj, self.video_encoder1, self.ctx_pos_embed)
-        s1 = self.encode_input(sub_feat, sub_mask, self.sub_input_proj, self.sub_encoder1, self.ctx_pos_embed)
+        v1 = self.encode_input(video_feat, video_mask, self.video_input_proj, self.video_encoder1, self.ctx_pos_embed,
+                               precision=precision)
+        s1 = self.encode_input(sub_feat, sub_mask, self.sub_input_proj, self.sub_encoder1, self.ctx_pos_embed,
+                               precision=precision)
         v2 = self.cross_context_encoder(v1, video_mask, s1, sub_mask, self.video_cross_att,
-                                        self.video_cross_layernorm, self.video_encoder2)
+                                        self.video_cross_layernorm, self.video_encoder2, precision=precision)
         s2 = self.cross_context_encoder(s1, sub_mask, v1, video_mask, self.sub_cross_att,
-                                        self.sub_cross_layernorm, self.sub_encoder2)
+                                        self.sub_cross_layernorm, self.sub_encoder2, precision=precision)
         return v1, v2, s1, s2
 
-    def non_cross_encode_context(self, context_feat, context_mask, module_name="video"):
+    def non_cross_encode_context(self, context_feat, context_mask, module_name="video",
+                                 precision=ops.DEFAULT_PRECISION):
         """reference model_xml.py:297-329: feat1 = enc1(...), feat2 = enc3(enc2(feat1))."""
         feat1 = self.encode_input(context_feat, context_mask, getattr(self, module_name + "_input_proj"),
-                                  getattr(self, module_name + "_encoder1"), self.ctx_pos_embed)
+                                  getattr(self, module_name + "_encoder1"), self.ctx_pos_embed, precision=precision)
         m3 = context_mask.unsqueeze(1)
-        feat2 = getattr(self, module_name + "_encoder2")(feat1, m3)
-        feat2 = getattr(self, module_name + "_encoder3")(feat2, m3)
+        feat2 = getattr(self, module_name + "_encoder2")(feat1, m3, precision=precision)
+        feat2 = getattr(self, module_name + "_encoder3")(feat2, m3, precision=precision)
         return feat1, feat2
 
-    # Linear-layer kernels used by encode_context: "f32" (exact SIMT, default: the corpus is encoded once and its
-    # padded rows feed ConvSE, so accuracy comes first) or "f16x3" / "bf16x3" (tcgen05, ~3x faster).
-    context_precision = "f32"
+    # Kernels used by encode_context: "f16x3" (default) / "bf16x3" = the tensor-core pipeline below (split-precision
+    # tcgen05 GEMMs with K-chunked fp32 accumulation + the fused tcgen05 attention kernel), "f32" = exact-fp32 SIMT
+    # kernels layer by layer.  Both reproduce the reference's fp32 values to ~1e-5.
+    context_precision = "f16x3"
 
     def encode_context(self, video_feat, video_mask, sub_feat, sub_mask):
         """reference model_xml.py:331-342."""
-        with ops.linear_precision(self.context_precision):
-            return self._encode_context(video_feat, video_mask, sub_feat, sub_mask)
+        return self._encode_context(video_feat, video_mask, sub_feat, sub_mask, self.context_precision)
 
-    def _encode_context(self, video_feat, video_mask, sub_feat, sub_mask):
+    def _encode_context(self, video_feat, video_mask, sub_feat, sub_mask, precision):
+        if self._tc_context_ok(video_feat if self.use_video else sub_feat, precision):
+            return self._encode_context_tc(video_feat, video_mask, sub_feat, sub_mask, precision == "bf16x3")
         if self.config.cross_att:
             assert self.use_video and self.use_sub
-            return self.cross_encode_context(video_feat, video_mask, sub_feat, sub_mask)
+            return self.cross_encode_context(video_feat, video_mask, sub_feat, sub_mask, precision=precision)
         v1 = v2 = s1 = s2 = None
         if self.use_video:
-            v1, v2 = self.non_cross_encode_context(video_feat, video_mask, module_name="video")
+            v1, v2 = self.non_cross_encode_context(video_feat, video_mask, module_name="video", precision=precision)
         if self.use_sub:
-            s1, s2 = self.non_cross_encode_context(sub_feat, sub_mask, module_name="sub")
+            s1, s2 = self.non_cross_encode_context(sub_feat, sub_mask, module_name="sub", precision=precision)
         return v1, v2, s1, s2
+
+    # ---- the context encoders on the tensor cores ------------------------------------------------------------
+    def _tc_context_ok(self, feat, precision):
+        """The fused tensor-core pipeline serves eval-mode batches of at least 256 clip rows whose head size the
+        attention kernel supports (64 / 128 / 192 / 256) and whose sequences are at most 256 clips long."""
+        if precision == "f32" or feat is None or not feat.is_cuda or self.training or torch.is_grad_enabled():
+            return False  # (inference only: the fused pipeline records no autograd graph)
+        n, length = feat.shape[:2]
+        return (n * length >= 256 and self.config.hidden_size % 64 == 0
+                and ops.attention_tc_supported(self.config.hidden_size, self.config.n_heads, length))
+
+    def _tc_input(self, feat, proj, bf16):
+        """LinearLayer + TrainablePositionalEncoding (reference model_components.py:156-163, 81-88):
+        LN -> split | GEMM + bias + ReLU | + position, LN -> (fp32 rows, split rows)."""
+        n, length, din = feat.shape
+        _, x16 = ops.add_layernorm_split(feat.reshape(n * length, din), proj.LayerNorm.weight, proj.LayerNorm.bias,
+                                         eps=proj.LayerNorm.eps, bf16=bf16, want_f32=False)
+        fc = proj.net[1]
+        h0, _, _ = ops.linear_tc_ex(x16, ops._weight_split(fc.weight, bf16), fc.bias, relu=True, bf16=bf16)
+        pe = self.ctx_pos_embed
+        if length > pe.position_embeddings.num_embeddings:
+            raise IndexError("sequence length %d exceeds the %d learned positions"
+                             % (length, pe.position_embeddings.num_embeddings))
+        return ops.add_layernorm_split(h0, pe.LayerNorm.weight, pe.LayerNorm.bias, add=pe.position_embeddings.weight,
+                                       add_rows=length, eps=pe.LayerNorm.eps, bf16=bf16)
+
+    def _tc_block(self, x, x16, mask3, enc, n, length, bf16):
+        """BertAttention (reference model_components.py:207-216, 266-317) on rows x (fp32) / x16 (split):
+        fused QKV GEMM (Q, K split row-major; V split transposed per sequence) | fused attention | output GEMM +
+        residual | LN -> (fp32 rows, split rows)."""
+        att, outp = enc.self, enc.output
+        hid, nh = self.config.hidden_size, att.num_attention_heads
+        w = ops._weight_split_cat([att.query.weight, att.key.weight, att.value.weight], bf16)
+        b = ops._bias_cat([att.query.bias, att.key.bias, att.value.bias])
+        _, qk16, vt16 = ops.linear_tc_ex(x16, w, b, bf16=bf16, want_f32=False, out16_cols=2 * hid, vt_col0=2 * hid,
+                                         vt_seq=length)
+        _, c16 = ops.attention_tc(qk16, 0, qk16, hid, vt16, mask3, n, length, length, hid, nh, bf16=bf16,
+                                  want_f32=False, want_split=True)
+        o, _, _ = ops.linear_tc_ex(c16, ops._weight_split(outp.dense.weight, bf16), outp.dense.bias, residual=x,
+                                   bf16=bf16)
+        return ops.add_layernorm_split(o, outp.LayerNorm.weight, outp.LayerNorm.bias, eps=outp.LayerNorm.eps,
+                                       bf16=bf16)
+
+    def _tc_cross(self, main, main16, main_mask, side16, side_mask, att, norm, enc2, n, length, bf16):
+        """cross_context_encoder (reference model_xml.py:357-373) on the tensor cores."""
+        hid, nh = self.config.hidden_size, att.num_attention_heads
+        _, q16, _ = ops.linear_tc_ex(main16, ops._weight_split(att.query.weight, bf16), att.query.bias, bf16=bf16,
+                                     want_f32=False, out16_cols=hid)
+        wkv = ops._weight_split_cat([att.key.weight, att.value.weight], bf16)
+        _, k16, vt16 = ops.linear_tc_ex(side16, wkv, ops._bias_cat([att.key.bias, att.value.bias]), bf16=bf16,
+                                        want_f32=False, out16_cols=hid, vt_col0=hid, vt_seq=length)
+        cross_mask = (main_mask.unsqueeze(2) * side_mask.unsqueeze(1)).contiguous()  # (N, Lq, Lk) {0,1}
+        x, _ = ops.attention_tc(q16, 0, k16, 0, vt16, cross_mask, n, length, length, hid, nh, bf16=bf16)
+        r, r16 = ops.add_layernorm_split(x, norm.weight, norm.bias, add=main, eps=norm.eps, bf16=bf16)
+        return self._tc_block(r, r16, main_mask.unsqueeze(1).contiguous(), enc2, n, length, bf16)[0]
+
+    @torch.no_grad()
+    def _encode_context_tc(self, video_feat, video_mask, sub_feat, sub_mask, bf16):
+        hid = self.config.hidden_size
+        streams = {}
+        for name, used, feat, mask in (("video", self.use_video, video_feat, video_mask),
+                                       ("sub", self.use_sub, sub_feat, sub_mask)):
+            if not used:
+                continue
+            n, length = feat.shape[:2]
+            h1, h16 = self._tc_input(feat.contiguous(), getattr(self, name + "_input_proj"), bf16)
+            m3 = mask.unsqueeze(1).contiguous()
+            f1, f16 = self._tc_block(h1, h16, m3, getattr(self, name + "_encoder1"), n, length, bf16)
+            streams[name] = (f1, f16, mask, m3, n, length)
+        out = {}
+        if self.config.cross_att:
+            assert self.use_video and self.use_sub
+            for main, side in (("video", "sub"), ("sub", "video")):
+                f1, f16, mask, m3, n, length = streams[main]
+                assert streams[side][4:] == (n, length), "video and subtitle batches must have the same shape"
+                f2 = self._tc_cross(f1, f16, mask, streams[side][1], streams[side][2],
+                                    getattr(self, main + "_cross_att"), getattr(self, main + "_cross_layernorm"),
+                                    getattr(self, main + "_encoder2"), n, length, bf16)
+                out[main] = (f1.view(n, length, hid), f2.view(n, length, hid))
+        else:
+            for name, (f1, f16, mask, m3, n, length) in streams.items():
+                f2, f2_16 = self._tc_block(f1, f16, m3, getattr(self, name + "_encoder2"), n, length, bf16)
+                f2, _ = self._tc_block(f2, f2_16, m3, getattr(self, name + "_encoder3"), n, length, bf16)
+                out[name] = (f1.view(n, length, hid), f2.view(n, length, hid))
+        v = out.get("video", (None, None))
+        s_ = out.get("sub", (None, None))
+        return v[0], v[1], s_[0], s_[1]
 
     # ------------------------------------------------------------------ scoring
     def _normalized_corpus(self, feat1):
@@ -431,11 +525,13 @@ class XML(nn.Module):
         return ops.span_logits(q, context_feat2, context_mask, getattr(self, module_name + "_st_predictor").weight,
                                getattr(self, module_name + "_ed_predictor").weight, lists=lists)
 
-    def span_streams(self, video_query, sub_query, video_feat2, sub_feat2, video_mask, sub_mask):
+    def span_streams(self, video_query, sub_query, video_feat2, sub_feat2, video_mask, sub_mask,
+                     precision=ops.DEFAULT_PRECISION):
         """Arguments of ops.span_logits for this model's stream layout (merged / two streams / one stream)."""
         if self.config.merge_two_stream and self.use_video and self.use_sub:
-            qv = ops.linear(video_query, self.video_query_linear.weight, self.video_query_linear.bias)
-            qs = ops.linear(sub_query, self.sub_query_linear.weight, self.sub_query_linear.bias)
+            qv = ops.linear(video_query, self.video_query_linear.weight, self.video_query_linear.bias,
+                            precision=precision)
+            qs = ops.linear(sub_query, self.sub_query_linear.weight, self.sub_query_linear.bias, precision=precision)
             return dict(q_a=qv, feat2_a=video_feat2, mask_a=video_mask, w_st_a=self.merged_st_predictor.weight,
                         w_ed_a=self.merged_ed_predictor.weight, q_b=qs, feat2_b=sub_feat2, mask_b=video_mask,
                         merged=True)
@@ -444,7 +540,7 @@ class XML(nn.Module):
                                      ("sub", self.use_sub, sub_query, sub_feat2, sub_mask)):
             if used:
                 fc = getattr(self, name + "_query_linear")
-                streams.append((ops.linear(q, fc.weight, fc.bias), f2, m,
+                streams.append((ops.linear(q, fc.weight, fc.bias, precision=precision), f2, m,
                                 getattr(self, name + "_st_predictor").weight,
                                 getattr(self, name + "_ed_predictor").weight))
         args = dict(zip(("q_a", "feat2_a", "mask_a", "w_st_a", "w_ed_a"), streams[0]), merged=False)
@@ -462,12 +558,13 @@ class XML(nn.Module):
             video_mask if self.use_video else None, sub_mask if self.use_sub else None)
 
     def get_pred_from_raw_query(self, query_feat, query_mask, video_feat1, video_feat2, video_mask, sub_feat1,
-                                sub_feat2, sub_mask, cross=False):
+                                sub_feat2, sub_mask, cross=False, precision=ops.DEFAULT_PRECISION):
         """reference model_xml.py:553-586 -> (q2ctx_scores, st_logits, ed_logits); st/ed are masked logits
         (-1e10 at padded clips).  cross=False: (N,N),(N,L),(N,L); cross=True: (Nq,Nv),(Nq,Nv,L),(Nq,Nv,L)."""
-        video_query, sub_query = self.encode_query(query_feat, query_mask)
+        video_query, sub_query = self.encode_query(query_feat, query_mask, precision=precision)
         q2c = self.video_scores(video_query, sub_query, video_feat1, sub_feat1, video_mask, sub_mask)
-        args = self.span_streams(video_query, sub_query, video_feat2, sub_feat2, video_mask, sub_mask)
+        args = self.span_streams(video_query, sub_query, video_feat2, sub_feat2, video_mask, sub_mask,
+                                 precision=precision)
         lists = None if cross else ops.diagonal_pair_lists(len(video_query), video_query.device)
         st, ed = ops.span_logits(lists=lists, **args)
         return q2c, st, ed

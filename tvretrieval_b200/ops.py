@@ -70,44 +70,21 @@ def add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
     return out
 
 
-# Precision of the Linear layers: "f16x3" / "bf16x3" = tcgen05 tensor cores with hi/lo-split operands (3 MMAs per
-# product, fp32 accumulate in TMEM), "f32" = exact-fp32 SIMT kernel (FMA, round-to-nearest).  Small problems always
-# use the latter.  Measured on B200: the tensor-core accumulator truncates instead of rounding, so the error grows
-# like (K/16 * 3 updates) * 0.5 ulp -- 2.6e-5 abs at K=768 for O(1) outputs vs 1e-6 for the SIMT kernel.  The corpus
-# (encoded once, off the query path) is therefore encoded with "f32" by default; queries use the tensor cores.
-_LINEAR_PRECISION = "f16x3"
+# Precision of the Linear layers, passed explicitly by every caller (no global state): "f16x3" / "bf16x3" = tcgen05
+# tensor cores with hi/lo-split operands (3 MMAs per product) and K-chunked fp32 accumulation (the TMEM accumulator
+# truncates; chunks of 128 are summed on the tensor core and added round-to-nearest in registers, csrc/linear_tc.cu),
+# "f32" = exact-fp32 SIMT kernel (FMA).  Small problems always use the latter.
+PRECISIONS = ("f16x3", "bf16x3", "f32")
+DEFAULT_PRECISION = "f16x3"
 _TC_MIN_ROWS = 256
 _WEIGHT_SPLITS = {}
-
-
-def set_linear_precision(precision):
-    global _LINEAR_PRECISION
-    assert precision in ("f16x3", "bf16x3", "f32"), precision
-    _LINEAR_PRECISION = precision  # (the weight-split cache is keyed by the 16-bit format: nothing to drop)
-
-
-def get_linear_precision():
-    return _LINEAR_PRECISION
-
-
-class linear_precision:
-    """Context manager: `with ops.linear_precision("f32"): ...`"""
-
-    def __init__(self, precision):
-        self.precision = precision
-
-    def __enter__(self):
-        self.saved = _LINEAR_PRECISION
-        set_linear_precision(self.precision)
-
-    def __exit__(self, *exc):
-        set_linear_precision(self.saved)
 
 
 def invalidate_weight_caches():
     """Drop the cached (hi, lo) weight splits: called after kernels that write parameters in place without going
     through torch (BertAdam.step), which leaves tensor._version unchanged."""
     _WEIGHT_SPLITS.clear()
+    _BIAS_CATS.clear()
 
 
 def _weight_split(weight, bf16):
@@ -126,9 +103,39 @@ def _weight_split(weight, bf16):
     return pair
 
 
-def linear(x, weight, bias=None, residual=None, relu=False):
+def _weight_split_cat(weights, bf16):
+    """(hi, lo) of several weight matrices stacked along the output dimension (the fused QKV / KV projections),
+    cached like _weight_split; -> ((hi, lo), [parameters])."""
+    key = tuple(w.data_ptr() for w in weights) + (bf16,)
+    hit = _WEIGHT_SPLITS.get(key)
+    if hit is not None and all(r() is w for r, w in zip(hit[0], weights)) and hit[1] == [w._version for w in weights]:
+        return hit[2]
+    if len(_WEIGHT_SPLITS) > 256:
+        _WEIGHT_SPLITS.clear()
+    pair = split_rows(torch.cat([w.detach() for w in weights], dim=0), bf16=bf16)
+    _WEIGHT_SPLITS[key] = ([weakref.ref(w) for w in weights], [w._version for w in weights], pair)
+    return pair
+
+
+_BIAS_CATS = {}
+
+
+def _bias_cat(biases):
+    key = tuple(b.data_ptr() for b in biases)
+    hit = _BIAS_CATS.get(key)
+    if hit is not None and all(r() is b for r, b in zip(hit[0], biases)) and hit[1] == [b._version for b in biases]:
+        return hit[2]
+    if len(_BIAS_CATS) > 256:
+        _BIAS_CATS.clear()
+    cat = torch.cat([b.detach() for b in biases]).contiguous()
+    _BIAS_CATS[key] = ([weakref.ref(b) for b in biases], [b._version for b in biases], cat)
+    return cat
+
+
+def linear(x, weight, bias=None, residual=None, relu=False, precision=DEFAULT_PRECISION):
+    assert precision in PRECISIONS, precision
     if autograd.recording(x, weight, bias, residual):
-        return autograd.linear(linear, x, weight, bias, residual, relu)
+        return autograd.linear(linear, x, weight, bias, residual, relu, precision)
     x = _f32(x, "x")
     weight = _f32(weight, "weight")
     out_dim, in_dim = weight.shape
@@ -138,8 +145,8 @@ def linear(x, weight, bias=None, residual=None, relu=False):
     residual = _f32(residual, "residual")
     if residual is not None:
         assert residual.shape == out.shape
-    if _LINEAR_PRECISION != "f32" and rows >= _TC_MIN_ROWS:
-        bf16 = _LINEAR_PRECISION == "bf16x3"
+    if precision != "f32" and rows >= _TC_MIN_ROWS:
+        bf16 = precision == "bf16x3"
         w_hi, w_lo = _weight_split(weight, bf16)
         x_hi, x_lo = split_rows(x, kpad=w_hi.shape[1], bf16=bf16)
         rc = _lib.lib().xmlb_linear_tc(_p(x_hi), _p(x_lo), _p(w_hi), _p(w_lo), _p(_f32(bias, "bias")), _p(residual),
@@ -151,6 +158,90 @@ def linear(x, weight, bias=None, residual=None, relu=False):
                                 in_dim, int(relu), _stream())
     _lib.check(rc, "xmlb_linear")
     return out
+
+
+def pad64(n):
+    return (n + 63) // 64 * 64
+
+
+def add_layernorm_split(x, gamma, beta, add=None, add_rows=None, add_index=None, eps=1e-5, bf16=False, want_f32=True):
+    """LayerNorm(x + add[...]) -> (fp32 rows or None, (hi, lo) int16 (rows, pad64(dim))): the normalised rows and
+    their 16-bit split in one pass (the split is the operand of the tensor-core Linear that follows)."""
+    x = _f32(x, "x")
+    dim = x.shape[-1]
+    rows = x.numel() // dim
+    add = _f32(add, "add")
+    if add is not None and add_rows is None:
+        add_rows = add.numel() // dim
+    kpad = pad64(dim)
+    out = torch.empty_like(x) if want_f32 else None
+    hi = torch.empty(rows, kpad, device=x.device, dtype=torch.int16)
+    lo = torch.empty_like(hi)
+    rc = _lib.lib().xmlb_add_layernorm_split(_p(x), _p(add), add_rows or 0, _p(_i32(add_index, "add_index")),
+                                             _p(_f32(gamma, "gamma")), _p(_f32(beta, "beta")), _p(out), _p(hi), _p(lo),
+                                             kpad, int(bf16), rows, dim, eps, _stream())
+    _lib.check(rc, "xmlb_add_layernorm_split")
+    return out, (hi, lo)
+
+
+def linear_tc_ex(x16, w16, bias=None, residual=None, relu=False, bf16=False, want_f32=True, out16_cols=0, vt_col0=None,
+                 vt_seq=0, k_chunk=0):
+    """Tensor-core Linear on pre-split operands with fused output formats (xmlb_linear_tc_ex).  x16 = (hi, lo) of
+    (rows, kpad); w16 = (hi, lo) of (out_dim, kpad).  -> (out fp32 (rows, out_dim) or None,
+    (hi, lo) (rows, out16_cols) split of the leading output columns or None,
+    (hi, lo) (rows / vt_seq * (out_dim - vt_col0), pad64(vt_seq)) transposed split of the trailing columns or None)."""
+    rows, kpad = x16[0].shape
+    out_dim = w16[0].shape[0]
+    assert w16[0].shape[1] == kpad
+    dev = x16[0].device
+    out = torch.empty(rows, out_dim, device=dev, dtype=torch.float32) if want_f32 else None
+    o16 = (None, None)
+    if out16_cols:
+        o16 = (torch.empty(rows, out16_cols, device=dev, dtype=torch.int16),
+               torch.empty(rows, out16_cols, device=dev, dtype=torch.int16))
+    vt, vt_ld = (None, None), 0
+    if vt_col0 is not None:
+        assert rows % vt_seq == 0
+        vt_ld = pad64(vt_seq)
+        n_rows = rows // vt_seq * (out_dim - vt_col0)
+        # positions beyond the sequence are read as zeros by the attention kernel: they must be finite
+        alloc = torch.empty if vt_ld == vt_seq else torch.zeros
+        vt = (alloc(n_rows, vt_ld, device=dev, dtype=torch.int16), alloc(n_rows, vt_ld, device=dev, dtype=torch.int16))
+    residual = _f32(residual, "residual")
+    rc = _lib.lib().xmlb_linear_tc_ex(_p(x16[0]), _p(x16[1]), _p(w16[0]), _p(w16[1]), _p(_f32(bias, "bias")),
+                                      _p(residual), _p(out), _p(o16[0]), _p(o16[1]), out16_cols, out16_cols, _p(vt[0]),
+                                      _p(vt[1]), vt_col0 or 0, vt_seq, vt_ld, _p(_sched_ws(dev)), rows, out_dim, kpad,
+                                      int(relu), int(bf16), k_chunk, _stream())
+    _lib.check(rc, "xmlb_linear_tc_ex")
+    return out, (o16 if out16_cols else None), (vt if vt_col0 is not None else None)
+
+
+def attention_tc(q16, q_col0, k16, k_col0, vt16, mask3, batch, len_q, len_k, hidden, n_heads, bf16=False,
+                 want_f32=True, want_split=False):
+    """Fused tensor-core attention (xmlb_attention_tc) on the split outputs of linear_tc_ex: q16 / k16 = (hi, lo) of
+    (batch * len, ld) with the heads at columns col0 + h * dh; vt16 = (hi, lo) of (batch * hidden, ld_v);
+    mask3 (batch, 1 or len_q, len_k) float {0,1}.  -> (fp32 (batch * len_q, hidden) or None, (hi, lo) or None)."""
+    mask3 = _f32(mask3, "mask")
+    assert mask3.shape[0] == batch and mask3.shape[2] == len_k and mask3.shape[1] in (1, len_q), mask3.shape
+    dev = q16[0].device
+    out = torch.empty(batch * len_q, hidden, device=dev, dtype=torch.float32) if want_f32 else None
+    o16 = (None, None)
+    if want_split:
+        assert hidden % 64 == 0
+        o16 = (torch.empty(batch * len_q, hidden, device=dev, dtype=torch.int16),
+               torch.empty(batch * len_q, hidden, device=dev, dtype=torch.int16))
+    mq = 0 if mask3.shape[1] == 1 else len_k
+    rc = _lib.lib().xmlb_attention_tc(_p(q16[0]), _p(q16[1]), q16[0].shape[1], q_col0, _p(k16[0]), _p(k16[1]),
+                                      k16[0].shape[1], k_col0, _p(vt16[0]), _p(vt16[1]), vt16[0].shape[1], _p(mask3),
+                                      mask3.shape[1] * len_k, mq, _p(out), _p(o16[0]), _p(o16[1]), hidden, batch, len_q,
+                                      len_k, hidden, n_heads, int(bf16), _stream())
+    _lib.check(rc, "xmlb_attention_tc")
+    return out, (o16 if want_split else None)
+
+
+def attention_tc_supported(hidden, n_heads, len_k):
+    dh = hidden // max(1, n_heads)
+    return hidden % n_heads == 0 and dh % 64 == 0 and dh <= 256 and 1 <= len_k <= 256
 
 
 def attention(q, k, v, mask3, n_heads, max_batch=8192, dropout_p=0.0, seed=0):
@@ -569,47 +660,98 @@ def span_logits(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b=None, feat2_b=None, ma
     return st, ed
 
 
-def topk_rows(values, k, alpha=1.0, apply_exp=False, ids=None, tie_desc=False, row_flags=None, out=None):
+class PeerSpec:
+    """Destination of a ranking kernel's output inside the symmetric workspaces of the ranks of a sharded search
+    (see xmlb_topk_rows_ex): per-rank base addresses of the idx / val regions (None = that half is not written),
+    mode 1 = "to the owner of each row", 2 = "to all ranks"; `per` = rows owned per rank."""
+
+    def __init__(self, idx_ptrs, val_ptrs, mode, per, self_rank):
+        import ctypes
+        ref = idx_ptrs if idx_ptrs is not None else val_ptrs
+        self.world, self.mode, self.per, self.self_rank = len(ref), mode, per, self_rank
+        arr = ctypes.c_longlong * self.world
+        self.idx = arr(*idx_ptrs) if idx_ptrs is not None else None
+        self.val = arr(*val_ptrs) if val_ptrs is not None else None
+
+    def args(self):
+        return (self.idx, self.val, self.world, self.mode, self.per, self.self_rank)
+
+
+_NO_PEER = (None, None, 0, 0, 0, 0)
+
+
+def topk_rows(values, k, alpha=1.0, apply_exp=False, ids=None, tie_desc=False, row_flags=None, out=None, n_rows=None,
+              segments=None, missing_neg=False, out_slice=None, pad=None, peer=None, want_idx=True):
     """-> (idx int32 (R, k), val fp32 (R, k)) ranked by (value desc, id asc).  ids: None (column index), (R, C)
     per-row ids or a 1-D (C,) table shared by all rows.  row_flags (R,) int32 + out=(idx, val): only the flagged
-    rows are recomputed, in place."""
+    rows are recomputed, in place.
+    Sharded-search extras (xmlb_topk_rows_ex): segments=(seg_k, seg_stride) reads each row as per-rank lists laid out
+    [source rank][row][seg_k] (`values` / `ids` are then the flat workspace regions and n_rows is given explicitly);
+    missing_neg: negative ids mark absent entries; out_slice=(first, count): only those ranks of each list are
+    written; pad=(to, idx, val): filler entries up to `to` per row; peer=PeerSpec: the lists are stored on other ranks
+    instead of (mode 1 / 2) the local output, and None is returned."""
     values = _f32(values, "values")
-    n_rows, n_cols = values.shape
-    if out is None:
-        assert row_flags is None
-        out_idx = torch.empty(n_rows, k, device=values.device, dtype=torch.int32)
-        out_val = torch.empty(n_rows, k, device=values.device, dtype=torch.float32)
+    if segments is None:
+        n_rows, n_cols = values.shape
+        seg_k, seg_stride = 0, 0
     else:
-        out_idx, out_val = out
-        assert out_idx.shape == (n_rows, k) and out_idx.is_contiguous() and out_val.is_contiguous()
+        seg_k, seg_stride, n_cols = segments
+    first, count = out_slice if out_slice is not None else (0, k)
+    pad_to, pad_idx, pad_val = pad if pad is not None else (0, 0, 0.0)
+    pitch = max(count, pad_to)
+    out_idx = out_val = None
+    if peer is None:
+        if out is None:
+            assert row_flags is None
+            out_idx = torch.empty(n_rows, pitch, device=values.device, dtype=torch.int32) if want_idx else None
+            out_val = torch.empty(n_rows, pitch, device=values.device, dtype=torch.float32)
+        else:
+            out_idx, out_val = out
+            assert out_idx.shape == (n_rows, pitch) and out_idx.is_contiguous() and out_val.is_contiguous()
     ids = _i32(ids, "ids")
-    shared = ids is not None and ids.dim() == 1
-    assert ids is None or ids.numel() == (n_cols if shared else n_rows * n_cols)
-    rc = _lib.lib().xmlb_topk_rows(_p(values), _p(ids), int(shared), n_rows, n_cols, k, alpha, int(apply_exp),
-                                   int(tie_desc), _p(row_flags), _p(out_idx), _p(out_val), _stream())
+    shared = ids is not None and ids.dim() == 1 and segments is None
+    assert ids is None or segments is not None or ids.numel() == (n_cols if shared else n_rows * n_cols)
+    rc = _lib.lib().xmlb_topk_rows_ex(_p(values), _p(ids), int(shared), n_rows, n_cols, k, alpha, int(apply_exp),
+                                      int(tie_desc), _p(row_flags), seg_k, seg_stride, int(missing_neg), first, count,
+                                      pad_to, pad_idx, pad_val, _p(out_idx), _p(out_val),
+                                      *(peer.args() if peer is not None else _NO_PEER), _stream())
     _lib.check(rc, "xmlb_topk_rows")
-    return out_idx, out_val
+    return None if peer is not None else (out_idx, out_val)
 
 
-def span_topk(st_prob, ed_prob, video_score, min_l, max_l, k, slot_valid=None, tie_desc=False, zero_fill=True):
-    """st/ed (Nq, n_slots, L) probabilities, video_score (Nq, n_slots) or None -> flat idx int32, score (Nq, k)."""
+def span_topk(st_prob, ed_prob, video_score, min_l, max_l, k, slot_valid=None, tie_desc=False, zero_fill=True,
+              peer=None):
+    """st/ed (Nq, n_slots, L) probabilities, video_score (Nq, n_slots) or None -> flat idx int32, score (Nq, k)
+    (peer=PeerSpec: stored on the owner ranks instead; returns None)."""
     st_prob, ed_prob = _f32(st_prob, "st_prob"), _f32(ed_prob, "ed_prob")
     nq, n_slots, length = st_prob.shape
-    out_idx = torch.empty(nq, k, device=st_prob.device, dtype=torch.int32)
-    out_val = torch.empty(nq, k, device=st_prob.device, dtype=torch.float32)
-    rc = _lib.lib().xmlb_span_topk(_p(st_prob), _p(ed_prob), _p(_f32(video_score, "video_score")),
-                                   _p(_u8(slot_valid, "slot_valid")), nq, n_slots, length, min_l, max_l, k,
-                                   int(tie_desc), int(zero_fill), _p(out_idx), _p(out_val), _stream())
+    out_idx = out_val = None
+    if peer is None:
+        out_idx = torch.empty(nq, k, device=st_prob.device, dtype=torch.int32)
+        out_val = torch.empty(nq, k, device=st_prob.device, dtype=torch.float32)
+    rc = _lib.lib().xmlb_span_topk_ex(_p(st_prob), _p(ed_prob), _p(_f32(video_score, "video_score")),
+                                      _p(_u8(slot_valid, "slot_valid")), nq, n_slots, length, min_l, max_l, k,
+                                      int(tie_desc), int(zero_fill), _p(out_idx), _p(out_val),
+                                      *(peer.args() if peer is not None else _NO_PEER), _stream())
     _lib.check(rc, "xmlb_span_topk")
-    return out_idx, out_val
+    return None if peer is not None else (out_idx, out_val)
 
 
-def span_zero_fill(flat_idx, score, total_cells, tie_desc=False):
+def span_zero_fill(flat_idx, score, total_cells, tie_desc=False, peer=None):
     assert flat_idx.dtype == torch.int32 and flat_idx.is_contiguous() and score.is_contiguous()
-    rc = _lib.lib().xmlb_span_zero_fill(_p(flat_idx), _p(score), flat_idx.shape[0], flat_idx.shape[1], total_cells,
-                                        int(tie_desc), _stream())
+    rc = _lib.lib().xmlb_span_zero_fill_ex(_p(flat_idx), _p(score), flat_idx.shape[0], flat_idx.shape[1], total_cells,
+                                           int(tie_desc), *(peer.args() if peer is not None else _NO_PEER), _stream())
     _lib.check(rc, "xmlb_span_zero_fill")
     return flat_idx, score
+
+
+def peer_copy(src, peer_ptrs):
+    """Copies the bytes of a contiguous local tensor to the given address on every rank (xmlb_peer_copy)."""
+    import ctypes
+    assert src.is_contiguous()
+    arr = (ctypes.c_longlong * len(peer_ptrs))(*peer_ptrs)
+    rc = _lib.lib().xmlb_peer_copy(_p(src), src.numel() * src.element_size(), arr, len(peer_ptrs), _stream())
+    _lib.check(rc, "xmlb_peer_copy")
 
 
 def temporal_nms(st, ed, score, iou_thd, max_out, video_idx=None, n_valid=None, max_per_group=100):

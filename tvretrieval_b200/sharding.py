@@ -133,6 +133,143 @@ def merge_ranked_lists(val, idx, k, group=None, tie_desc=False, finish=None):
     return both[..., 1].contiguous(), both[..., 0].contiguous().view(torch.float32)
 
 
+class SymmWorkspace:
+    """Peer-mapped ("symmetric") workspace of the sharded search: the same allocation on every GPU of the node,
+    each rank holding the addresses of all of them (torch.distributed._symmetric_memory: CUDA VMM + NVLink / NVSwitch
+    mappings).  The ranking kernels store their lists directly into the other ranks' workspaces (ops.PeerSpec) and a
+    device-side barrier on the signal pads separates producers from consumers -- the query path then contains no
+    NCCL collective, no pack / unpack pass and no host synchronisation."""
+
+    def __init__(self, group, device, nbytes):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.world, self.rank = self.hdl.world_size, self.hdl.rank
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        assert self.base[self.rank] == self.buf.data_ptr()
+        self.nbytes, self.cursor = int(nbytes), 0
+
+    def alloc(self, nbytes):
+        off = self.cursor
+        self.cursor = (off + int(nbytes) + 255) // 256 * 256
+        assert self.cursor <= self.nbytes, "symmetric workspace too small"
+        return off
+
+    def ptrs(self, off):
+        return [b + off for b in self.base]
+
+    def view(self, off, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= d
+        return self.buf[off:off + n * torch.empty(0, dtype=dtype).element_size()].view(dtype).view(shape)
+
+    def barrier(self):
+        """All ranks' earlier stores (to any rank) are visible to all ranks' later kernels; stream-ordered."""
+        self.hdl.barrier(channel=0)
+
+
+class PeerExchange:
+    """The four coupling points of the sharded search over a SymmWorkspace (see ShardedSearcher)."""
+
+    def __init__(self, group, device, plan, max_queries, hidden, k_videos, k_spans):
+        self.world, self.rank = plan.world_size, plan.rank
+        per = (max_queries + self.world - 1) // self.world
+        g, f = self.world, 4
+        sizes = dict(q_all=g * per * 2 * hidden * f, kth_own=g * per * k_videos * f, kth_all=g * per * f,
+                     vid_own_i=g * per * k_videos * f, vid_own_v=g * per * k_videos * f,
+                     vid_all_i=g * per * k_videos * f, vid_all_v=g * per * k_videos * f,
+                     span_own_i=g * per * k_spans * f, span_own_v=g * per * k_spans * f,
+                     span_all_i=g * per * k_spans * f, span_all_v=g * per * k_spans * f)
+        self.ws = SymmWorkspace(group, device, sum((v + 255) // 256 * 256 for v in sizes.values()) + 4096)
+        self.off = {k: self.ws.alloc(v) for k, v in sizes.items()}
+        self.max_per, self.hidden, self.k_videos, self.k_spans = per, hidden, k_videos, k_spans
+
+    def per(self, n):
+        per = (n + self.world - 1) // self.world
+        assert per <= self.max_per, "query block larger than the symmetric workspace was sized for"
+        return per
+
+    def owned(self, n):
+        per = self.per(n)
+        return max(0, min(per, n - self.rank * per))
+
+    def to_owner(self, name_i, name_v, per):
+        return ops.PeerSpec(self.ws.ptrs(self.off[name_i]) if name_i else None,
+                            self.ws.ptrs(self.off[name_v]) if name_v else None, 1, per, self.rank)
+
+    def to_all(self, name_i, name_v, per):
+        return ops.PeerSpec(self.ws.ptrs(self.off[name_i]) if name_i else None,
+                            self.ws.ptrs(self.off[name_v]) if name_v else None, 2, per, self.rank)
+
+    def region(self, name, shape, dtype):
+        return self.ws.view(self.off[name], shape, dtype)
+
+    # ---- coupling point 0: the pooled query vectors of every rank's slice -> all ranks
+    def gather_queries(self, packed, n):
+        """packed (per, 2, H) fp32: this rank's slice (zero rows beyond it) -> (n, 2, H) of all ranks."""
+        per = self.per(n)
+        assert packed.shape == (per, 2, self.hidden)
+        off = self.off["q_all"] + self.rank * per * 2 * self.hidden * 4
+        ops.peer_copy(packed.contiguous(), self.ws.ptrs(off))
+        self.ws.barrier()
+        return self.region("q_all", (self.world * per, 2, self.hidden), torch.float32)[:n]
+
+    # ---- coupling point 1: corpus-wide k-th largest approximate score
+    def global_kth(self, approx, k):
+        n, per, kv = len(approx), self.per(len(approx)), self.k_videos
+        assert k == kv
+        k_loc = min(k, approx.shape[1])
+        ops.topk_rows(approx, k_loc, pad=(k, 0, NEG) if k_loc < k else None, want_idx=False,
+                      peer=self.to_owner(None, "kth_own", per))
+        self.ws.barrier()
+        own = self.region("kth_own", (self.world * per * k,), torch.float32)
+        ops.topk_rows(own, k, n_rows=self.owned(n), segments=(k, per * k, self.world * k), out_slice=(k - 1, 1),
+                      peer=self.to_all(None, "kth_all", per))
+        self.ws.barrier()
+        return self.region("kth_all", (self.world * per,), torch.float32)[:n]
+
+    # ---- coupling point 2: exact per-rank video lists -> global top-k on every rank
+    def merge_videos(self, idx, val, k):
+        n, per = len(idx), self.per(len(idx))
+        k_loc = idx.shape[1]
+        # (already ranked lists: the k_loc-entry "selection" is the identity; it is the kernel that stores to peers)
+        ops.topk_rows(val, k_loc, ids=idx, pad=(k, 2 ** 31 - 1, NEG) if k_loc < k else None,
+                      peer=self.to_owner("vid_own_i", "vid_own_v", per))
+        self.ws.barrier()
+        ops.topk_rows(self.region("vid_own_v", (self.world * per * k,), torch.float32), k,
+                      ids=self.region("vid_own_i", (self.world * per * k,), torch.int32), n_rows=self.owned(n),
+                      segments=(k, per * k, self.world * k), peer=self.to_all("vid_all_i", "vid_all_v", per))
+        self.ws.barrier()
+        return (self.region("vid_all_i", (self.world * per, k), torch.int32)[:n].clone(),
+                self.region("vid_all_v", (self.world * per, k), torch.float32)[:n].clone())
+
+    # ---- coupling point 3: per-rank moment lists -> global top-m on every rank
+    def span_peer(self, n):
+        return self.to_owner("span_own_i", "span_own_v", self.per(n))
+
+    def merge_spans(self, n, m, total_cells, tie_desc=False):
+        """The per-rank lists were stored by span_topk(peer=span_peer(n)); -> (flat idx, score) (n, m) on all ranks."""
+        per = self.per(n)
+        assert m == self.k_spans
+        self.ws.barrier()
+        owned = self.owned(n)
+        dev = self.ws.buf.device
+        m_idx = torch.empty(max(owned, 1), m, device=dev, dtype=torch.int32)
+        m_val = torch.empty(max(owned, 1), m, device=dev, dtype=torch.float32)
+        if owned:
+            ops.topk_rows(self.region("span_own_v", (self.world * per * m,), torch.float32), m,
+                          ids=self.region("span_own_i", (self.world * per * m,), torch.int32), n_rows=owned,
+                          segments=(m, per * m, self.world * m), missing_neg=True, tie_desc=tie_desc,
+                          out=(m_idx[:owned], m_val[:owned]))
+            ops.span_zero_fill(m_idx[:owned], m_val[:owned], total_cells, tie_desc=tie_desc,
+                               peer=self.to_all("span_all_i", "span_all_v", per))
+        self.ws.barrier()
+        return (self.region("span_all_i", (self.world * per, m), torch.int32)[:n].clone(),
+                self.region("span_all_v", (self.world * per, m), torch.float32)[:n].clone())
+
+
 def local_slot_mask(top_ids, vid_lo, vid_hi):
     """1 where a selected (global) video id belongs to this rank's shard."""
     return ((top_ids >= vid_lo) & (top_ids < vid_hi)).to(torch.uint8)
@@ -141,10 +278,21 @@ def local_slot_mask(top_ids, vid_lo, vid_hi):
 class ShardedSearcher(VCMRSearcher):
     """Same `search()` contract as VCMRSearcher; `index` holds only this rank's videos (index.vid_lo set)."""
 
-    def __init__(self, model, index, n_videos_total, group=None, **kw):
+    def __init__(self, model, index, n_videos_total, group=None, transport=None, **kw):
+        """transport: "peer" = the ranking kernels store their lists straight into the other GPUs' symmetric
+        workspaces over NVLink (PeerExchange; needs NCCL + torch symmetric memory, one GPU per rank), "collective" =
+        all_to_all / all_gather through torch.distributed (any backend; used by the single-GPU gloo tests).
+        None = "peer" when available."""
         super().__init__(model, index, **kw)
         self.group = group
         self.plan = ShardPlan(n_videos_total, dist.get_world_size(group), dist.get_rank(group))
+        self.peer = None
+        if transport is None:
+            transport = "peer" if (dist.get_backend(group) == "nccl" and self.plan.world_size <= 8) else "collective"
+        if transport == "peer":
+            self.peer = PeerExchange(group, index.device, self.plan, self.query_chunk, model.config.hidden_size,
+                                     self.max_n_videos, self.max_before_nms)
+        self.transport = transport
         lo, hi = self.plan.video_range()
         assert index.vid_lo == lo and index.n_videos == hi - lo, "index does not hold this rank's shard"
         # The candidate filter compares scores of different shards against one corpus-wide threshold, so its error
@@ -167,6 +315,9 @@ class ShardedSearcher(VCMRSearcher):
         per rank, k-th largest of the union.  With it every rank keeps only the candidates that can reach the
         corpus-wide top-k (~(k + margin) / G per rank) instead of the candidates of its own local top-k (~k per
         rank), so the exact re-scoring work scales with 1 / G."""
+        if self.peer is not None:
+            with self._phase("gather_kth"):
+                return self.peer.global_kth(approx, k)
         with self._phase("gather_kth"):
             k_loc = min(k, approx.shape[1])
             idx, val = ops.topk_rows(approx, k_loc)
@@ -185,8 +336,27 @@ class ShardedSearcher(VCMRSearcher):
         if hi > lo:
             packed[:hi - lo, 0], packed[:hi - lo, 1] = video_query, sub_query
         with self._phase("gather_queries"):
-            allq = all_gather_rows(packed, self.group)[:n]
+            allq = self.peer.gather_queries(packed, n) if self.peer is not None else \
+                all_gather_rows(packed, self.group)[:n]
         return allq[:, 0].contiguous(), allq[:, 1].contiguous()
+
+    def _merge_spans(self, st, ed, video_score, valid, nq, n_slots, m, tie_desc=False):
+        """Local top-m moments of this rank's selected videos -> global top-m on every rank (+ zero fill)."""
+        ix = self.index
+        total = n_slots * ix.ctx_len * ix.ctx_len
+        st, ed = st.view(nq, n_slots, ix.ctx_len), ed.view(nq, n_slots, ix.ctx_len)
+        if self.peer is not None:
+            with self._phase("span_topk"):  # the lists go straight to the ranks that own the queries
+                ops.span_topk(st, ed, video_score, self.min_pred_l, self.max_pred_l, m, slot_valid=valid,
+                              tie_desc=tie_desc, zero_fill=False, peer=self.peer.span_peer(nq))
+            with self._phase("merge_spans"):
+                return self.peer.merge_spans(nq, m, total, tie_desc=tie_desc)
+        with self._phase("span_topk"):
+            idx, val = ops.span_topk(st, ed, video_score, self.min_pred_l, self.max_pred_l, m, slot_valid=valid,
+                                     tie_desc=tie_desc, zero_fill=False)
+        with self._phase("merge_spans"):
+            return merge_ranked_lists(val, idx, m, self.group, tie_desc=tie_desc,
+                                      finish=lambda i, v: ops.span_zero_fill(i, v, total, tie_desc=tie_desc))
 
     def _search_encoded(self, video_query, sub_query, gt_video_idx, tasks):
         ix = self.index
@@ -199,44 +369,35 @@ class ShardedSearcher(VCMRSearcher):
         elif "VR" in tasks or "VCMR" in tasks:
             k_loc = min(k, ix.n_videos)
             idx, val = self.top_videos(video_query, sub_query, k_loc, k_global=k)  # global ids, exp(alpha * score)
-            if k_loc < k:  # shard smaller than k: pad so every rank contributes k columns
-                idx = torch.cat([idx, idx.new_full((nq, k - k_loc), 2 ** 31 - 1)], 1)
-                val = torch.cat([val, val.new_full((nq, k - k_loc), NEG)], 1)
             with self._phase("merge_videos"):
-                o_val, o_idx = exchange_to_owners(val, idx, self.group)
-                m_idx, m_val = ops.topk_rows(o_val, k, ids=o_idx)
-                both = gather_from_owners(torch.stack([m_val.view(torch.int32), m_idx], dim=2), nq, self.group)
-                res.top_video_idx = both[..., 1].contiguous()
-                res.top_video_score = both[..., 0].contiguous().view(torch.float32)
+                if self.peer is not None:
+                    res.top_video_idx, res.top_video_score = self.peer.merge_videos(idx, val, k)
+                else:
+                    if k_loc < k:  # shard smaller than k: pad so every rank contributes k columns
+                        idx = torch.cat([idx, idx.new_full((nq, k - k_loc), 2 ** 31 - 1)], 1)
+                        val = torch.cat([val, val.new_full((nq, k - k_loc), NEG)], 1)
+                    o_val, o_idx = exchange_to_owners(val, idx, self.group)
+                    m_idx, m_val = ops.topk_rows(o_val, k, ids=o_idx)
+                    both = gather_from_owners(torch.stack([m_val.view(torch.int32), m_idx], dim=2), nq, self.group)
+                    res.top_video_idx = both[..., 1].contiguous()
+                    res.top_video_score = both[..., 0].contiguous().view(torch.float32)
         if "VCMR" in tasks:
-            m = self.max_before_nms
             with self._phase("pair_lists"):
                 valid = local_slot_mask(res.top_video_idx, vid_lo, vid_hi)
                 lists = self.span_lists(res.top_video_idx, slot_valid=valid)
             with self._phase("span_probs"):
                 st, ed = self.span_probs(video_query, sub_query, lists)
-            st, ed = st.view(nq, k, ix.ctx_len), ed.view(nq, k, ix.ctx_len)
-            with self._phase("span_topk"):
-                idx, val = ops.span_topk(st, ed, res.top_video_score, self.min_pred_l, self.max_pred_l, m,
-                                         slot_valid=valid, zero_fill=False)
-            with self._phase("merge_spans"):
-                total = k * ix.ctx_len * ix.ctx_len
-                res.span_flat_idx, res.span_score = merge_ranked_lists(
-                    val, idx, m, self.group, finish=lambda i, v: ops.span_zero_fill(i, v, total))
+            res.span_flat_idx, res.span_score = self._merge_spans(st, ed, res.top_video_score, valid, nq, k,
+                                                                  self.max_before_nms)
         if "SVMR" in tasks:
             assert gt_video_idx is not None, "SVMR needs the ground-truth video of every query"
-            m = self.max_before_nms
             gt = gt_video_idx.view(nq, 1).to(torch.int32)
             valid = local_slot_mask(gt, vid_lo, vid_hi)
             lists = self.span_lists(gt, slot_valid=valid)
             st, ed = self.span_probs(video_query, sub_query, lists)
-            idx, val = ops.span_topk(st.view(nq, 1, ix.ctx_len), ed.view(nq, 1, ix.ctx_len), None, self.min_pred_l,
-                                     self.max_pred_l, m, slot_valid=valid, tie_desc=True, zero_fill=False)
             # exactly one rank owns each query's ground-truth video: the others contribute only (-1, 0) rows
-            cells = ix.ctx_len * ix.ctx_len
-            res.svmr_flat_idx, res.svmr_score = merge_ranked_lists(
-                val, idx, m, self.group, tie_desc=True,
-                finish=lambda i, v: ops.span_zero_fill(i, v, cells, tie_desc=True))
+            res.svmr_flat_idx, res.svmr_score = self._merge_spans(st, ed, None, valid, nq, 1, self.max_before_nms,
+                                                                  tie_desc=True)
         return res
 
 
