@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, use_nccl, precision):
+def _worker(rank, world, port, use_nccl, precision, transport):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dev = torch.device("cuda", rank if use_nccl else 0)
     torch.cuda.set_device(dev)
@@ -46,23 +46,31 @@ def _worker(rank, world, port, use_nccl, precision):
             want = VCMRSearcher(model, full, two_pass=False, **kw).search(qf, qm, gt, tasks)
             # the shards additionally use the two-pass (filter + exact re-score) video retrieval
             kw["two_pass"] = precision != "f32"
-            got = ShardedSearcher(model, shard, n_videos_total=n_videos, **kw).search(qf, qm, gt, tasks)
+            sharded = ShardedSearcher(model, shard, n_videos_total=n_videos, transport=transport, **kw)
+            assert sharded.transport == (transport or ("peer" if use_nccl else "collective"))
+            got = sharded.search(qf, qm, gt, tasks)
+            again = sharded.search(qf, qm, gt, tasks)  # workspace re-use across calls
+            for name in ("top_video_idx", "span_flat_idx", "span_score", "svmr_flat_idx"):
+                assert torch.equal(getattr(got, name), getattr(again, name)), name
         for name in ("top_video_idx", "top_video_score", "span_flat_idx", "span_score", "svmr_flat_idx", "svmr_score"):
             a, b = getattr(got, name), getattr(want, name)
             assert torch.equal(a, b), "rank %d: %s differs from the single-GPU result" % (rank, name)
         assert (want.span_score[:, 0] > 0).all()
         # host-buffer entry point: every rank uploads only its query slice
-        host = ShardedSearcher(model, shard, n_videos_total=n_videos, **kw).search_host(qf.cpu(), qm.cpu(), gt.cpu(),
-                                                                                        tasks)
+        host = sharded.search_host(qf.cpu(), qm.cpu(), gt.cpu(), tasks)
         for name in ("top_video_idx", "span_flat_idx", "span_score", "svmr_flat_idx"):
             assert (torch.from_numpy(host[name]) == getattr(want, name).cpu()).all(), name
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", [None, "collective"])
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("precision", ["f32", "f16x3"])
-def test_sharded_search_equals_single_gpu(precision, world):
+def test_sharded_search_equals_single_gpu(precision, world, transport):
+    """transport None = peer-memory exchange when the ranks have a GPU each (NCCL), else the collective path."""
     use_nccl = torch.cuda.device_count() >= world
-    port = 29500 + (os.getpid() * 7 + len(precision) + 13 * world) % 2000
-    mp.spawn(_worker, args=(world, port, use_nccl, precision), nprocs=world, join=True)
+    if transport == "collective" and not use_nccl:
+        pytest.skip("same as transport=None on a single-GPU box")
+    port = 29500 + (os.getpid() * 7 + len(precision) + 13 * world + (5 if transport else 0)) % 2000
+    mp.spawn(_worker, args=(world, port, use_nccl, precision, transport), nprocs=world, join=True)

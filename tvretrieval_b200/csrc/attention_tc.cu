@@ -52,7 +52,7 @@ struct AttParams {
   unsigned short* o_hi;   // split output (batch * len_q, o_ld) or null
   unsigned short* o_lo;
   int o_ld;
-  float sqrt_dh;
+  float inv_sqrt_dh;
 };
 
 struct AttSmem {
@@ -223,61 +223,112 @@ attention_tc_kernel(const __grid_constant__ AttMaps maps, const __grid_constant_
       const float* mrow = p.mask + (long long)b * p.mask_batch_stride + (row_ok ? (long long)qi * p.mask_q_stride : 0);
       tc::mbar_wait(sm.s_full(), it & 1u);
       tc::fence_after_sync();
-      // ---- pass 1: row maximum of x = s / sqrt(dh) + (1 - m) * -10000 over the keys of the sequence ----
-      float mx = -INFINITY;
-      for (int j0 = 0; j0 < p.len_k; j0 += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(t_s + j0, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (j0 + i < p.len_k) {
-            const float madd = __fmul_rn(__fsub_rn(1.f, __ldg(mrow + j0 + i)), ATT_MASK_FILL);
-            mx = fmaxf(mx, __fadd_rn(__fdiv_rn(__uint_as_float(v[i]), p.sqrt_dh), madd));
-          }
-        }
-      }
-      // ---- pass 2: e = exp(x - max) -> (hi, lo) halves into the A slot of the stage of each 64-key chunk ----
-      float sum = 0.f;
+      // x = s / sqrt(dh) + (1 - m) * -10000, the reference's fp32 expression (the division is a multiplication by the
+      // reciprocal: exact for head sizes 64 and 256, within 1 ulp otherwise), e = exp(x - max).  Sequences of up to 128
+      // keys keep x in registers between the maximum and the exponentials (one pass over TMEM and the mask).
+      float mx = -INFINITY, sum = 0.f;
       n += p.n_kc;
-      for (int c = 0; c < p.n_jc; ++c, ++n) {
-        const int s = n % p.stages;
-        tc::mbar_wait(sm.empty(s), ((n / p.stages) & 1u) ^ 1u);  // the MMAs that last read this stage are done
-        const uint32_t a_hi = sm.stage(s) + row_off, a_lo = a_hi + AT_A_BYTES;
+      if (p.len_k <= 128) {
+        float x[128];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int j0 = c * AT_KC + half * 32;
-          float e[32];
-          if (j0 < p.len_k) {
+        for (int g = 0; g < 4; ++g) {
+          if (g * 32 < p.len_k) {
             uint32_t v[32];
-            tc::tmem_ld_32x32(t_s + j0, v);
+            tc::tmem_ld_32x32(t_s + g * 32, v);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              float x = 0.f;
-              if (j0 + i < p.len_k) {
-                const float madd = __fmul_rn(__fsub_rn(1.f, __ldg(mrow + j0 + i)), ATT_MASK_FILL);
-                x = expf(__fadd_rn(__fdiv_rn(__uint_as_float(v[i]), p.sqrt_dh), madd) - mx);
-                sum += x;
+              float xv = -INFINITY;  // keys beyond the sequence: weight exp(-inf) = 0
+              if (g * 32 + i < p.len_k) {
+                const float madd = __fmul_rn(__fsub_rn(1.f, __ldg(mrow + g * 32 + i)), ATT_MASK_FILL);
+                xv = __fadd_rn(__fmul_rn(__uint_as_float(v[i]), p.inv_sqrt_dh), madd);
               }
-              e[i] = x;
+              x[g * 32 + i] = xv;
+              mx = fmaxf(mx, xv);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) e[i] = 0.f;
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {  // 16-byte groups: chunk index (half * 4 + g) XOR (row & 7)
-            uint4 hi, lo;
-            split8(e + g * 8, p.is_bf16, hi, lo);
-            const uint32_t at = (((uint32_t)(half * 4 + g)) ^ rx) * 16u;
-            st_shared_v4(a_hi + at, hi);
-            st_shared_v4(a_lo + at, lo);
           }
         }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(sm.pfull(s));
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c < p.n_jc) {
+            const int s = n % p.stages;
+            tc::mbar_wait(sm.empty(s), ((n / p.stages) & 1u) ^ 1u);  // the MMAs that last read this stage are done
+            const uint32_t a_hi = sm.stage(s) + row_off, a_lo = a_hi + AT_A_BYTES;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {  // 16-byte groups of 8 keys: chunk index g XOR (row & 7)
+              float e[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int col = c * 64 + g * 8 + j;
+                e[j] = col < p.len_k ? __expf(x[col] - mx) : 0.f;
+                sum += e[j];
+              }
+              uint4 hi, lo;
+              split8(e, p.is_bf16, hi, lo);
+              const uint32_t at = (((uint32_t)g) ^ rx) * 16u;
+              st_shared_v4(a_hi + at, hi);
+              st_shared_v4(a_lo + at, lo);
+            }
+            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(sm.pfull(s));
+            ++n;
+          }
+        }
+      } else {
+        // ---- pass 1: row maximum ----
+        for (int j0 = 0; j0 < p.len_k; j0 += 32) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(t_s + j0, v);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (j0 + i < p.len_k) {
+              const float madd = __fmul_rn(__fsub_rn(1.f, __ldg(mrow + j0 + i)), ATT_MASK_FILL);
+              mx = fmaxf(mx, __fadd_rn(__fmul_rn(__uint_as_float(v[i]), p.inv_sqrt_dh), madd));
+            }
+          }
+        }
+        // ---- pass 2: e = exp(x - max) -> (hi, lo) halves into the A slot of the stage of each 64-key chunk ----
+        for (int c = 0; c < p.n_jc; ++c, ++n) {
+          const int s = n % p.stages;
+          tc::mbar_wait(sm.empty(s), ((n / p.stages) & 1u) ^ 1u);
+          const uint32_t a_hi = sm.stage(s) + row_off, a_lo = a_hi + AT_A_BYTES;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int j0 = c * AT_KC + half * 32;
+            float e[32];
+            if (j0 < p.len_k) {
+              uint32_t v[32];
+              tc::tmem_ld_32x32(t_s + j0, v);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float xe = 0.f;
+                if (j0 + i < p.len_k) {
+                  const float madd = __fmul_rn(__fsub_rn(1.f, __ldg(mrow + j0 + i)), ATT_MASK_FILL);
+                  xe = __expf(__fadd_rn(__fmul_rn(__uint_as_float(v[i]), p.inv_sqrt_dh), madd) - mx);
+                  sum += xe;
+                }
+                e[i] = xe;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) e[i] = 0.f;
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 hi, lo;
+              split8(e + g * 8, p.is_bf16, hi, lo);
+              const uint32_t at = (((uint32_t)(half * 4 + g)) ^ rx) * 16u;
+              st_shared_v4(a_hi + at, hi);
+              st_shared_v4(a_lo + at, lo);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(sm.pfull(s));
+        }
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -359,7 +410,7 @@ extern "C" int xmlb_attention_tc(const unsigned short* q_hi, const unsigned shor
   p.q_col0 = q_col0, p.k_col0 = k_col0, p.is_bf16 = is_bf16 ? 1 : 0;
   p.mask = mask, p.mask_batch_stride = mask_batch_stride, p.mask_q_stride = mask_q_stride;
   p.out = out, p.o_hi = out_hi, p.o_lo = out_lo, p.o_ld = out16_ld;
-  p.sqrt_dh = sqrtf((float)dh);
+  p.inv_sqrt_dh = 1.f / sqrtf((float)dh);
   const int stage_bytes = 2 * AT_A_BYTES + 2 * p.brows * AT_KC * 2;
   int stages = (227 * 1024 - 1024 - AT_BAR_BYTES) / stage_bytes;
   if (stages > AT_MAX_STAGES) stages = AT_MAX_STAGES;
