@@ -25,6 +25,9 @@ const char* xmlb_last_error(void);
 int xmlb_version(void);
 /* number of kernel launches issued through this library since load (bench.py: gpu_launches) */
 long long xmlb_launch_count(void);
+/* diagnostic counters of the selection kernels (host array of 4: span_topk rows that overflowed their survivor list,
+ * sum of survivor-list lengths, span_topk rows, reserved); synchronises the device */
+int xmlb_debug_counters(long long* out4, int reset);
 
 /* ---------------------------------------------------------------- encoder building blocks ---------- */
 

@@ -22,6 +22,10 @@ constexpr int MAX_K = 1024;
 constexpr int LIST_CAP = 3072;  // survivors of the span pre-filter kept in shared memory
 constexpr int SORT_CAP = 2048;  // rows up to this length are sorted whole (HIST ints = SORT_CAP 64-bit entries)
 
+// diagnostics (tools/gpu/kernel_bench.py): [0] span_topk rows whose survivor list overflowed (slow full selection),
+// [1] sum of survivor-list lengths, [2] span_topk rows
+__device__ unsigned long long g_debug_counters[4];
+
 struct SelSmem {
   int hist[HIST];
   int warp_tot[NT / 32];
@@ -350,31 +354,55 @@ __global__ void __launch_bounds__(NT) select_candidates_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Cells of one query: score[j][m][n] = (st[j][m] * vr[j]) * ed[j][n] for min_l <= n - m < max_l.  The generator walks
+// the rows (j, m) of a COMPACT list of slots (the valid ones of a sharded search, or those that can still reach the
+// current lower bound), one row per thread, and skips a row whose best possible cell a * max_n ed[j][n] is below
+// min_score -- with the bound of the pre-filter that removes ~90 % of the rows before their 14 cells are touched.
 struct SpanGen {
   const float* st;  // [n_slots][L] start probabilities of this query
   const float* ed;
   const float* vr;  // [n_slots] video scores (null -> 1)
-  const unsigned char* valid;  // [n_slots] or null
-  int n_slots, L, min_l, max_l, tie_desc;
+  const int* slots;     // shared memory: slot indices to visit, ascending
+  const float* emax;    // shared memory: per slot, max over n of ed[j][n]
+  int n_list, L, min_l, max_l, tie_desc;
   float min_score;  // cells below this known lower bound of the k-th best score are skipped (0: keep all positive)
   template <class F>
   __device__ void for_each(F f) const {
-    const int rows = n_slots * L;
-    const int dj = NT / L, dm = NT - dj * L;  // row r = j * L + m advances by NT per iteration, without divisions
-    int j = threadIdx.x / L, m = threadIdx.x - j * L;
-    for (int r = threadIdx.x; r < rows; r += NT, j += dj, m += dm) {
-      if (m >= L) m -= L, ++j;
-      if (valid && !valid[j]) continue;
-      float a = __ldg(st + r);
-      if (vr) a = __fmul_rn(a, __ldg(vr + j));  // (st * vr) first: the association torch.einsum uses
-      if (!(a > 0.f)) continue;
-      const int n_hi = min(m + max_l, L);
-      const float* e = ed + j * L;
-      for (int n = m + min_l; n < n_hi; ++n) {
-        const float s = __fmul_rn(a, __ldg(e + n));
-        if (s > 0.f && s >= min_score) {
-          const unsigned int id = (unsigned int)(r * L + n);
-          f(float_key(s), tie_desc ? id : ~id);
+    const int rows = n_list * L;
+    const int dj = NT / L, dm = NT - dj * L;  // row r = s * L + m advances by NT per iteration, without divisions
+    int s = threadIdx.x / L, m = threadIdx.x - s * L;
+    constexpr int U = 4;  // rows in flight per thread: their loads are issued before any of them is processed
+    for (int r0 = threadIdx.x; r0 < rows; r0 += U * NT) {
+      float a[U];
+      int jj[U], mm[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u] = 0.f, jj[u] = 0, mm[u] = m;
+        if (r0 + u * NT < rows) {
+          jj[u] = slots[s];
+          a[u] = __ldg(st + jj[u] * L + m);
+        }
+        s += dj, m += dm;
+        if (m >= L) m -= L, ++s;
+      }
+      if (vr) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (a[u] > 0.f) a[u] = __fmul_rn(a[u], __ldg(vr + jj[u]));  // (st * vr) first, like torch.einsum
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = jj[u];
+        if (!(a[u] > 0.f) || __fmul_ru(a[u], emax[j]) < min_score) continue;
+        const int n_hi = min(mm[u] + max_l, L);
+        const float* e = ed + j * L;
+        const int row = j * L + mm[u];
+        for (int n = mm[u] + min_l; n < n_hi; ++n) {
+          const float sc = __fmul_rn(a[u], __ldg(e + n));
+          if (sc > 0.f && sc >= min_score) {
+            const unsigned int id = (unsigned int)(row * L + n);
+            f(float_key(sc), tie_desc ? id : ~id);
+          }
         }
       }
     }
@@ -437,6 +465,26 @@ __device__ void zero_fill(SelSmem& sm, int n_pos, int k, long long total_cells, 
   for (int i = filled_s + t; i < k; i += NT) out_idx[i] = -1, out_val[i] = 0.f;
 }
 
+constexpr int MAX_SPAN_SLOTS = 1024;
+
+// Ascending compaction of the slots j < n_slots with keep(j) into list[] (warp 0; result count in *n_out).
+template <class Keep>
+__device__ void compact_slots(int n_slots, Keep keep, int* list, int* n_out) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int count = 0;
+    for (int base = 0; base < n_slots; base += 32) {
+      const int j = base + lane;
+      const bool v = j < n_slots && keep(j);
+      const unsigned int bal = __ballot_sync(0xffffffffu, v);
+      if (v) list[count + __popc(bal & ((1u << lane) - 1u))] = j;
+      count += __popc(bal);
+    }
+    if (lane == 0) *n_out = count;
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__ st, const float* __restrict__ ed,
                                                        const float* __restrict__ vr,
                                                        const unsigned char* __restrict__ slot_valid, int n_slots,
@@ -446,49 +494,97 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
                                                        const __grid_constant__ PeerOut po) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SelSmem& sm = *reinterpret_cast<SelSmem*>(smem_raw);
-  const long long q = blockIdx.x;
-  SpanGen gen{st + q * n_slots * L, ed + q * n_slots * L, vr ? vr + q * n_slots : nullptr,
-              slot_valid ? slot_valid + q * n_slots : nullptr, n_slots, L, min_l, max_l, tie_desc, 0.f};
-  // Pre-filter: the k-th best cell of the first few slots (the videos with the largest retrieval scores) is a lower
-  // bound of the k-th best cell overall.  ONE pass over all slots then collects the few cells at or above it into
-  // shared memory and the exact selection runs on that list (instead of 4 passes over ~180K cells per query).
-  constexpr int SUB_SLOTS = 8;
   unsigned long long* list = reinterpret_cast<unsigned long long*>(smem_raw + sizeof(SelSmem));
-  int n_out = -1;
-  if (n_slots > 2 * SUB_SLOTS) {
-    SpanGen sub = gen;
-    sub.n_slots = SUB_SLOTS;
-    if (gen.valid) {  // sharded search: most slots belong to other ranks -- take the first SUB_SLOTS VALID ones
-      __shared__ int sub_slots_s;
-      if (threadIdx.x == 0) {
-        int seen = 0, n = n_slots;
-        for (int j = 0; j < n_slots; ++j)
-          if (gen.valid[j] && ++seen == SUB_SLOTS) {
-            n = j + 1;
-            break;
-          }
-        sub_slots_s = n;
+  int* slots = reinterpret_cast<int*>(list + LIST_CAP);       // [n_slots] valid slots, ascending
+  int* live = slots + n_slots;                                // [n_slots] slots that can reach the lower bound
+  float* emax = reinterpret_cast<float*>(live + n_slots);     // [n_slots] max_n ed[j][n]
+  float* amax = emax + n_slots;                               // [n_slots] vr[j] * max_m st[j][m]
+  __shared__ int n_valid_s, n_live_s;
+  const long long q = blockIdx.x;
+  const float* st_q = st + q * n_slots * L;
+  const float* ed_q = ed + q * n_slots * L;
+  const float* vr_q = vr ? vr + q * n_slots : nullptr;
+  const unsigned char* valid = slot_valid ? slot_valid + q * n_slots : nullptr;
+  // per-slot maxima (four threads per slot, independent loads: this is the first touch of the query's rows) and the
+  // compact list of valid slots
+  for (int base = 0; base < n_slots; base += NT / 4) {
+    const int j = base + (threadIdx.x >> 2), part = threadIdx.x & 3;
+    float me = 0.f, ms = 0.f;
+    if (j < n_slots && (!valid || valid[j])) {
+      const float* e = ed_q + j * L;
+      const float* a = st_q + j * L;
+#pragma unroll 8
+      for (int n = part; n < L; n += 4) {
+        me = fmaxf(me, __ldg(e + n));
+        ms = fmaxf(ms, __ldg(a + n));
       }
-      __syncthreads();
-      sub.n_slots = sub_slots_s;
     }
-    unsigned int thr = 0;
-    int n_equal, need_equal, n_total;
-    const bool full = radix_select(sub, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; },
-                                   sm, k, thr, n_equal, need_equal, n_total);
+    me = fmaxf(me, __shfl_xor_sync(0xffffffffu, me, 1)), ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 1));
+    me = fmaxf(me, __shfl_xor_sync(0xffffffffu, me, 2)), ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, 2));
+    if (part == 0 && j < n_slots) emax[j] = me, amax[j] = vr_q ? __fmul_ru(ms, __ldg(vr_q + j)) : ms;
+  }
+  compact_slots(n_slots, [&](int j) { return !valid || valid[j] != 0; }, slots, &n_valid_s);
+  const int n_valid = n_valid_s;
+  SpanGen gen{st_q, ed_q, vr_q, slots, emax, n_valid, L, min_l, max_l, tie_desc, 0.f};
+  // Pre-filter: the k-th best cell of the first few valid slots (the videos with the largest retrieval scores) is a
+  // lower bound of the k-th best cell overall.  ONE pass over the slots that can still reach it then collects the few
+  // cells at or above it into shared memory and the exact selection runs on that list (instead of 4 passes over ~180K
+  // cells per query).
+  // (a quarter of the valid slots, between 2 and 8: a rank of a sharded search sees only its share of the slots)
+  const int sub_slots = min(8, max(2, n_valid / 4));
+  int n_out = -1;
+  if (n_valid >= 4) {
+    SpanGen sub = gen;
+    sub.n_list = sub_slots;
+    // ONE 4096-bin pass over the top 12 key bits (sign, exponent, 3 mantissa bits): the lower edge of the bin that
+    // holds the k-th largest cell of the subset is a lower bound of it (at most 12.5 % below), which is all the
+    // collection pass needs -- two more passes would only tighten the bound, at 2/3 of this phase's cost.
+    for (int i = threadIdx.x; i < HIST; i += NT) sm.hist[i] = 0;
+    __syncthreads();
+    sub.for_each([&](unsigned int key, unsigned int) { atomicAdd(&sm.hist[key >> 20], 1); });
+    __syncthreads();
+    find_bin(sm, HIST, k);
+    const bool full = sm.total >= k;
+    const unsigned int thr = (unsigned int)sm.sel_bin << 20;
     __syncthreads();
     if (full) {
-      gen.min_score = key_float(thr);
-      if (threadIdx.x == 0) sm.n_list = 0;
-      __syncthreads();
-      gen.for_each([&](unsigned int key, unsigned int idk) {
-        const int pos = atomicAdd(&sm.n_list, 1);
-        if (pos < LIST_CAP) list[pos] = ((unsigned long long)key << 32) | idk;
-      });
-      __syncthreads();
-      const int n_list = sm.n_list;
-      __syncthreads();
-      if (n_list <= LIST_CAP) n_out = block_topk(ListGen{list, n_list}, sm, k);
+      float bound = key_float(thr);
+      for (int attempt = 0; attempt < 2 && n_out < 0; ++attempt) {
+        // slots whose best conceivable cell amax * emax is below the bound drop out as a whole
+        compact_slots(n_valid, [&](int i) { const int j = slots[i]; return __fmul_ru(amax[j], emax[j]) >= bound; },
+                      live, &n_live_s);
+        for (int i = threadIdx.x; i < n_live_s; i += NT) live[i] = slots[live[i]];
+        if (threadIdx.x == 0) sm.n_list = 0;
+        __syncthreads();
+        SpanGen col = gen;
+        col.slots = live, col.n_list = n_live_s, col.min_score = bound;
+        col.for_each([&](unsigned int key, unsigned int idk) {
+          const int pos = atomicAdd(&sm.n_list, 1);
+          if (pos < LIST_CAP) list[pos] = ((unsigned long long)key << 32) | idk;
+        });
+        __syncthreads();
+        const int n_list = sm.n_list;
+        __syncthreads();
+        if (threadIdx.x == 0 && attempt == 0) {
+          atomicAdd(&g_debug_counters[1], (unsigned long long)n_list);
+          atomicAdd(&g_debug_counters[2], 1ull);
+        }
+        if (n_list <= LIST_CAP) {
+          n_out = block_topk(ListGen{list, n_list}, sm, k);
+        } else {
+          // Too many survivors: the LIST_CAP cells already collected are real cells, so their k-th largest is a valid
+          // -- and tighter -- lower bound of the k-th best overall; collect once more with it.
+          unsigned int t2 = 0;
+          int ne, nn, nt;
+          radix_select(ListGen{list, LIST_CAP},
+                       [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k, t2, ne,
+                       nn, nt);
+          __syncthreads();
+          bound = key_float(t2);
+          if (threadIdx.x == 0 && attempt == 1) atomicAdd(&g_debug_counters[0], 1ull);
+        }
+      }
+      if (n_out < 0) gen.min_score = bound;  // the slow full selection still skips what the bound excludes
     }
   }
   if (n_out < 0) n_out = block_topk(gen, sm, k);
@@ -552,6 +648,17 @@ __global__ void __launch_bounds__(NT) span_zero_fill_kernel(int* __restrict__ id
 }
 
 }  // namespace
+
+extern "C" int xmlb_debug_counters(long long* out4, int reset) {
+  unsigned long long h[4];
+  XMLB_CUDA(cudaMemcpyFromSymbol(h, g_debug_counters, sizeof(h)));
+  for (int i = 0; i < 4; ++i) out4[i] = (long long)h[i];
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    XMLB_CUDA(cudaMemcpyToSymbol(g_debug_counters, z, sizeof(z)));
+  }
+  return XMLB_OK;
+}
 
 static int check_topk_args(const char* who, int k) {
   XMLB_REQUIRE(k >= 1 && k <= MAX_K, "%s: k must be in [1, %d]", who, MAX_K);
@@ -645,7 +752,8 @@ extern "C" int xmlb_span_topk_ex(const float* st_prob, const float* ed_prob, con
   PeerOut po;
   if (int rc = make_peer_out(po, peer_idx, peer_val, world, peer_mode, per, self_rank, "xmlb_span_topk")) return rc;
   if (n_queries == 0) return XMLB_OK;
-  const size_t smem = sizeof(SelSmem) + (size_t)LIST_CAP * sizeof(unsigned long long);
+  XMLB_REQUIRE(n_slots <= MAX_SPAN_SLOTS, "xmlb_span_topk: at most %d slots per query", MAX_SPAN_SLOTS);
+  const size_t smem = sizeof(SelSmem) + (size_t)LIST_CAP * sizeof(unsigned long long) + (size_t)n_slots * 16;
   XMLB_CUDA(cudaFuncSetAttribute(span_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   span_topk_kernel<<<n_queries, NT, smem, (cudaStream_t)stream>>>(
       st_prob, ed_prob, video_score, slot_valid, n_slots, ctx_len, min_l, max_l, k, tie_desc, zero_fill_missing,

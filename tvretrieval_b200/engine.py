@@ -529,7 +529,23 @@ class VCMRSearcher:
     # 8 GPUs, 1,250 queries per rank: 2.1 ms packed vs 1.6 ms padded)
     packed_min_queries = 4096
 
-    def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None, tables_first=False, width=None):
+    def _piece_bounds(self, n, host):
+        """[lo, hi) of the pieces a slice of n queries is uploaded / encoded in.  From host buffers the first piece is
+        small (its upload is the only one nothing overlaps) and a short slice (one rank's share of a sharded search)
+        is still cut into a few pieces so that uploads and encoding overlap."""
+        step = self.encode_chunk
+        if not host:
+            return [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+        step = min(step, max(256, (n + 3) // 4))
+        first = max(min(128, step), step // 4)
+        cuts, lo = [], 0
+        while lo < n:
+            hi = min(n, lo + (first if lo == 0 else step))
+            cuts.append((lo, hi))
+            lo = hi
+        return cuts
+
+    def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None, tables_first=False, width=None, bounds=None):
         """pieces: iterable of (query_feat, query_mask) device tensors -> pooled (video_query, sub_query).
         lens_cpu: host int tensor, valid tokens of every query in piece order (None: padded encoding); `width` is
         the padded token count of the pieces.
@@ -543,15 +559,16 @@ class VCMRSearcher:
         with self._phase("encode_query"):
             lens = lens_cpu.numpy() if lens_cpu is not None else None
 
-            def piece_tables(lo):
-                return self.model.packed_query_tables(lens[lo:lo + self.encode_chunk], width, self.index.device)
+            def piece_tables(i):
+                lo, hi = bounds[i]
+                return self.model.packed_query_tables(lens[lo:hi], width, self.index.device)
             tables = None
             if lens is not None and tables_first:
-                tables = [piece_tables(lo) for lo in range(0, len(lens), self.encode_chunk)]
+                tables = [piece_tables(i) for i in range(len(bounds))]
             off = 0
             for i, (qf, qm) in enumerate(pieces):
                 if lens is not None:
-                    a, b = self.model.encode_query_packed(qf, tables=tables[i] if tables else piece_tables(off))
+                    a, b = self.model.encode_query_packed(qf, tables=tables[i] if tables else piece_tables(i))
                 else:
                     a, b = self.model.encode_query(qf, qm)
                 vq.append(a), sq.append(b)
@@ -568,11 +585,11 @@ class VCMRSearcher:
     # upload is exposed instead of the whole 0.9 GB.
     pipelined_filter = True
 
-    def _device_pieces(self, query_feat, query_mask):
-        for lo in range(0, len(query_feat), self.encode_chunk):
-            yield query_feat[lo:lo + self.encode_chunk], query_mask[lo:lo + self.encode_chunk]
+    def _device_pieces(self, query_feat, query_mask, bounds):
+        for lo, hi in bounds:
+            yield query_feat[lo:hi], query_mask[lo:hi]
 
-    def _host_pieces(self, query_feat_cpu, query_mask_cpu):
+    def _host_pieces(self, query_feat_cpu, query_mask_cpu, bounds):
         """Uploads the pieces on a side stream, so the copy of piece i+1 overlaps the encoding of piece i."""
         dev = self.index.device
         main = torch.cuda.current_stream(dev)
@@ -581,10 +598,10 @@ class VCMRSearcher:
         copy = self._copy_stream
         copy.wait_stream(main)
         staged = []
-        for lo in range(0, len(query_feat_cpu), self.encode_chunk):
+        for lo, hi in bounds:
             with torch.cuda.stream(copy):
-                qf = query_feat_cpu[lo:lo + self.encode_chunk].to(dev, non_blocking=True)
-                qm = query_mask_cpu[lo:lo + self.encode_chunk].to(dev, non_blocking=True)
+                qf = query_feat_cpu[lo:hi].to(dev, non_blocking=True)
+                qm = query_mask_cpu[lo:hi].to(dev, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(copy)
             staged.append((qf, qm, ready))
@@ -621,9 +638,10 @@ class VCMRSearcher:
                 # host buffers: the filter pass of piece i runs while piece i+1 is still being uploaded
                 self._prefilter = _Prefilter(self, n)
                 on_piece = self._prefilter.run
-            video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm) if host
-                                                         else self._device_pieces(qf, qm), lens, on_piece,
-                                                         tables_first=host, width=qm.shape[1])
+            bounds = self._piece_bounds(hi - lo, host)
+            video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm, bounds) if host
+                                                         else self._device_pieces(qf, qm, bounds), lens, on_piece,
+                                                         tables_first=host, width=qm.shape[1], bounds=bounds)
             video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
             gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
             self._external = None
@@ -673,8 +691,25 @@ class VCMRSearcher:
     # ---- host-buffer entry point (the e2e path bench.py times) --------------------------------------
     @torch.no_grad()
     def search_host(self, query_feat_cpu, query_mask_cpu, gt_video_idx_cpu=None, tasks=("VCMR", "VR"),
-                    external_topk=None):
-        """Pinned host buffers in, numpy arrays out; H2D / D2H copies are part of the call."""
+                    external_topk=None, result_rank=None):
+        """Pinned host buffers in, numpy arrays out; H2D / D2H copies are part of the call.  The arrays are views of
+        pinned staging buffers that the NEXT search_host call of this searcher overwrites.  result_rank (sharded
+        search): only that rank copies the (identical) result to its host, the others return None."""
         res = self.search(query_feat_cpu, query_mask_cpu, gt_video_idx_cpu, tasks, host=True,
                           external_topk=external_topk)
-        return {s: getattr(res, s).cpu().numpy() for s in SearchResult.__slots__ if getattr(res, s) is not None}
+        if result_rank is not None and getattr(self, "plan", None) is not None and self.plan.rank != result_rank:
+            torch.cuda.current_stream(self.index.device).synchronize()
+            return None
+        stage = self.__dict__.setdefault("_host_out", {})
+        out = {}
+        for s in SearchResult.__slots__:
+            t = getattr(res, s)
+            if t is None:
+                continue
+            buf = stage.get(s)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = stage[s] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            buf.copy_(t, non_blocking=True)
+            out[s] = buf
+        torch.cuda.current_stream(self.index.device).synchronize()
+        return {s: b.numpy() for s, b in out.items()}
