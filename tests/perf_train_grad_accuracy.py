@@ -36,13 +36,37 @@ def run_oracle(dev, dt):
     return loss.item(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)).double().cpu() for k, v in w.items()}
 l64, g64 = run_oracle('cuda', torch.float64)
 l32c, g32c = run_oracle('cpu', torch.float32)
-torch.manual_seed(11)
-loss, _ = model(query_feat=query.cuda(), query_mask=query_mask.cuda(), video_feat=video.cuda(), video_mask=video_mask.cuda(),
-                sub_feat=sub.cuda(), sub_mask=video_mask.cuda(), tef_feat=None, tef_mask=None, st_ed_indices=sted.cuda())
-loss.backward()
-gm = {k: p.grad.double().cpu() for k, p in model.named_parameters()}
-print("loss: float64 %.8f  torch CPU fp32 %.8f  kernels %.8f" % (l64, l32c, loss.item()))
+inputs = dict(query_feat=query.cuda(), query_mask=query_mask.cuda(), video_feat=video.cuda(), video_mask=video_mask.cuda(),
+              sub_feat=sub.cuda(), sub_mask=video_mask.cuda(), tef_feat=None, tef_mask=None, st_ed_indices=sted.cuda())
+grads, losses = {}, {}
+for prec in ("f32", "f16x3"):
+    model.train_precision = prec
+    model.zero_grad(set_to_none=True)
+    torch.manual_seed(11)
+    loss, _ = model(**inputs)
+    loss.backward()
+    grads[prec] = {k: p.grad.double().cpu() for k, p in model.named_parameters()}
+    losses[prec] = loss.item()
+print("loss: float64 %.8f  torch CPU fp32 %.8f  kernels f32 %.8f  kernels f16x3 %.8f" % (l64, l32c, losses["f32"], losses["f16x3"]))
+worst = {"cpu": 0.0, "f32": 0.0, "f16x3": 0.0}
 for k in g64:
     s = g64[k].abs().max().item()
     e = lambda d: (d[k] - g64[k]).abs().max().item() / max(s, 1e-12)
-    print("%-48s max |grad| %.2e   max err / max |grad|:  torch CPU fp32 %.1e   kernels %.1e" % (k, s, e(g32c), e(gm)))
+    errs = (e(g32c), e(grads["f32"]), e(grads["f16x3"]))
+    for name, v in zip(worst, errs):
+        worst[name] = max(worst[name], v)
+    print("%-48s max |grad| %.2e   max err / max |grad|:  torch CPU fp32 %.1e   kernels f32 %.1e   kernels f16x3 %.1e" % ((k, s) + errs))
+print("worst over all tensors: torch CPU fp32 %.1e   kernels f32 %.1e   kernels f16x3 %.1e" % (worst["cpu"], worst["f32"], worst["f16x3"]))
+# forward + backward time at the reference batch size (128), CUDA events, 5 repeats after 2 warm-ups
+import time
+rep = lambda t: t.repeat(4, *([1] * (t.dim() - 1)))
+big = {k: (rep(v) if torch.is_tensor(v) else v) for k, v in inputs.items()}
+for prec in ("f32", "f16x3"):
+    model.train_precision = prec
+    ts = []
+    for i in range(7):
+        model.zero_grad(set_to_none=True)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        loss, _ = model(**big); loss.backward()
+        torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+    print("forward + backward, bsz 128, train_precision=%s: %.1f ms" % (prec, 1e3 * sorted(ts[2:])[len(ts[2:]) // 2]))

@@ -98,6 +98,11 @@ class _Linear(torch.autograd.Function):
         g2, x2 = g.reshape(-1, out_dim), x.reshape(-1, in_dim)
         dx = dw = db = dres = None
         prec = ctx.precision
+        # output gradients are ~1e-6 and below: out of fp16's range (its halves would underflow), so on the tensor cores
+        # the backward GEMMs split both operands into bf16 halves (2 x 8 mantissa bits, fp32's exponent range; a
+        # kind::f16 MMA cannot mix fp16 and bf16 operands)
+        if prec == "f16x3":
+            prec = "bf16x3"
         with torch.no_grad():
             if ctx.needs_input_grad[1]:
                 dx = lin(g2, weight.t().contiguous(), None, None, False, prec).view(x.shape)      # dY . W
