@@ -287,7 +287,8 @@ def test_span_logits_lists_match_dense(ops):
 
 @pytest.mark.parametrize("nq,nv,length,hid,slots,chunk", [(150, 40, 64, 128, 9, 32), (300, 25, 128, 768, 12, 64),
                                                           (40, 30, 100, 500, 7, 32), (700, 12, 128, 256, 8, 128),
-                                                          (64, 64, 32, 64, 1, 32)])
+                                                          (64, 64, 32, 64, 1, 32), (260, 20, 256, 1024, 10, 128),
+                                                          (90, 16, 200, 256, 6, 64), (35, 9, 129, 128, 4, 32)])
 @pytest.mark.parametrize("precision", ["f16x3", "bf16x3"])
 def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
     """tcgen05 grouped similarity + ConvSE + softmax kernel vs the oracle (float64) on selected pairs."""
@@ -316,6 +317,12 @@ def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
     q_cat = torch.cat([pad(qv, (0, kpad - hid)), pad(qs, (0, kpad - hid))], 1).to(DEV)
     lists = ops.build_pair_lists(top.to(DEV), nv, chunk=chunk)
     got_st, got_ed = ops.span_probs_tc(f2cat, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length, bf16=bf16)
+    ops.TMA_GATHER = True  # same kernel with its producer gathering the query rows (TMA tile::gather4): same bits
+    try:
+        g_st, g_ed = ops.span_probs_tc(f2cat, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length, bf16=bf16)
+    finally:
+        ops.TMA_GATHER = False
+    assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed)
     got_st, got_ed = got_st.view(nq, slots, length).cpu(), got_ed.view(nq, slots, length).cpu()
     err = max((got_st.double() - want_st).abs().max().item(), (got_ed.double() - want_ed).abs().max().item())
     rel = ((got_st.double() - want_st).abs() / want_st.clamp_min(1e-30))[want_st > 1e-6].max().item()
@@ -422,6 +429,16 @@ def test_two_pass_top_videos(ops, nq, nv, length, hid, both, k, max_cand):
     print("candidates per query: mean %.1f max %d, flagged rows %d" % (n_cand.float().mean().item(), n_cand.max().item(),
                                                                      int(cand.row_flags.sum())))
     ops.vr_rescore_tc(qv, cs[0][:2], pk, cand, kpad, q_fp32_b=qs if both else None, c_b=cs[1][:2] if both else None)
+    val_copy, approx_val = cand.val.clone(), torch.gather(approx, 1, cand.col.clamp(min=0).long())
+    cand.val.copy_(approx_val)
+    ops.TMA_GATHER = True  # same kernel, query rows gathered by its producer (TMA tile::gather4): same bits
+    try:
+        ops.vr_rescore_tc(qv, cs[0][:2], pk, cand, kpad, q_fp32_b=qs if both else None, c_b=cs[1][:2] if both else None)
+    finally:
+        ops.TMA_GATHER = False
+    listed = cand.col >= 0
+    assert torch.equal(cand.val[listed], val_copy[listed])
+    cand.val.copy_(val_copy)
     ok = cand.col >= 0
     packed = ok & (cand.col < pk.n_packed)
     assert torch.equal(cand.val[packed], torch.gather(exact, 1, cand.col.clamp(min=0).long())[packed])

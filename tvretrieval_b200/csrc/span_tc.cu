@@ -16,7 +16,7 @@ namespace {
 
 using tc::BLOCK_K;
 using tc::BLOCK_M;
-constexpr int S_LD = 132;  // row pitch (floats) of the transposed similarity tile
+constexpr int MAX_L = 256;  // clips per video: up to two 128-row accumulator halves per (video, query chunk)
 
 struct SpanTcMaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -24,9 +24,11 @@ struct SpanTcMaps {
 
 struct SpanTcParams {
   int n_videos, ctx_len, k_blocks, block_n, stages, ksize, softmax;
+  int n_halves;          // 128-clip halves per video (2 when ctx_len > 128)
   const int4* units;     // {video, first entry row, entries in this chunk, 0}
   const int* n_units;    // device scalar
   const int* entry_out;  // [E] output row of each list entry
+  const int* entry_q;    // [E] query of each list entry: the B rows are gathered by the producer (null: pre-gathered)
   const float* mask;     // [Nv][L]
   const float* w_st;
   const float* w_ed;
@@ -39,61 +41,78 @@ struct SpanTcParams {
 struct SpanSched {
   const SpanTcMaps* maps;
   const SpanTcParams* p;
-  int n_units;
-  __device__ SpanSched(const SpanTcMaps* m, const SpanTcParams* pp) : maps(m), p(pp), n_units(__ldg(pp->n_units)) {}
+  int n_units, u, half;
+  int4 m;
+  __device__ SpanSched(const SpanTcMaps* mp, const SpanTcParams* pp)
+      : maps(mp), p(pp), n_units(__ldg(pp->n_units)), u(0), half(0) {}
   __device__ bool next(tc::UnitDesc& d) {
-    const int u = atomicAdd(p->unit_counter, 1);
-    if (u >= n_units) return false;
-    const int4 m = __ldg(p->units + u);
+    if (half == 0) {
+      u = atomicAdd(p->unit_counter, 1);
+      if (u >= n_units) return false;
+      m = __ldg(p->units + u);
+    }
     d.a_hi = &maps->a_hi, d.a_lo = &maps->a_lo, d.b_hi = &maps->b_hi, d.b_lo = &maps->b_lo;
-    d.a_row = m.x * p->ctx_len;
+    d.a_row = m.x * p->ctx_len + half * BLOCK_M;
     d.b_row = m.y;
+    d.g_count = m.z;
     d.k_blocks = p->k_blocks;
     d.idesc = p->idesc;
-    d.tag0 = u, d.tag1 = 0;
+    d.tag0 = u, d.tag1 = half;
+    if (++half == p->n_halves) half = 0;
     return true;
   }
 };
 
+// NC = 32-clip groups per video handled by a lane in the ConvSE phase: 4 (ctx_len <= 128, one accumulator half) or 8
+template <int NC>
 __global__ void __launch_bounds__(192, 1)
 span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_constant__ SpanTcParams p) {
+  constexpr int S_LD = 32 * NC + 4;  // row pitch (floats) of the transposed similarity tile
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
   const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
-    if (lane == 0) tc::tc_producer_loop(SpanSched(&maps, &p), pipe);
+    if (p.entry_q) {
+      tc::tc_producer_loop_gather(SpanSched(&maps, &p), pipe, lane, p.entry_q, 0, p.block_n);
+    } else if (lane == 0) {
+      tc::tc_producer_loop(SpanSched(&maps, &p), pipe);
+    }
   } else if (warp == 1) {
     if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
-    float* S = reinterpret_cast<float*>(smem_raw + (pipe.extra() - tc::smem_u32(smem_raw)));  // [block_n][S_LD]
-    const int clip = (warp & 3) * 32 + lane;  // accumulator row owned in the TMEM phase
-    const int ew = warp - 2;                  // 0..3: queries handled in the ConvSE phase
+    float* S = reinterpret_cast<float*>(smem_raw + (pipe.extra() - tc::smem_u32(smem_raw)));  // [block_n][s_ld]
+    const int row_in_half = (warp & 3) * 32 + lane;  // accumulator row owned in the TMEM phase
+    const int ew = warp - 2;                         // 0..3: queries handled in the ConvSE phase
     const int L = p.ctx_len, pad = p.ksize / 2;
-    int u, tag1;
-    for (uint32_t unit = 0; tc::epi_next(pipe, unit, u, tag1); ++unit) {
+    int u, half;
+    for (uint32_t unit = 0; tc::epi_next(pipe, unit, u, half); ++unit) {
       const int4 m = __ldg(p.units + u);
       const int v = m.x, e0 = m.y, ne = m.z;
       const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
       // ---- phase A: accumulator (clip x query) -> shared memory, transposed to (query x clip), halved
+      const int clip = (NC > 4 ? half * BLOCK_M : 0) + row_in_half;
       for (int c = 0; c * 32 < ne; ++c) {  // warp-uniform
         uint32_t r[32];
         tc::tmem_ld_32x32(taddr + c * 32, r);
         tc::tmem_ld_wait();
+        if (NC == 4 || clip < L) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) S[(c * 32 + i) * S_LD + clip] = __fmul_rn(__uint_as_float(r[i]), 0.5f);
+          for (int i = 0; i < 32; ++i) S[(c * 32 + i) * S_LD + clip] = __fmul_rn(__uint_as_float(r[i]), 0.5f);
+        }
       }
       tc::epi_release(pipe, unit);
+      if (NC > 4 && half != p.n_halves - 1) continue;  // the video's second half of clips follows as the next unit
       asm volatile("bar.sync 1, 128;" ::: "memory");
       // ---- phase B: per query: ConvSE start / end, mask_logits, softmax over clips
       for (int j = ew; j < ne; j += 4) {
         const float* s = S + j * S_LD;
         const long long row = __ldg(p.entry_out + e0 + j);
-        float st[4], ed[4];
+        float st[NC], ed[NC];
         float mx_st = -INFINITY, mx_ed = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
           const int l = lane + 32 * c;
           st[c] = 0.f, ed[c] = 0.f;
           if (l < L) {
@@ -113,7 +132,7 @@ span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_const
           mx_st = warp_max(mx_st), mx_ed = warp_max(mx_ed);
           float s_st = 0.f, s_ed = 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < NC; ++c) {
             if (lane + 32 * c < L) {
               st[c] = expf(st[c] - mx_st), ed[c] = expf(ed[c] - mx_ed);
               s_st += st[c], s_ed += ed[c];
@@ -121,10 +140,10 @@ span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_const
           }
           s_st = warp_sum(s_st), s_ed = warp_sum(s_ed);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) st[c] = __fdiv_rn(st[c], s_st), ed[c] = __fdiv_rn(ed[c], s_ed);
+          for (int c = 0; c < NC; ++c) st[c] = __fdiv_rn(st[c], s_st), ed[c] = __fdiv_rn(ed[c], s_ed);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NC; ++c) {
           const int l = lane + 32 * c;
           if (l < L) {
             p.out_st[row * L + l] = st[c];
@@ -161,27 +180,31 @@ extern "C" int xmlb_build_span_units(const int* vid_ptr, const int* chunk_ptr, i
   return XMLB_OK;
 }
 
-extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,
-                                  const unsigned short* qg_hi, const unsigned short* qg_lo, const float* mask,
-                                  const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
-                                  int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
-                                  const int* n_units, int max_units, const int* entry_out, float* out_st,
-                                  float* out_ed, int* sched_ws, int is_bf16, void* stream) {
+extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_lo,
+                                     const unsigned short* qg_hi, const unsigned short* qg_lo, const float* mask,
+                                     const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
+                                     int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
+                                     const int* n_units, int max_units, const int* entry_out, const int* entry_q,
+                                     long long n_query_rows, float* out_st, float* out_ed, int* sched_ws, int is_bf16,
+                                     void* stream) {
   XMLB_REQUIRE(f2_hi && f2_lo && qg_hi && qg_lo && mask && w_st && w_ed && units && n_units && entry_out && out_st &&
                    out_ed && sched_ws, "xmlb_span_probs_tc: null pointer");
-  XMLB_REQUIRE(ctx_len >= 1 && ctx_len <= BLOCK_M, "xmlb_span_probs_tc: ctx_len must be <= 128");
+  XMLB_REQUIRE(ctx_len >= 1 && ctx_len <= MAX_L, "xmlb_span_probs_tc: ctx_len must be <= 256");
   XMLB_REQUIRE(kcat >= 64 && kcat % 64 == 0, "xmlb_span_probs_tc: kcat must be a multiple of 64");
   XMLB_REQUIRE(block_n == 32 || block_n == 64 || block_n == 128, "xmlb_span_probs_tc: block_n must be 32, 64 or 128");
   XMLB_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= 31, "xmlb_span_probs_tc: ksize must be odd and <= 31");
   XMLB_REQUIRE(((uintptr_t)units & 15) == 0, "xmlb_span_probs_tc: units must be 16-byte aligned");
+  XMLB_REQUIRE(!entry_q || n_query_rows > 0, "xmlb_span_probs_tc: n_query_rows is required with entry_q");
   if (n_entries == 0 || max_units == 0 || n_videos == 0) return XMLB_OK;
   SpanTcParams p = {};
   p.n_videos = n_videos, p.ctx_len = ctx_len, p.k_blocks = kcat / BLOCK_K, p.block_n = block_n;
   p.ksize = ksize, p.softmax = apply_softmax;
-  p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out;
+  p.n_halves = ceil_div(ctx_len, BLOCK_M);
+  const int s_ld = ctx_len <= 128 ? 132 : 260;
+  p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out, p.entry_q = entry_q;
   p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed, p.unit_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
-  const int extra = block_n * S_LD * (int)sizeof(float);
+  const int extra = block_n * s_ld * (int)sizeof(float);
   p.stages = tc::pipe_stages(block_n, extra);
   XMLB_REQUIRE(p.stages >= 2, "xmlb_span_probs_tc: tile does not fit in shared memory");
   const size_t smem = tc::pipe_smem_bytes(block_n, p.stages, extra);
@@ -189,19 +212,38 @@ extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned sh
   SpanTcMaps maps;
   int rc;
   const unsigned long long corpus_rows = (unsigned long long)n_videos * ctx_len;
+  // gather mode: the B maps address single rows of the (n_query_rows, kcat) query arrays (TMA gather4)
+  const unsigned long long b_rows = entry_q ? (unsigned long long)n_query_rows : (unsigned long long)n_entries;
+  const unsigned int b_box = entry_q ? 1u : (unsigned int)block_n;
   if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi, f2_hi, corpus_rows, kcat, BLOCK_M, BLOCK_K))) return rc;
   if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo, f2_lo, corpus_rows, kcat, BLOCK_M, BLOCK_K))) return rc;
-  if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi, qg_hi, n_entries, kcat, block_n, BLOCK_K))) return rc;
-  if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo, qg_lo, n_entries, kcat, block_n, BLOCK_K))) return rc;
+  if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi, qg_hi, b_rows, kcat, b_box, BLOCK_K))) return rc;
+  if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo, qg_lo, b_rows, kcat, b_box, BLOCK_K))) return rc;
 
   int dev = 0, sms = 0;
   XMLB_CUDA(cudaGetDevice(&dev));
   XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = max_units < sms ? max_units : sms;
   XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
-  XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  span_probs_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  if (p.n_halves == 1) {
+    XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    span_probs_tc_kernel<4><<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  } else {
+    XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    span_probs_tc_kernel<8><<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  }
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
+}
+
+extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,
+                                  const unsigned short* qg_hi, const unsigned short* qg_lo, const float* mask,
+                                  const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
+                                  int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
+                                  const int* n_units, int max_units, const int* entry_out, float* out_st,
+                                  float* out_ed, int* sched_ws, int is_bf16, void* stream) {
+  return xmlb_span_probs_tc_ex(f2_hi, f2_lo, qg_hi, qg_lo, mask, w_st, w_ed, ksize, apply_softmax, n_videos, ctx_len,
+                               kcat, n_entries, block_n, units, n_units, max_units, entry_out, nullptr, 0, out_st,
+                               out_ed, sched_ws, is_bf16, stream);
 }

@@ -56,6 +56,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// Row gather: FOUR rows r0..r3 of a 2-D tensor (tensor map encoded with a box of ONE row) land in four consecutive
+// rows of the shared-memory tile, swizzled like a regular box load (the swizzle is a function of the destination
+// address) -- measured on B200: tools/gpu notes in DESIGN.md.  Completion: 4 * box_cols * 2 bytes on the mbarrier.
+__device__ __forceinline__ void tma_gather4_2d(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int r0,
+                                               int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_result, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols)

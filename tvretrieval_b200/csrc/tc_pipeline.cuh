@@ -41,6 +41,7 @@ struct UnitDesc {
   int a_row, b_row;   // first row of the A / B tile in their tensor maps
   int k_blocks;       // number of BLOCK_K-wide k-blocks to accumulate (> 0)
   int k_block0;       // first k-block (K-chunked accumulation: a unit may cover only a slice of K); 0 by default
+  int g_count;        // gather producer only: number of valid list entries of the gathered operand's tile
   uint32_t idesc;     // instruction descriptor (carries N of this unit)
   int tag0, tag1;     // kernel-specific payload handed to the epilogue (tile index, modality, ...)
 };
@@ -170,6 +171,69 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
     }
   }
   queue_push(p, n, 0, 0, 0, 0u);  // k_blocks == 0: end of work
+}
+
+// Producer of the grouped kernels whose A (gather_a != 0) or B operand is a set of rows picked by an index list
+// (the queries of a video's inverted list): the WHOLE warp 0 runs it.  Lane 0 schedules, waits for the stage and
+// loads the contiguous operand exactly like tc_producer_loop; every lane then fetches four rows of the other operand
+// with one TMA gather4 per half straight out of the un-gathered query array (which stays L2-resident), instead of a
+// separate kernel materialising the gathered rows in HBM for a box load.  u.a_row / u.b_row of the gathered operand
+// is the first list entry, u.g_count the number of entries in the tile (the rest of the tile reads row 0: ignored
+// by the epilogues); its tensor maps must be encoded with box rows = 1.  rows = tile height of the gathered operand.
+template <class Sched>
+__device__ __forceinline__ void tc_producer_loop_gather(Sched sched, const Pipe& p, int lane,
+                                                        const int* __restrict__ gather_idx, int gather_a, int rows) {
+  int stage = 0;
+  uint32_t phase = 0, n = 0;
+  UnitDesc u;
+  u.k_block0 = 0, u.g_count = 0;
+  const uint32_t a_lo_off = A_TILE_BYTES, b_hi_off = 2 * A_TILE_BYTES, b_lo_off = 2 * A_TILE_BYTES + p.b_tile_bytes;
+  for (;;) {
+    int has = 0;
+    if (lane == 0) has = sched.next(u) ? 1 : 0;
+    if (!__shfl_sync(0xffffffffu, has, 0)) break;
+    const int g0 = __shfl_sync(0xffffffffu, gather_a ? u.a_row : u.b_row, 0);
+    const int g_count = __shfl_sync(0xffffffffu, u.g_count, 0);
+    const int kb0 = __shfl_sync(0xffffffffu, u.k_block0, 0), kbn = __shfl_sync(0xffffffffu, u.k_blocks, 0);
+    const CUtensorMap* g_hi = reinterpret_cast<const CUtensorMap*>(
+        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(gather_a ? u.a_hi : u.b_hi), 0));
+    const CUtensorMap* g_lo = reinterpret_cast<const CUtensorMap*>(
+        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(gather_a ? u.a_lo : u.b_lo), 0));
+    int r[4] = {0, 0, 0, 0};
+    const bool mine = 4 * lane < rows;
+    if (mine) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = 4 * lane + i;
+        if (e < g_count) r[i] = max(0, __ldg(gather_idx + g0 + e));
+      }
+    }
+    if (lane == 0) queue_push(p, n, u.tag0, u.tag1, u.k_blocks, u.idesc);
+    ++n;
+    for (int kb = kb0; kb < kb0 + kbn; ++kb) {
+      const uint32_t sa = p.smem_base + stage * p.stage_bytes;
+      if (lane == 0) {
+        mbar_wait(p.empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(p.full_bar(stage), (uint32_t)p.stage_bytes);
+        if (gather_a) {
+          tma_load_2d(sa + b_hi_off, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+          tma_load_2d(sa + b_lo_off, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+        } else {
+          tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+          tma_load_2d(sa + a_lo_off, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+        }
+      }
+      __syncwarp();
+      if (mine) {
+        const uint32_t dst = sa + (gather_a ? 0u : b_hi_off) + (uint32_t)lane * (4u * BLOCK_K * 2u);
+        tma_gather4_2d(dst, g_hi, p.full_bar(stage), kb * BLOCK_K, r[0], r[1], r[2], r[3]);
+        tma_gather4_2d(dst + (gather_a ? a_lo_off : (uint32_t)p.b_tile_bytes), g_lo, p.full_bar(stage), kb * BLOCK_K, r[0],
+                       r[1], r[2], r[3]);
+      }
+      if (++stage == p.stages) stage = 0, phase ^= 1u;
+    }
+  }
+  if (lane == 0) queue_push(p, n, 0, 0, 0, 0u);  // k_blocks == 0: end of work
 }
 
 __device__ __forceinline__ void tc_mma_loop(const Pipe& p, uint32_t tmem_base) {

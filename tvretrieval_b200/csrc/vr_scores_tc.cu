@@ -215,6 +215,7 @@ struct VrRescoreParams {
   const int4* units;     // {packed ordinal, first list entry, entries in this chunk, 0}
   const int* n_units;    // device scalar
   const int* entry_out;  // [E] slot (row * max_cand + position) of each list entry
+  const int* entry_q;    // [E] query of each list entry: the A rows are gathered by the producer (null: pre-gathered)
   const int* row_start;  // [n_packed + 1] first packed row of each ordinal
   float* out;            // candidate scores, indexed by entry_out
   int* unit_counter;     // zeroed before the launch
@@ -237,6 +238,7 @@ struct VrRescoreSched {
     }
     d.a_hi = &maps->a_hi[mod], d.a_lo = &maps->a_lo[mod], d.b_hi = &maps->b_hi[mod], d.b_lo = &maps->b_lo[mod];
     d.a_row = m.y;
+    d.g_count = m.z;
     d.b_row = __ldg(p->row_start + m.x);
     d.k_blocks = p->k_blocks;
     d.idesc = p->idesc;
@@ -254,7 +256,11 @@ vr_rescore_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
-    if (lane == 0) tc::tc_producer_loop(VrRescoreSched(&maps, &p), pipe);
+    if (p.entry_q) {
+      tc::tc_producer_loop_gather(VrRescoreSched(&maps, &p), pipe, lane, p.entry_q, 1, BLOCK_M);
+    } else if (lane == 0) {
+      tc::tc_producer_loop(VrRescoreSched(&maps, &p), pipe);
+    }
   } else if (warp == 1) {
     if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5: one thread = one listed query =====================
@@ -619,13 +625,14 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   return XMLB_OK;
 }
 
-extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,
-                                  const unsigned short* qg_hi_b, const unsigned short* qg_lo_b,
-                                  const unsigned short* c_hi_a, const unsigned short* c_lo_a,
-                                  const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
-                                  const int* units, const int* n_units, int max_units, const int* entry_out,
-                                  float* cand_val, int* sched_ws, long long n_entries, long long n_packed_rows,
-                                  int max_len, int kpad, int is_bf16, void* stream) {
+extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,
+                                     const unsigned short* qg_hi_b, const unsigned short* qg_lo_b,
+                                     const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                                     const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
+                                     const int* units, const int* n_units, int max_units, const int* entry_out,
+                                     const int* entry_q, long long n_query_rows, float* cand_val, int* sched_ws,
+                                     long long n_entries, long long n_packed_rows, int max_len, int kpad, int is_bf16,
+                                     void* stream) {
   XMLB_REQUIRE(qg_hi_a && qg_lo_a && c_hi_a && c_lo_a && row_start && units && n_units && entry_out && cand_val &&
                    sched_ws, "xmlb_vr_rescore_tc: null pointer");
   const bool two = qg_hi_b != nullptr;
@@ -635,12 +642,13 @@ extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned 
   XMLB_REQUIRE(n_packed_rows > 0 && n_packed_rows < (1ll << 31) && n_entries < (1ll << 31),
                "xmlb_vr_rescore_tc: bad row count");
   XMLB_REQUIRE(((uintptr_t)units & 15) == 0, "xmlb_vr_rescore_tc: units must be 16-byte aligned");
+  XMLB_REQUIRE(!entry_q || n_query_rows > 0, "xmlb_vr_rescore_tc: n_query_rows is required with entry_q");
   if (n_entries == 0 || max_units == 0) return XMLB_OK;
   VrRescoreParams p = {};
   p.n_mod = two ? 2 : 1;
   p.k_blocks = kpad / BLOCK_K;
   p.block_n = max_len <= 64 ? 64 : max_len <= 128 ? 128 : 256;
-  p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out;
+  p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out, p.entry_q = entry_q;
   p.row_start = row_start, p.out = cand_val, p.unit_counter = sched_ws;
   p.divisor = (float)p.n_mod;
   p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
@@ -652,10 +660,13 @@ extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned 
   const unsigned short* ql[2] = {qg_lo_a, qg_lo_b};
   const unsigned short* ch[2] = {c_hi_a, c_hi_b};
   const unsigned short* cl[2] = {c_lo_a, c_lo_b};
+  // gather mode: the A maps address single rows of the (n_query_rows, kpad) query arrays (TMA gather4)
+  const unsigned long long a_rows = entry_q ? (unsigned long long)n_query_rows : (unsigned long long)n_entries;
+  const unsigned int a_box = entry_q ? 1u : (unsigned int)BLOCK_M;
   for (int m = 0; m < p.n_mod; ++m) {
     int rc;
-    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[m], qh[m], n_entries, kpad, BLOCK_M, BLOCK_K))) return rc;
-    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[m], ql[m], n_entries, kpad, BLOCK_M, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[m], qh[m], a_rows, kpad, a_box, BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[m], ql[m], a_rows, kpad, a_box, BLOCK_K))) return rc;
     if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi[m], ch[m], n_packed_rows, kpad, p.block_n, BLOCK_K))) return rc;
     if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo[m], cl[m], n_packed_rows, kpad, p.block_n, BLOCK_K))) return rc;
   }
@@ -672,4 +683,16 @@ extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned 
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
+}
+
+extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,
+                                  const unsigned short* qg_hi_b, const unsigned short* qg_lo_b,
+                                  const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                                  const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
+                                  const int* units, const int* n_units, int max_units, const int* entry_out,
+                                  float* cand_val, int* sched_ws, long long n_entries, long long n_packed_rows,
+                                  int max_len, int kpad, int is_bf16, void* stream) {
+  return xmlb_vr_rescore_tc_ex(qg_hi_a, qg_lo_a, qg_hi_b, qg_lo_b, c_hi_a, c_lo_a, c_hi_b, c_lo_b, row_start, units,
+                               n_units, max_units, entry_out, nullptr, 0, cand_val, sched_ws, n_entries, n_packed_rows,
+                               max_len, kpad, is_bf16, stream);
 }

@@ -148,7 +148,7 @@ class CorpusIndex:
         hi/lo-split operands (3 MMAs per product, fp32-accurate), "f32" = exact-fp32 SIMT kernel.
         packed=True stores only the valid clips for the tensor-core kernel (CorpusPacking).
         merged_spans=True additionally keeps [feat2_video | feat2_sub] as hi/lo halves for the tensor-core
-        similarity-curve kernel of the merged two-stream model (needs both modalities, L <= 128)."""
+        similarity-curve kernel of the merged two-stream model (needs both modalities, L <= 256)."""
         assert precision in self.PRECISIONS, precision
         ref = video_feat1 if video_feat1 is not None else sub_feat1
         self.n_videos, self.ctx_len, self.hidden = ref.shape
@@ -188,7 +188,7 @@ class CorpusIndex:
                                                  bf16=bf16)
                     self.sub_bits = ops.mask_bits(sub_mask, self.lp)
         if (precision != "f32" and merged_spans and video_feat2 is not None and sub_feat2 is not None
-                and self.ctx_len <= 128):
+                and self.ctx_len <= 256):
             rows = self.n_videos * self.ctx_len
             self.f2cat = (torch.empty(rows, 2 * self.kpad, device=self.device, dtype=torch.int16),
                           torch.empty(rows, 2 * self.kpad, device=self.device, dtype=torch.int16))

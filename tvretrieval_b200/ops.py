@@ -503,6 +503,14 @@ def _vr_packed_finish(out, packing, n_videos, ordinal, fill=True):
     return by_id
 
 
+# The grouped kernels (exact re-scoring, span similarity) read the queries of a video's list either from a copy in list
+# order made by xmlb_gather_rows16 (False, default) or straight from the query array with TMA tile::gather4 issued by
+# their producer warp (True).  Measured on B200 at the bench shape: gather4 moves only 4 x 64 B per instruction and the
+# TMA unit's per-instruction cost makes it 2-3x SLOWER than the extra HBM round trip of the copy (span similarity 6.7
+# -> 12.8 ms, re-scoring 5.5 -> 19 ms); kept selectable for that measurement.
+TMA_GATHER = False
+
+
 class Candidates:
     """Output of select_candidates: (R, max_cand) column / id / value tables + the overflow flags."""
 
@@ -545,18 +553,18 @@ def vr_rescore_tc(q_fp32_a, c_a, packing, cand, kpad, q_fp32_b=None, c_b=None, b
     rc = _lib.lib().xmlb_build_span_units(_p(lists.vid_ptr), _p(lists.chunk_ptr), packing.n_packed, lists.chunk,
                                           _p(units), _stream())
     _lib.check(rc, "xmlb_build_span_units")
-    def gathered(q_fp32, q_split):
-        if q_split is not None:
-            return gather_rows16(q_split, lists.entry_q)
-        return split_rows(q_fp32, kpad=kpad, normalize=True, bf16=bf16, row_index=lists.entry_q)
-    qa = gathered(q_fp32_a, q_split_a)
-    qb = gathered(q_fp32_b, q_split_b) if (q_fp32_b is not None or q_split_b is not None) else (None, None)
+    def halves(q_fp32, q_split):  # (hi, lo) of the normalised queries
+        q = q_split if q_split is not None else split_rows(q_fp32, kpad=kpad, normalize=True, bf16=bf16)
+        return q if TMA_GATHER else gather_rows16(q, lists.entry_q)
+    qa = halves(q_fp32_a, q_split_a)
+    qb = halves(q_fp32_b, q_split_b) if (q_fp32_b is not None or q_split_b is not None) else (None, None)
     cb = c_b if c_b is not None else (None, None)
-    rc = _lib.lib().xmlb_vr_rescore_tc(_p(qa[0]), _p(qa[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
-                                       _p(cb[1]), _p(packing.row_start), _p(units),
-                                       lists.chunk_ptr[packing.n_packed:].data_ptr(), lists.max_chunks,
-                                       _p(lists.entry_out), _p(cand.val), _p(_sched_ws(dev)), lists.entry_q.numel(),
-                                       packing.n_rows, packing.max_len, kpad, int(bf16), _stream())
+    rc = _lib.lib().xmlb_vr_rescore_tc_ex(_p(qa[0]), _p(qa[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
+                                          _p(cb[1]), _p(packing.row_start), _p(units),
+                                          lists.chunk_ptr[packing.n_packed:].data_ptr(), lists.max_chunks,
+                                          _p(lists.entry_out), _p(lists.entry_q) if TMA_GATHER else None,
+                                          qa[0].shape[0], _p(cand.val), _p(_sched_ws(dev)), lists.entry_q.numel(),
+                                          packing.n_rows, packing.max_len, kpad, int(bf16), _stream())
     _lib.check(rc, "xmlb_vr_rescore_tc")
     return cand.val
 
@@ -604,19 +612,22 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
     rc = _lib.lib().xmlb_build_span_units(_p(lists.vid_ptr), _p(lists.chunk_ptr), n_videos, lists.chunk, _p(units),
                                           _stream())
     _lib.check(rc, "xmlb_build_span_units")
-    # queries: split once, then copied into list order
-    qg = gather_rows16(split_rows(q_cat, kpad=kcat, bf16=bf16), lists.entry_q)
+    # queries: split once, then copied into list order (or gathered by the kernel's producer, see TMA_GATHER)
+    qg = split_rows(q_cat, kpad=kcat, bf16=bf16)
+    if not TMA_GATHER:
+        qg = gather_rows16(qg, lists.entry_q)
     rows = lists.n_rows if out_rows is None else out_rows
     # rows that no list entry covers (videos of other shards) must read as zeros
     alloc = torch.empty if (out_rows is None and getattr(lists, "complete", False)) else torch.zeros
     st = alloc(rows, ctx_len, device=dev, dtype=torch.float32)
     ed = alloc(rows, ctx_len, device=dev, dtype=torch.float32)
     w_st, w_ed = _f32(w_st.reshape(-1), "w_st"), _f32(w_ed.reshape(-1), "w_ed")
-    rc = _lib.lib().xmlb_span_probs_tc(_p(f2cat[0]), _p(f2cat[1]), _p(qg[0]), _p(qg[1]), _p(_f32(mask, "mask")),
-                                       _p(w_st), _p(w_ed), w_st.numel(), int(softmax), n_videos, ctx_len, kcat,
-                                       lists.entry_q.numel(), lists.chunk, _p(units),
-                                       lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
-                                       _p(st), _p(ed), _p(_sched_ws(dev)), int(bf16), _stream())
+    rc = _lib.lib().xmlb_span_probs_tc_ex(_p(f2cat[0]), _p(f2cat[1]), _p(qg[0]), _p(qg[1]), _p(_f32(mask, "mask")),
+                                          _p(w_st), _p(w_ed), w_st.numel(), int(softmax), n_videos, ctx_len, kcat,
+                                          lists.entry_q.numel(), lists.chunk, _p(units),
+                                          lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
+                                          _p(lists.entry_q) if TMA_GATHER else None, qg[0].shape[0], _p(st), _p(ed),
+                                          _p(_sched_ws(dev)), int(bf16), _stream())
     _lib.check(rc, "xmlb_span_probs_tc")
     return st, ed
 
