@@ -54,6 +54,9 @@ def parse_args(argv=None):
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--device-queries", action="store_true",
+                    help="generate the synthetic queries on the device, block by block (stress configs whose raw queries "
+                         "would not fit in pinned host memory on every rank); implies --no-e2e")
     ap.add_argument("--transport", default=None, choices=["peer", "collective"],
                     help="list exchanges of the sharded search: peer-memory stores from the ranking kernels (default with "
                          "NCCL) or torch.distributed collectives")
@@ -358,6 +361,8 @@ def run_ours(args):
     from tvretrieval_b200.model_xml import XML
     from tvretrieval_b200.synthetic import corpus_lengths, synthetic_queries
 
+    if args.device_queries:
+        args.no_e2e = args.no_parity = args.no_gpu_reference = args.no_cpu_baseline = True
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -386,9 +391,19 @@ def run_ours(args):
         del ctx
     torch.cuda.empty_cache()
 
-    qf_cpu, qm_cpu = synthetic_queries(args.n_queries, 30, 768)
-    qf_pin, qm_pin = qf_cpu.pin_memory(), qm_cpu.pin_memory()
-    qf, qm = qf_pin.to(device), qm_pin.to(device)
+    if args.device_queries:
+        gen = torch.Generator(device=device).manual_seed(4321)
+        qlen = torch.randint(5, 31, (args.n_queries,), generator=gen, device=device)
+        qm = (torch.arange(30, device=device)[None] < qlen[:, None]).float()
+        qf = torch.empty(args.n_queries, 30, 768, device=device)
+        for lo in range(0, args.n_queries, 8192):
+            x = torch.randn(min(8192, args.n_queries - lo), 30, 768, generator=gen, device=device)
+            qf[lo:lo + len(x)] = x / (x.norm(dim=-1, keepdim=True) + 1e-5) * qm[lo:lo + len(x)].unsqueeze(2)
+        qf_cpu = qm_cpu = qf_pin = qm_pin = None
+    else:
+        qf_cpu, qm_cpu = synthetic_queries(args.n_queries, 30, 768)
+        qf_pin, qm_pin = qf_cpu.pin_memory(), qm_cpu.pin_memory()
+        qf, qm = qf_pin.to(device), qm_pin.to(device)
 
     two_pass = False if args.one_pass else None  # None: automatic (on for the packed f16x3 index)
     if world == 1:
