@@ -352,6 +352,9 @@ int xmlb_add_layernorm_indexed(const float* x, const float* add, const int* add_
                                void* stream);
 int xmlb_attention_ragged(const float* q, const float* k, const float* v, const int* cu_seqlens, float* out,
                           int n_seqs, int max_len, int hidden, int n_heads, void* stream);
+/* xmlb_attention_ragged on the output of ONE fused Q|K|V projection: qkv (T, 3 * hidden), row = [q | k | v]. */
+int xmlb_attention_ragged_qkv(const float* qkv, const int* cu_seqlens, float* out, int n_seqs, int max_len, int hidden,
+                              int n_heads, void* stream);
 int xmlb_modular_pool_ragged(const float* encoded, const int* cu_seqlens, const float* w_mod, float* out0, float* out1,
                              int n_queries, int max_len, int hidden, int n_mod, void* stream);
 

@@ -20,7 +20,7 @@ constexpr int PAD = 4;   // row stride dh + 4 floats: for dh % 32 == 0 consecuti
 __global__ void __launch_bounds__(128) attention_ragged_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                                const float* __restrict__ v,
                                                                const int* __restrict__ cu_seqlens,
-                                                               float* __restrict__ out, int hidden, int dh) {
+                                                               float* __restrict__ out, int hidden, int dh, int in_ld) {
   extern __shared__ __align__(16) float smem[];
   const int ld = dh + PAD;
   float* Qs = smem;                 // [RL][ld]
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) attention_ragged_kernel(const float* __re
     const int r = i / vec, c = (i - r * vec) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, d = a;
     if (r < len) {
-      const long long g = (long long)(row0 + r) * hidden + h * dh + c;
+      const long long g = (long long)(row0 + r) * in_ld + h * dh + c;  // q / k / v rows are in_ld floats apart
       a = __ldg(reinterpret_cast<const float4*>(q + g));
       b = __ldg(reinterpret_cast<const float4*>(k + g));
       d = __ldg(reinterpret_cast<const float4*>(v + g));
@@ -113,9 +113,10 @@ __global__ void __launch_bounds__(128) attention_ragged_kernel(const float* __re
 
 }  // namespace
 
-extern "C" int xmlb_attention_ragged(const float* q, const float* k, const float* v, const int* cu_seqlens,
-                                     float* out, int n_seqs, int max_len, int hidden, int n_heads, void* stream) {
+static int attention_ragged_launch(const float* q, const float* k, const float* v, int in_ld, const int* cu_seqlens,
+                                   float* out, int n_seqs, int max_len, int hidden, int n_heads, void* stream) {
   XMLB_REQUIRE(q && k && v && cu_seqlens && out, "xmlb_attention_ragged: null pointer");
+  XMLB_REQUIRE(in_ld >= hidden && in_ld % 4 == 0, "xmlb_attention_ragged: in_ld must be >= hidden and a multiple of 4");
   XMLB_REQUIRE(n_heads > 0 && hidden % n_heads == 0, "xmlb_attention_ragged: hidden %% n_heads != 0");
   const int dh = hidden / n_heads;
   XMLB_REQUIRE(dh % 4 == 0, "xmlb_attention_ragged: head size must be a multiple of 4 (16-byte row pieces)");
@@ -128,8 +129,20 @@ extern "C" int xmlb_attention_ragged(const float* q, const float* k, const float
   XMLB_REQUIRE(smem <= 227 * 1024, "xmlb_attention_ragged: head size too large for shared memory");
   XMLB_CUDA(cudaFuncSetAttribute(attention_ragged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_ragged_kernel<<<dim3(n_seqs, n_heads), 128, smem, (cudaStream_t)stream>>>(q, k, v, cu_seqlens, out, hidden,
-                                                                                    dh);
+                                                                                    dh, in_ld);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
+}
+
+extern "C" int xmlb_attention_ragged(const float* q, const float* k, const float* v, const int* cu_seqlens,
+                                     float* out, int n_seqs, int max_len, int hidden, int n_heads, void* stream) {
+  return attention_ragged_launch(q, k, v, hidden, cu_seqlens, out, n_seqs, max_len, hidden, n_heads, stream);
+}
+
+extern "C" int xmlb_attention_ragged_qkv(const float* qkv, const int* cu_seqlens, float* out, int n_seqs, int max_len,
+                                         int hidden, int n_heads, void* stream) {
+  XMLB_REQUIRE(qkv, "xmlb_attention_ragged_qkv: null pointer");
+  return attention_ragged_launch(qkv, qkv + hidden, qkv + 2 * hidden, 3 * hidden, cu_seqlens, out, n_seqs, max_len,
+                                 hidden, n_heads, stream);
 }

@@ -534,7 +534,8 @@ class VCMRSearcher:
         small (its upload is the only one nothing overlaps) and a short slice (one rank's share of a sharded search)
         is still cut into a few pieces so that uploads and encoding overlap."""
         step = self.encode_chunk
-        if not host:
+        if not host:  # device-resident queries: nothing to overlap, few large pieces = few launches
+            step = max(step, 8192)
             return [(lo, min(n, lo + step)) for lo in range(0, n, step)]
         step = min(step, max(256, (n + 3) // 4))
         first = max(min(128, step), step // 4)

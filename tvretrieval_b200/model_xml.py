@@ -288,7 +288,7 @@ class XML(nn.Module):
         return t[:len(rows)], t[len(rows):2 * len(rows)], t[2 * len(rows):], max_len
 
     @torch.no_grad()
-    def encode_query_packed(self, query_feat, lens_cpu=None, tables=None):
+    def encode_query_packed(self, query_feat, lens_cpu=None, tables=None, precision=ops.DEFAULT_PRECISION):
         """encode_query (reference model_xml.py:291-295) on the VALID tokens only: query_feat (N, Lq, Dq) padded
         features on the device, lens_cpu (N,) host ints = valid tokens per query (masks are prefix masks,
         utils/tensor_utils.py:5-53), or `tables` = packed_query_tables(...) made earlier.  The tokens are packed into
@@ -301,16 +301,34 @@ class XML(nn.Module):
         rows_d, pos_d, cu_d, max_len = tables
         assert cu_d.numel() == n + 1
         x = query_feat.reshape(n * width, -1).index_select(0, rows_d)
-        h = self.query_input_proj(x)
-        pe = self.query_pos_embed
-        h = ops.add_layernorm_indexed(h, pe.LayerNorm.weight, pe.LayerNorm.bias, pe.position_embeddings.weight, pos_d,
-                                      eps=pe.LayerNorm.eps)
+        pe, proj = self.query_pos_embed, self.query_input_proj
         att, outp = self.query_encoder.self, self.query_encoder.output
-        q = ops.linear(h, att.query.weight, att.query.bias)
-        k = ops.linear(h, att.key.weight, att.key.bias)
-        v = ops.linear(h, att.value.weight, att.value.bias)
-        ctx = ops.attention_ragged(q, k, v, cu_d, max_len, att.num_attention_heads)
-        o = ops.linear(ctx, outp.dense.weight, outp.dense.bias, residual=h)
+        if len(x) >= 256 and precision != "f32" and self.config.hidden_size % 64 == 0:
+            # tensor-core pipeline with fused stages: LN -> split | GEMM + ReLU | position LN -> (fp32, split) |
+            # ONE GEMM for Q, K and V | fused ragged attention | split | output GEMM + residual | LN | ragged pooling
+            bf16 = precision == "bf16x3"
+            _, x16 = ops.add_layernorm_split(x, proj.LayerNorm.weight, proj.LayerNorm.bias, eps=proj.LayerNorm.eps,
+                                             bf16=bf16, want_f32=False)
+            fc = proj.net[1]
+            h0, _, _ = ops.linear_tc_ex(x16, ops._weight_split(fc.weight, bf16), fc.bias, relu=True, bf16=bf16)
+            h, h16 = ops.add_layernorm_split(h0, pe.LayerNorm.weight, pe.LayerNorm.bias,
+                                             add=pe.position_embeddings.weight, add_index=pos_d,
+                                             eps=pe.LayerNorm.eps, bf16=bf16)
+            w = ops._weight_split_cat([att.query.weight, att.key.weight, att.value.weight], bf16)
+            b = ops._bias_cat([att.query.bias, att.key.bias, att.value.bias])
+            qkv, _, _ = ops.linear_tc_ex(h16, w, b, bf16=bf16)
+            ctx = ops.attention_ragged_qkv(qkv, cu_d, max_len, att.num_attention_heads)
+            o, _, _ = ops.linear_tc_ex(ops.split_rows(ctx, bf16=bf16), ops._weight_split(outp.dense.weight, bf16),
+                                       outp.dense.bias, residual=h, bf16=bf16)
+        else:
+            h = proj(x, precision=precision)
+            h = ops.add_layernorm_indexed(h, pe.LayerNorm.weight, pe.LayerNorm.bias, pe.position_embeddings.weight,
+                                          pos_d, eps=pe.LayerNorm.eps)
+            q = ops.linear(h, att.query.weight, att.query.bias, precision=precision)
+            k = ops.linear(h, att.key.weight, att.key.bias, precision=precision)
+            v = ops.linear(h, att.value.weight, att.value.bias, precision=precision)
+            ctx = ops.attention_ragged(q, k, v, cu_d, max_len, att.num_attention_heads)
+            o = ops.linear(ctx, outp.dense.weight, outp.dense.bias, residual=h, precision=precision)
         o = ops.add_layernorm(o, outp.LayerNorm.weight, outp.LayerNorm.bias, eps=outp.LayerNorm.eps)
         return ops.modular_pool_ragged(o, cu_d, self.PACKED_MAX_LEN, self.modular_vector_mapping.weight)
 

@@ -307,6 +307,17 @@ def attention_ragged(q, k, v, cu_seqlens, max_len, n_heads):
     return out
 
 
+def attention_ragged_qkv(qkv, cu_seqlens, max_len, n_heads):
+    """attention_ragged on the (T, 3H) output of a fused Q|K|V projection -> (T, H)."""
+    qkv = _f32(qkv, "qkv")
+    hid = qkv.shape[-1] // 3
+    out = torch.empty(qkv.shape[0], hid, device=qkv.device, dtype=torch.float32)
+    rc = _lib.lib().xmlb_attention_ragged_qkv(_p(qkv), _p(_i32(cu_seqlens, "cu_seqlens")), _p(out),
+                                              cu_seqlens.numel() - 1, max_len, hid, n_heads, _stream())
+    _lib.check(rc, "xmlb_attention_ragged_qkv")
+    return out
+
+
 def modular_pool_ragged(encoded, cu_seqlens, max_len, w_mod):
     """modular_pool on packed token rows -> (video_query, sub_query), each (n_sequences, H)."""
     encoded, w_mod = _f32(encoded, "encoded"), _f32(w_mod, "w_mod")
