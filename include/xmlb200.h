@@ -252,22 +252,24 @@ int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,
 
 /* Gather variants of the two grouped kernels: entry_q (n_entries ints, the query of every list entry, as
  * xmlb_build_pair_lists returns it) is given and the q arrays are the UN-gathered (n_query_rows, k) halves of all
- * queries; the kernels' TMA producer fetches the listed rows itself (cp.async.bulk.tensor ... tile::gather4, four
- * rows per instruction) instead of reading a gathered copy that xmlb_gather_rows16 first had to write to HBM.
- * entry_q == NULL is the pre-gathered contract of xmlb_vr_rescore_tc / xmlb_span_probs_tc.  xmlb_span_probs_tc_ex
- * accepts ctx_len <= 256 (two 128-clip accumulator halves per video). */
+ * queries; the kernels fetch the listed rows themselves instead of reading a gathered copy that xmlb_gather_rows16
+ * first had to write to HBM: gather_warps != 0 -- four extra warps copy 16-byte pieces (ld.global, L2-resident) into
+ * the swizzled shared-memory tile; gather_warps == 0 -- the TMA producer issues cp.async.bulk.tensor ...
+ * tile::gather4 (four rows per instruction; measured slower).  entry_q == NULL is the pre-gathered contract of
+ * xmlb_vr_rescore_tc / xmlb_span_probs_tc.  xmlb_span_probs_tc_ex accepts ctx_len <= 256 (two 128-clip accumulator
+ * halves per video). */
 int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a, const unsigned short* qg_hi_b,
                           const unsigned short* qg_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                           const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
                           const int* units, const int* n_units, int max_units, const int* entry_out, const int* entry_q,
-                          long long n_query_rows, float* cand_val, int* sched_ws, long long n_entries,
+                          int gather_warps, long long n_query_rows, float* cand_val, int* sched_ws, long long n_entries,
                           long long n_packed_rows, int max_len, int kpad, int is_bf16, void* stream);
 int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_lo, const unsigned short* qg_hi,
                           const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
                           int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,
                           int block_n, const int* units, const int* n_units, int max_units, const int* entry_out,
-                          const int* entry_q, long long n_query_rows, float* out_st, float* out_ed, int* sched_ws,
-                          int is_bf16, void* stream);
+                          const int* entry_q, int gather_warps, long long n_query_rows, float* out_st, float* out_ed,
+                          int* sched_ws, int is_bf16, void* stream);
 
 /* Filter pass of the two-pass video retrieval on CTA pairs (tcgen05 cta_group::2, M = 256): the hi-only
  * (1 MMA per product) scores of xmlb_vr_scores_tc_packed(hi_only = 1) for all (query, video) pairs, same packed

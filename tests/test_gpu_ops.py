@@ -317,12 +317,14 @@ def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
     q_cat = torch.cat([pad(qv, (0, kpad - hid)), pad(qs, (0, kpad - hid))], 1).to(DEV)
     lists = ops.build_pair_lists(top.to(DEV), nv, chunk=chunk)
     got_st, got_ed = ops.span_probs_tc(f2cat, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length, bf16=bf16)
-    ops.TMA_GATHER = True  # same kernel with its producer gathering the query rows (TMA tile::gather4): same bits
+    saved = ops.GATHER  # the three ways of fetching the listed query rows give the same bits
     try:
-        g_st, g_ed = ops.span_probs_tc(f2cat, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length, bf16=bf16)
+        for mode in ("copy", "warps", "tma"):
+            ops.GATHER = mode
+            g_st, g_ed = ops.span_probs_tc(f2cat, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length, bf16=bf16)
+            assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), mode
     finally:
-        ops.TMA_GATHER = False
-    assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed)
+        ops.GATHER = saved
     got_st, got_ed = got_st.view(nq, slots, length).cpu(), got_ed.view(nq, slots, length).cpu()
     err = max((got_st.double() - want_st).abs().max().item(), (got_ed.double() - want_ed).abs().max().item())
     rel = ((got_st.double() - want_st).abs() / want_st.clamp_min(1e-30))[want_st > 1e-6].max().item()
@@ -431,13 +433,17 @@ def test_two_pass_top_videos(ops, nq, nv, length, hid, both, k, max_cand):
     ops.vr_rescore_tc(qv, cs[0][:2], pk, cand, kpad, q_fp32_b=qs if both else None, c_b=cs[1][:2] if both else None)
     val_copy, approx_val = cand.val.clone(), torch.gather(approx, 1, cand.col.clamp(min=0).long())
     cand.val.copy_(approx_val)
-    ops.TMA_GATHER = True  # same kernel, query rows gathered by its producer (TMA tile::gather4): same bits
-    try:
-        ops.vr_rescore_tc(qv, cs[0][:2], pk, cand, kpad, q_fp32_b=qs if both else None, c_b=cs[1][:2] if both else None)
-    finally:
-        ops.TMA_GATHER = False
+    saved = ops.GATHER  # the three ways of fetching the listed query rows give the same bits
     listed = cand.col >= 0
-    assert torch.equal(cand.val[listed], val_copy[listed])
+    try:
+        for mode in ("copy", "warps", "tma"):
+            ops.GATHER = mode
+            cand.val.copy_(approx_val)
+            ops.vr_rescore_tc(qv, cs[0][:2], pk, cand, kpad, q_fp32_b=qs if both else None,
+                              c_b=cs[1][:2] if both else None)
+            assert torch.equal(cand.val[listed], val_copy[listed]), mode
+    finally:
+        ops.GATHER = saved
     cand.val.copy_(val_copy)
     ok = cand.col >= 0
     packed = ok & (cand.col < pk.n_packed)

@@ -68,7 +68,10 @@ def main():
             c = counters()
             print("span_topk (1/%d of the slots valid, as on %d GPUs): %.3f ms; overflowed rows %d of %d, mean survivors %.0f"
                   % (frac, frac, t, c[0], c[2], c[1] / max(1, c[2])))
-        print("span_probs: %.3f ms" % timed(lambda: s.span_probs(vq, sq, lists)))
+        for mode in ("copy", "warps"):
+            ops.GATHER = mode
+            print("span_probs [%s]: %.3f ms" % (mode, timed(lambda: s.span_probs(vq, sq, lists))))
+            print("top_videos [%s] (filter + select + rescore + topk): %.3f ms" % (mode, timed(lambda: s.top_videos(vq, sq, 100), 3)))
         print("pair lists: %.3f ms" % timed(lambda: s.span_lists(res.top_video_idx)))
         print("top_videos (filter + select + rescore + topk): %.3f ms" % timed(lambda: s.top_videos(vq, sq, 100), 3))
         bounds = s._piece_bounds(len(qf), False)

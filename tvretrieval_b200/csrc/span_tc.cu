@@ -28,7 +28,11 @@ struct SpanTcParams {
   const int4* units;     // {video, first entry row, entries in this chunk, 0}
   const int* n_units;    // device scalar
   const int* entry_out;  // [E] output row of each list entry
-  const int* entry_q;    // [E] query of each list entry: the B rows are gathered by the producer (null: pre-gathered)
+  const int* entry_q;    // [E] query of each list entry: the B rows are gathered in the kernel (null: pre-gathered)
+  int gather_warps;      // with entry_q: 1 = gather warps (ld.global -> swizzled st.shared), 0 = TMA gather4 producer
+  const unsigned short* q_hi;  // gather warps: the un-gathered (n_queries, kcat) halves
+  const unsigned short* q_lo;
+  int kcat;
   const float* mask;     // [Nv][L]
   const float* w_st;
   const float* w_ed;
@@ -65,22 +69,29 @@ struct SpanSched {
 
 // NC = 32-clip groups per video handled by a lane in the ConvSE phase: 4 (ctx_len <= 128, one accumulator half) or 8
 template <int NC>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192 + 32 * tc::GATHER_WARPS, 1)
 span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_constant__ SpanTcParams p) {
   constexpr int S_LD = 32 * NC + 4;  // row pitch (floats) of the transposed similarity tile
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n);
+  const bool gw = p.entry_q && p.gather_warps;
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 3, 4, gw ? 2 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
-    if (p.entry_q) {
+    if (p.entry_q && !gw) {
       tc::tc_producer_loop_gather(SpanSched(&maps, &p), pipe, lane, p.entry_q, 0, p.block_n);
     } else if (lane == 0) {
       tc::tc_producer_loop(SpanSched(&maps, &p), pipe);
     }
   } else if (warp == 1) {
     if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+  } else if (warp >= 6) {  // ===================== gather warps 6..9: the listed queries -> B tile =====================
+    tc::tc_gather_loop(pipe, threadIdx.x - 192, p.entry_q, p.block_n, p.kcat,
+                       [&](int u, int, int& e0, int& ne, const unsigned short*& hi, const unsigned short*& lo) {
+                         const int4 m = __ldg(p.units + u);
+                         e0 = m.y, ne = m.z, hi = p.q_hi, lo = p.q_lo;
+                       });
   } else {  // ===================== epilogue warps 2..5 =====================
     float* S = reinterpret_cast<float*>(smem_raw + (pipe.extra() - tc::smem_u32(smem_raw)));  // [block_n][s_ld]
     const int row_in_half = (warp & 3) * 32 + lane;  // accumulator row owned in the TMEM phase
@@ -185,8 +196,8 @@ extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned
                                      const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
                                      int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
                                      const int* n_units, int max_units, const int* entry_out, const int* entry_q,
-                                     long long n_query_rows, float* out_st, float* out_ed, int* sched_ws, int is_bf16,
-                                     void* stream) {
+                                     int gather_warps, long long n_query_rows, float* out_st, float* out_ed,
+                                     int* sched_ws, int is_bf16, void* stream) {
   XMLB_REQUIRE(f2_hi && f2_lo && qg_hi && qg_lo && mask && w_st && w_ed && units && n_units && entry_out && out_st &&
                    out_ed && sched_ws, "xmlb_span_probs_tc: null pointer");
   XMLB_REQUIRE(ctx_len >= 1 && ctx_len <= MAX_L, "xmlb_span_probs_tc: ctx_len must be <= 256");
@@ -202,6 +213,7 @@ extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned
   p.n_halves = ceil_div(ctx_len, BLOCK_M);
   const int s_ld = ctx_len <= 128 ? 132 : 260;
   p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out, p.entry_q = entry_q;
+  p.gather_warps = entry_q && gather_warps ? 1 : 0, p.q_hi = qg_hi, p.q_lo = qg_lo, p.kcat = kcat;
   p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed, p.unit_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
   const int extra = block_n * s_ld * (int)sizeof(float);
@@ -225,12 +237,13 @@ extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned
   XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = max_units < sms ? max_units : sms;
   XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
+  const int threads = p.gather_warps ? 192 + 32 * tc::GATHER_WARPS : 192;
   if (p.n_halves == 1) {
     XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    span_probs_tc_kernel<4><<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+    span_probs_tc_kernel<4><<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
   } else {
     XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    span_probs_tc_kernel<8><<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+    span_probs_tc_kernel<8><<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
   }
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
@@ -244,6 +257,6 @@ extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned sh
                                   const int* n_units, int max_units, const int* entry_out, float* out_st,
                                   float* out_ed, int* sched_ws, int is_bf16, void* stream) {
   return xmlb_span_probs_tc_ex(f2_hi, f2_lo, qg_hi, qg_lo, mask, w_st, w_ed, ksize, apply_softmax, n_videos, ctx_len,
-                               kcat, n_entries, block_n, units, n_units, max_units, entry_out, nullptr, 0, out_st,
+                               kcat, n_entries, block_n, units, n_units, max_units, entry_out, nullptr, 0, 0, out_st,
                                out_ed, sched_ws, is_bf16, stream);
 }

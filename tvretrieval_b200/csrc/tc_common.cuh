@@ -56,6 +56,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       : "memory");
 }
 
+// L2 eviction-priority policies for streaming operands (evict_first) and small re-used ones (evict_last): the
+// pre-encoded descriptors CUTLASS uses (cute::TMA::CacheHintSm90); `createpolicy` at run time trapped as an illegal
+// instruction in these kernels on B200.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { return 0x12F0000000000000ull; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { return 0x14F0000000000000ull; }
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+      "[%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
 // Row gather: FOUR rows r0..r3 of a 2-D tensor (tensor map encoded with a box of ONE row) land in four consecutive
 // rows of the shared-memory tile, swizzled like a regular box load (the swizzle is a function of the destination
 // address) -- measured on B200: tools/gpu notes in DESIGN.md.  Completion: 4 * box_cols * 2 bytes on the mbarrier.

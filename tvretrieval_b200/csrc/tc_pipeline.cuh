@@ -32,6 +32,7 @@ constexpr int ACC_COLS = 256;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int QUEUE_DEPTH = 4;
 constexpr int PIPE_FIXED_BYTES = 512;  // barriers + TMEM slot + unit queue
+constexpr int GATHER_WARPS = 4;        // extra warps of the kernels whose A or B rows are picked by an index list
 
 struct UnitDesc {
   const CUtensorMap* a_hi;
@@ -53,6 +54,7 @@ struct Pipe {
   int stages, stage_bytes, b_tile_bytes;
   int probe;  // limiter experiments (XMLB_VR_PROBE): bit 1 = the producer skips the B tiles
   int epi_warps;  // epilogue warps that consume every unit (4, or 8 when two warps share a TMEM lane quadrant)
+  int gather;     // 0: both operands by TMA; 1 / 2: the A / B tile is filled by GATHER_WARPS extra warps (tc_gather_loop)
   int terms;  // 3: split precision (hi*lo + lo*hi + hi*hi, stage = A_hi|A_lo|B_hi|B_lo); 1: hi*hi only (A_hi|B_hi)
   __device__ uint32_t full_bar(int s) const { return bar_base + 8u * s; }
   __device__ uint32_t empty_bar(int s) const { return bar_base + 8u * (stages + s); }
@@ -79,19 +81,20 @@ inline size_t pipe_smem_bytes(int block_n, int stages, int extra_bytes, int term
 
 // Called by all threads (64 + 32 * epi_warps) at kernel start.  Returns the TMEM base address.
 __device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw, int stages, int block_n,
-                                               int terms = 3, int epi_warps = 4) {
+                                               int terms = 3, int epi_warps = 4, int gather = 0) {
   p.smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   p.stages = stages;
   p.terms = terms;
   p.probe = 0;
   p.epi_warps = epi_warps;
+  p.gather = gather;
   p.b_tile_bytes = block_n * BLOCK_K * 2;
   p.stage_bytes = (terms == 3 ? 2 : 1) * (A_TILE_BYTES + p.b_tile_bytes);
   p.bar_base = p.smem_base + stages * p.stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(p.full_bar(s), 1);
+      mbar_init(p.full_bar(s), gather ? 1 + 32 * GATHER_WARPS : 1);  // TMA transaction (+ one arrival per gather thread)
       mbar_init(p.empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -100,7 +103,7 @@ __device__ __forceinline__ uint32_t pipe_setup(Pipe& p, unsigned char* smem_raw,
     }
     for (int i = 0; i < QUEUE_DEPTH; ++i) {
       mbar_init(p.qfull_bar(i), 1);
-      mbar_init(p.qempty_bar(i), 1 + epi_warps);  // MMA thread + one arrival per epilogue warp
+      mbar_init(p.qempty_bar(i), 1 + epi_warps + (gather ? GATHER_WARPS : 0));  // MMA thread + consumer warps
     }
     fence_barrier_init();
   }
@@ -150,11 +153,28 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
   uint32_t phase = 0, n = 0;
   UnitDesc u;
   u.k_block0 = 0;
+  const uint64_t stream_policy = l2_policy_evict_first();
   while (sched.next(u)) {
     queue_push(p, n++, u.tag0, u.tag1, u.k_blocks, u.idesc);
     for (int kb = u.k_block0; kb < u.k_block0 + u.k_blocks; ++kb) {
       mbar_wait(p.empty_bar(stage), phase ^ 1u);
       const uint32_t sa = p.smem_base + stage * p.stage_bytes;
+      if (p.gather) {  // (terms == 3) the other operand's tile is written by the gather warps
+        // the corpus streams through L2 once (evict_first) so that it does not push out the query rows the gather
+        // warps keep re-reading (evict_last)
+        if (p.gather == 1) {
+          mbar_expect_tx(p.full_bar(stage), 2u * p.b_tile_bytes);
+          tma_load_2d_hint(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row, stream_policy);
+          tma_load_2d_hint(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row,
+                           stream_policy);
+        } else {
+          mbar_expect_tx(p.full_bar(stage), 2u * A_TILE_BYTES);
+          tma_load_2d_hint(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row, stream_policy);
+          tma_load_2d_hint(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row, stream_policy);
+        }
+        if (++stage == p.stages) stage = 0, phase ^= 1u;
+        continue;
+      }
       mbar_expect_tx(p.full_bar(stage), (p.probe & 2) ? (uint32_t)A_TILE_BYTES : (uint32_t)p.stage_bytes);
       if (p.terms == 3) {
         tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
@@ -236,6 +256,63 @@ __device__ __forceinline__ void tc_producer_loop_gather(Sched sched, const Pipe&
   if (lane == 0) queue_push(p, n, 0, 0, 0, 0u);  // k_blocks == 0: end of work
 }
 
+// Gather warps (GATHER_WARPS warps after the epilogue warps; `t` = thread index among them, 0 .. 32 * GATHER_WARPS - 1):
+// fill the A (p.gather == 1) or B (== 2) tile of every stage with rows picked by an index list -- the queries of a
+// video's inverted list -- straight from the un-gathered (rows, ld) 16-bit arrays, which stay L2-resident, with
+// 16-byte cp.async copies into the 64B-swizzled K-major layout TMA would have produced (piece c of row r at
+// r * 64 + ((c ^ ((r >> 1) & 3)) * 16)).  Nothing is staged in registers and nothing waits for the data: as soon as a
+// stage is free its copies are issued and cp.async.mbarrier.arrive.noinc makes each thread's arrival on the stage's
+// full barrier happen when its copies have landed, so the gather runs ahead over all free stages.  The copies are
+// generic-proxy writes: the MMA thread issues fence.proxy.async after the full-barrier wait (tc_mma_loop).
+// `info(tag0, tag1, e0, ne, src_hi, src_lo)` maps a unit to its first list entry, entry count and source arrays.
+template <class Info>
+__device__ __forceinline__ void tc_gather_loop(const Pipe& p, int t, const int* __restrict__ entry_q, int rows,
+                                               int ld, Info info) {
+  constexpr int NT_G = 32 * GATHER_WARPS, MAX_ITEMS = BLOCK_M * 8 / NT_G;  // 16-byte pieces per thread and stage
+  const uint32_t tile_off = p.gather == 1 ? 0u : 2u * A_TILE_BYTES;
+  const uint32_t lo_off = p.gather == 1 ? (uint32_t)A_TILE_BYTES : (uint32_t)p.b_tile_bytes;
+  const int n_items = rows * 8;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (uint32_t unit = 0;; ++unit) {
+    int tag0, tag1, k_blocks;
+    uint32_t idesc;
+    queue_pop(p, unit, false, tag0, tag1, k_blocks, idesc);
+    __syncwarp();
+    if ((t & 31) == 0) mbar_arrive(p.qempty_bar(unit % QUEUE_DEPTH));
+    if (k_blocks <= 0) break;
+    int e0, ne;
+    const unsigned short *src_hi, *src_lo;
+    info(tag0, tag1, e0, ne, src_hi, src_lo);
+    const uint4* src[MAX_ITEMS];
+    uint32_t dst[MAX_ITEMS];
+#pragma unroll
+    for (int j = 0; j < MAX_ITEMS; ++j) {
+      const int i = t + j * NT_G, row = i >> 3, piece = i & 7;
+      src[j] = nullptr, dst[j] = 0;
+      if (i < n_items && row < ne) {  // tile rows beyond the list keep stale (finite) data: the epilogues ignore them
+        const int q = max(0, __ldg(entry_q + e0 + row));
+        src[j] = reinterpret_cast<const uint4*>((piece < 4 ? src_hi : src_lo) + (long long)q * ld) + (piece & 3);
+        dst[j] = tile_off + (piece < 4 ? 0u : lo_off) + (uint32_t)row * 64u +
+                 ((uint32_t)((piece & 3) ^ ((row >> 1) & 3)) * 16u);
+      }
+    }
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(p.empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = p.smem_base + stage * p.stage_bytes;
+#pragma unroll
+      for (int j = 0; j < MAX_ITEMS; ++j) {
+        if (src[j])
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + dst[j]),
+                       "l"(src[j] + kb * (BLOCK_K / 8))  // a k-block = 4 pieces of 8 elements
+                       : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(p.full_bar(stage)) : "memory");
+      if (++stage == p.stages) stage = 0, phase ^= 1u;
+    }
+  }
+}
+
 __device__ __forceinline__ void tc_mma_loop(const Pipe& p, uint32_t tmem_base) {
   int stage = 0;
   uint32_t phase = 0;
@@ -250,6 +327,7 @@ __device__ __forceinline__ void tc_mma_loop(const Pipe& p, uint32_t tmem_base) {
     const uint32_t tmem_acc = tmem_base + acc * ACC_COLS;
     for (int kb = 0; kb < k_blocks; ++kb) {
       mbar_wait(p.full_bar(stage), phase);
+      if (p.gather) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async-written tile -> async proxy
       fence_after_sync();
       const uint32_t sa = p.smem_base + stage * p.stage_bytes;
       if (p.terms == 3) {

@@ -215,7 +215,12 @@ struct VrRescoreParams {
   const int4* units;     // {packed ordinal, first list entry, entries in this chunk, 0}
   const int* n_units;    // device scalar
   const int* entry_out;  // [E] slot (row * max_cand + position) of each list entry
-  const int* entry_q;    // [E] query of each list entry: the A rows are gathered by the producer (null: pre-gathered)
+  const int* entry_q;    // [E] query of each list entry: the A rows are gathered in the kernel (null: pre-gathered)
+  int gather_warps;      // with entry_q: 1 = gather warps (ld.global -> swizzled st.shared), 0 = TMA gather4 producer
+  int is_bf16;
+  const unsigned short* q_hi[2];  // gather warps: the un-gathered (n_queries, kpad) halves per modality
+  const unsigned short* q_lo[2];
+  int kpad;
   const int* row_start;  // [n_packed + 1] first packed row of each ordinal
   float* out;            // candidate scores, indexed by entry_out
   int* unit_counter;     // zeroed before the launch
@@ -241,28 +246,38 @@ struct VrRescoreSched {
     d.g_count = m.z;
     d.b_row = __ldg(p->row_start + m.x);
     d.k_blocks = p->k_blocks;
-    d.idesc = p->idesc;
+    // N of this unit's MMAs = the video's clips rounded up to 16 (the B box always holds block_n rows; the columns
+    // beyond the video are simply not computed)
+    const int len = __ldg(p->row_start + m.x + 1) - d.b_row;
+    d.idesc = tc::idesc_f16(BLOCK_M, min(p->block_n, (len + 15) & ~15), p->is_bf16);
     d.tag0 = u, d.tag1 = mod;
     if (++mod == p->n_mod) mod = 0;
     return true;
   }
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192 + 32 * tc::GATHER_WARPS, 1)
 vr_rescore_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrRescoreParams p) {
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n);
+  const bool gw = p.entry_q && p.gather_warps;
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 3, 4, gw ? 1 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
-    if (p.entry_q) {
+    if (p.entry_q && !gw) {
       tc::tc_producer_loop_gather(VrRescoreSched(&maps, &p), pipe, lane, p.entry_q, 1, BLOCK_M);
     } else if (lane == 0) {
       tc::tc_producer_loop(VrRescoreSched(&maps, &p), pipe);
     }
   } else if (warp == 1) {
     if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+  } else if (warp >= 6) {  // ===================== gather warps 6..9: the listed queries -> A tile =====================
+    tc::tc_gather_loop(pipe, threadIdx.x - 192, p.entry_q, BLOCK_M, p.kpad,
+                       [&](int u, int mod, int& e0, int& ne, const unsigned short*& hi, const unsigned short*& lo) {
+                         const int4 m = __ldg(p.units + u);
+                         e0 = m.y, ne = m.z, hi = p.q_hi[mod], lo = p.q_lo[mod];
+                       });
   } else {  // ===================== epilogue warps 2..5: one thread = one listed query =====================
     const int row = (warp & 3) * 32 + lane;
     float first = 0.f;
@@ -630,9 +645,9 @@ extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsign
                                      const unsigned short* c_hi_a, const unsigned short* c_lo_a,
                                      const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
                                      const int* units, const int* n_units, int max_units, const int* entry_out,
-                                     const int* entry_q, long long n_query_rows, float* cand_val, int* sched_ws,
-                                     long long n_entries, long long n_packed_rows, int max_len, int kpad, int is_bf16,
-                                     void* stream) {
+                                     const int* entry_q, int gather_warps, long long n_query_rows, float* cand_val,
+                                     int* sched_ws, long long n_entries, long long n_packed_rows, int max_len, int kpad,
+                                     int is_bf16, void* stream) {
   XMLB_REQUIRE(qg_hi_a && qg_lo_a && c_hi_a && c_lo_a && row_start && units && n_units && entry_out && cand_val &&
                    sched_ws, "xmlb_vr_rescore_tc: null pointer");
   const bool two = qg_hi_b != nullptr;
@@ -649,6 +664,8 @@ extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsign
   p.k_blocks = kpad / BLOCK_K;
   p.block_n = max_len <= 64 ? 64 : max_len <= 128 ? 128 : 256;
   p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out, p.entry_q = entry_q;
+  p.gather_warps = entry_q && gather_warps ? 1 : 0, p.kpad = kpad, p.is_bf16 = is_bf16 ? 1 : 0;
+  p.q_hi[0] = qg_hi_a, p.q_lo[0] = qg_lo_a, p.q_hi[1] = two ? qg_hi_b : qg_hi_a, p.q_lo[1] = two ? qg_lo_b : qg_lo_a;
   p.row_start = row_start, p.out = cand_val, p.unit_counter = sched_ws;
   p.divisor = (float)p.n_mod;
   p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
@@ -679,7 +696,7 @@ extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsign
   const int grid = max_units < sms ? max_units : sms;
   XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
   XMLB_CUDA(cudaFuncSetAttribute(vr_rescore_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  vr_rescore_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(maps, p);
+  vr_rescore_tc_kernel<<<grid, p.gather_warps ? 192 + 32 * tc::GATHER_WARPS : 192, smem, (cudaStream_t)stream>>>(maps, p);
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
@@ -693,6 +710,6 @@ extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned 
                                   float* cand_val, int* sched_ws, long long n_entries, long long n_packed_rows,
                                   int max_len, int kpad, int is_bf16, void* stream) {
   return xmlb_vr_rescore_tc_ex(qg_hi_a, qg_lo_a, qg_hi_b, qg_lo_b, c_hi_a, c_lo_a, c_hi_b, c_lo_b, row_start, units,
-                               n_units, max_units, entry_out, nullptr, 0, cand_val, sched_ws, n_entries, n_packed_rows,
-                               max_len, kpad, is_bf16, stream);
+                               n_units, max_units, entry_out, nullptr, 0, 0, cand_val, sched_ws, n_entries,
+                               n_packed_rows, max_len, kpad, is_bf16, stream);
 }

@@ -514,12 +514,13 @@ def _vr_packed_finish(out, packing, n_videos, ordinal, fill=True):
     return by_id
 
 
-# The grouped kernels (exact re-scoring, span similarity) read the queries of a video's list either from a copy in list
-# order made by xmlb_gather_rows16 (False, default) or straight from the query array with TMA tile::gather4 issued by
-# their producer warp (True).  Measured on B200 at the bench shape: gather4 moves only 4 x 64 B per instruction and the
-# TMA unit's per-instruction cost makes it 2-3x SLOWER than the extra HBM round trip of the copy (span similarity 6.7
-# -> 12.8 ms, re-scoring 5.5 -> 19 ms); kept selectable for that measurement.
-TMA_GATHER = False
+# How the grouped kernels (exact re-scoring, span similarity) get the query rows of a video's inverted list:
+#   "warps": four extra warps of the kernel copy them, 16 bytes at a time, from the L2-resident query array into the
+#            swizzled shared-memory tile (no HBM round trip of a gathered copy);
+#   "copy" : xmlb_gather_rows16 first materialises the rows in list order, the kernel box-loads them with TMA;
+#   "tma"  : the kernel's producer warp issues TMA tile::gather4 (bit-equal, but 256 B per instruction: measured 2-3x
+#            slower than "copy" at the bench shape -- kept for that measurement).
+GATHER = "copy"
 
 
 class Candidates:
@@ -566,16 +567,17 @@ def vr_rescore_tc(q_fp32_a, c_a, packing, cand, kpad, q_fp32_b=None, c_b=None, b
     _lib.check(rc, "xmlb_build_span_units")
     def halves(q_fp32, q_split):  # (hi, lo) of the normalised queries
         q = q_split if q_split is not None else split_rows(q_fp32, kpad=kpad, normalize=True, bf16=bf16)
-        return q if TMA_GATHER else gather_rows16(q, lists.entry_q)
+        return q if GATHER != "copy" else gather_rows16(q, lists.entry_q)
     qa = halves(q_fp32_a, q_split_a)
     qb = halves(q_fp32_b, q_split_b) if (q_fp32_b is not None or q_split_b is not None) else (None, None)
     cb = c_b if c_b is not None else (None, None)
     rc = _lib.lib().xmlb_vr_rescore_tc_ex(_p(qa[0]), _p(qa[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
                                           _p(cb[1]), _p(packing.row_start), _p(units),
                                           lists.chunk_ptr[packing.n_packed:].data_ptr(), lists.max_chunks,
-                                          _p(lists.entry_out), _p(lists.entry_q) if TMA_GATHER else None,
-                                          qa[0].shape[0], _p(cand.val), _p(_sched_ws(dev)), lists.entry_q.numel(),
-                                          packing.n_rows, packing.max_len, kpad, int(bf16), _stream())
+                                          _p(lists.entry_out), _p(lists.entry_q) if GATHER != "copy" else None,
+                                          int(GATHER == "warps"), qa[0].shape[0], _p(cand.val), _p(_sched_ws(dev)),
+                                          lists.entry_q.numel(), packing.n_rows, packing.max_len, kpad, int(bf16),
+                                          _stream())
     _lib.check(rc, "xmlb_vr_rescore_tc")
     return cand.val
 
@@ -625,7 +627,7 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
     _lib.check(rc, "xmlb_build_span_units")
     # queries: split once, then copied into list order (or gathered by the kernel's producer, see TMA_GATHER)
     qg = split_rows(q_cat, kpad=kcat, bf16=bf16)
-    if not TMA_GATHER:
+    if GATHER == "copy":
         qg = gather_rows16(qg, lists.entry_q)
     rows = lists.n_rows if out_rows is None else out_rows
     # rows that no list entry covers (videos of other shards) must read as zeros
@@ -637,8 +639,8 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
                                           _p(w_st), _p(w_ed), w_st.numel(), int(softmax), n_videos, ctx_len, kcat,
                                           lists.entry_q.numel(), lists.chunk, _p(units),
                                           lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
-                                          _p(lists.entry_q) if TMA_GATHER else None, qg[0].shape[0], _p(st), _p(ed),
-                                          _p(_sched_ws(dev)), int(bf16), _stream())
+                                          _p(lists.entry_q) if GATHER != "copy" else None, int(GATHER == "warps"),
+                                          qg[0].shape[0], _p(st), _p(ed), _p(_sched_ws(dev)), int(bf16), _stream())
     _lib.check(rc, "xmlb_span_probs_tc")
     return st, ed
 
