@@ -527,7 +527,7 @@ class VCMRSearcher:
     # ... for blocks of at least this many queries on this GPU: the layout tables are built on the host (one D2H of
     # the lengths when the masks live on the device), which costs more than it saves on small slices (measured at
     # 8 GPUs, 1,250 queries per rank: 2.1 ms packed vs 1.6 ms padded)
-    packed_min_queries = 4096
+    packed_min_queries = 1024
 
     def _piece_bounds(self, n, host):
         """[lo, hi) of the pieces a slice of n queries is uploaded / encoded in.  From host buffers the first piece is

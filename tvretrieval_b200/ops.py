@@ -1,6 +1,7 @@
 """Thin tensor-level wrappers over the C ABI (include/xmlb200.h).  PyTorch is used only to own device
 memory and streams; every computation below is one or more hand-written sm_100a kernels.  All inputs must be
 CUDA fp32 (or int32/uint8 where stated) tensors; there is no CPU path."""
+import os
 import weakref
 
 import torch
@@ -515,12 +516,15 @@ def _vr_packed_finish(out, packing, n_videos, ordinal, fill=True):
 
 
 # How the grouped kernels (exact re-scoring, span similarity) get the query rows of a video's inverted list:
-#   "warps": four extra warps of the kernel copy them, 16 bytes at a time, from the L2-resident query array into the
-#            swizzled shared-memory tile (no HBM round trip of a gathered copy);
+#   "warps": four extra warps of the kernel copy them, 16 bytes at a time (cp.async), from the query array into the
+#            swizzled shared-memory tile -- no gathered copy in HBM, no work for unlisted table slots (default);
 #   "copy" : xmlb_gather_rows16 first materialises the rows in list order, the kernel box-loads them with TMA;
-#   "tma"  : the kernel's producer warp issues TMA tile::gather4 (bit-equal, but 256 B per instruction: measured 2-3x
-#            slower than "copy" at the bench shape -- kept for that measurement).
-GATHER = "copy"
+#   "tma"  : the kernel's producer warp issues TMA tile::gather4 (256 B per instruction: 2-3x slower, kept for that
+#            measurement).
+# All three give the same bits (tests/test_gpu_ops.py).  Measured on B200 in the full search (bench.py, 21.8K videos x
+# 10K queries): "warps" vs "copy" -- re-scoring 3.6 vs 5.4 ms, span similarity 6.5 vs 7.9 ms at N=1; 0.44 vs 1.32 ms and
+# 1.08 vs 1.39 ms per rank at N=8 (the copy also touches every empty slot of the (Nq, max_candidates) table).
+GATHER = os.environ.get("XMLB_GATHER", "warps")
 
 
 class Candidates:
