@@ -331,7 +331,7 @@ int xmlb_span_zero_fill(int* flat_idx, float* score, int n_queries, int k, long 
 
 /* Greedy temporal NMS per query over ranked lists, replaces utils/temporal_nms.py:25-74 as wrapped by
  * baselines/clip_alignment_with_language/inference.py:189-265.  video_idx NULL = one group (SVMR).
- * out_idx (n_queries, max_out): indices into the input list, ranked; out_count (n_queries). n_in <= 1024. */
+ * out_idx (n_queries, max_out): indices into the input list, ranked; out_count (n_queries). n_in <= 4096. */
 int xmlb_temporal_nms(const int* video_idx, const float* st, const float* ed, const float* score,
                       const int* n_valid, int n_queries, int n_in, double iou_thd, int max_per_group, int max_out,
                       int* out_idx, int* out_count, void* stream);

@@ -493,6 +493,31 @@ def test_index_grows_and_round_trips_through_a_file(precision, tmp_path):
         CorpusIndex.load(str(bad), DEV)
 
 
+def test_normalized_corpus_cache_is_not_served_to_a_new_corpus():
+    """get_pred_from_raw_query caches the L2-normalised corpus per tensor object: a NEW corpus of the same shape that
+    the allocator places at the freed address of the old one (kernel-written tensors all have _version 0) must not
+    be scored against the old normalisation."""
+    cfg, model, weights, ds = tvr_case("video_sub", 4, 4, 64, 16, 32, seed=3)
+    g = torch.Generator().manual_seed(0)
+    qf = torch.randn(5, 6, 768, generator=g).to(DEV)
+    qm = torch.ones(5, 6, device=DEV)
+    mask = torch.ones(7, 16, device=DEV)
+    with torch.no_grad():
+        outs = []
+        for seed in (1, 2):
+            gg = torch.Generator().manual_seed(seed)
+            v1, s1 = (torch.randn(7, 16, 64, generator=gg).to(DEV) for _ in range(2))
+            v2, s2 = (torch.randn(7, 16, 64, generator=gg).to(DEV) for _ in range(2))
+            ptr = v1.data_ptr()
+            q2c, _, _ = model.get_pred_from_raw_query(qf, qm, v1, v2, mask, s1, s2, mask, cross=True)
+            want = O.pred_from_raw_query(dict(cfg), weights, qf.cpu(), qm.cpu(), v1.cpu(), v2.cpu(), mask.cpu(),
+                                         s1.cpu(), s2.cpu(), mask.cpu(), cross=True)[0]
+            close(q2c, want, rtol=1e-4, atol=2e-6)
+            outs.append((ptr, q2c))
+            del v1, s1, v2, s2  # the next iteration's tensors typically re-use these addresses
+    assert not torch.equal(outs[0][1], outs[1][1])
+
+
 def test_model_rejects_cpu_tensors():
     from tvretrieval_b200._lib import XmlbError
     cfg, model, weights, ds = tvr_case("video", 4, 4, 64, 16, 32, seed=3)

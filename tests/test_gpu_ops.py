@@ -562,6 +562,24 @@ def test_temporal_nms_known_answers(ops):
         assert np.array_equal(got, z["out/%d" % i]), i
 
 
+@pytest.mark.parametrize("n_in", [900, 3000])
+def test_temporal_nms_long_lists_vs_oracle(ops, n_in):
+    """Per-video NMS over long ranked lists (up to 4096 predictions per query; the reference's max_before_nms default
+    is 1000) against the oracle restatement of filter_vcmr_by_nms."""
+    g = torch.Generator().manual_seed(n_in)
+    nq, max_out = 3, 100
+    vid = torch.randint(0, 25, (nq, n_in), generator=g)
+    st = torch.randint(0, 80, (nq, n_in), generator=g).float() * 1.5
+    ed = st + torch.randint(2, 16, (nq, n_in), generator=g).float() * 1.5
+    score = torch.sort(torch.rand(nq, n_in, generator=g), dim=1, descending=True)[0]
+    kept, cnt = ops.temporal_nms(st.to(DEV), ed.to(DEV), score.to(DEV), 0.5, max_out, video_idx=vid.to(DEV))
+    for q in range(nq):
+        preds = [[int(vid[q, i]), float(st[q, i]), float(ed[q, i]), float(score[q, i])] for i in range(n_in)]
+        want = O.vcmr_nms(preds, 0.5, n_in, max_out)
+        got = [preds[i] for i in kept[q, :int(cnt[q])].cpu().tolist()]
+        assert got == want, q
+
+
 # ---------------------------------------------------------------------------------------------------------
 # packed (ragged) query encoder
 # ---------------------------------------------------------------------------------------------------------

@@ -11,19 +11,22 @@
 
 namespace {
 constexpr int NMS_T = 256;
-constexpr int NMS_MAX = 1024;
+constexpr int NMS_MAX = 4096;  // ranked spans per query (12-bit fields of the sort key; 116 KB of shared memory)
+constexpr int NMS_BITS = 12;
 
+template <int CAP>  // capacity in spans: 1024 (29 KB, several CTAs per SM) or NMS_MAX
 struct NmsSmem {
-  int vid[NMS_MAX];
-  float st[NMS_MAX], ed[NMS_MAX], score[NMS_MAX];
-  short leader[NMS_MAX];
-  short kept_in_group[NMS_MAX];
-  unsigned char state[NMS_MAX];  // 0 = pending, 1 = kept, 2 = suppressed/dropped
-  unsigned long long key[NMS_MAX];
+  int vid[CAP];
+  float st[CAP], ed[CAP], score[CAP];
+  short leader[CAP];
+  short kept_in_group[CAP];
+  unsigned char state[CAP];  // 0 = pending, 1 = kept, 2 = suppressed/dropped
+  unsigned long long key[CAP];
 };
 
 __device__ __forceinline__ unsigned int pos_float_key(float f) { return __float_as_uint(f) | 0x80000000u; }
 
+template <int CAP>
 __global__ void __launch_bounds__(NMS_T) temporal_nms_kernel(const int* __restrict__ video_idx,
                                                              const float* __restrict__ st, const float* __restrict__ ed,
                                                              const float* __restrict__ score,
@@ -31,7 +34,7 @@ __global__ void __launch_bounds__(NMS_T) temporal_nms_kernel(const int* __restri
                                                              int max_per_group, int max_out, int* __restrict__ out_idx,
                                                              int* __restrict__ out_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  NmsSmem& sm = *reinterpret_cast<NmsSmem*>(smem_raw);
+  NmsSmem<CAP>& sm = *reinterpret_cast<NmsSmem<CAP>*>(smem_raw);
   const long long q = blockIdx.x;
   const int t = threadIdx.x;
   const int n = n_valid ? min(n_valid[q], n_in) : n_in;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(NMS_T) temporal_nms_kernel(const int* __restri
   for (int i = t; i < pow2; i += NMS_T) {
     unsigned long long k = 0ull;
     if (i < n && sm.state[i] == 1)
-      k = ((unsigned long long)pos_float_key(sm.score[i]) << 32) | ((unsigned long long)(NMS_MAX - 1 - sm.leader[i]) << 10) |
+      k = ((unsigned long long)pos_float_key(sm.score[i]) << 32) | ((unsigned long long)(NMS_MAX - 1 - sm.leader[i]) << NMS_BITS) |
           (unsigned long long)(NMS_MAX - 1 - i);
     sm.key[i] = k;
   }
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(NMS_T) temporal_nms_kernel(const int* __restri
   int cnt = 0;
   for (int i = t; i < max_out; i += NMS_T) {
     const bool ok = i < pow2 && sm.key[i] != 0ull;
-    out_idx[q * max_out + i] = ok ? NMS_MAX - 1 - (int)(sm.key[i] & 1023ull) : -1;
+    out_idx[q * max_out + i] = ok ? NMS_MAX - 1 - (int)(sm.key[i] & (unsigned long long)(NMS_MAX - 1)) : -1;
     cnt += ok;
   }
   cnt = warp_sum_int(cnt);
@@ -125,9 +128,17 @@ extern "C" int xmlb_temporal_nms(const int* video_idx, const float* st, const fl
   XMLB_REQUIRE(n_in >= 1 && n_in <= NMS_MAX, "xmlb_temporal_nms: n_in must be in [1, %d]", NMS_MAX);
   XMLB_REQUIRE(max_out >= 1 && max_per_group >= 1, "xmlb_temporal_nms: bad limits");
   if (n_queries == 0) return XMLB_OK;
-  XMLB_CUDA(cudaFuncSetAttribute(temporal_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NmsSmem)));
-  temporal_nms_kernel<<<n_queries, NMS_T, sizeof(NmsSmem), (cudaStream_t)stream>>>(
-      video_idx, st, ed, score, n_valid, n_in, iou_thd, max_per_group, max_out, out_idx, out_count);
+  if (n_in <= 1024) {
+    XMLB_CUDA(cudaFuncSetAttribute(temporal_nms_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(NmsSmem<1024>)));
+    temporal_nms_kernel<1024><<<n_queries, NMS_T, sizeof(NmsSmem<1024>), (cudaStream_t)stream>>>(
+        video_idx, st, ed, score, n_valid, n_in, iou_thd, max_per_group, max_out, out_idx, out_count);
+  } else {
+    XMLB_CUDA(cudaFuncSetAttribute(temporal_nms_kernel<NMS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(NmsSmem<NMS_MAX>)));
+    temporal_nms_kernel<NMS_MAX><<<n_queries, NMS_T, sizeof(NmsSmem<NMS_MAX>), (cudaStream_t)stream>>>(
+        video_idx, st, ed, score, n_valid, n_in, iou_thd, max_per_group, max_out, out_idx, out_count);
+  }
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;

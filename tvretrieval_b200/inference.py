@@ -284,8 +284,14 @@ def get_submission_top_n(submission, top_n=100):
     return out
 
 
+NMS_MAX_PREDICTIONS = 4096  # xmlb_temporal_nms works on up to this many ranked predictions per query
+
+
 def _nms_lists(res_list, nms_thd, max_before_nms, max_after_nms, per_video, device="cuda"):
     n_in = min(max_before_nms, max(len(e["predictions"]) for e in res_list))
+    if n_in > NMS_MAX_PREDICTIONS:
+        raise ValueError("temporal NMS handles at most %d predictions per query (got max_before_nms=%d with lists of "
+                         "up to %d); lower max_before_nms" % (NMS_MAX_PREDICTIONS, max_before_nms, n_in))
     nq = len(res_list)
     arr = np.zeros((nq, n_in, 4), dtype=np.float64)
     cnt = np.zeros(nq, dtype=np.int32)
