@@ -29,7 +29,8 @@ def to_dev(inputs):
     return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in inputs.items()}
 
 
-def assert_grads_close(model, want, rtol=2e-3):
+def assert_grads_close(model, want, rtol=2e-3, loose=(), loose_rtol=1e-2):
+    """`loose`: substrings of parameter names checked at `loose_rtol` instead (see the TVR-shaped test)."""
     got = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
     assert set(got) == set(want)
     largest = max(w.abs().max().item() for w in want.values())
@@ -41,7 +42,7 @@ def assert_grads_close(model, want, rtol=2e-3):
         # when the span loss weight is 0.01): there only rounding noise is left on both sides
         scale = max(w.abs().max().item(), 1e-4 * largest)
         err = (g - w).abs().max().item()
-        if err > rtol * scale:
+        if err > (loose_rtol if any(x in k for x in loose) else rtol) * scale:
             bad.append("%s: max |grad diff| %.3e vs largest entry %.3e" % (k, err, scale))
     assert not bad, "\n".join(bad)
 
@@ -243,17 +244,26 @@ def test_tvr_shaped_step_vs_oracle_and_training_reduces_loss():
 
     sample_seed = next(s for s in range(11, 111) if torch.equal(sampled(q2c_gpu, s), sampled(q2c_cpu, s)))
     torch.manual_seed(sample_seed)
-    loss, parts = model(**dev_inputs)
-    loss.backward()
-    torch.manual_seed(sample_seed)
     o_loss, o_parts = O.train_forward(cfg, w, query64, query_mask64, video64, video_mask64, sub64, video_mask64,
                                       inputs["st_ed_indices"])
     o_loss.backward()
-    assert abs(loss.item() - o_loss.item()) <= 1e-4 * abs(o_loss.item())
-    for k in o_parts:
-        assert abs(parts[k] - o_parts[k]) <= 1e-4 * max(1e-3, abs(o_parts[k])), k
-    assert_grads_close(model, {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in w.items()},
-                       rtol=1e-3)
+    want = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in w.items()}
+    assert model.train_precision == "f16x3"
+    for prec in ("f32", "f16x3"):
+        model.train_precision = prec
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(sample_seed)
+        loss, parts = model(**dev_inputs)
+        loss.backward()
+        assert abs(loss.item() - o_loss.item()) <= 1e-4 * abs(o_loss.item())
+        for k in o_parts:
+            assert abs(parts[k] - o_parts[k]) <= 1e-4 * max(1e-3, abs(o_parts[k])), k
+        # Every gradient within 1e-3 of float64 (relative to the tensor's largest entry).  Exception for the default
+        # tensor-core mode: the input projections, whose ReLU masks flip for the few pre-activations that lie within
+        # the forward rounding error of zero -- a property of ANY fp32-accurate forward pass (measured on this very
+        # batch: torch's own CPU fp32 is off by 17 % on video_input_proj, the tensor-core mode by 0.4 % on
+        # sub_input_proj, the exact-fp32 kernels by 0.01 %; profiles/r02_train_grad_accuracy.txt).
+        assert_grads_close(model, want, rtol=1e-3, loose=("input_proj",) if prec == "f16x3" else ())
     # a few fused optimizer steps on the same batch reduce the loss
     no_decay = ("bias", "LayerNorm.bias", "LayerNorm.weight")
     named = list(model.named_parameters())

@@ -155,10 +155,14 @@ class XML(nn.Module):
     def set_train_st_ed(self, lw_st_ed):
         self.config.lw_st_ed = lw_st_ed
 
-    # Linear-layer kernels of the training step (forward and the dX / dW GEMMs of the backward pass): "f32" = exact
-    # SIMT FMA (default: gradients then match the reference to ~1e-4), "f16x3" / "bf16x3" = split-precision tcgen05
-    # (several times faster; its truncating accumulator costs ~1e-2 relative on the long-K dW sums).
-    train_precision = "f32"
+    # Linear-layer kernels of the training step (forward and the dX / dW GEMMs of the backward pass): "f16x3" (default)
+    # = split-precision tcgen05 GEMMs with K-chunked fp32 accumulation; the backward GEMMs use bf16 halves because
+    # output gradients (~1e-6) are out of fp16's range.  Measured at TVR dims against float64
+    # (profiles/r02_train_grad_accuracy.txt): median gradient error 6e-6 of each tensor's largest entry; the worst
+    # tensor (3.7e-3, an input projection) is where ReLU activations within rounding of zero flip their gradient mask
+    # -- torch's own fp32 CPU evaluation of the same batch shows 1.7e-1 on the corresponding tensor.  "f32" = exact
+    # SIMT FMA GEMMs (3x slower).
+    train_precision = "f16x3"
 
     def forward(self, query_feat, query_mask, video_feat, video_mask, sub_feat, sub_mask, tef_feat, tef_mask,
                 st_ed_indices):
