@@ -35,6 +35,11 @@ def parse_args(argv=None):
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="search", choices=["search", "train"],
+                    help="search = full-corpus VCMR queries/s (BASELINE metric, default); train = the training step of "
+                         "BASELINE configs[3] (bsz 128 per GPU, hard negatives, VR + SVMR losses, BertAdam), "
+                         "data-parallel over the GPUs")
+    ap.add_argument("--train-bsz", type=int, default=128)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_gpu"],
                     help="ours = the CUDA kernels; reference = the reference's own code on the host CPU cores; "
                          "torch_gpu = the reference's own code through PyTorch on the same GPU")
@@ -679,9 +684,149 @@ def run_torch_gpu(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ training step
+def run_train(args):
+    """BASELINE configs[3]: XML.forward + backward + BertAdam.step on a synthetic batch of `--train-bsz` items per GPU
+    (video_sub, H=768, Dv=3072, L<=128, in-batch hard negatives, lw_st_ed=0.01), data-parallel: every rank its own
+    batch, gradients averaged with one NCCL all-reduce (sharding.all_reduce_gradients) before the fused optimizer
+    step.  `value` = training samples/s over all ranks; `gpu_reference` = the unmodified reference model (baseline/_ref)
+    with torch eager fp32 + the reference's BertAdam on the same GPU, same batch (N=1 only)."""
+    from tvretrieval_b200 import _lib
+    from tvretrieval_b200.model_xml import XML
+    from tvretrieval_b200.optimization import BertAdam
+    from tvretrieval_b200.sharding import all_reduce_gradients
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    cfg = model_config(args)
+    cfg.update(use_hard_negative=True, hard_pool_size=20, lw_st_ed=0.01, lw_neg_q=1, lw_neg_ctx=1, margin=0.1)
+    n, L = args.train_bsz, args.max_ctx_l
+
+    def batch(dev, seed):
+        g = torch.Generator().manual_seed(seed)
+        lens = torch.randint(16, L + 1, (n,), generator=g)
+        lens[0] = L
+        qlens = torch.randint(5, 31, (n,), generator=g)
+        vm = (torch.arange(L)[None] < lens[:, None]).float()
+        qm = (torch.arange(30)[None] < qlens[:, None]).float()
+        unit = lambda t: t / (t.norm(dim=-1, keepdim=True) + 1e-5)  # noqa: E731
+        st = (torch.rand(n, generator=g) * (lens - 1)).long()
+        d = dict(query_feat=unit(torch.randn(n, 30, 768, generator=g)) * qm[..., None], query_mask=qm,
+                 video_feat=unit(torch.randn(n, L, args.video_dim, generator=g)) * vm[..., None], video_mask=vm,
+                 sub_feat=unit(torch.randn(n, L, 768, generator=g)) * vm[..., None], sub_mask=vm, tef_feat=None,
+                 tef_mask=None, st_ed_indices=torch.stack([st, torch.minimum(lens - 1, st + 3)], 1))
+        return {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()}
+
+    def optimizer(model, cls):
+        no_decay = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+        named = list(model.named_parameters())
+        return cls([{"params": [p for k, p in named if not any(nd in k for nd in no_decay)], "weight_decay": 0.01},
+                    {"params": [p for k, p in named if any(nd in k for nd in no_decay)], "weight_decay": 0.0}],
+                   lr=1e-4, warmup=0.01, t_total=1000, schedule="warmup_linear")
+
+    torch.manual_seed(2018)
+    model = XML(cfg).to(device).train()
+    weights = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    opt = optimizer(model, BertAdam)
+    inputs = batch(device, 1234 + rank)
+    phases = {"forward_backward": 0.0, "all_reduce": 0.0, "optimizer": 0.0}
+
+    def step(timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        opt.zero_grad()
+        ev[0].record()
+        loss, _ = model(**inputs)
+        loss.backward()
+        ev[1].record()
+        if world > 1:
+            all_reduce_gradients(model.parameters())
+        ev[2].record()
+        opt.step()
+        ev[3].record()
+        return ev, loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step(False)
+    torch.cuda.synchronize()
+    sampler.mark()
+    barrier()
+    launches0 = _lib.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    evs = [step(True) for _ in range(args.steps)]
+    end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    ms_total = start.elapsed_time(end)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    for ev, _ in evs:
+        phases["forward_backward"] += ev[0].elapsed_time(ev[1]) / args.steps
+        phases["all_reduce"] += ev[1].elapsed_time(ev[2]) / args.steps
+        phases["optimizer"] += ev[2].elapsed_time(ev[3]) / args.steps
+    ms_per_step = ms_total / args.steps
+    n_params = sum(p.numel() for p in model.parameters())
+    line = {"metric": "training samples/sec, XML video_sub step (configs[3])", "value": world * n / (ms_per_step / 1e3),
+            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (GEMMs: 16-bit hi/lo split tensor-core products, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": "XML.forward + backward + BertAdam.step, video_sub resnet_i3d, bsz %d per GPU, L<=%d, "
+                                   "H=%d, Dv=%d, hard negatives (pool 20), lw_st_ed 0.01; data parallel, gradients averaged "
+                                   "by one NCCL all-reduce over a flat %.0f MB buffer"
+                                   % (n, L, args.hidden, args.video_dim, n_params * 4 / 1e6),
+                       "train_precision": model.train_precision, "parameters": n_params},
+            "clocks": clocks, "gpu_launches": launches, "phases_ms_per_step": phases, "loss_last": float(evs[-1][1])}
+    if rank == 0 and world == 1 and not args.no_gpu_reference:
+        ref_ns, ref_model = reference_model(cfg, weights, device)
+        if ref_model is not None:
+            from baselines.crossmodal_moment_localization.optimization import BertAdam as RefAdam
+            ref_model.train()
+            ropt = optimizer(ref_model, RefAdam)
+            times = []
+            for i in range(3 + args.steps):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ropt.zero_grad()
+                rloss, _ = ref_model(**inputs)
+                rloss.backward()
+                ropt.step()
+                torch.cuda.synchronize()
+                times.append(time.perf_counter() - t0)
+            t_ref = sum(times[3:]) / args.steps
+            line["gpu_reference"] = {"api": "baseline/_ref XML.forward + backward + reference BertAdam.step, torch eager "
+                                            "fp32 on the same GPU and batch", "ms_per_step": 1e3 * t_ref,
+                                     "samples_per_s": n / t_ref}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
+    if a.workload == "train":
+        run_train(a)
+    elif a.impl == "reference":
         run_reference(a)
     elif a.impl == "torch_gpu":
         run_torch_gpu(a)
