@@ -336,6 +336,15 @@ int xmlb_temporal_nms(const int* video_idx, const float* st, const float* ed, co
                       const int* n_valid, int n_queries, int n_in, double iou_thd, int max_per_group, int max_out,
                       int* out_idx, int* out_count, void* stream);
 
+/* Retrieval metrics on ranked DEVICE lists, the per-query part of standalone_eval/eval.py:83-252:
+ * first_hit[q][t] = rank of the first prediction of query q that is correct at IoU threshold iou_thds[t] (INT_MAX if
+ * none); mode 0 = VCMR (right video and IoU >= thd), 1 = SVMR (ranks count only predictions on the ground-truth
+ * video), 2 = VR (right video; n_thds = 1, spans / thresholds may be NULL).  IoU = intersection / convex hull in fp32
+ * (eval.py:54-69).  pred_* (n_queries, n_pred), n_valid NULL = all n_pred; R@K = mean(first_hit < K). */
+int xmlb_eval_first_hit(const int* pred_vid, const float* pred_st, const float* pred_ed, const int* n_valid,
+                        const int* gt_vid, const float* gt_st, const float* gt_ed, const float* iou_thds, int n_thds,
+                        int n_queries, int n_pred, int mode, int* first_hit, void* stream);
+
 /* ---------------------------------------------------------------- packed (ragged) query encoder -------- */
 /* The query encoder on a PACKED token layout: only the valid tokens of each query are stored, sequence s owns rows
  * [cu_seqlens[s], cu_seqlens[s+1]) of every (T, hidden) activation.  Padded tokens have exactly zero weight as

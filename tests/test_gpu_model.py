@@ -200,9 +200,52 @@ def test_eval_epoch_writes_submission_and_metrics(tmp_path):
     again = eval_retrieval(sub, ds.query_data, verbose=False)
     assert json.load(open(paths[1])) == json.loads(json.dumps(again)) == json.loads(json.dumps(metrics))
     assert set(metrics_nms) == {"VCMR", "SVMR", "VCMR_by_type", "SVMR_by_type"}
+    # the device path (no lists, no host evaluator) returns the metrics eval_epoch wrote
+    dev_metrics = I.eval_metrics_device(model, ds, opt, tasks=("VCMR", "SVMR", "VR"), max_after_nms=20)
+    assert json.dumps(dev_metrics) == json.dumps(metrics)
     assert metrics["SVMR"]["0.5-r100"] >= metrics["SVMR"]["0.5-r1"]
     after = json.load(open(paths[2]))
     assert set(after) == {"video2idx", "VCMR", "SVMR"}
+
+
+def test_device_metrics_equal_the_evaluator_on_the_submission():
+    """eval_metrics.eval_search_result_device (xmlb_eval_first_hit on the engine's device tensors) returns exactly the
+    dictionaries the evaluator computes from the submission built out of the same result (reference
+    standalone_eval/eval.py:83-276 semantics: R@K at IoU 0.5 / 0.7, overall and by description type)."""
+    import json
+    from tvretrieval_b200 import inference as I
+    from tvretrieval_b200.eval_metrics import DESC_TYPE2IDX, eval_retrieval, eval_search_result_device
+    from tvretrieval_b200.synthetic import SyntheticEvalDataset
+    g = GoldenCase("video_sub_vcmr")
+    ds = SyntheticEvalDataset(max_ctx_l=g.cfg["max_ctx_l"], max_desc_l=g.cfg["max_desc_l"],
+                              video_dim=g.cfg["visual_input_size"], sub_dim=g.cfg["sub_input_size"],
+                              query_dim=g.cfg["query_input_size"], ctx_mode=g.cfg["ctx_mode"], min_ctx_l=3,
+                              **g.case["data"])
+    for i, q in enumerate(ds.query_data):  # all three description types, ground-truth spans of varying length
+        q["type"] = ("v", "t", "vt")[i % 3]
+        q["ts"] = [1.5 * (i % 4), 1.5 * (i % 4) + 3.0 + 1.5 * (i % 3)]
+    model = build_model(g.cfg, g.weights)
+    opt = Opt(g.case, g.cfg)
+    ctx = I.compute_context_info(model, ds, opt)
+    k_vid, k_span = g.case["max_n_videos"], g.case["max_before_nms"]
+    searcher = I._searcher(model, opt, ctx, k_span, k_vid)
+    metas = ctx["video_metas"]
+    pos = {m["vid_name"]: i for i, m in enumerate(metas)}
+    gt_pos = torch.tensor([pos[q["vid_name"]] for q in ds.query_data], dtype=torch.int32)
+    qf, qm = GoldenCase.pad(ds.query_feats)
+    res = searcher.search(qf.to(DEV), qm.to(DEV), gt_pos.to(DEV), tasks=("VCMR", "VR", "SVMR"))
+    out = {s: getattr(res, s).cpu().numpy() for s in res.__slots__ if getattr(res, s) is not None}
+    query_metas = [dict(desc_id=q["desc_id"], desc=q["desc"], vid_name=q["vid_name"]) for q in ds.query_data]
+    sub = I.host_section(out, query_metas, metas, ds.video2idx, searcher.index.ctx_len, 1.5, ("VCMR", "VR", "SVMR"))
+    sub["video2idx"] = ds.video2idx
+    want = eval_retrieval(sub, ds.query_data, verbose=False)
+    got = eval_search_result_device(res, gt_pos, [q["ts"] for q in ds.query_data], searcher.index.ctx_len, 1.5,
+                                    desc_types=[DESC_TYPE2IDX[q["type"]] for q in ds.query_data])
+    assert list(got) == list(want)
+    diff = {(t, k): (got[t].get(k), want[t][k]) for t in want for k in want[t] if got[t].get(k) != want[t][k]}
+    assert not diff, diff
+    assert json.dumps(got, sort_keys=False) == json.dumps(want, sort_keys=False)
+    assert want["SVMR"]["0.5-r100"] > 0 and want["VR"]["r100"] > 0  # (the case is not degenerate)
 
 
 def test_golden_visualization_data():

@@ -133,3 +133,80 @@ def eval_retrieval(submission, ground_truth, iou_thds=(0.5, 0.7), verbose=True, 
         for task in submitted:
             out[task + "_by_type"] = raw[task + "_by_type"]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device path: metrics straight from the search engine's device tensors (no prediction lists, no host loop)
+# ---------------------------------------------------------------------------------------------------------------
+def eval_search_result_device(result, gt_video_pos, gt_ts, ctx_len, clip_length=1.5, desc_types=None,
+                              iou_thds=(0.5, 0.7), recall_topks=(1, 5, 10, 100), max_pred_per_query=100, tasks=None):
+    """eval_retrieval for an engine.SearchResult that still lives on the GPU: the same metric dictionaries (keys, order,
+    rounding) the reference evaluator gives for the submission built from that result, computed by xmlb_eval_first_hit.
+    gt_video_pos (Nq,) int: corpus position (index into video_metas) of each query's ground-truth video; gt_ts
+    (Nq, 2) float seconds; desc_types (Nq,) ints 0 / 1 / 2 = "v" / "t" / "vt" (None: no by-type metrics).
+    -> OrderedDict like eval_retrieval's (tasks present in `result`, or the given subset)."""
+    import torch
+    from . import _lib
+    dev = result.top_video_idx.device if result.top_video_idx is not None else result.svmr_flat_idx.device
+    gt_vid = torch.as_tensor(gt_video_pos, device=dev).to(torch.int32).contiguous()
+    ts = torch.as_tensor(gt_ts, device=dev, dtype=torch.float32)
+    gs, ge = ts[:, 0].contiguous(), ts[:, 1].contiguous()
+    thds = torch.tensor(list(iou_thds), device=dev, dtype=torch.float32)
+    nq = len(gt_vid)
+    stream = torch.cuda.current_stream().cuda_stream
+    types = None if desc_types is None else np.asarray(desc_types)
+
+    def first_hit(mode, vid, st=None, ed=None):
+        n_thd = 1 if mode == 2 else len(iou_thds)
+        vid = vid[:, :max_pred_per_query].to(torch.int32).contiguous()
+        st = None if st is None else st[:, :max_pred_per_query].contiguous()
+        ed = None if ed is None else ed[:, :max_pred_per_query].contiguous()
+        out = torch.empty(nq, n_thd, device=dev, dtype=torch.int32)
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        rc = _lib.lib().xmlb_eval_first_hit(p(vid), p(st), p(ed), None, p(gt_vid), p(gs), p(ge), p(thds), n_thd, nq,
+                                            vid.shape[1], mode, p(out), stream)
+        _lib.check(rc, "xmlb_eval_first_hit")
+        return out.cpu().numpy()
+
+    def metrics_of(fh, prefixes):
+        overall, by_type = OrderedDict(), OrderedDict()
+        for j, prefix in enumerate(prefixes):
+            for k in recall_topks:
+                overall["{}r{}".format(prefix, k)] = get_rounded_percentage(np.mean(fh[:, j] < k))
+        if types is not None:
+            for name, t in DESC_TYPE2IDX.items():
+                sel = types == t
+                for j, prefix in enumerate(prefixes):
+                    for k in recall_topks:
+                        with np.errstate(invalid="ignore", divide="ignore"):
+                            by_type["{}-{}r{}".format(name, prefix, k)] = get_rounded_percentage(
+                                1.0 * np.sum((fh[:, j] < k) & sel) / np.sum(sel))
+            by_type["desc_type_ratio"] = "v {} t {} vt {}".format(
+                *[get_rounded_percentage(1.0 * np.sum(types == DESC_TYPE2IDX[k]) / len(types)) for k in ["v", "t", "vt"]])
+        return overall, by_type
+
+    raw = OrderedDict()
+    span_prefixes = ["{}-".format(t) for t in iou_thds]
+    cells = ctx_len * ctx_len
+    want = lambda t: tasks is None or t in tasks  # noqa: E731
+    if result.span_flat_idx is not None and want("VCMR"):
+        flat = result.span_flat_idx.long()
+        rank, rem = flat // cells, flat % cells
+        vid = torch.gather(result.top_video_idx.long(), 1, rank)
+        st = (rem // ctx_len).float() * clip_length
+        ed = (rem % ctx_len).float() * clip_length + clip_length
+        raw["VCMR"] = metrics_of(first_hit(0, vid, st, ed), span_prefixes)
+    if result.svmr_flat_idx is not None and want("SVMR"):
+        flat = result.svmr_flat_idx.long()
+        st = (flat // ctx_len).float() * clip_length
+        ed = ((flat % ctx_len) + 1).float() * clip_length
+        vid = gt_vid.view(-1, 1).expand_as(flat)  # SVMR predictions are made on the ground-truth video
+        raw["SVMR"] = metrics_of(first_hit(1, vid, st, ed), span_prefixes)
+    if result.top_video_idx is not None and want("VR"):
+        raw["VR"] = metrics_of(first_hit(2, result.top_video_idx), [""])
+    out = OrderedDict((t, raw[t][0]) for t in TASK_TYPES if t in raw)
+    if types is not None:
+        for t in TASK_TYPES:
+            if t in raw:
+                out[t + "_by_type"] = raw[t][1]
+    return out

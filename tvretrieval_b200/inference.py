@@ -272,6 +272,32 @@ def get_eval_res(model, eval_dataset, opt, tasks, max_after_nms):
     return eval_res
 
 
+def eval_metrics_device(model, eval_dataset, opt, tasks=("SVMR", "VCMR", "VR"), ctx_info=None, max_after_nms=100):
+    """Per-epoch validation metrics without prediction lists: the retrieval of get_eval_res on the device and the
+    metrics of standalone_eval.eval_retrieval (reference inference.py:489-500 on top of eval.py:83-276) computed from
+    the engine's device tensors by xmlb_eval_first_hit -- the numbers eval_epoch writes to *_metrics.json, at the cost
+    of the search itself (the list building and the Python evaluator take ~1 s per 10 K queries).  Ground truth comes
+    from eval_dataset.query_data (vid_name, ts, type), like in the reference.  No NMS, top-100 predictions."""
+    from .eval_metrics import DESC_TYPE2IDX, eval_search_result_device
+    model.eval()
+    if ctx_info is None:
+        ctx_info = compute_context_info(model, eval_dataset, opt)
+    query_metas, qfeat, qmask = _gather_queries(eval_dataset, opt, True)
+    searcher = _searcher(model, opt, ctx_info, opt.max_before_nms, opt.max_vcmr_video)
+    meta_idx = {m["vid_name"]: i for i, m in enumerate(ctx_info["video_metas"])}
+    gt_by_id = {q["desc_id"]: q for q in eval_dataset.query_data}
+    gts = [gt_by_id[m["desc_id"]] for m in query_metas]
+    gt = torch.tensor([meta_idx[g["vid_name"]] for g in gts], dtype=torch.int32)
+    run_tasks = tuple(t for t in ("VCMR", "VR", "SVMR") if t in tasks)
+    dev = searcher.index.device
+    with torch.no_grad():
+        res = searcher.search(qfeat.to(dev), qmask.to(dev), gt.to(dev), run_tasks)
+    use_types = all("type" in g for g in gts)
+    return eval_search_result_device(res, gt, [g["ts"] for g in gts], searcher.index.ctx_len, opt.clip_length,
+                                     desc_types=[DESC_TYPE2IDX[g["type"]] for g in gts] if use_types else None,
+                                     max_pred_per_query=min(100, max_after_nms), tasks=run_tasks)
+
+
 # ------------------------------------------------------------------------------------------------ post-processing
 def get_submission_top_n(submission, top_n=100):
     """reference baselines/clip_alignment_with_language/inference.py:503-515."""
