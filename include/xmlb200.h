@@ -96,6 +96,10 @@ int xmlb_split_rows(const float* x, const int* row_index, long long n_groups, in
                     int kpad, int out_ld, int out_col0, int normalize, int is_bf16, unsigned short* hi,
                     unsigned short* lo, float* hi_err, void* stream);
 int xmlb_mask_bits(const float* mask, int n_videos, int ctx_len, int lp, unsigned int* bits, void* stream);
+/* Transposing split: x (rows, cols) fp32 -> hi, lo (cols, rpad) uint16 with hi[c][r] + lo[c][r] ~= x[r][c]; columns
+ * r >= rows are zero (rpad multiple of 64, >= rows).  Operands of the dW = dY^T . X GEMM of the training step. */
+int xmlb_split_rows_t(const float* x, long long rows, int cols, long long rpad, int is_bf16, unsigned short* hi,
+                      unsigned short* lo, void* stream);
 /* dst_{hi,lo}[r] = src_{hi,lo}[row_index[r]] for rows of kpad 16-bit elements (negative index: row left untouched):
  * brings operands that were split once (queries of a block) into inverted-list order for xmlb_vr_rescore_tc and
  * xmlb_span_probs_tc -- same bits as xmlb_split_rows with row_index, without re-reading the fp32 rows. */

@@ -103,11 +103,18 @@ class _Linear(torch.autograd.Function):
         # kind::f16 MMA cannot mix fp16 and bf16 operands)
         if prec == "f16x3":
             prec = "bf16x3"
+        from . import ops
         with torch.no_grad():
             if ctx.needs_input_grad[1]:
                 dx = lin(g2, weight.t().contiguous(), None, None, False, prec).view(x.shape)      # dY . W
             if ctx.needs_input_grad[2]:
-                dw = lin(g2.t().contiguous(), x2.t().contiguous(), None, None, False, prec)       # dY^T . X
+                if prec != "f32" and out_dim >= 16 and g2.shape[0] >= 256 and g2.is_cuda:
+                    # dY^T . X on the tensor cores: both operands transposed AND split in one pass each
+                    bf16 = prec == "bf16x3"
+                    dw, _, _ = ops.linear_tc_ex(ops.split_rows_t(g2, bf16=bf16), ops.split_rows_t(x2, bf16=bf16),
+                                                bf16=bf16)
+                else:
+                    dw = lin(g2.t().contiguous(), x2.t().contiguous(), None, None, False, prec)   # dY^T . X
             if ctx.has_bias and ctx.needs_input_grad[3]:
                 db = g2.sum(0)
             if ctx.has_res and ctx.needs_input_grad[4]:

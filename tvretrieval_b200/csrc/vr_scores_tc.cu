@@ -480,6 +480,51 @@ __global__ void __launch_bounds__(256) gather_rows16_kernel(const uint4* __restr
   }
 }
 
+// Transposing split: x (rows, cols) fp32 -> hi / lo (cols, rpad) 16-bit with hi[c][r] + lo[c][r] ~= x[r][c], columns
+// r >= rows zero-filled (rpad multiple of 64).  One pass through a 32 x 33 shared-memory tile instead of a transposing
+// copy followed by xmlb_split_rows: the operands of the dW = dY^T . X GEMM of the training step (K = rows).
+template <bool BF16>
+__global__ void __launch_bounds__(256) split_rows_t_kernel(const float* __restrict__ x, long long rows, int cols,
+                                                           long long rpad, unsigned short* __restrict__ hi,
+                                                           unsigned short* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const long long r0 = blockIdx.y * 32ll;
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const long long r = r0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? __ldg(x + r * cols + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long r = r0 + tx;
+    if (c < cols && r < rpad) {
+      unsigned short a, b;
+      split16<BF16>(tile[tx][j], a, b);
+      hi[c * rpad + r] = a, lo[c * rpad + r] = b;
+    }
+  }
+}
+
+extern "C" int xmlb_split_rows_t(const float* x, long long rows, int cols, long long rpad, int is_bf16,
+                                 unsigned short* hi, unsigned short* lo, void* stream) {
+  XMLB_REQUIRE(x && hi && lo, "xmlb_split_rows_t: null pointer");
+  XMLB_REQUIRE(rows >= 1 && cols >= 1 && rpad >= rows && rpad % 64 == 0, "xmlb_split_rows_t: rpad must be a multiple of 64, >= rows");
+  XMLB_REQUIRE((rpad + 31) / 32 <= 65535, "xmlb_split_rows_t: too many rows");
+  const dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)((rpad + 31) / 32));
+  if (is_bf16)
+    split_rows_t_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, rpad, hi, lo);
+  else
+    split_rows_t_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, rpad, hi, lo);
+  xmlb_count_launch(1);
+  XMLB_LAUNCH_CHECK();
+  return XMLB_OK;
+}
+
 extern "C" int xmlb_gather_rows16(const unsigned short* src_hi, const unsigned short* src_lo, const int* row_index,
                                   long long rows_out, int kpad, unsigned short* dst_hi, unsigned short* dst_lo,
                                   void* stream) {

@@ -438,6 +438,18 @@ def split_rows(x, group_in=1, group_out=1, kpad=None, normalize=False, bf16=Fals
     return (hi, lo, err) if hi_err else (hi, lo)
 
 
+def split_rows_t(x, bf16=False):
+    """x (rows, cols) fp32 -> (hi, lo) int16 (cols, pad64(rows)) of the TRANSPOSE (xmlb_split_rows_t)."""
+    x = _f32(x, "x")
+    rows, cols = x.shape
+    rpad = pad64(rows)
+    hi = torch.empty(cols, rpad, device=x.device, dtype=torch.int16)
+    lo = torch.empty_like(hi)
+    rc = _lib.lib().xmlb_split_rows_t(_p(x), rows, cols, rpad, int(bf16), _p(hi), _p(lo), _stream())
+    _lib.check(rc, "xmlb_split_rows_t")
+    return hi, lo
+
+
 def gather_rows16(src, row_index):
     """src = (hi, lo) int16 (rows, kpad) -> (hi, lo) gathered at row_index (int32; negative = row left unwritten)."""
     row_index = _i32(row_index, "row_index")
