@@ -287,11 +287,26 @@ class ShardedSearcher(VCMRSearcher):
         self.group = group
         self.plan = ShardPlan(n_videos_total, dist.get_world_size(group), dist.get_rank(group))
         self.peer = None
-        if transport is None:
+        auto = transport is None
+        if auto:
             transport = "peer" if (dist.get_backend(group) == "nccl" and self.plan.world_size <= 8) else "collective"
         if transport == "peer":
-            self.peer = PeerExchange(group, index.device, self.plan, self.query_chunk, model.config.hidden_size,
-                                     self.max_n_videos, self.max_before_nms)
+            try:
+                self.peer = PeerExchange(group, index.device, self.plan, self.query_chunk, model.config.hidden_size,
+                                         self.max_n_videos, self.max_before_nms)
+            except Exception as exc:  # no peer access between the GPUs / symmetric memory not available
+                if not auto:
+                    raise
+                import sys
+                print("xmlb200: symmetric memory unavailable (%s: %s); list exchanges use torch.distributed collectives"
+                      % (type(exc).__name__, exc), file=sys.stderr)
+                ok = torch.zeros(1, device=index.device)
+            else:
+                ok = torch.ones(1, device=index.device)
+            if auto:  # every rank must use the same transport
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                if float(ok) == 0:
+                    self.peer, transport = None, "collective"
         self.transport = transport
         lo, hi = self.plan.video_range()
         assert index.vid_lo == lo and index.n_videos == hi - lo, "index does not hold this rank's shard"
