@@ -388,6 +388,43 @@ int xmlb_attention_train(const float* q, const float* k, const float* v, const f
                          int batch, int len_q, int len_k, int hidden, int n_heads, float dropout_p,
                          unsigned long long seed, unsigned long long index0, void* stream);
 
+/* ---- backward kernels of the training step (everything that is not a Linear layer; fp32, deterministic) ----------
+ * xmlb_sum_rows: out[p][c] = sum_g in[(g * group_rows + p) * dim + c] in a fixed order (bias / LayerNorm / position
+ *   table / ConvSE gradients); ws: 2 * ceil(n_groups / 64) * group_rows * dim floats (NULL when n_groups <= 64).
+ * xmlb_layernorm_backward: for y = LN(x + add[r % add_rows]) * gamma + beta (xmlb_add_layernorm): dx = gradient w.r.t.
+ *   (x + add), dy_xhat = dy * xhat (column sums = dgamma; column sums of dy = dbeta).
+ * xmlb_l2norm_backward, xmlb_relu_backward (dx = out > 0 ? g : 0): the obvious ones.
+ * xmlb_modular_pool_backward: d_encoded and dlogit (n, len, 2) of xmlb_modular_pool; xmlb_modular_mapping_grad:
+ *   dW (n_mod, hidden) = dlogit^T . encoded.
+ * xmlb_vr_scores_backward: one modality of xmlb_vr_scores_f32 for the in-batch (Nq, Nv) scores: g (Nq, Nv) upstream
+ *   gradient, scale = 1 / number of modalities; dq (Nq, H), dc (Nv, L, H) (fully written); argmax_ws Nq * Nv ints.
+ * xmlb_span_logits_diag_backward: xmlb_span_logits in diagonal list mode (item b on its own video), merged or separate
+ *   streams; dw_partial (n, 2 streams, 2 predictors, 31) per-item ConvSE weight gradients (sum with xmlb_sum_rows).
+ * xmlb_attention_backward: xmlb_attention / xmlb_attention_train; probabilities recomputed, dropout mask re-derived
+ *   from (seed, index0); ws_p / ws_g: batch * n_heads * len_q * len_k floats each. */
+int xmlb_sum_rows(const float* in, long long n_groups, int group_rows, int dim, float* out, float* ws, void* stream);
+int xmlb_layernorm_backward(const float* x, const float* add, long long add_rows, const float* gamma, const float* dy,
+                            long long rows, int dim, float eps, float* dx, float* dy_xhat, void* stream);
+int xmlb_l2norm_backward(const float* x, const float* dy, long long rows, int dim, float eps, float* dx, void* stream);
+int xmlb_relu_backward(const float* g, const float* out, long long n, float* dx, void* stream);
+int xmlb_modular_pool_backward(const float* encoded, const float* mask, const float* w_mod, const float* dout0,
+                               const float* dout1, int n_queries, int len, int hidden, int n_mod, float* d_encoded,
+                               float* dlogit, void* stream);
+int xmlb_modular_mapping_grad(const float* dlogit, const float* encoded, long long rows, int hidden, int n_mod, float* dw,
+                              void* stream);
+int xmlb_vr_scores_backward(const float* q_n, const float* c_n, const float* mask, const float* g, float scale,
+                            int n_queries, int n_videos, int ctx_len, int hidden, int* argmax_ws, float* dq, float* dc,
+                            void* stream);
+int xmlb_span_logits_diag_backward(const float* q_a, const float* q_b, const float* feat2_a, const float* feat2_b,
+                                   const float* mask_a, const float* mask_b, const float* w_st_a, const float* w_ed_a,
+                                   const float* w_st_b, const float* w_ed_b, int ksize, int merged, int n, int ctx_len,
+                                   int hidden, const float* dst, const float* ded, float* dq_a, float* dq_b,
+                                   float* dfeat2_a, float* dfeat2_b, float* dw_partial, void* stream);
+int xmlb_attention_backward(const float* q, const float* k, const float* v, const float* mask,
+                            long long mask_batch_stride, long long mask_q_stride, const float* dout, float* dq, float* dk,
+                            float* dv, float* ws_p, float* ws_g, int batch, int len_q, int len_k, int hidden, int n_heads,
+                            float dropout_p, unsigned long long seed, unsigned long long index0, void* stream);
+
 /* One BertAdam.step (optimization.py:273-338) over all parameter tensors in two launches.
  * chunk_table: n_chunks rows of 6 x int64 {param*, grad*, m*, v* (offset to the chunk), elements, tensor id};
  * tensor_table: n_tensors rows of {int first_chunk, int n_chunks, float lr_scheduled, float weight_decay};

@@ -3,16 +3,18 @@ driven by train.py:77-85) needs on top of the inference kernels.
 
 Forward values always come from the CUDA kernels (include/xmlb200.h).  Backward:
   * Linear layers -- the bulk of the FLOPs -- use the same kernels: dX = dY . W and dW = dY^T . X are two more calls
-    of xmlb_linear / xmlb_linear_tc on transposed operands;
+    of xmlb_linear / xmlb_linear_tc (operands transposed and split by xmlb_split_rows_t);
   * every other op (LayerNorm, attention core, modular pooling, L2 normalisation, masked-max video scores,
-    similarity + ConvSE) is differentiated by RECOMPUTATION: its saved inputs are pushed through the equivalent
-    torch expression under autograd (SURVEY.md section 8f rank 3 allows either).  Hand-written backward kernels for
-    these memory-bound ops are future work; nothing here runs on the CPU.
+    similarity + ConvSE, ReLU masks, bias / LayerNorm / position-table / ConvSE reductions) has a hand-written
+    backward kernel (csrc/backward.cu; BACKWARD = "kernels", the default).  BACKWARD = "twins" differentiates them by
+    recomputing the equivalent torch expression under autograd instead -- kept only so that the tests can compare
+    the two op by op.
 Inference never enters this module: the dispatch in ops.py only routes here when autograd is recording.
 """
 import torch
 import torch.nn.functional as F
 
+BACKWARD = "kernels"   # or "twins" (torch recomputation; test reference)
 MASK_FILL = -1e10      # reference model_xml.py:640-641
 ATT_MASK_FILL = -10000.0  # reference model_components.py:277
 
@@ -93,7 +95,7 @@ class _Linear(torch.autograd.Function):
         lin = ctx.kernel_fn
         g = g.contiguous()
         if ctx.relu:
-            g = g * (out > 0)
+            g = _relu_backward(g, out) if BACKWARD == "kernels" else g * (out > 0)
         out_dim, in_dim = weight.shape
         g2, x2 = g.reshape(-1, out_dim), x.reshape(-1, in_dim)
         dx = dw = db = dres = None
@@ -116,7 +118,7 @@ class _Linear(torch.autograd.Function):
                 else:
                     dw = lin(g2.t().contiguous(), x2.t().contiguous(), None, None, False, prec)   # dY^T . X
             if ctx.has_bias and ctx.needs_input_grad[3]:
-                db = g2.sum(0)
+                db = _sum_rows(g2).view(-1) if BACKWARD == "kernels" else g2.sum(0)
             if ctx.has_res and ctx.needs_input_grad[4]:
                 dres = g
         return None, dx, dw, db, dres, None, None
@@ -141,6 +143,260 @@ class Dropout(torch.autograd.Function):
         from . import ops
         with torch.no_grad():
             return ops.dropout(g.contiguous(), *ctx.args), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ backward kernels
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _sum_rows(t, group_rows=1):
+    """t (n_groups * group_rows, dim) -> (group_rows, dim): out[p] = sum_g t[g * group_rows + p], fixed order."""
+    from . import _lib
+    t = t.contiguous()
+    dim = t.shape[-1]
+    n_groups = t.numel() // dim // group_rows
+    out = torch.empty(group_rows, dim, device=t.device, dtype=torch.float32)
+    ws = None
+    if n_groups > 64:
+        ws = torch.empty(2 * ((n_groups + 63) // 64) * group_rows * dim, device=t.device, dtype=torch.float32)
+    _lib.check(_lib.lib().xmlb_sum_rows(_p(t), n_groups, group_rows, dim, _p(out), _p(ws), _stream()), "xmlb_sum_rows")
+    return out
+
+
+def _relu_backward(g, out):
+    from . import _lib
+    dx = torch.empty_like(g)
+    _lib.check(_lib.lib().xmlb_relu_backward(_p(g), _p(out.contiguous()), g.numel(), _p(dx), _stream()),
+               "xmlb_relu_backward")
+    return dx
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kernel_fn, x, gamma, beta, add, add_rows, eps):
+        out = kernel_fn(x, gamma, beta, add=add, add_rows=add_rows, eps=eps)
+        ctx.save_for_backward(x, gamma, add)
+        ctx.add_rows, ctx.eps = add_rows, eps
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        x, gamma, add = ctx.saved_tensors
+        x, g = x.contiguous(), g.contiguous()
+        dim = x.shape[-1]
+        rows = x.numel() // dim
+        add_rows = ctx.add_rows
+        if add is not None and add_rows is None:
+            add_rows = add.numel() // dim
+        dx, dyx = torch.empty_like(x), torch.empty_like(x)
+        rc = _lib.lib().xmlb_layernorm_backward(_p(x), _p(add.contiguous()) if add is not None else None, add_rows or 0,
+                                                _p(gamma.contiguous()), _p(g), rows, dim, ctx.eps, _p(dx), _p(dyx),
+                                                _stream())
+        _lib.check(rc, "xmlb_layernorm_backward")
+        dgamma = _sum_rows(dyx.view(rows, dim)).view_as(gamma) if ctx.needs_input_grad[2] else None
+        dbeta = _sum_rows(g.view(rows, dim)).view_as(gamma) if ctx.needs_input_grad[3] else None
+        dadd = None
+        if add is not None and ctx.needs_input_grad[4]:
+            if add_rows == rows and add.numel() == x.numel():
+                dadd = dx.view_as(add)
+            else:  # a (position) table whose first add_rows rows were broadcast over the batch
+                dadd = torch.zeros_like(add)
+                dadd.view(-1, dim)[:add_rows] = _sum_rows(dx.view(rows, dim), group_rows=add_rows)
+        return None, (dx if ctx.needs_input_grad[1] else None), dgamma, dbeta, dadd, None, None
+
+
+class _L2Norm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kernel_fn, x, eps):
+        ctx.save_for_backward(x)
+        ctx.eps = eps
+        return kernel_fn(x, eps=eps)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        (x,) = ctx.saved_tensors
+        x, g = x.contiguous(), g.contiguous()
+        dim = x.shape[-1]
+        dx = torch.empty_like(x)
+        rc = _lib.lib().xmlb_l2norm_backward(_p(x), _p(g), x.numel() // dim, dim, ctx.eps, _p(dx), _stream())
+        _lib.check(rc, "xmlb_l2norm_backward")
+        return None, dx, None
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kernel_fn, q, k, v, mask3, n_heads, max_batch, dropout_p, seed):
+        ctx.save_for_backward(q, k, v, mask3)
+        ctx.args = (n_heads, max_batch, dropout_p, seed)
+        return kernel_fn(q, k, v, mask3, n_heads, max_batch=max_batch, dropout_p=dropout_p, seed=seed)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        q, k, v, mask3 = (t.contiguous() for t in ctx.saved_tensors)
+        n_heads, max_batch, dropout_p, seed = ctx.args
+        g = g.contiguous()
+        n, lq, hid = q.shape
+        lk = k.shape[1]
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        # same batch pieces (and dropout counter offsets) as the forward launch loop in ops.attention
+        step = max(1, min(max_batch, 65535 // n_heads, max(1, (1 << 28) // max(1, n_heads * lq * lk))))
+        ws = torch.empty(2, min(n, step) * n_heads * lq * lk, device=q.device, dtype=torch.float32)
+        mq = 0 if mask3.shape[1] == 1 else lk
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            rc = _lib.lib().xmlb_attention_backward(
+                _p(q[lo:hi]), _p(k[lo:hi]), _p(v[lo:hi]), _p(mask3[lo:hi]), mask3.shape[1] * lk, mq, _p(g[lo:hi]),
+                _p(dq[lo:hi]), _p(dk[lo:hi]), _p(dv[lo:hi]), _p(ws[0]), _p(ws[1]), hi - lo, lq, lk, hid, n_heads,
+                dropout_p, seed, lo * n_heads * lq * lk, _stream())
+            _lib.check(rc, "xmlb_attention_backward")
+        return None, dq, dk, dv, None, None, None, None, None
+
+
+class _ModularPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kernel_fn, encoded, mask, w_mod):
+        ctx.save_for_backward(encoded, mask, w_mod)
+        return kernel_fn(encoded, mask, w_mod)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from . import _lib
+        encoded, mask, w_mod = (t.contiguous() for t in ctx.saved_tensors)
+        n, length, hid = encoded.shape
+        n_mod = w_mod.shape[0]
+        gs = [(g.contiguous() if g is not None else torch.zeros(n, hid, device=encoded.device)) for g in grads[:n_mod]]
+        d_enc = torch.empty_like(encoded)
+        dlogit = torch.empty(n, length, 2, device=encoded.device, dtype=torch.float32)
+        rc = _lib.lib().xmlb_modular_pool_backward(_p(encoded), _p(mask), _p(w_mod), _p(gs[0]),
+                                                   _p(gs[1]) if n_mod == 2 else None, n, length, hid, n_mod, _p(d_enc),
+                                                   _p(dlogit), _stream())
+        _lib.check(rc, "xmlb_modular_pool_backward")
+        dw = None
+        if ctx.needs_input_grad[3]:
+            dw = torch.empty_like(w_mod)
+            rc = _lib.lib().xmlb_modular_mapping_grad(_p(dlogit), _p(encoded), n * length, hid, n_mod, _p(dw), _stream())
+            _lib.check(rc, "xmlb_modular_mapping_grad")
+        return None, d_enc, None, dw
+
+
+class _VrScores(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kernel_fn, q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask):
+        ctx.save_for_backward(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask)
+        return kernel_fn(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask)
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        qv, qs, cv, cs, mv, ms = ctx.saved_tensors
+        g = g.contiguous()
+        n_mod = (qv is not None) + (qs is not None)
+        grads = {}
+        for name, q, c, m in (("v", qv, cv, mv), ("s", qs, cs, ms)):
+            if q is None:
+                grads[name] = (None, None)
+                continue
+            q, c, m = q.contiguous(), c.contiguous(), m.contiguous()
+            nq, hid = q.shape
+            nv, length, _ = c.shape
+            dq, dc = torch.empty_like(q), torch.empty_like(c)
+            arg = torch.empty(nq * nv, device=q.device, dtype=torch.int32)
+            rc = _lib.lib().xmlb_vr_scores_backward(_p(q), _p(c), _p(m), _p(g), 1.0 / n_mod, nq, nv, length, hid, _p(arg),
+                                                    _p(dq), _p(dc), _stream())
+            _lib.check(rc, "xmlb_vr_scores_backward")
+            grads[name] = (dq, dc)
+        return None, grads["v"][0], grads["s"][0], grads["v"][1], grads["s"][1], None, None
+
+
+class _SpanLogitsDiag(torch.autograd.Function):
+    """ops.span_logits in diagonal list mode without softmax (XML.forward, cross=False)."""
+
+    @staticmethod
+    def forward(ctx, kernel_fn, lists, merged, q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b, feat2_b, mask_b, w_st_b, w_ed_b):
+        ctx.save_for_backward(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b, feat2_b, mask_b, w_st_b, w_ed_b)
+        ctx.merged = merged
+        return kernel_fn(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b=q_b, feat2_b=feat2_b, mask_b=mask_b, w_st_b=w_st_b,
+                         w_ed_b=w_ed_b, merged=merged, softmax=False, lists=lists)
+
+    @staticmethod
+    def backward(ctx, dst, ded):
+        from . import _lib
+        q_a, f2_a, mask_a, w_st_a, w_ed_a, q_b, f2_b, mask_b, w_st_b, w_ed_b = ctx.saved_tensors
+        c = lambda t: None if t is None else t.contiguous()  # noqa: E731
+        q_a, f2_a, mask_a, q_b, f2_b, mask_b = map(c, (q_a, f2_a, mask_a, q_b, f2_b, mask_b))
+        n, length, hid = f2_a.shape
+        dev = q_a.device
+        zeros = lambda: torch.zeros(n, length, device=dev)  # noqa: E731
+        dst = dst.contiguous() if dst is not None else zeros()
+        ded = ded.contiguous() if ded is not None else zeros()
+        ksize = w_st_a.numel()
+        flat = lambda t: None if t is None else t.reshape(-1).contiguous()  # noqa: E731
+        dq_a, df_a = torch.empty_like(q_a), torch.empty_like(f2_a)
+        dq_b = torch.empty_like(q_b) if q_b is not None else None
+        df_b = torch.empty_like(f2_b) if f2_b is not None else None
+        dw = torch.empty(n, 4 * 31, device=dev, dtype=torch.float32)
+        ws = [flat(w_st_a), flat(w_ed_a), flat(w_st_b), flat(w_ed_b)]
+        rc = _lib.lib().xmlb_span_logits_diag_backward(
+            _p(q_a), _p(q_b), _p(f2_a), _p(f2_b), _p(mask_a), _p(mask_b), _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]),
+            ksize, int(ctx.merged), n, length, hid, _p(dst), _p(ded), _p(dq_a), _p(dq_b), _p(df_a), _p(df_b), _p(dw),
+            _stream())
+        _lib.check(rc, "xmlb_span_logits_diag_backward")
+        dws = _sum_rows(dw).view(2, 2, 31)[:, :, :ksize]  # [stream][start | end][tap]
+        gw = lambda w, x, which: None if w is None else dws[x, which].reshape(w.shape).clone()  # noqa: E731
+        return (None, None, None, dq_a, df_a, None, gw(w_st_a, 0, 0), gw(w_ed_a, 0, 1), dq_b, df_b, None,
+                gw(w_st_b, 1, 0), gw(w_ed_b, 1, 1))
+
+
+# ---- dispatch used by ops.py (kernels by default; torch twins for the op-by-op comparison tests) ----------------
+def add_layernorm(kernel_fn, x, gamma, beta, add, add_rows, eps):
+    if BACKWARD == "kernels":
+        return _AddLayerNorm.apply(kernel_fn, x, gamma, beta, add, add_rows, eps)
+    return recompute_op(kernel_fn, t_add_layernorm, (x, gamma, beta), dict(add=add, add_rows=add_rows, eps=eps))
+
+
+def l2norm_rows(kernel_fn, x, eps):
+    if BACKWARD == "kernels":
+        return _L2Norm.apply(kernel_fn, x, eps)
+    return recompute_op(kernel_fn, t_l2norm_rows, (x,), dict(eps=eps))
+
+
+def attention(kernel_fn, q, k, v, mask3, n_heads, max_batch, dropout_p, seed):
+    if BACKWARD == "kernels":
+        return _Attention.apply(kernel_fn, q, k, v, mask3, n_heads, max_batch, dropout_p, seed)
+    return recompute_op(kernel_fn, t_attention, (q, k, v, mask3, n_heads),
+                        dict(max_batch=max_batch, dropout_p=dropout_p, seed=seed))
+
+
+def modular_pool(kernel_fn, encoded, mask, w_mod):
+    if BACKWARD == "kernels":
+        return _ModularPool.apply(kernel_fn, encoded, mask, w_mod)
+    return recompute_op(kernel_fn, t_modular_pool, (encoded, mask, w_mod), {})
+
+
+def vr_scores(kernel_fn, q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask):
+    if BACKWARD == "kernels":
+        return _VrScores.apply(kernel_fn, q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask)
+    return recompute_op(kernel_fn, t_vr_scores, (q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask),
+                        {})
+
+
+def span_logits(kernel_fn, q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b, feat2_b, mask_b, w_st_b, w_ed_b, merged, softmax,
+                lists, out_rows):
+    diagonal = lists is not None and getattr(lists, "diagonal", False)
+    if BACKWARD == "kernels" and diagonal and not softmax and out_rows is None:
+        return _SpanLogitsDiag.apply(kernel_fn, lists, merged, q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b, feat2_b, mask_b,
+                                     w_st_b, w_ed_b)
+    return recompute_op(kernel_fn, t_span_logits, (q_a, feat2_a, mask_a, w_st_a, w_ed_a),
+                        dict(q_b=q_b, feat2_b=feat2_b, mask_b=mask_b, w_st_b=w_st_b, w_ed_b=w_ed_b, merged=merged,
+                             softmax=softmax, lists=lists, out_rows=out_rows))
 
 
 # ------------------------------------------------------------------------------------------------ torch twins

@@ -74,3 +74,24 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else
     atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
+
+// Counter-based dropout mask (xmlb_dropout, xmlb_attention_train and their backward passes): keep(i) depends only on
+// (seed, i) -- two rounds of a 32-bit multiply-xorshift mix (the murmur3 finaliser) over both halves of the 64-bit
+// element index and seed, compared with p * 2^32 -- so no mask is ever stored.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long i, uint32_t threshold) {
+  uint32_t h = mix32((uint32_t)i ^ (uint32_t)seed);
+  h = mix32(h + 0x9E3779B9u * (uint32_t)(i >> 32) + (uint32_t)(seed >> 32));
+  return h >= threshold;
+}
+static inline uint32_t dropout_threshold(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+}

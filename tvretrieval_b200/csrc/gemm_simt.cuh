@@ -18,6 +18,7 @@ struct GemmParams {
   int M, N, K;
   long long lda, ldb, ldc;
   int b_is_kn;
+  int a_is_km;  // A stored [k][m] (lda = pitch between k rows): C = A^T-stored . B, the dW / dV / dK products of backward
   int batch1;  // blockIdx.z = b0 * batch1 + b1
   long long sA0, sA1, sB0, sB1, sC0, sC1;
   int epilogue;
@@ -54,12 +55,22 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
   float ra[A_PER], rb[B_PER];
 
   auto load_tiles = [&](int k0) {
+    if (!p.a_is_km) {
 #pragma unroll
-    for (int i = 0; i < A_PER; ++i) {
-      int idx = t + i * 256;
-      int k = idx % BK, m = idx / BK;
-      int gm = m0 + m, gk = k0 + k;
-      ra[i] = (gm < p.M && gk < p.K) ? __ldg(A + (long long)gm * p.lda + gk) : 0.f;
+      for (int i = 0; i < A_PER; ++i) {
+        int idx = t + i * 256;
+        int k = idx % BK, m = idx / BK;
+        int gm = m0 + m, gk = k0 + k;
+        ra[i] = (gm < p.M && gk < p.K) ? __ldg(A + (long long)gm * p.lda + gk) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        int idx = t + i * 256;
+        int m = idx % BM, k = idx / BM;
+        int gm = m0 + m, gk = k0 + k;
+        ra[i] = (gm < p.M && gk < p.K) ? __ldg(A + (long long)gk * p.lda + gm) : 0.f;
+      }
     }
     if (!p.b_is_kn) {
 #pragma unroll
@@ -80,10 +91,18 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
     }
   };
   auto store_tiles = [&](int buf) {
+    if (!p.a_is_km) {
 #pragma unroll
-    for (int i = 0; i < A_PER; ++i) {
-      int idx = t + i * 256;
-      As[buf][idx % BK][idx / BK] = ra[i];
+      for (int i = 0; i < A_PER; ++i) {
+        int idx = t + i * 256;
+        As[buf][idx % BK][idx / BK] = ra[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < A_PER; ++i) {
+        int idx = t + i * 256;
+        As[buf][idx / BM][idx % BM] = ra[i];
+      }
     }
     if (!p.b_is_kn) {
 #pragma unroll

@@ -7,22 +7,7 @@
 #include "xmlb200.h"
 
 // ---------------------------------------------------------------------------------------------- dropout
-// keep(i) depends only on (seed, i): two rounds of a 32-bit multiply-xorshift mix over both halves of the 64-bit
-// element index and seed (the murmur3 finaliser), compared with p * 2^32.
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {
-  h ^= h >> 16;
-  h *= 0x85EBCA6Bu;
-  h ^= h >> 13;
-  h *= 0xC2B2AE35u;
-  h ^= h >> 16;
-  return h;
-}
-__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long i, uint32_t threshold) {
-  uint32_t h = mix32((uint32_t)i ^ (uint32_t)seed);
-  h = mix32(h + 0x9E3779B9u * (uint32_t)(i >> 32) + (uint32_t)(seed >> 32));
-  return h >= threshold;
-}
-
+// keep(i) depends only on (seed, i): dropout_keep in common.cuh
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ out, long long n,
                                                       uint32_t threshold, float scale, unsigned long long seed,
                                                       unsigned long long index0) {

@@ -56,8 +56,7 @@ def _sched_ws(device):
 def add_layernorm(x, gamma, beta, add=None, add_rows=None, eps=1e-5):
     """LayerNorm(x + add[row % add_rows]) over the last dim."""
     if autograd.recording(x, gamma, beta, add):
-        return autograd.recompute_op(add_layernorm, autograd.t_add_layernorm, (x, gamma, beta),
-                                     dict(add=add, add_rows=add_rows, eps=eps))
+        return autograd.add_layernorm(add_layernorm, x, gamma, beta, add, add_rows, eps)
     x = _f32(x, "x")
     dim = x.shape[-1]
     rows = x.numel() // dim
@@ -249,8 +248,7 @@ def attention(q, k, v, mask3, n_heads, max_batch=8192, dropout_p=0.0, seed=0):
     """q (N, Lq, H), k/v (N, Lk, H), mask3 (N, 1 or Lq, Lk) float {0,1} -> (N, Lq, H).
     dropout_p > 0 (train mode): dropout on the attention probabilities with the counter-based mask of `seed`."""
     if autograd.recording(q, k, v):
-        return autograd.recompute_op(attention, autograd.t_attention, (q, k, v, mask3, n_heads),
-                                     dict(max_batch=max_batch, dropout_p=dropout_p, seed=seed))
+        return autograd.attention(attention, q, k, v, mask3, n_heads, max_batch, dropout_p, seed)
     q, k, v, mask3 = _f32(q, "q"), _f32(k, "k"), _f32(v, "v"), _f32(mask3, "mask")
     n, lq, hid = q.shape
     lk = k.shape[1]
@@ -361,7 +359,7 @@ def new_seed():
 def modular_pool(encoded, mask, w_mod):
     """-> (video_query, sub_query); the same vector twice for a single-modality model (model_xml.py:420-423)."""
     if autograd.recording(encoded, w_mod):
-        outs = autograd.recompute_op(_modular_pool_outputs, autograd.t_modular_pool, (encoded, mask, w_mod), {})
+        outs = autograd.modular_pool(_modular_pool_outputs, encoded, mask, w_mod)
     else:
         outs = _modular_pool_outputs(encoded, mask, w_mod)
     return (outs[0], outs[1]) if len(outs) == 2 else (outs[0], outs[0])
@@ -369,7 +367,7 @@ def modular_pool(encoded, mask, w_mod):
 
 def l2norm_rows(x, eps=1e-12):
     if autograd.recording(x):
-        return autograd.recompute_op(l2norm_rows, autograd.t_l2norm_rows, (x,), dict(eps=eps))
+        return autograd.l2norm_rows(l2norm_rows, x, eps)
     x = _f32(x, "x")
     out = torch.empty_like(x)
     dim = x.shape[-1]
@@ -390,8 +388,7 @@ def softmax_rows(x):
 def vr_scores_f32(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask):
     """-> q2c (Nq, Nv).  Inputs already L2-normalised; a modality is skipped when None."""
     if autograd.recording(q_video_n, q_sub_n, feat1_video_n, feat1_sub_n):
-        return autograd.recompute_op(vr_scores_f32, autograd.t_vr_scores,
-                                     (q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask), {})
+        return autograd.vr_scores(vr_scores_f32, q_video_n, q_sub_n, feat1_video_n, feat1_sub_n, video_mask, sub_mask)
     ref_q = q_video_n if q_video_n is not None else q_sub_n
     ref_c = feat1_video_n if feat1_video_n is not None else feat1_sub_n
     nq, hid = ref_q.shape
@@ -673,9 +670,8 @@ def span_logits(q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b=None, feat2_b=None, ma
                 merged=False, softmax=False, lists=None, out_rows=None):
     """Dense (lists=None): -> st, ed of shape (Nq, Nv, L).  List mode: -> (out_rows, L) each."""
     if autograd.recording(q_a, feat2_a, w_st_a, w_ed_a, q_b, feat2_b, w_st_b, w_ed_b):
-        return autograd.recompute_op(span_logits, autograd.t_span_logits, (q_a, feat2_a, mask_a, w_st_a, w_ed_a),
-                                     dict(q_b=q_b, feat2_b=feat2_b, mask_b=mask_b, w_st_b=w_st_b, w_ed_b=w_ed_b,
-                                          merged=merged, softmax=softmax, lists=lists, out_rows=out_rows))
+        return autograd.span_logits(span_logits, q_a, feat2_a, mask_a, w_st_a, w_ed_a, q_b, feat2_b, mask_b, w_st_b,
+                                    w_ed_b, merged, softmax, lists, out_rows)
     q_a, feat2_a = _f32(q_a, "q_a"), _f32(feat2_a, "feat2_a")
     nq, hid = q_a.shape
     nv, length, _ = feat2_a.shape
