@@ -18,14 +18,17 @@ using tc::BLOCK_K;
 using tc::BLOCK_M;
 constexpr int MAX_L = 256;  // clips per video: up to two 128-row accumulator halves per (video, query chunk)
 
+constexpr int N_BOXES = 8;  // A boxes of 16, 32, ..., 128 clip rows
 struct SpanTcMaps {
-  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  CUtensorMap a_hi[N_BOXES], a_lo[N_BOXES], b_hi, b_lo;
 };
 
 struct SpanTcParams {
   int n_videos, ctx_len, k_blocks, block_n, stages, ksize, softmax;
   int n_halves;          // 128-clip halves per video (2 when ctx_len > 128)
-  const int4* units;     // {video, first entry row, entries in this chunk, 0}
+  const int4* units;     // {video, first entry row, entries in this chunk, clip rows to load (clip_boxes) or 0}
+  int clip_boxes;        // 1: units[].w = number of leading clip rows of the video the epilogue can need (every
+                         // unmasked clip and its ConvSE neighbours); only those are loaded, in 16-row steps
   const int* n_units;    // device scalar
   const int* entry_out;  // [E] output row of each list entry
   const int* entry_q;    // [E] query of each list entry: the B rows are gathered in the kernel (null: pre-gathered)
@@ -55,7 +58,10 @@ struct SpanSched {
       if (u >= n_units) return false;
       m = __ldg(p->units + u);
     }
-    d.a_hi = &maps->a_hi, d.a_lo = &maps->a_lo, d.b_hi = &maps->b_hi, d.b_lo = &maps->b_lo;
+    int box = N_BOXES - 1;
+    if (p->clip_boxes) box = min(N_BOXES - 1, max(0, (m.w - half * BLOCK_M + 15) / 16 - 1));
+    d.a_hi = &maps->a_hi[box], d.a_lo = &maps->a_lo[box], d.b_hi = &maps->b_hi, d.b_lo = &maps->b_lo;
+    d.a_bytes = (box + 1) * 16 * tc::SWIZZLE_BYTES;
     d.a_row = m.x * p->ctx_len + half * BLOCK_M;
     d.b_row = m.y;
     d.g_count = m.z;
@@ -127,14 +133,18 @@ span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_const
           const int l = lane + 32 * c;
           st[c] = 0.f, ed[c] = 0.f;
           if (l < L) {
-            float a = 0.f, b = 0.f;
-            for (int t = 0; t < p.ksize; ++t) {
-              const int src = l + t - pad;
-              const float x = (src >= 0 && src < L) ? s[src] : 0.f;
-              a = fmaf(__ldg(p.w_st + t), x, a);
-              b = fmaf(__ldg(p.w_ed + t), x, b);
-            }
             const float mk = __ldg(p.mask + (long long)v * L + l);
+            float a = 0.f, b = 0.f;
+            // a masked clip is -1e10 whatever its (finite) logit: its similarity neighbourhood is not read -- with
+            // clip_boxes those rows may not have been loaded at all
+            if (mk != 0.f) {
+              for (int t = 0; t < p.ksize; ++t) {
+                const int src = l + t - pad;
+                const float x = (src >= 0 && src < L) ? s[src] : 0.f;
+                a = fmaf(__ldg(p.w_st + t), x, a);
+                b = fmaf(__ldg(p.w_ed + t), x, b);
+              }
+            }
             st[c] = mask_logit(a, mk), ed[c] = mask_logit(b, mk);
             mx_st = fmaxf(mx_st, st[c]), mx_ed = fmaxf(mx_ed, ed[c]);
           }
@@ -168,36 +178,42 @@ span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_const
   tc::pipe_teardown(tmem_base);
 }
 
-// units[chunk_ptr[v] + c] = {v, vid_ptr[v] + c * chunk, min(chunk, remaining), 0}
+// units[chunk_ptr[v] + c] = {v, vid_ptr[v] + c * chunk, min(chunk, remaining), video_rows ? video_rows[v] : 0}
 __global__ void span_units_kernel(const int* __restrict__ vid_ptr, const int* __restrict__ chunk_ptr, int n_videos,
-                                  int chunk, int4* __restrict__ units) {
+                                  int chunk, const int* __restrict__ video_rows, int4* __restrict__ units) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n_videos) return;
   const int e_lo = vid_ptr[v], e_hi = vid_ptr[v + 1];
+  const int rows = video_rows ? video_rows[v] : 0;
   int u = chunk_ptr[v];
-  for (int e = e_lo; e < e_hi; e += chunk, ++u) units[u] = make_int4(v, e, min(chunk, e_hi - e), 0);
+  for (int e = e_lo; e < e_hi; e += chunk, ++u) units[u] = make_int4(v, e, min(chunk, e_hi - e), rows);
 }
 
 }  // namespace
 
-extern "C" int xmlb_build_span_units(const int* vid_ptr, const int* chunk_ptr, int n_videos, int chunk, int* units,
-                                     void* stream) {
+extern "C" int xmlb_build_span_units_rows(const int* vid_ptr, const int* chunk_ptr, int n_videos, int chunk,
+                                          const int* video_rows, int* units, void* stream) {
   XMLB_REQUIRE(vid_ptr && chunk_ptr && units && n_videos > 0 && chunk > 0, "xmlb_build_span_units: bad argument");
   XMLB_REQUIRE(((uintptr_t)units & 15) == 0, "xmlb_build_span_units: units must be 16-byte aligned");
   span_units_kernel<<<ceil_div(n_videos, 256), 256, 0, (cudaStream_t)stream>>>(vid_ptr, chunk_ptr, n_videos, chunk,
-                                                                              reinterpret_cast<int4*>(units));
+                                                                              video_rows, reinterpret_cast<int4*>(units));
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
 }
 
-extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_lo,
-                                     const unsigned short* qg_hi, const unsigned short* qg_lo, const float* mask,
-                                     const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
-                                     int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
-                                     const int* n_units, int max_units, const int* entry_out, const int* entry_q,
-                                     int gather_warps, long long n_query_rows, float* out_st, float* out_ed,
-                                     int* sched_ws, int is_bf16, void* stream) {
+extern "C" int xmlb_build_span_units(const int* vid_ptr, const int* chunk_ptr, int n_videos, int chunk, int* units,
+                                     void* stream) {
+  return xmlb_build_span_units_rows(vid_ptr, chunk_ptr, n_videos, chunk, nullptr, units, stream);
+}
+
+extern "C" int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const unsigned short* f2_lo,
+                                          const unsigned short* qg_hi, const unsigned short* qg_lo, const float* mask,
+                                          const float* w_st, const float* w_ed, int ksize, int apply_softmax,
+                                          int n_videos, int ctx_len, int kcat, long long n_entries, int block_n,
+                                          const int* units, const int* n_units, int max_units, const int* entry_out,
+                                          const int* entry_q, int gather_warps, long long n_query_rows, int clip_boxes,
+                                          float* out_st, float* out_ed, int* sched_ws, int is_bf16, void* stream) {
   XMLB_REQUIRE(f2_hi && f2_lo && qg_hi && qg_lo && mask && w_st && w_ed && units && n_units && entry_out && out_st &&
                    out_ed && sched_ws, "xmlb_span_probs_tc: null pointer");
   XMLB_REQUIRE(ctx_len >= 1 && ctx_len <= MAX_L, "xmlb_span_probs_tc: ctx_len must be <= 256");
@@ -214,6 +230,8 @@ extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned
   const int s_ld = ctx_len <= 128 ? 132 : 260;
   p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out, p.entry_q = entry_q;
   p.gather_warps = entry_q && gather_warps ? 1 : 0, p.q_hi = qg_hi, p.q_lo = qg_lo, p.kcat = kcat;
+  XMLB_REQUIRE(!clip_boxes || p.gather_warps, "xmlb_span_probs_tc: clip_boxes needs the gather-warps mode");
+  p.clip_boxes = clip_boxes ? 1 : 0;
   p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed, p.unit_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
   const int extra = block_n * s_ld * (int)sizeof(float);
@@ -227,8 +245,10 @@ extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned
   // gather mode: the B maps address single rows of the (n_query_rows, kcat) query arrays (TMA gather4)
   const unsigned long long b_rows = entry_q ? (unsigned long long)n_query_rows : (unsigned long long)n_entries;
   const unsigned int b_box = entry_q ? 1u : (unsigned int)block_n;
-  if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi, f2_hi, corpus_rows, kcat, BLOCK_M, BLOCK_K))) return rc;
-  if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo, f2_lo, corpus_rows, kcat, BLOCK_M, BLOCK_K))) return rc;
+  for (int b = clip_boxes ? 0 : N_BOXES - 1; b < N_BOXES; ++b) {  // box b: the first 16 (b + 1) clip rows of a tile
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[b], f2_hi, corpus_rows, kcat, 16 * (b + 1), BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[b], f2_lo, corpus_rows, kcat, 16 * (b + 1), BLOCK_K))) return rc;
+  }
   if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi, qg_hi, b_rows, kcat, b_box, BLOCK_K))) return rc;
   if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo, qg_lo, b_rows, kcat, b_box, BLOCK_K))) return rc;
 
@@ -248,6 +268,18 @@ extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
+}
+
+extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_lo,
+                                     const unsigned short* qg_hi, const unsigned short* qg_lo, const float* mask,
+                                     const float* w_st, const float* w_ed, int ksize, int apply_softmax, int n_videos,
+                                     int ctx_len, int kcat, long long n_entries, int block_n, const int* units,
+                                     const int* n_units, int max_units, const int* entry_out, const int* entry_q,
+                                     int gather_warps, long long n_query_rows, float* out_st, float* out_ed,
+                                     int* sched_ws, int is_bf16, void* stream) {
+  return xmlb_span_probs_tc_clipped(f2_hi, f2_lo, qg_hi, qg_lo, mask, w_st, w_ed, ksize, apply_softmax, n_videos,
+                                    ctx_len, kcat, n_entries, block_n, units, n_units, max_units, entry_out, entry_q,
+                                    gather_warps, n_query_rows, 0, out_st, out_ed, sched_ws, is_bf16, stream);
 }
 
 extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,

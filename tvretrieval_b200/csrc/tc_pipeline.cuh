@@ -43,6 +43,8 @@ struct UnitDesc {
   int k_blocks;       // number of BLOCK_K-wide k-blocks to accumulate (> 0)
   int k_block0;       // first k-block (K-chunked accumulation: a unit may cover only a slice of K); 0 by default
   int g_count;        // gather producer only: number of valid list entries of the gathered operand's tile
+  int a_bytes;        // bytes one A box (hi or lo) delivers: A_TILE_BYTES unless the unit's A maps have a shorter box
+                      // (honoured on the gather-warps path, p.gather == 2, only)
   uint32_t idesc;     // instruction descriptor (carries N of this unit)
   int tag0, tag1;     // kernel-specific payload handed to the epilogue (tile index, modality, ...)
 };
@@ -152,7 +154,7 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
   int stage = 0;
   uint32_t phase = 0, n = 0;
   UnitDesc u;
-  u.k_block0 = 0;
+  u.k_block0 = 0, u.a_bytes = A_TILE_BYTES;
   const uint64_t stream_policy = l2_policy_evict_first();
   while (sched.next(u)) {
     queue_push(p, n++, u.tag0, u.tag1, u.k_blocks, u.idesc);
@@ -168,7 +170,7 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
           tma_load_2d_hint(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row,
                            stream_policy);
         } else {
-          mbar_expect_tx(p.full_bar(stage), 2u * A_TILE_BYTES);
+          mbar_expect_tx(p.full_bar(stage), 2u * (uint32_t)u.a_bytes);
           tma_load_2d_hint(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row, stream_policy);
           tma_load_2d_hint(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row, stream_policy);
         }
