@@ -248,6 +248,9 @@ int xmlb_build_pair_lists(const int* top_idx, const unsigned char* slot_valid, i
  * order (xmlb_split_rows with row_index = entry_q).  ctx_len <= 128; block_n in {32, 64, 128} = chunk. */
 int xmlb_build_span_units(const int* vid_ptr, const int* chunk_ptr, int n_videos, int chunk, int* units,
                           void* stream);
+/* ... with units[].w = video_rows[v] (NULL: 0), the operand rows xmlb_span_probs_tc_clipped loads for video v */
+int xmlb_build_span_units_rows(const int* vid_ptr, const int* chunk_ptr, int n_videos, int chunk,
+                               const int* video_rows, int* units, void* stream);
 int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo, const unsigned short* qg_hi,
                        const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
                        int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,
@@ -274,6 +277,18 @@ int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_
                           int block_n, const int* units, const int* n_units, int max_units, const int* entry_out,
                           const int* entry_q, int gather_warps, long long n_query_rows, float* out_st, float* out_ed,
                           int* sched_ws, int is_bf16, void* stream);
+
+/* xmlb_span_probs_tc_ex with clip_boxes != 0 (gather-warps mode only): units[].w (xmlb_build_span_units_rows) is the
+ * number of leading clip rows of the video whose similarity the epilogue can need -- (last unmasked clip + 1 +
+ * ksize / 2), at most ctx_len.  Only those rows of f2_* are loaded (TMA boxes of 16, 32, ..., 128 rows picked per
+ * unit) instead of all ctx_len padded rows; masked clips never read their neighbourhood (mask_logits gives -1e10
+ * for any finite logit, model_xml.py:640-641), so the results are identical. */
+int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const unsigned short* f2_lo, const unsigned short* qg_hi,
+                               const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
+                               int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,
+                               int block_n, const int* units, const int* n_units, int max_units, const int* entry_out,
+                               const int* entry_q, int gather_warps, long long n_query_rows, int clip_boxes,
+                               float* out_st, float* out_ed, int* sched_ws, int is_bf16, void* stream);
 
 /* Filter pass of the two-pass video retrieval on CTA pairs (tcgen05 cta_group::2, M = 256): the hi-only
  * (1 MMA per product) scores of xmlb_vr_scores_tc_packed(hi_only = 1) for all (query, video) pairs, same packed

@@ -323,6 +323,20 @@ def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
             ops.GATHER = mode
             g_st, g_ed = ops.span_probs_tc(f2cat, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length, bf16=bf16)
             assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), mode
+        # per-video clip boxes: only the rows an unmasked clip's ConvSE taps can read are loaded; the same bits,
+        # even when the rows beyond them hold NaNs (nothing may depend on the padded tail of a video)
+        ops.GATHER = "warps"
+        clip_rows = ops.span_clip_rows(mask.to(DEV), t0.numel())
+        assert int(clip_rows.max()) <= length and int(clip_rows.min()) >= 1
+        poisoned = tuple(t.clone().view(nv, length, -1) for t in f2cat)
+        beyond = torch.arange(length, device=DEV)[None, :] >= ((clip_rows[:, None] + 15) // 16 * 16)
+        for t in poisoned:
+            t[beyond] = 0x7e00 if not bf16 else 0x7fc0  # NaN
+        poisoned = tuple(t.view(nv * length, -1) for t in poisoned)
+        for operands in (f2cat, poisoned):
+            g_st, g_ed = ops.span_probs_tc(operands, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length,
+                                           bf16=bf16, clip_rows=clip_rows)
+            assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), "clip boxes"
     finally:
         ops.GATHER = saved
     got_st, got_ed = got_st.view(nq, slots, length).cpu(), got_ed.view(nq, slots, length).cpu()

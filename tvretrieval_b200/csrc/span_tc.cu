@@ -73,15 +73,25 @@ struct SpanSched {
   }
 };
 
-// NC = 32-clip groups per video handled by a lane in the ConvSE phase: 4 (ctx_len <= 128, one accumulator half) or 8
-template <int NC>
-__global__ void __launch_bounds__(192 + 32 * tc::GATHER_WARPS, 1)
+constexpr int EPI_WARPS = 8;  // two per TMEM lane quadrant
+constexpr int S_OFF = 2;      // zero floats on both sides of a similarity row (the reach of the common 5-tap ConvSE)
+
+// NC = 32-clip groups per video handled by a lane in the ConvSE phase: 4 (ctx_len <= 128, one accumulator half) or 8.
+// KS = 5: the usual 5-tap detectors, taps in registers, neighbours read from the zero-margined row without bounds
+// checks; KS = 0: any odd ksize <= 31.
+// The epilogue used to be the kernel's bottleneck (ncu source view: its four warps, one per scheduler with nothing to
+// hide a latency behind, never waited for an accumulator: ~5000 cycles per query, chains of L1 loads of taps, mask and
+// output row inside the tap loop).  Now: eight warps, everything that does not depend on the query (mask values,
+// output rows of the list chunk, taps) is fetched before the accumulator wait, and two queries are processed per
+// iteration as one straight-line block.  Same operations in the same order per output: bit-identical results.
+template <int NC, int KS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS + 32 * tc::GATHER_WARPS, 1)
 span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_constant__ SpanTcParams p) {
-  constexpr int S_LD = 32 * NC + 4;  // row pitch (floats) of the transposed similarity tile
+  constexpr int S_LD = 32 * NC + 2 * S_OFF;  // row pitch (floats) of the transposed similarity tile
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
   const bool gw = p.entry_q && p.gather_warps;
-  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 3, 4, gw ? 2 : 0);
+  const uint32_t tmem_base = tc::pipe_setup(pipe, smem_raw, p.stages, p.block_n, 3, EPI_WARPS, gw ? 2 : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0) {
@@ -92,87 +102,132 @@ span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
-  } else if (warp >= 6) {  // ===================== gather warps 6..9: the listed queries -> B tile =====================
-    tc::tc_gather_loop(pipe, threadIdx.x - 192, p.entry_q, p.block_n, p.kcat,
+  } else if (warp >= 2 + EPI_WARPS) {  // ============ gather warps: the listed queries -> B tile ============
+    tc::tc_gather_loop(pipe, threadIdx.x - 32 * (2 + EPI_WARPS), p.entry_q, p.block_n, p.kcat,
                        [&](int u, int, int& e0, int& ne, const unsigned short*& hi, const unsigned short*& lo) {
                          const int4 m = __ldg(p.units + u);
                          e0 = m.y, ne = m.z, hi = p.q_hi, lo = p.q_lo;
                        });
-  } else {  // ===================== epilogue warps 2..5 =====================
-    float* S = reinterpret_cast<float*>(smem_raw + (pipe.extra() - tc::smem_u32(smem_raw)));  // [block_n][s_ld]
-    const int row_in_half = (warp & 3) * 32 + lane;  // accumulator row owned in the TMEM phase
-    const int ew = warp - 2;                         // 0..3: queries handled in the ConvSE phase
+  } else {  // ===================== epilogue warps 2 .. 9 =====================
+    float* S = reinterpret_cast<float*>(smem_raw + (pipe.extra() - tc::smem_u32(smem_raw)));  // [block_n][S_LD]
+    float* W = S + p.block_n * S_LD;                 // [2][32] taps: start | end
+    const int row_in_half = (warp & 3) * 32 + lane;  // accumulator row (TMEM lane) owned in phase A
+    const int ew = warp - 2;                         // 0..7: queries handled in the ConvSE phase
+    const int col_half = ew >> 2;                    // the two warps of a lane quadrant alternate 32-column groups
     const int L = p.ctx_len, pad = p.ksize / 2;
+    {  // once: zero margins of every row, taps
+      const int et = threadIdx.x - 64;
+      for (int r = et; r < p.block_n; r += 32 * EPI_WARPS) {
+#pragma unroll
+        for (int i = 0; i < S_OFF; ++i) S[r * S_LD + i] = 0.f, S[r * S_LD + S_LD - 1 - i] = 0.f;
+      }
+      if (et < 64) W[et] = (et & 31) < p.ksize ? __ldg((et < 32 ? p.w_st : p.w_ed) + (et & 31)) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    }
+    float wst[5], wed[5];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) wst[t] = W[t], wed[t] = W[32 + t];
     int u, half;
     for (uint32_t unit = 0; tc::epi_next(pipe, unit, u, half); ++unit) {
       const int4 m = __ldg(p.units + u);
       const int v = m.x, e0 = m.y, ne = m.z;
+      // query-independent inputs of phase B, in flight while the accumulator is still being produced
+      float mk[NC];
+      int orow[4];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) mk[c] = lane + 32 * c < L ? __ldg(p.mask + (long long)v * L + lane + 32 * c) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) orow[k] = lane + 32 * k < ne ? __ldg(p.entry_out + e0 + lane + 32 * k) : 0;
       const uint32_t taddr = tc::epi_wait(pipe, unit, tmem_base);
-      // ---- phase A: accumulator (clip x query) -> shared memory, transposed to (query x clip), halved
+      // ---- phase A: accumulator (clip x query) -> shared memory, transposed to (query x clip), halved; clips
+      // beyond ctx_len read as zero (the ConvSE zero padding)
       const int clip = (NC > 4 ? half * BLOCK_M : 0) + row_in_half;
-      for (int c = 0; c * 32 < ne; ++c) {  // warp-uniform
+      for (int c = col_half; c * 32 < ne; c += 2) {  // warp-uniform
         uint32_t r[32];
         tc::tmem_ld_32x32(taddr + c * 32, r);
         tc::tmem_ld_wait();
-        if (NC == 4 || clip < L) {
+        if (clip < 32 * NC) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) S[(c * 32 + i) * S_LD + clip] = __fmul_rn(__uint_as_float(r[i]), 0.5f);
+          for (int i = 0; i < 32; ++i)
+            S[(c * 32 + i) * S_LD + S_OFF + clip] = clip < L ? __fmul_rn(__uint_as_float(r[i]), 0.5f) : 0.f;
         }
       }
       tc::epi_release(pipe, unit);
       if (NC > 4 && half != p.n_halves - 1) continue;  // the video's second half of clips follows as the next unit
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // ---- phase B: per query: ConvSE start / end, mask_logits, softmax over clips
-      for (int j = ew; j < ne; j += 4) {
-        const float* s = S + j * S_LD;
-        const long long row = __ldg(p.entry_out + e0 + j);
-        float st[NC], ed[NC];
-        float mx_st = -INFINITY, mx_ed = -INFINITY;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      // ---- phase B: per query: ConvSE start / end, mask_logits, softmax over clips; two queries per iteration
+      for (int j0 = ew; j0 < ne; j0 += 2 * EPI_WARPS) {
+        const bool has2 = j0 + EPI_WARPS < ne;  // warp-uniform
+        const int jq[2] = {j0, has2 ? j0 + EPI_WARPS : j0};
+        float st[2][NC], ed[2][NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int l = lane + 32 * c;
-          st[c] = 0.f, ed[c] = 0.f;
-          if (l < L) {
-            const float mk = __ldg(p.mask + (long long)v * L + l);
+        for (int q = 0; q < 2; ++q) {
+          const float* s = S + jq[q] * S_LD + S_OFF;  // s[l] = similarity of clip l
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const int l = lane + 32 * c;
             float a = 0.f, b = 0.f;
-            // a masked clip is -1e10 whatever its (finite) logit: its similarity neighbourhood is not read -- with
-            // clip_boxes those rows may not have been loaded at all
-            if (mk != 0.f) {
+            if (KS == 5) {
+#pragma unroll
+              for (int t = 0; t < 5; ++t) {
+                const float x = s[l + t - 2];
+                a = fmaf(wst[t], x, a), b = fmaf(wed[t], x, b);
+              }
+            } else if (l < L) {
               for (int t = 0; t < p.ksize; ++t) {
                 const int src = l + t - pad;
                 const float x = (src >= 0 && src < L) ? s[src] : 0.f;
-                a = fmaf(__ldg(p.w_st + t), x, a);
-                b = fmaf(__ldg(p.w_ed + t), x, b);
+                a = fmaf(W[t], x, a), b = fmaf(W[32 + t], x, b);
               }
             }
-            st[c] = mask_logit(a, mk), ed[c] = mask_logit(b, mk);
-            mx_st = fmaxf(mx_st, st[c]), mx_ed = fmaxf(mx_ed, ed[c]);
+            // a masked clip is -1e10 whatever its (finite) logit; its neighbourhood may not even have been loaded
+            // (clip_boxes), so whatever was accumulated from it is dropped
+            a = mk[c] != 0.f ? a : 0.f, b = mk[c] != 0.f ? b : 0.f;
+            st[q][c] = mask_logit(a, mk[c]), ed[q][c] = mask_logit(b, mk[c]);
           }
         }
         if (p.softmax) {
-          mx_st = warp_max(mx_st), mx_ed = warp_max(mx_ed);
-          float s_st = 0.f, s_ed = 0.f;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            if (lane + 32 * c < L) {
-              st[c] = expf(st[c] - mx_st), ed[c] = expf(ed[c] - mx_ed);
-              s_st += st[c], s_ed += ed[c];
+          for (int q = 0; q < 2; ++q) {
+            float mx_st = -INFINITY, mx_ed = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+              if (lane + 32 * c < L) mx_st = fmaxf(mx_st, st[q][c]), mx_ed = fmaxf(mx_ed, ed[q][c]);
+            mx_st = warp_max(mx_st), mx_ed = warp_max(mx_ed);
+            float s_st = 0.f, s_ed = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              if (lane + 32 * c < L) {
+                st[q][c] = expf(st[q][c] - mx_st), ed[q][c] = expf(ed[q][c] - mx_ed);
+                s_st += st[q][c], s_ed += ed[q][c];
+              }
             }
-          }
-          s_st = warp_sum(s_st), s_ed = warp_sum(s_ed);
+            s_st = warp_sum(s_st), s_ed = warp_sum(s_ed);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) st[c] = __fdiv_rn(st[c], s_st), ed[c] = __fdiv_rn(ed[c], s_ed);
+            for (int c = 0; c < NC; ++c) st[q][c] = __fdiv_rn(st[q][c], s_st), ed[q][c] = __fdiv_rn(ed[q][c], s_ed);
+          }
         }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int l = lane + 32 * c;
-          if (l < L) {
-            p.out_st[row * L + l] = st[c];
-            p.out_ed[row * L + l] = ed[c];
+        for (int q = 0; q < 2; ++q) {
+          int row = 0;  // output row of query jq[q]: held by lane jq & 31 in orow[jq >> 5]
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = __shfl_sync(0xffffffffu, orow[k], jq[q] & 31);
+            if ((jq[q] >> 5) == k) row = r;
+          }
+          if (q == 0 || has2) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              const int l = lane + 32 * c;
+              if (l < L) {
+                p.out_st[(long long)row * L + l] = st[q][c];
+                p.out_ed[(long long)row * L + l] = ed[q][c];
+              }
+            }
           }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // S may be overwritten by the next unit
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");  // S may be overwritten by the next unit
     }
   }
   tc::pipe_teardown(tmem_base);
@@ -227,14 +282,14 @@ extern "C" int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const uns
   p.n_videos = n_videos, p.ctx_len = ctx_len, p.k_blocks = kcat / BLOCK_K, p.block_n = block_n;
   p.ksize = ksize, p.softmax = apply_softmax;
   p.n_halves = ceil_div(ctx_len, BLOCK_M);
-  const int s_ld = ctx_len <= 128 ? 132 : 260;
+  const int s_ld = (ctx_len <= 128 ? 128 : 256) + 2 * S_OFF;
   p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out, p.entry_q = entry_q;
   p.gather_warps = entry_q && gather_warps ? 1 : 0, p.q_hi = qg_hi, p.q_lo = qg_lo, p.kcat = kcat;
   XMLB_REQUIRE(!clip_boxes || p.gather_warps, "xmlb_span_probs_tc: clip_boxes needs the gather-warps mode");
   p.clip_boxes = clip_boxes ? 1 : 0;
   p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed, p.unit_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
-  const int extra = block_n * s_ld * (int)sizeof(float);
+  const int extra = block_n * s_ld * (int)sizeof(float) + 64 * (int)sizeof(float);  // similarity tile + taps
   p.stages = tc::pipe_stages(block_n, extra);
   XMLB_REQUIRE(p.stages >= 2, "xmlb_span_probs_tc: tile does not fit in shared memory");
   const size_t smem = tc::pipe_smem_bytes(block_n, p.stages, extra);
@@ -257,13 +312,16 @@ extern "C" int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const uns
   XMLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = max_units < sms ? max_units : sms;
   XMLB_CUDA(cudaMemsetAsync(sched_ws, 0, sizeof(int), (cudaStream_t)stream));
-  const int threads = p.gather_warps ? 192 + 32 * tc::GATHER_WARPS : 192;
+  const int threads = 64 + 32 * EPI_WARPS + (p.gather_warps ? 32 * tc::GATHER_WARPS : 0);
+  auto launch = [&](auto kernel) -> int {
+    XMLB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
+    return XMLB_OK;
+  };
   if (p.n_halves == 1) {
-    XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    span_probs_tc_kernel<4><<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
+    if ((rc = ksize == 5 ? launch(span_probs_tc_kernel<4, 5>) : launch(span_probs_tc_kernel<4, 0>))) return rc;
   } else {
-    XMLB_CUDA(cudaFuncSetAttribute(span_probs_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    span_probs_tc_kernel<8><<<grid, threads, smem, (cudaStream_t)stream>>>(maps, p);
+    if ((rc = ksize == 5 ? launch(span_probs_tc_kernel<8, 5>) : launch(span_probs_tc_kernel<8, 0>))) return rc;
   }
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();

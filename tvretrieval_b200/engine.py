@@ -505,9 +505,13 @@ class VCMRSearcher:
             if ix.kpad != ix.hidden:
                 qv = torch.nn.functional.pad(qv, (0, ix.kpad - ix.hidden))
                 qs = torch.nn.functional.pad(qs, (0, ix.kpad - ix.hidden))
+            ksize = m.merged_st_predictor.weight.numel()
+            rows = getattr(ix, "_span_clip_rows", None)  # (mask it was made from, ksize, rows)
+            if rows is None or rows[0] is not ix.video_mask or rows[1] != ksize:
+                rows = ix._span_clip_rows = (ix.video_mask, ksize, ops.span_clip_rows(ix.video_mask, ksize))
             return ops.span_probs_tc(ix.f2cat, torch.cat([qv, qs], dim=1), lists, ix.video_mask,
                                      m.merged_st_predictor.weight, m.merged_ed_predictor.weight, ix.ctx_len,
-                                     softmax=True, bf16=ix.precision == "bf16x3")
+                                     softmax=True, bf16=ix.precision == "bf16x3", clip_rows=rows[2])
         args = self.model.span_streams(video_query, sub_query, ix.video_feat2, ix.sub_feat2, ix.video_mask,
                                        ix.sub_mask)
         return ops.span_logits(softmax=True, lists=lists, **args)

@@ -626,17 +626,29 @@ def build_pair_lists(top_idx, n_videos, vid_lo=0, slot_valid=None, chunk=32):
     return lists
 
 
-def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, bf16=False, out_rows=None):
+def span_clip_rows(mask, ksize):
+    """Per video: how many leading clip rows the similarity kernel has to load -- every unmasked clip plus the
+    ksize // 2 neighbours its ConvSE taps read (int32, on the mask's device)."""
+    length = mask.shape[1]
+    last = ((mask != 0) * torch.arange(1, length + 1, device=mask.device)).amax(1)
+    return (last + ksize // 2).clamp_(max=length).to(torch.int32).contiguous()
+
+
+def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, bf16=False, out_rows=None,
+                  clip_rows=None):
     """tcgen05 similarity curves + ConvSE + mask (+ softmax) for listed (query, video) pairs of the merged model.
     f2cat = (hi, lo) of [feat2_video | feat2_sub] (Nv * L, kcat); q_cat fp32 (Nq, kcat) = [q'_video | q'_sub] with
-    each half zero-padded to kcat / 2; lists built with chunk in {32, 64, 128}.  -> st, ed of shape (rows, L)."""
+    each half zero-padded to kcat / 2; lists built with chunk in {32, 64, 128}.  -> st, ed of shape (rows, L).
+    clip_rows = span_clip_rows(mask, ksize) (gather-warps mode): only those rows of every video are read."""
     n_videos = f2cat[0].shape[0] // ctx_len
     kcat = f2cat[0].shape[1]
     assert q_cat.shape[1] == kcat and lists.chunk in (32, 64, 128)
     dev = q_cat.device
     units = torch.empty(lists.max_chunks * 4 + 4, device=dev, dtype=torch.int32)
-    rc = _lib.lib().xmlb_build_span_units(_p(lists.vid_ptr), _p(lists.chunk_ptr), n_videos, lists.chunk, _p(units),
-                                          _stream())
+    if GATHER != "warps":
+        clip_rows = None
+    rc = _lib.lib().xmlb_build_span_units_rows(_p(lists.vid_ptr), _p(lists.chunk_ptr), n_videos, lists.chunk,
+                                               _p(clip_rows), _p(units), _stream())
     _lib.check(rc, "xmlb_build_span_units")
     # queries: split once, then copied into list order (or gathered by the kernel's producer, see TMA_GATHER)
     qg = split_rows(q_cat, kpad=kcat, bf16=bf16)
@@ -648,12 +660,12 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
     st = alloc(rows, ctx_len, device=dev, dtype=torch.float32)
     ed = alloc(rows, ctx_len, device=dev, dtype=torch.float32)
     w_st, w_ed = _f32(w_st.reshape(-1), "w_st"), _f32(w_ed.reshape(-1), "w_ed")
-    rc = _lib.lib().xmlb_span_probs_tc_ex(_p(f2cat[0]), _p(f2cat[1]), _p(qg[0]), _p(qg[1]), _p(_f32(mask, "mask")),
-                                          _p(w_st), _p(w_ed), w_st.numel(), int(softmax), n_videos, ctx_len, kcat,
-                                          lists.entry_q.numel(), lists.chunk, _p(units),
-                                          lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
-                                          _p(lists.entry_q) if GATHER != "copy" else None, int(GATHER == "warps"),
-                                          qg[0].shape[0], _p(st), _p(ed), _p(_sched_ws(dev)), int(bf16), _stream())
+    rc = _lib.lib().xmlb_span_probs_tc_clipped(
+        _p(f2cat[0]), _p(f2cat[1]), _p(qg[0]), _p(qg[1]), _p(_f32(mask, "mask")), _p(w_st), _p(w_ed), w_st.numel(),
+        int(softmax), n_videos, ctx_len, kcat, lists.entry_q.numel(), lists.chunk, _p(units),
+        lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
+        _p(lists.entry_q) if GATHER != "copy" else None, int(GATHER == "warps"), qg[0].shape[0],
+        int(clip_rows is not None), _p(st), _p(ed), _p(_sched_ws(dev)), int(bf16), _stream())
     _lib.check(rc, "xmlb_span_probs_tc")
     return st, ed
 
