@@ -282,13 +282,17 @@ int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_
  * number of leading clip rows of the video whose similarity the epilogue can need -- (last unmasked clip + 1 +
  * ksize / 2), at most ctx_len.  Only those rows of f2_* are loaded (TMA boxes of 16, 32, ..., 128 rows picked per
  * unit) instead of all ctx_len padded rows; masked clips never read their neighbourhood (mask_logits gives -1e10
- * for any finite logit, model_xml.py:640-641), so the results are identical. */
+ * for any finite logit, model_xml.py:640-641), so the results are identical.
+ * f2_kblocked != 0: f2_* are stored K-BLOCKED, [kcat / 32][n_videos * ctx_len][32] -- the
+ * 32 elements a k-step reads from consecutive clips are contiguous in HBM (one run of rows * 64 bytes per TMA box
+ * instead of `rows` separate 64-byte pieces 2 * kcat bytes apart, each in its own DRAM page). */
 int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const unsigned short* f2_lo, const unsigned short* qg_hi,
                                const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
                                int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,
                                int block_n, const int* units, const int* n_units, int max_units, const int* entry_out,
                                const int* entry_q, int gather_warps, long long n_query_rows, int clip_boxes,
-                               float* out_st, float* out_ed, int* sched_ws, int is_bf16, void* stream);
+                               int f2_kblocked, float* out_st, float* out_ed, int* sched_ws, int is_bf16,
+                               void* stream);
 
 /* Filter pass of the two-pass video retrieval on CTA pairs (tcgen05 cta_group::2, M = 256): the hi-only
  * (1 MMA per product) scores of xmlb_vr_scores_tc_packed(hi_only = 1) for all (query, video) pairs, same packed

@@ -337,6 +337,17 @@ def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
             g_st, g_ed = ops.span_probs_tc(operands, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length,
                                            bf16=bf16, clip_rows=clip_rows)
             assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), "clip boxes"
+            # ... and from the k-blocked operand layout (contiguous TMA boxes)
+            kb = tuple(ops.kblock_rows(t) for t in operands)
+            for rows_arg in (None, clip_rows):
+                g_st, g_ed = ops.span_probs_tc(kb, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length,
+                                               bf16=bf16, clip_rows=rows_arg)
+                assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), "k-blocked layout"
+        for mode in ("copy", "tma"):  # the other producers read the k-blocked layout too
+            ops.GATHER = mode
+            g_st, g_ed = ops.span_probs_tc(tuple(ops.kblock_rows(t) for t in f2cat), q_cat, lists, mask.to(DEV),
+                                           t0.to(DEV), t1.to(DEV), length, bf16=bf16)
+            assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), "k-blocked layout, " + mode
     finally:
         ops.GATHER = saved
     got_st, got_ed = got_st.view(nq, slots, length).cpu(), got_ed.view(nq, slots, length).cpu()
@@ -647,3 +658,24 @@ def test_packed_query_encoder_equals_padded(name):
     for a, b, key in zip(got, want, ("video_query", "sub_query")):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
         torch.testing.assert_close(a.cpu(), g.t(key), rtol=1e-4, atol=1e-5)  # and the reference's own vectors
+
+
+def test_packed_tables_made_on_the_device_equal_the_host_layout():
+    """XML.packed_query_tables_device (cumsum / repeat_interleave on the GPU, per piece) == packed_layout (numpy)."""
+    import numpy as np
+    from tvretrieval_b200.model_xml import XML, AttrDict, packed_layout, xml_base_config
+    model = XML(AttrDict(xml_base_config, hidden_size=64, visual_input_size=64, query_input_size=64, sub_input_size=64))
+    g = torch.Generator().manual_seed(7)
+    width = 30
+    lens = torch.randint(0, width + 3, (517,), generator=g).numpy()  # some empty, some longer than the padded width
+    lens[5] = 0
+    lens = np.minimum(lens, width)
+    bounds = [(0, 100), (100, 101), (101, 517)]
+    for lens_dev in (None, torch.from_numpy(lens).to(DEV)):
+        tables = model.packed_query_tables_device(lens, width, torch.device(DEV), bounds, lens_dev=lens_dev)
+        assert len(tables) == len(bounds)
+        for (lo, hi), (rows, pos, cu, max_len) in zip(bounds, tables):
+            w_rows, w_pos, w_cu, w_max = packed_layout(lens[lo:hi], width)
+            assert rows.dtype == pos.dtype == cu.dtype == torch.int32
+            assert np.array_equal(rows.cpu().numpy(), w_rows) and np.array_equal(pos.cpu().numpy(), w_pos)
+            assert np.array_equal(cu.cpu().numpy(), w_cu) and max_len == w_max

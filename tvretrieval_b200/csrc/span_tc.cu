@@ -27,6 +27,7 @@ struct SpanTcParams {
   int n_videos, ctx_len, k_blocks, block_n, stages, ksize, softmax;
   int n_halves;          // 128-clip halves per video (2 when ctx_len > 128)
   const int4* units;     // {video, first entry row, entries in this chunk, clip rows to load (clip_boxes) or 0}
+  int a_kb_rows;         // > 0: f2 is stored k-blocked, [kcat / 32][a_kb_rows = n_videos * ctx_len][32]
   int clip_boxes;        // 1: units[].w = number of leading clip rows of the video the epilogue can need (every
                          // unmasked clip and its ConvSE neighbours); only those are loaded, in 16-row steps
   const int* n_units;    // device scalar
@@ -62,6 +63,7 @@ struct SpanSched {
     if (p->clip_boxes) box = min(N_BOXES - 1, max(0, (m.w - half * BLOCK_M + 15) / 16 - 1));
     d.a_hi = &maps->a_hi[box], d.a_lo = &maps->a_lo[box], d.b_hi = &maps->b_hi, d.b_lo = &maps->b_lo;
     d.a_bytes = (box + 1) * 16 * tc::SWIZZLE_BYTES;
+    d.a_kb_rows = p->a_kb_rows;
     d.a_row = m.x * p->ctx_len + half * BLOCK_M;
     d.b_row = m.y;
     d.g_count = m.z;
@@ -268,7 +270,8 @@ extern "C" int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const uns
                                           int n_videos, int ctx_len, int kcat, long long n_entries, int block_n,
                                           const int* units, const int* n_units, int max_units, const int* entry_out,
                                           const int* entry_q, int gather_warps, long long n_query_rows, int clip_boxes,
-                                          float* out_st, float* out_ed, int* sched_ws, int is_bf16, void* stream) {
+                                          int f2_kblocked, float* out_st, float* out_ed, int* sched_ws, int is_bf16,
+                                          void* stream) {
   XMLB_REQUIRE(f2_hi && f2_lo && qg_hi && qg_lo && mask && w_st && w_ed && units && n_units && entry_out && out_st &&
                    out_ed && sched_ws, "xmlb_span_probs_tc: null pointer");
   XMLB_REQUIRE(ctx_len >= 1 && ctx_len <= MAX_L, "xmlb_span_probs_tc: ctx_len must be <= 256");
@@ -286,7 +289,10 @@ extern "C" int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const uns
   p.units = reinterpret_cast<const int4*>(units), p.n_units = n_units, p.entry_out = entry_out, p.entry_q = entry_q;
   p.gather_warps = entry_q && gather_warps ? 1 : 0, p.q_hi = qg_hi, p.q_lo = qg_lo, p.kcat = kcat;
   XMLB_REQUIRE(!clip_boxes || p.gather_warps, "xmlb_span_probs_tc: clip_boxes needs the gather-warps mode");
+  XMLB_REQUIRE(!f2_kblocked || (long long)n_videos * ctx_len * (kcat / BLOCK_K) < (1ll << 31),
+               "xmlb_span_probs_tc: k-blocked f2 too large for 32-bit TMA coordinates");
   p.clip_boxes = clip_boxes ? 1 : 0;
+  p.a_kb_rows = f2_kblocked ? n_videos * ctx_len : 0;
   p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed, p.unit_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
   const int extra = block_n * s_ld * (int)sizeof(float) + 64 * (int)sizeof(float);  // similarity tile + taps
@@ -301,8 +307,10 @@ extern "C" int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const uns
   const unsigned long long b_rows = entry_q ? (unsigned long long)n_query_rows : (unsigned long long)n_entries;
   const unsigned int b_box = entry_q ? 1u : (unsigned int)block_n;
   for (int b = clip_boxes ? 0 : N_BOXES - 1; b < N_BOXES; ++b) {  // box b: the first 16 (b + 1) clip rows of a tile
-    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[b], f2_hi, corpus_rows, kcat, 16 * (b + 1), BLOCK_K))) return rc;
-    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[b], f2_lo, corpus_rows, kcat, 16 * (b + 1), BLOCK_K))) return rc;
+    const unsigned long long a_rows = f2_kblocked ? corpus_rows * (kcat / BLOCK_K) : corpus_rows;
+    const unsigned long long a_cols = f2_kblocked ? BLOCK_K : kcat;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[b], f2_hi, a_rows, a_cols, 16 * (b + 1), BLOCK_K))) return rc;
+    if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[b], f2_lo, a_rows, a_cols, 16 * (b + 1), BLOCK_K))) return rc;
   }
   if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi, qg_hi, b_rows, kcat, b_box, BLOCK_K))) return rc;
   if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo, qg_lo, b_rows, kcat, b_box, BLOCK_K))) return rc;
@@ -337,7 +345,7 @@ extern "C" int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned
                                      int* sched_ws, int is_bf16, void* stream) {
   return xmlb_span_probs_tc_clipped(f2_hi, f2_lo, qg_hi, qg_lo, mask, w_st, w_ed, ksize, apply_softmax, n_videos,
                                     ctx_len, kcat, n_entries, block_n, units, n_units, max_units, entry_out, entry_q,
-                                    gather_warps, n_query_rows, 0, out_st, out_ed, sched_ws, is_bf16, stream);
+                                    gather_warps, n_query_rows, 0, 0, out_st, out_ed, sched_ws, is_bf16, stream);
 }
 
 extern "C" int xmlb_span_probs_tc(const unsigned short* f2_hi, const unsigned short* f2_lo,

@@ -45,6 +45,9 @@ struct UnitDesc {
   int g_count;        // gather producer only: number of valid list entries of the gathered operand's tile
   int a_bytes;        // bytes one A box (hi or lo) delivers: A_TILE_BYTES unless the unit's A maps have a shorter box
                       // (honoured on the gather-warps path, p.gather == 2, only)
+  int a_kb_rows;      // 0 = A is (rows, K) row-major; > 0 = A is stored K-BLOCKED, [K / BLOCK_K][a_kb_rows][BLOCK_K]
+                      // (its maps describe a (K / BLOCK_K * a_kb_rows, BLOCK_K) array): the box of a k-block is one
+                      // contiguous run of box_rows * 64 bytes in HBM instead of box_rows separate 64-byte pieces
   uint32_t idesc;     // instruction descriptor (carries N of this unit)
   int tag0, tag1;     // kernel-specific payload handed to the epilogue (tile index, modality, ...)
 };
@@ -154,7 +157,7 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
   int stage = 0;
   uint32_t phase = 0, n = 0;
   UnitDesc u;
-  u.k_block0 = 0, u.a_bytes = A_TILE_BYTES;
+  u.k_block0 = 0, u.a_bytes = A_TILE_BYTES, u.a_kb_rows = 0;
   const uint64_t stream_policy = l2_policy_evict_first();
   while (sched.next(u)) {
     queue_push(p, n++, u.tag0, u.tag1, u.k_blocks, u.idesc);
@@ -171,16 +174,18 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
                            stream_policy);
         } else {
           mbar_expect_tx(p.full_bar(stage), 2u * (uint32_t)u.a_bytes);
-          tma_load_2d_hint(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row, stream_policy);
-          tma_load_2d_hint(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row, stream_policy);
+          const int c0 = u.a_kb_rows ? 0 : kb * BLOCK_K, c1 = u.a_row + kb * u.a_kb_rows;
+          tma_load_2d_hint(sa, u.a_hi, p.full_bar(stage), c0, c1, stream_policy);
+          tma_load_2d_hint(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), c0, c1, stream_policy);
         }
         if (++stage == p.stages) stage = 0, phase ^= 1u;
         continue;
       }
       mbar_expect_tx(p.full_bar(stage), (p.probe & 2) ? (uint32_t)A_TILE_BYTES : (uint32_t)p.stage_bytes);
       if (p.terms == 3) {
-        tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
-        tma_load_2d(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+        const int c0 = u.a_kb_rows ? 0 : kb * BLOCK_K, c1 = u.a_row + kb * u.a_kb_rows;
+        tma_load_2d(sa, u.a_hi, p.full_bar(stage), c0, c1);
+        tma_load_2d(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), c0, c1);
         tma_load_2d(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
         tma_load_2d(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
       } else if (p.probe & 2) {
@@ -208,7 +213,7 @@ __device__ __forceinline__ void tc_producer_loop_gather(Sched sched, const Pipe&
   int stage = 0;
   uint32_t phase = 0, n = 0;
   UnitDesc u;
-  u.k_block0 = 0, u.g_count = 0;
+  u.k_block0 = 0, u.g_count = 0, u.a_kb_rows = 0;
   const uint32_t a_lo_off = A_TILE_BYTES, b_hi_off = 2 * A_TILE_BYTES, b_lo_off = 2 * A_TILE_BYTES + p.b_tile_bytes;
   for (;;) {
     int has = 0;
@@ -241,8 +246,9 @@ __device__ __forceinline__ void tc_producer_loop_gather(Sched sched, const Pipe&
           tma_load_2d(sa + b_hi_off, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
           tma_load_2d(sa + b_lo_off, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
         } else {
-          tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
-          tma_load_2d(sa + a_lo_off, u.a_lo, p.full_bar(stage), kb * BLOCK_K, u.a_row);
+          const int c0 = u.a_kb_rows ? 0 : kb * BLOCK_K, c1 = u.a_row + kb * u.a_kb_rows;
+          tma_load_2d(sa, u.a_hi, p.full_bar(stage), c0, c1);
+          tma_load_2d(sa + a_lo_off, u.a_lo, p.full_bar(stage), c0, c1);
         }
       }
       __syncwarp();

@@ -292,6 +292,37 @@ class XML(nn.Module):
         return t[:len(rows)], t[len(rows):2 * len(rows)], t[2 * len(rows):], max_len
 
     @torch.no_grad()
+    def packed_query_tables_device(self, lens_cpu, width, dev, bounds, lens_dev=None):
+        """packed_query_tables for all pieces `bounds` = [(lo, hi), ...] of a block of queries at once, with the
+        per-token tables made ON THE DEVICE (cumsum / repeat_interleave over the lengths): the host only needs the few
+        sums that size the tensors.  Building them in numpy cost ~2 ms per 8 K queries during which the GPU had
+        nothing to do.  lens_dev: the lengths already on the device (else lens_cpu is uploaded, 4 bytes per query).
+        -> list of (rows, pos, cu_seqlens, max_len) per piece, equal to packed_layout()'s."""
+        import numpy as np
+        lens_np = np.minimum(np.asarray(lens_cpu, dtype=np.int64), width)
+        n = len(lens_np)
+        cu_np = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens_np, out=cu_np[1:])
+        total = int(cu_np[-1])
+        if lens_dev is None:
+            lens_dev = self._upload_ints(lens_np.astype(np.int32), dev)
+        lens_dev = lens_dev.to(torch.int64).clamp(max=width)
+        cu = torch.zeros(n + 1, device=dev, dtype=torch.int64)
+        torch.cumsum(lens_dev, 0, out=cu[1:])
+        seq = torch.repeat_interleave(torch.arange(n, device=dev), lens_dev, output_size=total)
+        pos = torch.arange(total, device=dev) - cu[seq]
+        rows = seq * width + pos
+        pos = pos.to(torch.int32)
+        tables = []
+        for lo, hi in bounds:
+            t0, t1 = int(cu_np[lo]), int(cu_np[hi])
+            max_len = int(max(1, lens_np[lo:hi].max(initial=1)))
+            assert max_len <= self.PACKED_MAX_LEN
+            tables.append(((rows[t0:t1] - lo * width).to(torch.int32), pos[t0:t1],
+                           (cu[lo:hi + 1] - t0).to(torch.int32), max_len))
+        return tables
+
+    @torch.no_grad()
     def encode_query_packed(self, query_feat, lens_cpu=None, tables=None, precision=ops.DEFAULT_PRECISION):
         """encode_query (reference model_xml.py:291-295) on the VALID tokens only: query_feat (N, Lq, Dq) padded
         features on the device, lens_cpu (N,) host ints = valid tokens per query (masks are prefix masks,

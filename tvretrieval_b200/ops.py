@@ -634,14 +634,25 @@ def span_clip_rows(mask, ksize):
     return (last + ksize // 2).clamp_(max=length).to(torch.int32).contiguous()
 
 
+def kblock_rows(t, block=32):
+    """(rows, k) 16-bit operand -> the K-BLOCKED layout (k / block, rows, block) the similarity kernel streams with
+    contiguous TMA boxes (one run of box_rows * 64 bytes per k-step)."""
+    rows, k = t.shape
+    assert k % block == 0
+    return t.view(rows, k // block, block).permute(1, 0, 2).contiguous()
+
+
 def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, bf16=False, out_rows=None,
                   clip_rows=None):
     """tcgen05 similarity curves + ConvSE + mask (+ softmax) for listed (query, video) pairs of the merged model.
     f2cat = (hi, lo) of [feat2_video | feat2_sub] (Nv * L, kcat); q_cat fp32 (Nq, kcat) = [q'_video | q'_sub] with
     each half zero-padded to kcat / 2; lists built with chunk in {32, 64, 128}.  -> st, ed of shape (rows, L).
     clip_rows = span_clip_rows(mask, ksize) (gather-warps mode): only those rows of every video are read."""
-    n_videos = f2cat[0].shape[0] // ctx_len
-    kcat = f2cat[0].shape[1]
+    kblocked = f2cat[0].dim() == 3  # (kcat / 32, Nv * L, 32), see kblock_rows
+    if kblocked:
+        n_videos, kcat = f2cat[0].shape[1] // ctx_len, f2cat[0].shape[0] * f2cat[0].shape[2]
+    else:
+        n_videos, kcat = f2cat[0].shape[0] // ctx_len, f2cat[0].shape[1]
     assert q_cat.shape[1] == kcat and lists.chunk in (32, 64, 128)
     dev = q_cat.device
     units = torch.empty(lists.max_chunks * 4 + 4, device=dev, dtype=torch.int32)
@@ -665,7 +676,7 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
         int(softmax), n_videos, ctx_len, kcat, lists.entry_q.numel(), lists.chunk, _p(units),
         lists.chunk_ptr[n_videos:].data_ptr(), lists.max_chunks, _p(lists.entry_out),
         _p(lists.entry_q) if GATHER != "copy" else None, int(GATHER == "warps"), qg[0].shape[0],
-        int(clip_rows is not None), _p(st), _p(ed), _p(_sched_ws(dev)), int(bf16), _stream())
+        int(clip_rows is not None), int(kblocked), _p(st), _p(ed), _p(_sched_ws(dev)), int(bf16), _stream())
     _lib.check(rc, "xmlb_span_probs_tc")
     return st, ed
 
