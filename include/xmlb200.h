@@ -271,6 +271,16 @@ int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsigned short* q
                           const int* units, const int* n_units, int max_units, const int* entry_out, const int* entry_q,
                           int gather_warps, long long n_query_rows, float* cand_val, int* sched_ws, long long n_entries,
                           long long n_packed_rows, int max_len, int kpad, int is_bf16, void* stream);
+/* xmlb_vr_rescore_tc_ex with c_kblocked != 0: the corpus halves c_* are stored K-BLOCKED, [kpad / 32][n_packed_rows][32]
+ * (xmlb_span_probs_tc_clipped explains why).  In gather-warps mode only the quarters of the clip tile that hold the
+ * video's clips are loaded. */
+int xmlb_vr_rescore_tc_kb(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a, const unsigned short* qg_hi_b,
+                          const unsigned short* qg_lo_b, const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                          const unsigned short* c_hi_b, const unsigned short* c_lo_b, int c_kblocked,
+                          const int* row_start, const int* units, const int* n_units, int max_units,
+                          const int* entry_out, const int* entry_q, int gather_warps, long long n_query_rows,
+                          float* cand_val, int* sched_ws, long long n_entries, long long n_packed_rows, int max_len,
+                          int kpad, int is_bf16, void* stream);
 int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_lo, const unsigned short* qg_hi,
                           const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
                           int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,

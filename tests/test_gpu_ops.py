@@ -467,6 +467,11 @@ def test_two_pass_top_videos(ops, nq, nv, length, hid, both, k, max_cand):
             ops.vr_rescore_tc(qv, cs[0][:2], pk, cand, kpad, q_fp32_b=qs if both else None,
                               c_b=cs[1][:2] if both else None)
             assert torch.equal(cand.val[listed], val_copy[listed]), mode
+            # ... and from the k-blocked corpus layout (contiguous TMA boxes; quarter boxes in gather-warps mode)
+            ckb = [tuple(ops.kblock_rows(t) for t in c[:2]) for c in cs]
+            cand.val.copy_(approx_val)
+            ops.vr_rescore_tc(qv, ckb[0], pk, cand, kpad, q_fp32_b=qs if both else None, c_b=ckb[1] if both else None)
+            assert torch.equal(cand.val[listed], val_copy[listed]), mode + ", k-blocked"
     finally:
         ops.GATHER = saved
     cand.val.copy_(val_copy)

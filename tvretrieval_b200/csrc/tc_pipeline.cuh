@@ -45,6 +45,8 @@ struct UnitDesc {
   int g_count;        // gather producer only: number of valid list entries of the gathered operand's tile
   int a_bytes;        // bytes one A box (hi or lo) delivers: A_TILE_BYTES unless the unit's A maps have a shorter box
                       // (honoured on the gather-warps path, p.gather == 2, only)
+  int b_bytes;        // the same for the B boxes (p.b_tile_bytes by default; honoured on the p.gather == 1 path only)
+  int b_kb_rows;      // > 0: B is stored k-blocked (see a_kb_rows)
   int a_kb_rows;      // 0 = A is (rows, K) row-major; > 0 = A is stored K-BLOCKED, [K / BLOCK_K][a_kb_rows][BLOCK_K]
                       // (its maps describe a (K / BLOCK_K * a_kb_rows, BLOCK_K) array): the box of a k-block is one
                       // contiguous run of box_rows * 64 bytes in HBM instead of box_rows separate 64-byte pieces
@@ -157,7 +159,7 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
   int stage = 0;
   uint32_t phase = 0, n = 0;
   UnitDesc u;
-  u.k_block0 = 0, u.a_bytes = A_TILE_BYTES, u.a_kb_rows = 0;
+  u.k_block0 = 0, u.a_bytes = A_TILE_BYTES, u.a_kb_rows = 0, u.b_bytes = p.b_tile_bytes, u.b_kb_rows = 0;
   const uint64_t stream_policy = l2_policy_evict_first();
   while (sched.next(u)) {
     queue_push(p, n++, u.tag0, u.tag1, u.k_blocks, u.idesc);
@@ -168,10 +170,10 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
         // the corpus streams through L2 once (evict_first) so that it does not push out the query rows the gather
         // warps keep re-reading (evict_last)
         if (p.gather == 1) {
-          mbar_expect_tx(p.full_bar(stage), 2u * p.b_tile_bytes);
-          tma_load_2d_hint(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row, stream_policy);
-          tma_load_2d_hint(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row,
-                           stream_policy);
+          mbar_expect_tx(p.full_bar(stage), 2u * (uint32_t)u.b_bytes);
+          const int c0 = u.b_kb_rows ? 0 : kb * BLOCK_K, c1 = u.b_row + kb * u.b_kb_rows;
+          tma_load_2d_hint(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), c0, c1, stream_policy);
+          tma_load_2d_hint(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), c0, c1, stream_policy);
         } else {
           mbar_expect_tx(p.full_bar(stage), 2u * (uint32_t)u.a_bytes);
           const int c0 = u.a_kb_rows ? 0 : kb * BLOCK_K, c1 = u.a_row + kb * u.a_kb_rows;
@@ -186,8 +188,9 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
         const int c0 = u.a_kb_rows ? 0 : kb * BLOCK_K, c1 = u.a_row + kb * u.a_kb_rows;
         tma_load_2d(sa, u.a_hi, p.full_bar(stage), c0, c1);
         tma_load_2d(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), c0, c1);
-        tma_load_2d(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
-        tma_load_2d(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+        const int d0 = u.b_kb_rows ? 0 : kb * BLOCK_K, d1 = u.b_row + kb * u.b_kb_rows;
+        tma_load_2d(sa + 2 * A_TILE_BYTES, u.b_hi, p.full_bar(stage), d0, d1);
+        tma_load_2d(sa + 2 * A_TILE_BYTES + p.b_tile_bytes, u.b_lo, p.full_bar(stage), d0, d1);
       } else if (p.probe & 2) {
         tma_load_2d(sa, u.a_hi, p.full_bar(stage), kb * BLOCK_K, u.a_row);
       } else {
@@ -213,7 +216,7 @@ __device__ __forceinline__ void tc_producer_loop_gather(Sched sched, const Pipe&
   int stage = 0;
   uint32_t phase = 0, n = 0;
   UnitDesc u;
-  u.k_block0 = 0, u.g_count = 0, u.a_kb_rows = 0;
+  u.k_block0 = 0, u.g_count = 0, u.a_kb_rows = 0, u.b_kb_rows = 0;
   const uint32_t a_lo_off = A_TILE_BYTES, b_hi_off = 2 * A_TILE_BYTES, b_lo_off = 2 * A_TILE_BYTES + p.b_tile_bytes;
   for (;;) {
     int has = 0;
@@ -243,8 +246,9 @@ __device__ __forceinline__ void tc_producer_loop_gather(Sched sched, const Pipe&
         mbar_wait(p.empty_bar(stage), phase ^ 1u);
         mbar_expect_tx(p.full_bar(stage), (uint32_t)p.stage_bytes);
         if (gather_a) {
-          tma_load_2d(sa + b_hi_off, u.b_hi, p.full_bar(stage), kb * BLOCK_K, u.b_row);
-          tma_load_2d(sa + b_lo_off, u.b_lo, p.full_bar(stage), kb * BLOCK_K, u.b_row);
+          const int d0 = u.b_kb_rows ? 0 : kb * BLOCK_K, d1 = u.b_row + kb * u.b_kb_rows;
+          tma_load_2d(sa + b_hi_off, u.b_hi, p.full_bar(stage), d0, d1);
+          tma_load_2d(sa + b_lo_off, u.b_lo, p.full_bar(stage), d0, d1);
         } else {
           const int c0 = u.a_kb_rows ? 0 : kb * BLOCK_K, c1 = u.a_row + kb * u.a_kb_rows;
           tma_load_2d(sa, u.a_hi, p.full_bar(stage), c0, c1);

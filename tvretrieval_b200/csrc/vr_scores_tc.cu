@@ -210,8 +210,15 @@ vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_con
 // modality.  A = the queries gathered in list order (xmlb_split_rows with row_index = entry_q), B = the video's
 // clips in the packed corpus (the tile is loaded with a fixed box of block_n rows; columns beyond the video's
 // length belong to the next videos and are ignored).  Same arithmetic per product as the one-pass kernel.
+constexpr int RESCORE_BOXES = 4;  // B boxes of 1/4, 2/4, 3/4, 4/4 of block_n rows
+struct VrRescoreMaps {
+  CUtensorMap a_hi[2], a_lo[2], b_hi[2][RESCORE_BOXES], b_lo[2][RESCORE_BOXES];
+};
+
 struct VrRescoreParams {
   int n_mod, k_blocks, stages, block_n;
+  int c_kb_rows;         // > 0: the corpus halves are stored k-blocked, [kpad / 32][c_kb_rows = n_packed_rows][32]
+  int clip_boxes;        // 1: only the quarter-tiles of the B box that hold the video's clips are loaded
   const int4* units;     // {packed ordinal, first list entry, entries in this chunk, 0}
   const int* n_units;    // device scalar
   const int* entry_out;  // [E] slot (row * max_cand + position) of each list entry
@@ -229,11 +236,11 @@ struct VrRescoreParams {
 };
 
 struct VrRescoreSched {
-  const VrMaps* maps;
+  const VrRescoreMaps* maps;
   const VrRescoreParams* p;
   int n_units, u, mod;
   int4 m;
-  __device__ VrRescoreSched(const VrMaps* mp, const VrRescoreParams* pp)
+  __device__ VrRescoreSched(const VrRescoreMaps* mp, const VrRescoreParams* pp)
       : maps(mp), p(pp), n_units(__ldg(pp->n_units)), u(0), mod(0) {}
   __device__ bool next(tc::UnitDesc& d) {
     if (mod == 0) {
@@ -241,14 +248,18 @@ struct VrRescoreSched {
       if (u >= n_units) return false;
       m = __ldg(p->units + u);
     }
-    d.a_hi = &maps->a_hi[mod], d.a_lo = &maps->a_lo[mod], d.b_hi = &maps->b_hi[mod], d.b_lo = &maps->b_lo[mod];
     d.a_row = m.y;
     d.g_count = m.z;
     d.b_row = __ldg(p->row_start + m.x);
     d.k_blocks = p->k_blocks;
-    // N of this unit's MMAs = the video's clips rounded up to 16 (the B box always holds block_n rows; the columns
-    // beyond the video are simply not computed)
+    // N of this unit's MMAs = the video's clips rounded up to 16; the B box holds the quarters of block_n rows that
+    // cover them (all block_n rows without clip_boxes; the columns beyond the video are simply not computed)
     const int len = __ldg(p->row_start + m.x + 1) - d.b_row;
+    const int quarter = p->block_n / RESCORE_BOXES;
+    const int box = p->clip_boxes ? min(RESCORE_BOXES - 1, max(0, (len - 1) / quarter)) : RESCORE_BOXES - 1;
+    d.a_hi = &maps->a_hi[mod], d.a_lo = &maps->a_lo[mod], d.b_hi = &maps->b_hi[mod][box], d.b_lo = &maps->b_lo[mod][box];
+    d.b_bytes = (box + 1) * quarter * tc::SWIZZLE_BYTES;
+    d.b_kb_rows = p->c_kb_rows;
     d.idesc = tc::idesc_f16(BLOCK_M, min(p->block_n, (len + 15) & ~15), p->is_bf16);
     d.tag0 = u, d.tag1 = mod;
     if (++mod == p->n_mod) mod = 0;
@@ -257,7 +268,7 @@ struct VrRescoreSched {
 };
 
 __global__ void __launch_bounds__(192 + 32 * tc::GATHER_WARPS, 1)
-vr_rescore_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__ VrRescoreParams p) {
+vr_rescore_tc_kernel(const __grid_constant__ VrRescoreMaps maps, const __grid_constant__ VrRescoreParams p) {
   extern __shared__ unsigned char smem_raw[];
   tc::Pipe pipe;
   const bool gw = p.entry_q && p.gather_warps;
@@ -685,14 +696,14 @@ extern "C" int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsi
   return XMLB_OK;
 }
 
-extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,
+extern "C" int xmlb_vr_rescore_tc_kb(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,
                                      const unsigned short* qg_hi_b, const unsigned short* qg_lo_b,
                                      const unsigned short* c_hi_a, const unsigned short* c_lo_a,
-                                     const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
-                                     const int* units, const int* n_units, int max_units, const int* entry_out,
-                                     const int* entry_q, int gather_warps, long long n_query_rows, float* cand_val,
-                                     int* sched_ws, long long n_entries, long long n_packed_rows, int max_len, int kpad,
-                                     int is_bf16, void* stream) {
+                                     const unsigned short* c_hi_b, const unsigned short* c_lo_b, int c_kblocked,
+                                     const int* row_start, const int* units, const int* n_units, int max_units,
+                                     const int* entry_out, const int* entry_q, int gather_warps,
+                                     long long n_query_rows, float* cand_val, int* sched_ws, long long n_entries,
+                                     long long n_packed_rows, int max_len, int kpad, int is_bf16, void* stream) {
   XMLB_REQUIRE(qg_hi_a && qg_lo_a && c_hi_a && c_lo_a && row_start && units && n_units && entry_out && cand_val &&
                    sched_ws, "xmlb_vr_rescore_tc: null pointer");
   const bool two = qg_hi_b != nullptr;
@@ -716,8 +727,12 @@ extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsign
   p.idesc = tc::idesc_f16(BLOCK_M, p.block_n, is_bf16 ? 1 : 0);
   p.stages = tc::pipe_stages(p.block_n, 0);
   XMLB_REQUIRE(p.stages >= 2, "xmlb_vr_rescore_tc: tile does not fit in shared memory");
+  XMLB_REQUIRE(!c_kblocked || n_packed_rows * (kpad / BLOCK_K) < (1ll << 31),
+               "xmlb_vr_rescore_tc: k-blocked corpus too large for 32-bit TMA coordinates");
+  p.c_kb_rows = c_kblocked ? (int)n_packed_rows : 0;
+  p.clip_boxes = p.gather_warps;  // (the other producers expect whole stages)
   const size_t smem = tc::pipe_smem_bytes(p.block_n, p.stages, 0);
-  VrMaps maps;
+  VrRescoreMaps maps;
   const unsigned short* qh[2] = {qg_hi_a, qg_hi_b};
   const unsigned short* ql[2] = {qg_lo_a, qg_lo_b};
   const unsigned short* ch[2] = {c_hi_a, c_hi_b};
@@ -729,11 +744,17 @@ extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsign
     int rc;
     if ((rc = xmlb_make_tmap_2d_u16(&maps.a_hi[m], qh[m], a_rows, kpad, a_box, BLOCK_K))) return rc;
     if ((rc = xmlb_make_tmap_2d_u16(&maps.a_lo[m], ql[m], a_rows, kpad, a_box, BLOCK_K))) return rc;
-    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi[m], ch[m], n_packed_rows, kpad, p.block_n, BLOCK_K))) return rc;
-    if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo[m], cl[m], n_packed_rows, kpad, p.block_n, BLOCK_K))) return rc;
+    const unsigned long long b_rows = c_kblocked ? (unsigned long long)n_packed_rows * (kpad / BLOCK_K) : n_packed_rows;
+    const unsigned long long b_cols = c_kblocked ? BLOCK_K : kpad;
+    for (int b = p.clip_boxes ? 0 : RESCORE_BOXES - 1; b < RESCORE_BOXES; ++b) {
+      const unsigned int box_rows = (unsigned int)(p.block_n / RESCORE_BOXES * (b + 1));
+      if ((rc = xmlb_make_tmap_2d_u16(&maps.b_hi[m][b], ch[m], b_rows, b_cols, box_rows, BLOCK_K))) return rc;
+      if ((rc = xmlb_make_tmap_2d_u16(&maps.b_lo[m][b], cl[m], b_rows, b_cols, box_rows, BLOCK_K))) return rc;
+    }
   }
   if (!two) {
-    maps.a_hi[1] = maps.a_hi[0], maps.a_lo[1] = maps.a_lo[0], maps.b_hi[1] = maps.b_hi[0], maps.b_lo[1] = maps.b_lo[0];
+    maps.a_hi[1] = maps.a_hi[0], maps.a_lo[1] = maps.a_lo[0];
+    for (int b = 0; b < RESCORE_BOXES; ++b) maps.b_hi[1][b] = maps.b_hi[0][b], maps.b_lo[1][b] = maps.b_lo[0][b];
   }
   int dev = 0, sms = 0;
   XMLB_CUDA(cudaGetDevice(&dev));
@@ -745,6 +766,19 @@ extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsign
   xmlb_count_launch(1);
   XMLB_LAUNCH_CHECK();
   return XMLB_OK;
+}
+
+extern "C" int xmlb_vr_rescore_tc_ex(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,
+                                     const unsigned short* qg_hi_b, const unsigned short* qg_lo_b,
+                                     const unsigned short* c_hi_a, const unsigned short* c_lo_a,
+                                     const unsigned short* c_hi_b, const unsigned short* c_lo_b, const int* row_start,
+                                     const int* units, const int* n_units, int max_units, const int* entry_out,
+                                     const int* entry_q, int gather_warps, long long n_query_rows, float* cand_val,
+                                     int* sched_ws, long long n_entries, long long n_packed_rows, int max_len, int kpad,
+                                     int is_bf16, void* stream) {
+  return xmlb_vr_rescore_tc_kb(qg_hi_a, qg_lo_a, qg_hi_b, qg_lo_b, c_hi_a, c_lo_a, c_hi_b, c_lo_b, 0, row_start, units,
+                               n_units, max_units, entry_out, entry_q, gather_warps, n_query_rows, cand_val, sched_ws,
+                               n_entries, n_packed_rows, max_len, kpad, is_bf16, stream);
 }
 
 extern "C" int xmlb_vr_rescore_tc(const unsigned short* qg_hi_a, const unsigned short* qg_lo_a,

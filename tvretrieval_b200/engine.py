@@ -143,12 +143,17 @@ class CorpusIndex:
 
     @torch.no_grad()
     def __init__(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
-                 sub_mask=None, vid_lo=0, precision="f16x3", packed=True, merged_spans=True):
+                 sub_mask=None, vid_lo=0, precision="f16x3", packed=True, merged_spans=True, rescore_kblocked=False):
         """precision selects the video-level-score kernel: "f16x3" / "bf16x3" = tcgen05 tensor cores with
         hi/lo-split operands (3 MMAs per product, fp32-accurate), "f32" = exact-fp32 SIMT kernel.
         packed=True stores only the valid clips for the tensor-core kernel (CorpusPacking).
         merged_spans=True additionally keeps [feat2_video | feat2_sub] as hi/lo halves for the tensor-core
-        similarity-curve kernel of the merged two-stream model (needs both modalities, L <= 256)."""
+        similarity-curve kernel of the merged two-stream model (needs both modalities, L <= 256).
+        rescore_kblocked=True keeps a second, K-BLOCKED copy of the packed corpus halves for the exact re-scoring
+        kernel of the two-pass search (+1x the packed operand, 9.6 GB at the bench shape): it streams every
+        candidate video's clips as one contiguous run per k-step instead of 64-byte pieces 2 Kpad bytes apart.
+        Off by default: bit-equal but measured no faster (3.57 vs 3.59 ms per 10 K queries) -- unlike the similarity
+        kernel, the re-scoring kernel waits on the L2 round trips of its query gather, not on the corpus stream."""
         assert precision in self.PRECISIONS, precision
         ref = video_feat1 if video_feat1 is not None else sub_feat1
         self.n_videos, self.ctx_len, self.hidden = ref.shape
@@ -157,6 +162,7 @@ class CorpusIndex:
         self.precision = precision
         self.video_feat1n = self.sub_feat1n = None
         self.video_tc = self.sub_tc = self.video_bits = self.sub_bits = self.packing = self.f2cat = None
+        self.video_tc_kb = self.sub_tc_kb = None
         if video_feat1 is not None and sub_feat1 is not None and not torch.equal(video_mask, sub_mask):
             packed = False  # the packed layout shares one packing between the modalities
         if precision == "f32":
@@ -177,6 +183,8 @@ class CorpusIndex:
                         hi, lo, err = ops.split_rows(feat, kpad=self.kpad, normalize=True, bf16=bf16,
                                                      row_index=self.packing.src_rows, hi_err=True)
                         setattr(self, name + "_tc", (hi, lo))
+                        if rescore_kblocked:
+                            setattr(self, name + "_tc_kb", (ops.kblock_rows(hi), ops.kblock_rows(lo)))
                         self.tc_err[name] = float(err.max()) if err.numel() else 0.0
             else:
                 if video_feat1 is not None:
@@ -208,17 +216,18 @@ class CorpusIndex:
         self.sub_mask = sub_mask.contiguous() if sub_mask is not None else None
 
     @classmethod
-    def from_ctx_info(cls, ctx_info, vid_lo=0, precision="f16x3", packed=True, merged_spans=True):
+    def from_ctx_info(cls, ctx_info, vid_lo=0, precision="f16x3", packed=True, merged_spans=True,
+                      rescore_kblocked=False):
         return cls(ctx_info.get("video_feat1"), ctx_info.get("video_feat2"), ctx_info.get("video_mask"),
                    ctx_info.get("sub_feat1"), ctx_info.get("sub_feat2"), ctx_info.get("sub_mask"), vid_lo=vid_lo,
-                   precision=precision, packed=packed, merged_spans=merged_spans)
+                   precision=precision, packed=packed, merged_spans=merged_spans, rescore_kblocked=rescore_kblocked)
 
     # ---- incremental growth and persistence (the reference re-encodes and keeps the
     # corpus in Python lists of tensors, inference.py:32-97, and its profiling scenario is "1K videos are added",
     # baselines/profiling/profile_main.py:1-4) -------------------------------------------------------------------
     TENSORS = ("video_feat1n", "sub_feat1n", "video_feat2", "sub_feat2", "video_mask", "sub_mask", "video_bits",
                "sub_bits")
-    PAIRS = ("video_tc", "sub_tc", "f2cat")
+    PAIRS = ("video_tc", "sub_tc", "f2cat", "video_tc_kb", "sub_tc_kb")
 
     @torch.no_grad()
     def add_videos(self, video_feat1=None, video_feat2=None, video_mask=None, sub_feat1=None, sub_feat2=None,
@@ -234,7 +243,8 @@ class CorpusIndex:
             return torch.nn.functional.pad(t, pad)
         args = [widen(t) for t in (video_feat1, video_feat2, video_mask, sub_feat1, sub_feat2, sub_mask)]
         new = CorpusIndex(*args, vid_lo=self.vid_lo + self.n_videos, precision=self.precision,
-                          packed=self.packing is not None, merged_spans=self.f2cat is not None)
+                          packed=self.packing is not None, merged_spans=self.f2cat is not None,
+                          rescore_kblocked=(self.video_tc_kb or self.sub_tc_kb) is not None)
         assert (new.packing is None) == (self.packing is None) and (new.f2cat is None) == (self.f2cat is None)
         for name in self.TENSORS:
             a, b = getattr(self, name), getattr(new, name)
@@ -332,7 +342,7 @@ class CorpusIndex:
     def nbytes(self):
         tensors = [self.video_feat1n, self.sub_feat1n, self.video_feat2, self.sub_feat2, self.video_mask,
                    self.sub_mask, self.video_bits, self.sub_bits]
-        for pair in (self.video_tc, self.sub_tc, self.f2cat):
+        for pair in (self.video_tc, self.sub_tc, self.f2cat, self.video_tc_kb, self.sub_tc_kb):
             tensors.extend(pair or ())
         return sum(t.numel() * t.element_size() for t in tensors if t is not None)
 
@@ -473,8 +483,10 @@ class VCMRSearcher:
                                          const, self.max_candidates, ids=self.score_ids(),
                                          row_kth=self._global_kth(approx, k_global or k))
         with self._phase("vr_rescore"):
-            ops.vr_rescore_tc(used[0][0], ca, pk, cand, ix.kpad, q_fp32_b=used[1][0] if len(used) == 2 else None,
-                              c_b=cb, bf16=bf16, q_split_a=qa, q_split_b=qb)
+            kb = [c for c, on in ((ix.video_tc_kb, m.use_video), (ix.sub_tc_kb, m.use_sub)) if on]
+            ca_r, cb_r = (kb[0], kb[1] if len(used) == 2 else None) if all(c is not None for c in kb) else (ca, cb)
+            ops.vr_rescore_tc(used[0][0], ca_r, pk, cand, ix.kpad, q_fp32_b=used[1][0] if len(used) == 2 else None,
+                              c_b=cb_r, bf16=bf16, q_split_a=qa, q_split_b=qb)
         if self.debug is not None:
             self.debug["cand"] = cand
         with self._phase("topk_videos"):

@@ -570,7 +570,8 @@ def select_candidates(approx, k, row_err_a, row_err_b, err_scale, err_const, max
 def vr_rescore_tc(q_fp32_a, c_a, packing, cand, kpad, q_fp32_b=None, c_b=None, bf16=False, q_split_a=None,
                   q_split_b=None):
     """Overwrites cand.val with the exact split-precision scores of the candidate (query, packed video) pairs.
-    q_fp32_* (Nq, H) pooled query vectors (normalised here, gathered per video list); c_* packed corpus (hi, lo).
+    q_fp32_* (Nq, H) pooled query vectors (normalised here, gathered per video list); c_* packed corpus (hi, lo),
+    row-major (rows, kpad) or k-blocked (kblock_rows: contiguous TMA boxes).
     q_split_* = (hi, lo) of the normalised queries when the caller already has them (then only copied)."""
     lists = build_pair_lists(cand.col, packing.n_packed, chunk=128)
     dev = cand.col.device
@@ -584,8 +585,10 @@ def vr_rescore_tc(q_fp32_a, c_a, packing, cand, kpad, q_fp32_b=None, c_b=None, b
     qa = halves(q_fp32_a, q_split_a)
     qb = halves(q_fp32_b, q_split_b) if (q_fp32_b is not None or q_split_b is not None) else (None, None)
     cb = c_b if c_b is not None else (None, None)
-    rc = _lib.lib().xmlb_vr_rescore_tc_ex(_p(qa[0]), _p(qa[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
-                                          _p(cb[1]), _p(packing.row_start), _p(units),
+    kblocked = c_a[0].dim() == 3  # (kpad / 32, packed rows, 32), see kblock_rows
+    assert c_b is None or (c_b[0].dim() == 3) == kblocked
+    rc = _lib.lib().xmlb_vr_rescore_tc_kb(_p(qa[0]), _p(qa[1]), _p(qb[0]), _p(qb[1]), _p(c_a[0]), _p(c_a[1]), _p(cb[0]),
+                                          _p(cb[1]), int(kblocked), _p(packing.row_start), _p(units),
                                           lists.chunk_ptr[packing.n_packed:].data_ptr(), lists.max_chunks,
                                           _p(lists.entry_out), _p(lists.entry_q) if GATHER != "copy" else None,
                                           int(GATHER == "warps"), qa[0].shape[0], _p(cand.val), _p(_sched_ws(dev)),
