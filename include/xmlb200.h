@@ -295,7 +295,11 @@ int xmlb_span_probs_tc_ex(const unsigned short* f2_hi, const unsigned short* f2_
  * for any finite logit, model_xml.py:640-641), so the results are identical.
  * f2_kblocked != 0: f2_* are stored K-BLOCKED, [kcat / 32][n_videos * ctx_len][32] -- the
  * 32 elements a k-step reads from consecutive clips are contiguous in HBM (one run of rows * 64 bytes per TMA box
- * instead of `rows` separate 64-byte pieces 2 * kcat bytes apart, each in its own DRAM page). */
+ * instead of `rows` separate 64-byte pieces 2 * kcat bytes apart, each in its own DRAM page).
+ * f2_kblocked == 2 (gather-warps mode, ctx_len % 8 == 0): ... and the four 16-byte pieces of every row are already
+ * permuted the way SWIZZLE_64B places them in shared memory (piece c of row r at position c ^ ((r >> 1) & 3)), i.e.
+ * HBM holds the shared-memory image of every tile: a k-step's rows are fetched with ONE plain cp.async.bulk instead
+ * of a tensor box, which the TMA unit walks one 64-byte row at a time (the rate that bounded the kernel). */
 int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const unsigned short* f2_lo, const unsigned short* qg_hi,
                                const unsigned short* qg_lo, const float* mask, const float* w_st, const float* w_ed,
                                int ksize, int apply_softmax, int n_videos, int ctx_len, int kcat, long long n_entries,

@@ -343,6 +343,11 @@ def test_span_probs_tc(ops, nq, nv, length, hid, slots, chunk, precision):
                 g_st, g_ed = ops.span_probs_tc(kb, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length,
                                                bf16=bf16, clip_rows=rows_arg)
                 assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), "k-blocked layout"
+                if length % 8 == 0:  # ... and from the shared-memory image (plain bulk copies)
+                    img = tuple(ops.kblock_rows(t, swizzle=True) for t in operands)
+                    g_st, g_ed = ops.span_probs_tc(img, q_cat, lists, mask.to(DEV), t0.to(DEV), t1.to(DEV), length,
+                                                   bf16=bf16, clip_rows=rows_arg)
+                    assert torch.equal(g_st, got_st) and torch.equal(g_ed, got_ed), "shared-memory image layout"
         for mode in ("copy", "tma"):  # the other producers read the k-blocked layout too
             ops.GATHER = mode
             g_st, g_ed = ops.span_probs_tc(tuple(ops.kblock_rows(t) for t in f2cat), q_cat, lists, mask.to(DEV),

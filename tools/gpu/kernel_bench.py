@@ -68,7 +68,7 @@ def main():
             c = counters()
             print("span_topk (1/%d of the slots valid, as on %d GPUs): %.3f ms; overflowed rows %d of %d, mean survivors %.0f"
                   % (frac, frac, t, c[0], c[2], c[1] / max(1, c[2])))
-        for mode in (("warps",) if index.f2cat is not None and index.f2cat[0].dim() == 3 else ("copy", "warps")):
+        for mode in (("warps",) if index.f2cat is not None and index.f2cat[0].dim() >= 3 else ("copy", "warps")):
             ops.GATHER = mode
             print("span_probs [%s]: %.3f ms" % (mode, timed(lambda: s.span_probs(vq, sq, lists))))
             print("top_videos [%s] (filter + select + rescore + topk): %.3f ms" % (mode, timed(lambda: s.top_videos(vq, sq, 100), 3)))

@@ -28,6 +28,8 @@ struct SpanTcParams {
   int n_halves;          // 128-clip halves per video (2 when ctx_len > 128)
   const int4* units;     // {video, first entry row, entries in this chunk, clip rows to load (clip_boxes) or 0}
   int a_kb_rows;         // > 0: f2 is stored k-blocked, [kcat / 32][a_kb_rows = n_videos * ctx_len][32]
+  const unsigned short* f2_hi_bulk;  // != null: ... as the shared-memory image (pieces pre-swizzled): plain bulk copies
+  const unsigned short* f2_lo_bulk;
   int clip_boxes;        // 1: units[].w = number of leading clip rows of the video the epilogue can need (every
                          // unmasked clip and its ConvSE neighbours); only those are loaded, in 16-row steps
   const int* n_units;    // device scalar
@@ -64,6 +66,9 @@ struct SpanSched {
     d.a_hi = &maps->a_hi[box], d.a_lo = &maps->a_lo[box], d.b_hi = &maps->b_hi, d.b_lo = &maps->b_lo;
     d.a_bytes = (box + 1) * 16 * tc::SWIZZLE_BYTES;
     d.a_kb_rows = p->a_kb_rows;
+    d.a_hi_bulk = p->f2_hi_bulk, d.a_lo_bulk = p->f2_lo_bulk;
+    if (p->f2_hi_bulk)  // a plain copy has no out-of-bounds fill: never past the video's own rows
+      d.a_bytes = min((box + 1) * 16, p->ctx_len - half * BLOCK_M) * tc::SWIZZLE_BYTES;
     d.a_row = m.x * p->ctx_len + half * BLOCK_M;
     d.b_row = m.y;
     d.g_count = m.z;
@@ -103,7 +108,7 @@ span_probs_tc_kernel(const __grid_constant__ SpanTcMaps maps, const __grid_const
       tc::tc_producer_loop(SpanSched(&maps, &p), pipe);
     }
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+    tc::tc_mma_loop_warp(pipe, tmem_base);
   } else if (warp >= 2 + EPI_WARPS) {  // ============ gather warps: the listed queries -> B tile ============
     tc::tc_gather_loop(pipe, threadIdx.x - 32 * (2 + EPI_WARPS), p.entry_q, p.block_n, p.kcat,
                        [&](int u, int, int& e0, int& ne, const unsigned short*& hi, const unsigned short*& lo) {
@@ -293,6 +298,11 @@ extern "C" int xmlb_span_probs_tc_clipped(const unsigned short* f2_hi, const uns
                "xmlb_span_probs_tc: k-blocked f2 too large for 32-bit TMA coordinates");
   p.clip_boxes = clip_boxes ? 1 : 0;
   p.a_kb_rows = f2_kblocked ? n_videos * ctx_len : 0;
+  if (f2_kblocked == 2) {
+    XMLB_REQUIRE(p.gather_warps && ctx_len % 8 == 0,
+                 "xmlb_span_probs_tc: the pre-swizzled f2 layout needs the gather-warps mode and ctx_len %% 8 == 0");
+    p.f2_hi_bulk = f2_hi, p.f2_lo_bulk = f2_lo;
+  }
   p.mask = mask, p.w_st = w_st, p.w_ed = w_ed, p.out_st = out_st, p.out_ed = out_ed, p.unit_counter = sched_ws;
   p.idesc = tc::idesc_f16(BLOCK_M, block_n, is_bf16 ? 1 : 0);
   const int extra = block_n * s_ld * (int)sizeof(float) + 64 * (int)sizeof(float);  // similarity tile + taps

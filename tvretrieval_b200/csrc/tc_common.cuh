@@ -115,6 +115,29 @@ __host__ __device__ constexpr uint32_t idesc_f16(int m, int n, int is_bf16) {
          ((uint32_t)(m >> 4) << 24);
 }
 
+// One lane of a CONVERGED warp (all 32 lanes must execute it): true for the elected leader -- always the same lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Plain contiguous bulk copy global -> shared (no tensor map, no per-row processing), completion on an mbarrier
+// (bytes); size and both addresses multiples of 16.
+__device__ __forceinline__ void bulk_load_hint(uint32_t smem_dst, const void* src, uint32_t bytes, uint32_t bar,
+                                               uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {

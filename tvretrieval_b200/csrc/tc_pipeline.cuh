@@ -45,6 +45,10 @@ struct UnitDesc {
   int g_count;        // gather producer only: number of valid list entries of the gathered operand's tile
   int a_bytes;        // bytes one A box (hi or lo) delivers: A_TILE_BYTES unless the unit's A maps have a shorter box
                       // (honoured on the gather-warps path, p.gather == 2, only)
+  const unsigned short* a_hi_bulk;  // != null (p.gather == 2 path): A is stored as the k-blocked SHARED-MEMORY IMAGE of its
+  const unsigned short* a_lo_bulk;  // tiles (a_kb_rows > 0 and the 16-byte pieces of every row already permuted like
+                                    // SWIZZLE_64B would place them): a k-block's rows are fetched with ONE plain bulk
+                                    // copy of a_bytes instead of a tensor box that the TMA unit walks row by row
   int b_bytes;        // the same for the B boxes (p.b_tile_bytes by default; honoured on the p.gather == 1 path only)
   int b_kb_rows;      // > 0: B is stored k-blocked (see a_kb_rows)
   int a_kb_rows;      // 0 = A is (rows, K) row-major; > 0 = A is stored K-BLOCKED, [K / BLOCK_K][a_kb_rows][BLOCK_K]
@@ -160,6 +164,7 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
   uint32_t phase = 0, n = 0;
   UnitDesc u;
   u.k_block0 = 0, u.a_bytes = A_TILE_BYTES, u.a_kb_rows = 0, u.b_bytes = p.b_tile_bytes, u.b_kb_rows = 0;
+  u.a_hi_bulk = u.a_lo_bulk = nullptr;
   const uint64_t stream_policy = l2_policy_evict_first();
   while (sched.next(u)) {
     queue_push(p, n++, u.tag0, u.tag1, u.k_blocks, u.idesc);
@@ -177,8 +182,14 @@ __device__ __forceinline__ void tc_producer_loop(Sched sched, const Pipe& p) {
         } else {
           mbar_expect_tx(p.full_bar(stage), 2u * (uint32_t)u.a_bytes);
           const int c0 = u.a_kb_rows ? 0 : kb * BLOCK_K, c1 = u.a_row + kb * u.a_kb_rows;
-          tma_load_2d_hint(sa, u.a_hi, p.full_bar(stage), c0, c1, stream_policy);
-          tma_load_2d_hint(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), c0, c1, stream_policy);
+          if (u.a_hi_bulk) {
+            const size_t off = (size_t)c1 * BLOCK_K;  // elements: row c1 of the (k-blocks * rows, 32) image
+            bulk_load_hint(sa, u.a_hi_bulk + off, (uint32_t)u.a_bytes, p.full_bar(stage), stream_policy);
+            bulk_load_hint(sa + A_TILE_BYTES, u.a_lo_bulk + off, (uint32_t)u.a_bytes, p.full_bar(stage), stream_policy);
+          } else {
+            tma_load_2d_hint(sa, u.a_hi, p.full_bar(stage), c0, c1, stream_policy);
+            tma_load_2d_hint(sa + A_TILE_BYTES, u.a_lo, p.full_bar(stage), c0, c1, stream_policy);
+          }
         }
         if (++stage == p.stages) stage = 0, phase ^= 1u;
         continue;
@@ -367,6 +378,62 @@ __device__ __forceinline__ void tc_mma_loop(const Pipe& p, uint32_t tmem_base) {
       if (++stage == p.stages) stage = 0, phase ^= 1u;
     }
     umma_commit(p.tfull_bar(acc));  // accumulator complete
+  }
+}
+
+// The same loop run by ALL 32 lanes of the MMA warp: every lane follows the barriers, one elected lane issues.  When a
+// single thread runs tc_mma_loop inside `if (lane == 0)`, the compiler cannot tell that only one thread is active and
+// wraps every tcgen05.mma / commit in an elect-and-retry loop (ELECT, PLOP3, BRA.U.ANY around each UTCHMMA, ncu source
+// view) -- comparable to the tensor time of an MMA of the grouped kernels, whose N is only the 32..80 rows of one
+// video's list.  With the warp converged and elect.sync in the source the six MMAs of a k-block issue back to back.
+__device__ __forceinline__ void tc_mma_loop_warp(const Pipe& p, uint32_t tmem_base) {
+  const bool lane0 = (threadIdx.x & 31) == 0;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (uint32_t unit = 0;; ++unit) {
+    int tag0, tag1, k_blocks;
+    uint32_t idesc;
+    queue_pop(p, unit, false, tag0, tag1, k_blocks, idesc);
+    __syncwarp();  // every lane has read the entry before the slot is handed back
+    if (lane0) mbar_arrive(p.qempty_bar(unit % QUEUE_DEPTH));
+    if (k_blocks <= 0) break;
+    const uint32_t acc = unit & 1u, use = unit >> 1;
+    mbar_wait(p.tempty_bar(acc), (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
+    fence_after_sync();
+    const uint32_t tmem_acc = tmem_base + acc * ACC_COLS;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      mbar_wait(p.full_bar(stage), phase);
+      if (p.gather) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async-written tile -> async proxy
+      fence_after_sync();
+      __syncwarp();
+      const uint32_t sa = p.smem_base + stage * p.stage_bytes;
+      if (elect_one()) {
+        if (p.terms == 3) {
+          const uint64_t a_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa);
+          const uint64_t a_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + A_TILE_BYTES);
+          const uint64_t b_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES + p.b_tile_bytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);  // advance 32 B inside the swizzle row
+            umma_f16(tmem_acc, a_hi + off, b_lo + off, idesc, (kb | k) != 0);
+            umma_f16(tmem_acc, a_lo + off, b_hi + off, idesc, 1u);
+            umma_f16(tmem_acc, a_hi + off, b_hi + off, idesc, 1u);
+          }
+        } else {
+          const uint64_t a_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa);
+          const uint64_t b_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);
+            umma_f16(tmem_acc, a_hi + off, b_hi + off, idesc, (kb | k) != 0);
+          }
+        }
+        umma_commit(p.empty_bar(stage));  // the smem stage is reusable once these MMAs have read it
+        if (kb == k_blocks - 1) umma_commit(p.tfull_bar(acc));  // accumulator complete
+      }
+      if (++stage == p.stages) stage = 0, phase ^= 1u;
+    }
   }
 }
 

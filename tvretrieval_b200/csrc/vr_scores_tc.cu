@@ -282,7 +282,7 @@ vr_rescore_tc_kernel(const __grid_constant__ VrRescoreMaps maps, const __grid_co
       tc::tc_producer_loop(VrRescoreSched(&maps, &p), pipe);
     }
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+    tc::tc_mma_loop_warp(pipe, tmem_base);
   } else if (warp >= 6) {  // ===================== gather warps 6..9: the listed queries -> A tile =====================
     tc::tc_gather_loop(pipe, threadIdx.x - 192, p.entry_q, BLOCK_M, p.kpad,
                        [&](int u, int mod, int& e0, int& ne, const unsigned short*& hi, const unsigned short*& lo) {

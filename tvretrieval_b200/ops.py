@@ -637,12 +637,26 @@ def span_clip_rows(mask, ksize):
     return (last + ksize // 2).clamp_(max=length).to(torch.int32).contiguous()
 
 
-def kblock_rows(t, block=32):
+def kblock_rows(t, block=32, swizzle=False):
     """(rows, k) 16-bit operand -> the K-BLOCKED layout (k / block, rows, block) the similarity kernel streams with
-    contiguous TMA boxes (one run of box_rows * 64 bytes per k-step)."""
+    contiguous TMA boxes (one run of box_rows * 64 bytes per k-step).  swizzle=True additionally permutes the four
+    16-byte pieces of every 64-byte row the way SWIZZLE_64B places them in shared memory (piece c of row r at
+    position c ^ ((r >> 1) & 3)) and returns a 4-D (k / block, rows, 4, 8) tensor: the shared-memory IMAGE of the
+    tiles, fetched by plain bulk copies (tiles must start at rows that are multiples of 8)."""
     rows, k = t.shape
     assert k % block == 0
-    return t.view(rows, k // block, block).permute(1, 0, 2).contiguous()
+    out = t.view(rows, k // block, block).permute(1, 0, 2).contiguous()
+    if not swizzle:
+        return out
+    assert block == 32
+    s = (torch.arange(rows, device=t.device) >> 1) & 3
+    src = torch.arange(4, device=t.device)[None, :] ^ s[:, None]               # (rows, 4): piece held by position j
+    img = torch.empty(k // block, rows, 4, 8, device=t.device, dtype=t.dtype)
+    step = max(1, (1 << 28) // max(1, rows * block))                            # bounded temporaries
+    for lo in range(0, k // block, step):
+        part = out[lo:lo + step].view(-1, rows, 4, 8)
+        img[lo:lo + step] = torch.gather(part, 2, src[None, :, :, None].expand(part.shape[0], rows, 4, 8))
+    return img
 
 
 def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, bf16=False, out_rows=None,
@@ -651,9 +665,11 @@ def span_probs_tc(f2cat, q_cat, lists, mask, w_st, w_ed, ctx_len, softmax=True, 
     f2cat = (hi, lo) of [feat2_video | feat2_sub] (Nv * L, kcat); q_cat fp32 (Nq, kcat) = [q'_video | q'_sub] with
     each half zero-padded to kcat / 2; lists built with chunk in {32, 64, 128}.  -> st, ed of shape (rows, L).
     clip_rows = span_clip_rows(mask, ksize) (gather-warps mode): only those rows of every video are read."""
-    kblocked = f2cat[0].dim() == 3  # (kcat / 32, Nv * L, 32), see kblock_rows
+    # (kcat / 32, Nv * L, 32) = k-blocked, (kcat / 32, Nv * L, 4, 8) = k-blocked shared-memory image, see kblock_rows
+    kblocked = {2: 0, 3: 1, 4: 2}[f2cat[0].dim()]
     if kblocked:
-        n_videos, kcat = f2cat[0].shape[1] // ctx_len, f2cat[0].shape[0] * f2cat[0].shape[2]
+        assert kblocked == 1 or (GATHER == "warps" and ctx_len % 8 == 0)
+        n_videos, kcat = f2cat[0].shape[1] // ctx_len, f2cat[0].shape[0] * 32
     else:
         n_videos, kcat = f2cat[0].shape[0] // ctx_len, f2cat[0].shape[1]
     assert q_cat.shape[1] == kcat and lists.chunk in (32, 64, 128)
