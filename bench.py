@@ -469,17 +469,23 @@ def run_ours(args):
             rr = 0 if world > 1 else None  # sharded: the (identical) result is copied to the host of rank 0 only
             for _ in range(max(1, args.warmup // 2)):
                 searcher.search_host(qf_pin, qm_pin, result_rank=rr)
+            e2e_timer = PhaseTimer()
+            searcher.timer = e2e_timer
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 out = searcher.search_host(qf_pin, qm_pin, result_rank=rr)
             barrier()
             t_e2e = max_over_ranks(time.perf_counter() - t0)
+            searcher.timer = None
             d2h = sum(v.nbytes for v in out.values()) if out is not None else 0
             e2e = {"value": args.n_queries * args.steps / t_e2e, "unit": "queries/s",
                    "h2d_bytes_per_step": qf_pin.numel() * 4 + qm_pin.numel() * 4, "d2h_bytes_per_step": d2h,
                    "h2d_note": "summed over ranks: each rank uploads only its slice of the queries",
                    "ms_per_step": 1e3 * t_e2e / args.steps,
+                   # device time of the phases of the host-buffer call (per-piece filter passes summed); what is
+                   # left of ms_per_step is exposed upload, result download and host / launch gaps
+                   "phases_ms_per_step": {k: v / args.steps for k, v in e2e_timer.totals_ms().items()},
                    "api": "tvretrieval_b200.engine.VCMRSearcher.search_host (the call compute_query2ctx_info makes)"}
 
     ms_per_step = ms_total / args.steps

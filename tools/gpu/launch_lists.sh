@@ -6,3 +6,6 @@ timeout 600 $NCU --log-file gpurun_out/launches_step.csv python bench.py --steps
 timeout 300 $NCU --log-file gpurun_out/launches_encode.csv python tools/gpu/profile_encode.py > gpurun_out/launches_encode.log 2>&1
 tail -2 gpurun_out/launches_step.log | cut -c1-200; tail -2 gpurun_out/launches_encode.log
 python tools/gpu/profile_encode.py
+# ... and of one training step (forward + backward, bsz 128)
+timeout 300 $NCU --log-file gpurun_out/launches_train.csv python tools/gpu/profile_train.py > gpurun_out/launches_train.log 2>&1
+tail -1 gpurun_out/launches_train.log | cut -c1-200

@@ -565,12 +565,18 @@ class VCMRSearcher:
             step = max(step, 8192)
             return [(lo, min(n, lo + step)) for lo in range(0, n, step)]
         step = min(step, max(256, (n + 3) // 4))
-        first = max(min(128, step), step // 4)
+        # geometric ramp: a piece's upload (~1.7 us per query over PCIe) hides behind the encoding + filter pass of
+        # the piece before it (~4.5 us per query) as long as it is at most ~2.5x as large; only the first upload is
+        # exposed, so it is small (with a first piece of step / 4 the GPU idled ~2 ms per 10 K-query block waiting
+        # for the first two uploads)
+        size = 256 if step >= 1024 else max(min(128, step), step // 4)
         cuts, lo = [], 0
         while lo < n:
-            hi = min(n, lo + (first if lo == 0 else step))
+            hi = min(n, lo + size)
+            if n - hi < size // 2:  # no tiny last piece
+                hi = n
             cuts.append((lo, hi))
-            lo = hi
+            lo, size = hi, min(step, 2 * size)
         return cuts
 
     def _encode_pieces(self, pieces, lens_cpu=None, on_piece=None, tables_first=False, width=None, bounds=None,
