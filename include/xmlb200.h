@@ -141,8 +141,9 @@ int xmlb_vr_scores_tc_packed(const unsigned short* q_hi_a, const unsigned short*
  *
  * xmlb_select_candidates: per row r of approx (n_rows, n_cols), with error bound
  *   eps[r] = err_scale * (row_err_a[r] + row_err_b[r]) + err_const        (row_err_b may be NULL)
- * keeps every column with approx >= (k-th largest approx of the row) - 2 * eps[r] -- a superset of the exact
- * top-k whenever |approx - exact| <= eps[r].  row_kth (NULL, or n_rows floats): the k-th largest approx value
+ * keeps every column with approx >= kth - 2 * eps[r], kth = a lower bound of the row's k-th largest approx at most
+ * 3.1e-5 below it (lower edge of a 2^-15-wide bin of max - approx; the exact value when fewer than k scores lie within
+ * 1/8 of the row maximum) -- a superset of the exact top-k whenever |approx - exact| <= eps[r].  row_kth (NULL, or n_rows floats): the k-th largest approx value
  * supplied by the caller instead -- for a corpus sharded over GPUs it is taken over ALL shards (one small
  * all-gather), so each shard keeps only its part of the GLOBAL candidate set (n_cols < k is then allowed).  Outputs (n_rows, max_cand): cand_col = column, cand_id = ids[column]
  * (ids NULL: column), cand_val = approx value; unused slots are (-1, INT_MAX, -1e10).  A row with more than

@@ -298,8 +298,9 @@ def train_forward(cfg, w: Weights, query_feat, query_mask, video_feat, video_mas
     loss_neg_ctx = cfg["lw_neg_ctx"] * loss_neg_ctx
     loss_neg_q = cfg["lw_neg_q"] * loss_neg_q
     loss = loss_st_ed + loss_neg_ctx + loss_neg_q
-    return loss, {"loss_st_ed": float(loss_st_ed), "loss_neg_ctx": float(loss_neg_ctx),
-                  "loss_neg_q": float(loss_neg_q), "loss_overall": float(loss)}
+    val = lambda t: float(t.detach()) if torch.is_tensor(t) else float(t)  # noqa: E731
+    return loss, {"loss_st_ed": val(loss_st_ed), "loss_neg_ctx": val(loss_neg_ctx),
+                  "loss_neg_q": val(loss_neg_q), "loss_overall": val(loss)}
 
 
 # --------------------------------------------------------------------------------------

@@ -100,7 +100,7 @@ linear_tc_kernel(const __grid_constant__ LinMaps maps, const __grid_constant__ L
   if (warp == 0) {
     if (lane == 0) tc::tc_producer_loop(LinSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+    tc::tc_mma_loop_warp(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..9 =====================
     const int row_in_tile = (warp & 3) * 32 + lane;   // TMEM lane = output row of the tile
     const int half = (warp - 2) >> 2;                 // which half of the accumulator columns

@@ -1,7 +1,7 @@
 // Shared warp-specialised mainloop of the split-precision tcgen05 GEMM kernels (vr_scores_tc.cu, linear_tc.cu,
 // span_tc.cu).  One CTA = 192 threads:
 //   warp 0 lane 0 : scheduler + TMA producer  -> tc_producer_loop
-//   warp 1 lane 0 : MMA issuer                 -> tc_mma_loop
+//   warp 1        : MMA issuer (converged warp, one elected lane issues) -> tc_mma_loop_warp
 //   warps 2..5    : epilogue (kernel specific), driven by epi_next / epi_wait / epi_release
 // A unit = one accumulation D[128 x n] = sum over k-blocks of A_tile . B_tile^T with both operands given as (hi, lo)
 // 16-bit pairs: 3 MMAs per k-step (hi*lo + lo*hi + hi*hi), fp32 accumulate in TMEM.  Units alternate between two
@@ -286,7 +286,7 @@ __device__ __forceinline__ void tc_producer_loop_gather(Sched sched, const Pipe&
 // r * 64 + ((c ^ ((r >> 1) & 3)) * 16)).  Nothing is staged in registers and nothing waits for the data: as soon as a
 // stage is free its copies are issued and cp.async.mbarrier.arrive.noinc makes each thread's arrival on the stage's
 // full barrier happen when its copies have landed, so the gather runs ahead over all free stages.  The copies are
-// generic-proxy writes: the MMA thread issues fence.proxy.async after the full-barrier wait (tc_mma_loop).
+// generic-proxy writes: the MMA warp issues fence.proxy.async after the full-barrier wait (tc_mma_loop_warp).
 // `info(tag0, tag1, e0, ne, src_hi, src_lo)` maps a unit to its first list entry, entry count and source arrays.
 template <class Info>
 __device__ __forceinline__ void tc_gather_loop(const Pipe& p, int t, const int* __restrict__ entry_q, int rows,
@@ -336,53 +336,8 @@ __device__ __forceinline__ void tc_gather_loop(const Pipe& p, int t, const int* 
   }
 }
 
-__device__ __forceinline__ void tc_mma_loop(const Pipe& p, uint32_t tmem_base) {
-  int stage = 0;
-  uint32_t phase = 0;
-  for (uint32_t unit = 0;; ++unit) {
-    int tag0, tag1, k_blocks;
-    uint32_t idesc;
-    queue_pop(p, unit, true, tag0, tag1, k_blocks, idesc);
-    if (k_blocks <= 0) break;
-    const uint32_t acc = unit & 1u, use = unit >> 1;
-    mbar_wait(p.tempty_bar(acc), (use & 1u) ^ 1u);  // the epilogue has drained this accumulator
-    fence_after_sync();
-    const uint32_t tmem_acc = tmem_base + acc * ACC_COLS;
-    for (int kb = 0; kb < k_blocks; ++kb) {
-      mbar_wait(p.full_bar(stage), phase);
-      if (p.gather) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async-written tile -> async proxy
-      fence_after_sync();
-      const uint32_t sa = p.smem_base + stage * p.stage_bytes;
-      if (p.terms == 3) {
-        const uint64_t a_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa);
-        const uint64_t a_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + A_TILE_BYTES);
-        const uint64_t b_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES);
-        const uint64_t b_lo = smem_desc_kmajor<SWIZZLE_BYTES>(sa + 2 * A_TILE_BYTES + p.b_tile_bytes);
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);  // advance 32 B inside the swizzle row
-          umma_f16(tmem_acc, a_hi + off, b_lo + off, idesc, (kb | k) != 0);
-          umma_f16(tmem_acc, a_lo + off, b_hi + off, idesc, 1u);
-          umma_f16(tmem_acc, a_hi + off, b_hi + off, idesc, 1u);
-        }
-      } else {
-        const uint64_t a_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa);
-        const uint64_t b_hi = smem_desc_kmajor<SWIZZLE_BYTES>(sa + A_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t off = (uint64_t)(k * UMMA_K * 2 >> 4);
-          umma_f16(tmem_acc, a_hi + off, b_hi + off, idesc, (kb | k) != 0);
-        }
-      }
-      umma_commit(p.empty_bar(stage));  // the smem stage is reusable once these MMAs have read it
-      if (++stage == p.stages) stage = 0, phase ^= 1u;
-    }
-    umma_commit(p.tfull_bar(acc));  // accumulator complete
-  }
-}
-
-// The same loop run by ALL 32 lanes of the MMA warp: every lane follows the barriers, one elected lane issues.  When a
-// single thread runs tc_mma_loop inside `if (lane == 0)`, the compiler cannot tell that only one thread is active and
+// MMA loop, run by ALL 32 lanes of the MMA warp: every lane follows the barriers, one elected lane issues.  When a
+// single thread runs such a loop inside `if (lane == 0)`, the compiler cannot tell that only one thread is active and
 // wraps every tcgen05.mma / commit in an elect-and-retry loop (ELECT, PLOP3, BRA.U.ANY around each UTCHMMA, ncu source
 // view) -- comparable to the tensor time of an MMA of the grouped kernels, whose N is only the 32..80 rows of one
 // video's list.  With the warp converged and elect.sync in the source the six MMAs of a k-block issue back to back.

@@ -318,11 +318,42 @@ __global__ void __launch_bounds__(NT) select_candidates_kernel(
   if (row_kth) {  // k-th largest approximate score over a LARGER set of columns (all shards of a sharded corpus)
     kth = __ldg(row_kth + r);
   } else {
-    unsigned int thr = 0;
-    int n_equal, need_equal, n_total;
-    radix_select(gen, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k, thr,
-                 n_equal, need_equal, n_total);
-    kth = key_float(thr);
+    // Any LOWER bound of the k-th largest score keeps the candidate list a superset (it only lowers the cut), so the
+    // three radix passes -- whose first histogram piles a whole row of similar cosines into a dozen exponent bins --
+    // are replaced by: row maximum, then ONE histogram of (max - x) in HIST linear bins of width 2^-15 covering
+    // [max - 1/8, max] (the top of the row spreads over hundreds of bins; scores further down are not counted), and
+    // the lower edge of the bin that holds the k-th largest is the bound: at most 3.1e-5 below it, against a
+    // window of 2 eps ~ 1e-3.  Rows with fewer than k scores inside the range fall back to the exact selection.
+    constexpr float SCALE = 32768.f;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < n_cols; c += NT) mx = fmaxf(mx, __ldg(row + c));
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) reinterpret_cast<float*>(sm.warp_tot)[threadIdx.x >> 5] = mx;
+    for (int i = threadIdx.x; i < HIST; i += NT) sm.hist[i] = 0;
+    __syncthreads();
+    mx = reinterpret_cast<float*>(sm.warp_tot)[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) mx = fmaxf(mx, reinterpret_cast<float*>(sm.warp_tot)[w]);
+    __syncthreads();  // warp_tot is reused by find_bin
+    for (int c = threadIdx.x; c < n_cols; c += NT) {
+      const float t = __fmul_rn(__fsub_rn(mx, __ldg(row + c)), SCALE);  // >= 0; NaN / inf fail the test below
+      if (t < (float)HIST) atomicAdd(&sm.hist[HIST - 1 - (int)t], 1);
+    }
+    __syncthreads();
+    find_bin(sm, HIST, k);
+    if (sm.total >= k) {
+      // every score counted in bins >= sel_bin satisfies x > mx - (HIST - sel_bin) / SCALE - 1.2e-7 (rounding of the
+      // subtraction); the extra 4e-7 also covers the rounding of this expression
+      kth = __fsub_rd(__fsub_rd(mx, __fdiv_ru((float)(HIST - sm.sel_bin), SCALE)), 4e-7f);
+      __syncthreads();
+    } else {
+      __syncthreads();
+      unsigned int thr = 0;
+      int n_equal, need_equal, n_total;
+      radix_select(gen, [](unsigned int key, unsigned int, unsigned int& out) { out = key; return true; }, sm, k, thr,
+                   n_equal, need_equal, n_total);
+      kth = key_float(thr);
+    }
   }
   const float eps = fmaf(err_scale, __ldg(err_a + r) + (err_b ? __ldg(err_b + r) : 0.f), err_const);
   const float cut = __fmaf_rd(-2.f, eps, kth);

@@ -75,7 +75,7 @@ vr_scores_tc_kernel(const __grid_constant__ VrMaps maps, const __grid_constant__
   if (warp == 0) {
     if (lane == 0) tc::tc_producer_loop(VrSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+    tc::tc_mma_loop_warp(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
     const int row = (warp & 3) * 32 + lane;
     const int chunks = p.lp >> 5;
@@ -175,7 +175,7 @@ vr_scores_tc_packed_kernel(const __grid_constant__ VrMaps maps, const __grid_con
   if (warp == 0) {
     if (lane == 0) tc::tc_producer_loop(VrPackedSched(&maps, &p), pipe);
   } else if (warp == 1) {
-    if (lane == 0) tc::tc_mma_loop(pipe, tmem_base);
+    tc::tc_mma_loop_warp(pipe, tmem_base);
   } else {  // ===================== epilogue warps 2..5 =====================
     // per query row, the first modality's maxima are parked in shared memory (nothing on the accumulator-release
     // path waits on global memory).  Scores are written in PACKED ORDINAL order: the videos of a tile are adjacent
