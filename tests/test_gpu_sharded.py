@@ -60,6 +60,14 @@ def _worker(rank, world, port, use_nccl, precision, transport):
         host = sharded.search_host(qf.cpu(), qm.cpu(), gt.cpu(), tasks)
         for name in ("top_video_idx", "span_flat_idx", "span_score", "svmr_flat_idx"):
             assert (torch.from_numpy(host[name]) == getattr(want, name).cpu()).all(), name
+        # ... in several pieces per block: every rank encodes its share of EACH piece, the shares are exchanged and
+        # the filter pass runs piece by piece (with 3 ranks the last rank's share of a 4-query piece is empty)
+        sharded.min_piece, sharded.encode_chunk = 4, 8
+        assert len(sharded._piece_bounds(16, True)) == 4
+        for _ in range(2):  # twice: the exchange workspace is re-used across calls
+            host = sharded.search_host(qf.cpu(), qm.cpu(), gt.cpu(), tasks)
+            for name in ("top_video_idx", "span_flat_idx", "span_score", "svmr_flat_idx"):
+                assert (torch.from_numpy(host[name]) == getattr(want, name).cpu()).all(), name + " (pieces)"
     finally:
         dist.destroy_process_group()
 

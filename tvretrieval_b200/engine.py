@@ -544,6 +544,10 @@ class VCMRSearcher:
         """Part [lo, hi) of a block of n queries that THIS process encodes (all of it on one GPU)."""
         return 0, n
 
+    def _n_ranks(self):
+        """Processes that search the corpus together (ShardedSearcher: the shards)."""
+        return 1
+
     def _gather_encoded(self, video_query, sub_query, n):
         """Pooled query vectors of the whole block from the locally encoded slice (identity on one GPU)."""
         return video_query, sub_query
@@ -556,6 +560,8 @@ class VCMRSearcher:
     # 8 GPUs, 1,250 queries per rank: 2.1 ms packed vs 1.6 ms padded)
     packed_min_queries = 1024
 
+    min_piece = 256  # (tests lower it to exercise the multi-piece paths on tiny blocks)
+
     def _piece_bounds(self, n, host):
         """[lo, hi) of the pieces a slice of n queries is uploaded / encoded in.  From host buffers the first piece is
         small (its upload is the only one nothing overlaps) and a short slice (one rank's share of a sharded search)
@@ -564,7 +570,7 @@ class VCMRSearcher:
         if not host:  # device-resident queries: nothing to overlap, few large pieces = few launches
             step = max(step, 8192)
             return [(lo, min(n, lo + step)) for lo in range(0, n, step)]
-        step = min(step, max(256, (n + 3) // 4))
+        step = min(step, max(self.min_piece, (n + 3) // 4))
         # geometric ramp: a piece's upload (~1.7 us per query over PCIe) hides behind the encoding + filter pass of
         # the piece before it (~4.5 us per query) as long as it is at most ~2.5x as large; only the first upload is
         # exposed, so it is small (with a first piece of step / 4 the GPU idled ~2 ms per 10 K-query block waiting
@@ -597,7 +603,9 @@ class VCMRSearcher:
                                                                lens_dev=lens_dev)
             off = 0
             for i, (qf, qm) in enumerate(pieces):
-                if tables is not None:
+                if len(qf) == 0:  # (a rank's empty share of a piece of a sharded search)
+                    a = b = torch.zeros(0, hid, device=self.index.device)
+                elif tables is not None:
                     a, b = self.model.encode_query_packed(qf, tables=tables[i])
                 else:
                     a, b = self.model.encode_query(qf, qm)
@@ -666,17 +674,24 @@ class VCMRSearcher:
                 lens = lens.to(torch.int64).cpu()
             on_piece = None
             self._prefilter = None
-            if (host and self.pipelined_filter and external_topk is None and ("VR" in tasks or "VCMR" in tasks)
-                    and self.two_pass and self.index.n_videos >= self.max_n_videos and lo == 0 and hi == n):
-                # host buffers: the filter pass of piece i runs while piece i+1 is still being uploaded
-                self._prefilter = _Prefilter(self, n)
-                on_piece = self._prefilter.run
-            bounds = self._piece_bounds(hi - lo, host)
-            video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm, bounds) if host
-                                                         else self._device_pieces(qf, qm, bounds), lens, on_piece,
-                                                         tables_first=host, width=qm.shape[1], bounds=bounds,
-                                                         lens_dev=lens_dev)
-            video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
+            pipelined = (host and self.pipelined_filter and external_topk is None and self.two_pass
+                         and ("VR" in tasks or "VCMR" in tasks))
+            if pipelined and self._n_ranks() > 1:  # (the same decision on every rank)
+                # sharded search from host buffers: pieces of the block are encoded by all ranks together, shared
+                # and filtered while the next piece uploads (ShardedSearcher._encode_block_pipelined)
+                video_query, sub_query = self._encode_block_pipelined(query_feat[b_lo:b_lo + n],
+                                                                      query_mask[b_lo:b_lo + n], n)
+            else:
+                if pipelined and self.index.n_videos >= self.max_n_videos:
+                    # host buffers: the filter pass of piece i runs while piece i+1 is still being uploaded
+                    self._prefilter = _Prefilter(self, n)
+                    on_piece = self._prefilter.run
+                bounds = self._piece_bounds(hi - lo, host)
+                video_query, sub_query = self._encode_pieces(self._host_pieces(qf, qm, bounds) if host
+                                                             else self._device_pieces(qf, qm, bounds), lens, on_piece,
+                                                             tables_first=host, width=qm.shape[1], bounds=bounds,
+                                                             lens_dev=lens_dev)
+                video_query, sub_query = self._gather_encoded(video_query, sub_query, n)
             gt = None if gt_video_idx is None else gt_video_idx[b_lo:b_lo + n].to(dev, non_blocking=True)
             self._external = None
             if external_topk is not None:

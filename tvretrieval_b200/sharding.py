@@ -325,6 +325,61 @@ class ShardedSearcher(VCMRSearcher):
         lo, hi, _ = self.plan.query_range(n)
         return lo, hi
 
+    def _n_ranks(self):
+        return self.plan.world_size
+
+    def _encode_block_pipelined(self, query_feat_cpu, query_mask_cpu, n):
+        """Host-buffer search, encoding + filter pass of one block of n queries: the block is cut into GLOBAL pieces
+        (the geometric ramp of _piece_bounds) and every rank uploads and encodes its 1 / world share of EACH piece;
+        the pooled vectors of a piece are shared (peer stores into every rank's symmetric workspace + one device-side
+        barrier, or one all-gather) and the filter pass over this rank's shard runs on the piece while the shares of
+        the next piece are still uploading.  With one contiguous slice per rank (search() from device-resident
+        queries) the filter cannot start before every rank has uploaded and encoded everything: end to end the
+        uploads of the 8 ranks -- which share the host's PCIe / memory bandwidth -- were fully exposed.
+        -> pooled (video_query, sub_query) of all n queries; self._prefilter holds the finished filter pass."""
+        from .engine import _Prefilter
+        world, rank = self.plan.world_size, self.plan.rank
+        dev, hid = self.index.device, self.model.config.hidden_size
+        pieces = self._piece_bounds(n, True)
+        shares, mine = [], []
+        for g_lo, g_hi in pieces:
+            q = -(-(g_hi - g_lo) // world)
+            lo = min(g_hi, g_lo + rank * q)
+            shares.append(q), mine.append((lo, min(g_hi, lo + q)))
+        width = query_mask_cpu.shape[1]
+        lens = None
+        if (self.packed_queries and n // world >= self.packed_min_queries and width <= self.model.PACKED_MAX_LEN):
+            lens = (query_mask_cpu != 0).sum(1).to(torch.int64)
+        pre = _Prefilter(self, n)
+        if self.peer is not None:
+            per = self.peer.per(n)
+            all_q = self.peer.region("q_all", (world * per, 2, hid), torch.float32)[:n]
+        else:
+            all_q = torch.empty(n, 2, hid, device=dev)
+        done = [0]
+
+        def on_piece(_lo, _hi, a, b):
+            j = done[0]
+            done[0] += 1
+            (g_lo, g_hi), (lo, hi) = pieces[j], mine[j]
+            with self._phase("gather_queries"):
+                if self.peer is not None:
+                    if hi > lo:
+                        off = self.peer.off["q_all"] + lo * 2 * hid * 4
+                        ops.peer_copy(torch.stack([a, b], 1).contiguous(), self.peer.ws.ptrs(off))
+                    self.peer.ws.barrier()
+                else:
+                    share = torch.zeros(shares[j], 2, hid, device=dev)
+                    if hi > lo:
+                        share[:hi - lo, 0], share[:hi - lo, 1] = a, b
+                    all_q[g_lo:g_hi] = all_gather_rows(share, self.group)[:g_hi - g_lo]
+            pre.run(g_lo, g_hi, all_q[g_lo:g_hi, 0].contiguous(), all_q[g_lo:g_hi, 1].contiguous())
+
+        self._encode_pieces(self._host_pieces(query_feat_cpu, query_mask_cpu, mine), lens, on_piece, width=width,
+                            bounds=mine)
+        self._prefilter = pre
+        return all_q[:, 0].contiguous(), all_q[:, 1].contiguous()
+
     def _global_kth(self, approx, k):
         """The k-th largest APPROXIMATE score over all shards: local top-k values, one all-gather of (Nq, k) floats
         per rank, k-th largest of the union.  With it every rank keeps only the candidates that can reach the
