@@ -362,7 +362,7 @@ def ncu_traffic(args, world, searcher):
 
 def run_ours(args):
     from tvretrieval_b200 import _lib
-    from tvretrieval_b200.engine import CorpusIndex, PhaseTimer, VCMRSearcher
+    from tvretrieval_b200.engine import CorpusIndex, PhaseTimer, VCMRSearcher, host_memory_near
     from tvretrieval_b200.model_xml import XML
     from tvretrieval_b200.synthetic import corpus_lengths, synthetic_queries
 
@@ -407,7 +407,8 @@ def run_ours(args):
         qf_cpu = qm_cpu = qf_pin = qm_pin = None
     else:
         qf_cpu, qm_cpu = synthetic_queries(args.n_queries, 30, 768)
-        qf_pin, qm_pin = qf_cpu.pin_memory(), qm_cpu.pin_memory()
+        with host_memory_near(device):  # the pinned upload buffers on the GPU's own NUMA node
+            qf_pin, qm_pin = qf_cpu.pin_memory(), qm_cpu.pin_memory()
         qf, qm = qf_pin.to(device), qm_pin.to(device)
 
     two_pass = False if args.one_pass else None  # None: automatic (on for the packed f16x3 index)

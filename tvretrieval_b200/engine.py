@@ -18,6 +18,37 @@ import torch
 from . import ops
 
 
+@contextlib.contextmanager
+def host_memory_near(device):
+    """Context in which the calling thread runs on the CPUs next to `device` (NVML's ideal CPU affinity of the GPU),
+    so that host buffers allocated AND first touched inside it -- the pinned query / result buffers of
+    VCMRSearcher.search_host -- live on the GPU's own NUMA node: an upload from the other socket's memory runs at
+    about half the PCIe rate, and the ranks of a multi-GPU search otherwise all pull from whichever node their
+    processes happened to start on.  The previous affinity is restored on exit; without NVML this does nothing."""
+    old = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+        except Exception:
+            bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        old = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+    except Exception:
+        old = None
+    try:
+        yield
+    finally:
+        if old is not None:
+            try:
+                os.sched_setaffinity(0, old)
+            except OSError:
+                pass
+
+
 class PhaseTimer:
     """CUDA-event timers around the phases of a search (events are recorded on the stream the kernels are
     launched on).  bench.py uses it to report the dominant kernel's duration inside the timed region."""
