@@ -494,6 +494,22 @@ def test_two_pass_search_equals_one_pass(precision, max_cand):
     for name in ("top_video_idx", "top_video_score", "span_flat_idx", "span_score"):
         assert torch.equal(getattr(got, name), getattr(want, name)), name
     assert VCMRSearcher(model, index, **kw).two_pass == (precision == "f16x3")  # automatic choice
+    if max_cand is None:
+        # the optional operand layouts (k-blocked corpus copy for the re-scoring kernel, shared-memory image of
+        # f2cat fetched by plain bulk copies) and the host-buffer entry point in several pieces per block
+        # (per-piece filter passes behind the uploads): the same bits
+        os.environ["XMLB_F2_IMAGE"] = "1"
+        try:
+            alt = CorpusIndex(v1, v2, mask, s1, s2, mask, precision=precision, rescore_kblocked=True)
+        finally:
+            del os.environ["XMLB_F2_IMAGE"]
+        assert alt.f2cat[0].dim() == 4 and alt.video_tc_kb[0].dim() == 3 and index.video_tc_kb is None
+        searcher = VCMRSearcher(model, alt, two_pass=True, encode_chunk=64, **kw)
+        searcher.min_piece = 32
+        assert len(searcher._piece_bounds(256, True)) >= 4
+        host = searcher.search_host(qf.cpu().pin_memory(), qm.cpu().pin_memory())
+        for name in ("top_video_idx", "top_video_score", "span_flat_idx", "span_score"):
+            assert (torch.from_numpy(host[name]) == getattr(want, name).cpu()).all(), name
 
 
 @pytest.mark.parametrize("precision", ["f16x3", "f32"])
