@@ -438,6 +438,68 @@ struct SpanGen {
       }
     }
   }
+
+  // The same cells, in two phases: (1) every thread tests its rows and appends the surviving ones -- those whose best
+  // possible cell can reach min_score -- to `row_list` (shared memory, `cap` entries); (2) the listed rows are shared
+  // out EVENLY, one row (its ~14 cells) per thread at a time.  In for_each the cells of a surviving row are evaluated
+  // by the thread that owns the row, and since the survivors are the first clips of a few short, well-ranked videos
+  // they all belong to the same few warps: each of those ran ~300 dependent L1 / L2 round trips while the other warps
+  // sat at the barrier that ends the pass (ncu: a third of the kernel's samples).  Rows that do not fit into the list
+  // are evaluated in place as before.  Must be called by all NT threads; *row_count is zeroed by the caller.
+  template <class F>
+  __device__ void for_each_balanced(F f, int* row_list, int* row_count, int cap) const {
+    const int rows = n_list * L;
+    const int dj = NT / L, dm = NT - dj * L;
+    int s = threadIdx.x / L, m = threadIdx.x - s * L;
+    auto cells = [&](int j, int mm, float a) {
+      const int n_hi = min(mm + max_l, L);
+      const float* e = ed + j * L;
+      const int row = j * L + mm;
+      for (int n = mm + min_l; n < n_hi; ++n) {
+        const float sc = __fmul_rn(a, __ldg(e + n));
+        if (sc > 0.f && sc >= min_score) {
+          const unsigned int id = (unsigned int)(row * L + n);
+          f(float_key(sc), tie_desc ? id : ~id);
+        }
+      }
+    };
+    constexpr int U = 4;
+    for (int r0 = threadIdx.x; r0 < rows; r0 += U * NT) {
+      float a[U];
+      int jj[U], mm[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        a[u] = 0.f, jj[u] = 0, mm[u] = m;
+        if (r0 + u * NT < rows) {
+          jj[u] = slots[s];
+          a[u] = __ldg(st + jj[u] * L + m);
+        }
+        s += dj, m += dm;
+        if (m >= L) m -= L, ++s;
+      }
+      if (vr) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (a[u] > 0.f) a[u] = __fmul_rn(a[u], __ldg(vr + jj[u]));  // (st * vr) first, like torch.einsum
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!(a[u] > 0.f) || __fmul_ru(a[u], emax[jj[u]]) < min_score) continue;
+        const int pos = atomicAdd(row_count, 1);
+        if (pos < cap) row_list[pos] = jj[u] * L + mm[u];
+        else cells(jj[u], mm[u], a[u]);
+      }
+    }
+    __syncthreads();
+    const int n_rows = min(*row_count, cap);
+    for (int i = threadIdx.x; i < n_rows; i += NT) {
+      const int r = row_list[i];
+      const int j = r / L, mm_ = r - j * L;
+      float a = __ldg(st + r);
+      if (vr) a = __fmul_rn(a, __ldg(vr + j));
+      cells(j, mm_, a);
+    }
+  }
 };
 
 // generator over a compact (key, id) list in shared memory
@@ -585,14 +647,15 @@ __global__ void __launch_bounds__(NT) span_topk_kernel(const float* __restrict__
         compact_slots(n_valid, [&](int i) { const int j = slots[i]; return __fmul_ru(amax[j], emax[j]) >= bound; },
                       live, &n_live_s);
         for (int i = threadIdx.x; i < n_live_s; i += NT) live[i] = slots[live[i]];
-        if (threadIdx.x == 0) sm.n_list = 0;
+        if (threadIdx.x == 0) sm.n_list = 0, sm.count = 0;
         __syncthreads();
         SpanGen col = gen;
         col.slots = live, col.n_list = n_live_s, col.min_score = bound;
-        col.for_each([&](unsigned int key, unsigned int idk) {
+        // (the surviving-row list lives in the histogram array, which is idle during this pass)
+        col.for_each_balanced([&](unsigned int key, unsigned int idk) {
           const int pos = atomicAdd(&sm.n_list, 1);
           if (pos < LIST_CAP) list[pos] = ((unsigned long long)key << 32) | idk;
-        });
+        }, sm.hist, &sm.count, HIST);
         __syncthreads();
         const int n_list = sm.n_list;
         __syncthreads();
