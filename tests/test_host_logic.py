@@ -203,3 +203,50 @@ def test_eval_retrieval_matches_reference_evaluator():
     sub["VCMR"][0]["predictions"] = []
     m = eval_retrieval(sub, z["ground_truth"], verbose=False)
     assert set(m) == {"VCMR", "SVMR", "VR", "VCMR_by_type", "SVMR_by_type", "VR_by_type"}
+
+
+def test_operand_layout_helpers():
+    """ops.kblock_rows (k-blocked and shared-memory-image layouts of a 16-bit operand) and ops.span_clip_rows are
+    plain index arithmetic: checked here against their definitions, element by element."""
+    from tvretrieval_b200 import ops
+    rows, k = 40, 96
+    t = torch.arange(rows * k, dtype=torch.int16).view(rows, k)
+    kb = ops.kblock_rows(t)
+    assert kb.shape == (k // 32, rows, 32) and kb.is_contiguous()
+    for b in range(k // 32):
+        assert torch.equal(kb[b], t[:, 32 * b:32 * b + 32])
+    img = ops.kblock_rows(t, swizzle=True)
+    assert img.shape == (k // 32, rows, 4, 8) and img.is_contiguous()
+    for r in range(rows):
+        s = (r >> 1) & 3  # SWIZZLE_64B: 16-byte piece c of row r lands at position c ^ ((r >> 1) & 3)
+        for c in range(4):
+            assert torch.equal(img[:, r, c ^ s], kb[:, r, 8 * c:8 * c + 8])
+    # rows a ConvSE of `ksize` taps can read from an unmasked clip: last unmasked clip + 1 + ksize // 2, at most L
+    mask = torch.zeros(5, 12)
+    mask[0, :12] = 1
+    mask[1, :3] = 1
+    mask[2, :10] = 1
+    mask[4, 5] = 1  # (not a prefix mask: still covered)
+    assert ops.span_clip_rows(mask, 5).tolist() == [12, 5, 12, 2, 8]
+    assert ops.span_clip_rows(mask, 1).tolist() == [12, 3, 10, 0, 6]
+
+
+def test_host_upload_pieces_cover_the_block_and_ramp_up():
+    """VCMRSearcher._piece_bounds: contiguous cover of [0, n); from host buffers the pieces at most double (so that an
+    upload hides behind the work on the piece before it) up to encode_chunk, and there is no tiny last piece."""
+    from tvretrieval_b200.engine import VCMRSearcher
+
+    class Cfg:
+        encode_chunk, min_piece = 2048, 256
+
+    for n in (1, 100, 255, 256, 300, 1250, 2048, 5000, 10000, 16384):
+        for host in (True, False):
+            cuts = VCMRSearcher._piece_bounds(Cfg, n, host)
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:])) and all(hi > lo for lo, hi in cuts)
+            sizes = [hi - lo for lo, hi in cuts]
+            if host:
+                assert all(b <= 2 * a + a // 2 for a, b in zip(sizes, sizes[1:]))  # (the last piece absorbs a remainder)
+                assert max(sizes) <= Cfg.encode_chunk + Cfg.encode_chunk // 2
+                assert sizes[0] <= 256
+    assert [hi - lo for lo, hi in VCMRSearcher._piece_bounds(Cfg, 10000, True)] == [256, 512, 1024, 2048, 2048, 2048, 2064]
