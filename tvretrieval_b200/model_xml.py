@@ -265,7 +265,10 @@ class XML(nn.Module):
     def _upload_ints(self, arr, dev):
         """Small host int32 table -> device through a ring of reusable pinned staging buffers (a pageable source makes
         the copy synchronous with the stream, and pinning a fresh buffer per call costs more than the encoder)."""
-        ring = self.__dict__.setdefault("_pin_ring", {"slots": [None] * 8, "next": 0})
+        ring = self.__dict__.get("_pin_ring")
+        if ring is None:  # all slots at once: pinning a buffer costs about a millisecond and synchronises the device
+            ring = self.__dict__["_pin_ring"] = {"next": 0, "slots": [
+                [torch.empty(max(arr.size, 1 << 17), dtype=torch.int32).pin_memory(), None] for _ in range(8)]}
         i = ring["next"]
         ring["next"] = (i + 1) % len(ring["slots"])
         slot = ring["slots"][i]
